@@ -1,0 +1,156 @@
+/*
+ * b200unet — C ABI of the B200-native (sm_100a) U-Net hot path.
+ *
+ * Drop-in boundary for the hot path of caki35/UNet-Torch (reference = /root/reference):
+ *   Model.py:7-169  (DoubleConv / Down / Up / OutConv / UNet.forward)  and
+ *   loss.py:215-251, 442-516 (DiceLoss, calc_loss 'dice_bce_mc' / 'CE' / 'mse' / 'mseMC').
+ * The reference has no native code; every entry point below replaces the PyTorch library op the
+ * reference calls at the cited line. The Python host layer (unet-torch_b200/) binds these with ctypes.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller; kernels never allocate or free.
+ *   - Activations are NHWC bf16. `*_cs` arguments are the pixel pitch in ELEMENTS (>= channel count), so
+ *     a tensor may be a channel slice of a wider buffer (the decoder concat buffer, Model.py:79).
+ *   - `stream` is the caller's cudaStream_t. All launches are asynchronous; nothing synchronises.
+ *   - Return 0 on success, non-zero on bad shape / alignment / launch failure; text via b200unet_last_error().
+ *   - No CPU fallback anywhere: an unsupported shape is an error.
+ */
+#ifndef B200UNET_H_
+#define B200UNET_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+int b200unet_version(void);
+const char* b200unet_last_error(void);
+/* Number of kernels launched through this library since load (for bench.py's gpu_launches). */
+int64_t b200unet_launch_count(void);
+
+/* ---- tile geometry shared with the host (pixel tile of the implicit GEMMs) ------------------------------- */
+int b200unet_tile_h(void); /* 8  */
+int b200unet_tile_w(void); /* 16 */
+
+/* ---- weight preparation (fp32 master parameters -> bf16 GEMM operands), once per optimizer step ---------- */
+/* nn.Conv2d weight OIHW fp32 [K][C][3][3] (Model.py:15-16,19-20) -> fprop operand [K][3][3][C] bf16 and
+ * dgrad operand [C][3][3][K] bf16 with the taps rotated by 180 degrees. Either output may be NULL. */
+int b200unet_prep_conv3x3_weight(const float* w_oihw, void* w_fprop, void* w_dgrad, int K, int C,
+                                 b200_stream_t stream);
+/* nn.ConvTranspose2d weight [Cin][Cup][2][2] fp32 (Model.py:56-57) -> fprop operand [(i,j,d)][ci] bf16 and
+ * dgrad operand [ci][(i,j,d)] bf16. */
+int b200unet_prep_convt2x2_weight(const float* w, void* w_fprop, void* w_dgrad, int Cin, int Cup,
+                                  b200_stream_t stream);
+
+/* ---- tensor-core implicit GEMMs (tcgen05 / TMEM / TMA) ---------------------------------------------------- */
+/* 3x3, pad 1, no bias (nn.Conv2d, Model.py:15-16,19-20). y[n,h,w,k] = sum_{r,s,c} x[n,h+r-1,w+s-1,c] w[k,r,s,c].
+ * Used for fprop (w = fprop operand) and for dgrad (x = dy, w = dgrad operand, Cin/Cout swapped).
+ * stats_partial: NULL or fp32 [mtiles][2][Cout] (per pixel-tile sum and sum of squares of the bf16 outputs),
+ * mtiles = N * ceil(H/tile_h) * ceil(W/tile_w); feeds BatchNorm2d (Model.py:17,21).
+ * Requires Cin % 64 == 0 and Cout % 64 == 0. */
+int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial,
+                           int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
+/* ConvTranspose2d(Cin, Cup, 2, 2) + bias (Model.py:56-57,66): out[n,2h+i,2w+j,d] = b[d] + sum_c x[n,h,w,c] W[c,d,i,j],
+ * written with pitch out_cs into a (H2 x W2) canvas at row/col offset (pad_top, pad_left) (F.pad, Model.py:69-73). */
+int b200unet_convt2x2_fprop(const void* x, int x_cs, const void* w_fprop, const float* bias, void* out, int out_cs,
+                            int N, int H, int W, int Cin, int Cup, int H2, int W2, int pad_top, int pad_left,
+                            b200_stream_t stream);
+/* its backward-data: dx[n,h,w,c] = sum_{d,i,j} du[n,2h+i,2w+j,d] W[c,d,i,j]. */
+int b200unet_convt2x2_dgrad(const void* du, int du_cs, const void* w_dgrad, void* dx, int dx_cs, int N, int H,
+                            int W, int Cin, int Cup, int H2, int W2, int pad_top, int pad_left,
+                            b200_stream_t stream);
+
+/* Weight gradients. partial = fp32 workspace of b200unet_wgrad_workspace_floats() floats; dw = fp32 gradient in
+ * the PARAMETER's own layout (OIHW for conv, [Cin][Cup][2][2] for convT), overwritten (not accumulated). */
+int64_t b200unet_conv3x3_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout);
+int b200unet_conv3x3_wgrad(const void* x, int x_cs, const void* dy, int dy_cs, float* partial, float* dw_oihw,
+                           int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
+int64_t b200unet_convt2x2_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cup);
+int b200unet_convt2x2_wgrad(const void* x, int x_cs, const void* du, int du_cs, float* partial, float* dw,
+                            int N, int H, int W, int Cin, int Cup, int H2, int W2, int pad_top, int pad_left,
+                            b200_stream_t stream);
+
+/* ---- first layer and head (tiny channel counts: bandwidth-bound CUDA-core kernels) ------------------------ */
+/* inc.conv1: x fp32 NCHW [N][Cin<=4][H][W] (Trainer.py:700-702 hands fp32 NCHW) -> y bf16 NHWC [..][Cout] + stats. */
+int b200unet_conv3x3_first_fprop(const float* x_nchw, const float* w_oihw, void* y, int y_cs, float* stats_partial,
+                                 int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
+int64_t b200unet_conv3x3_first_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout);
+int b200unet_conv3x3_first_wgrad(const float* x_nchw, const void* dy, int dy_cs, float* partial, float* dw_oihw,
+                                 int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
+/* OutConv 1x1 + bias (Model.py:86-92): a bf16 NHWC [..][Cin] -> logits fp32 NCHW [N][ncls][H][W]. ncls <= 8. */
+int b200unet_head_fprop(const void* a, int a_cs, const float* w, const float* bias, float* logits_nchw, int N,
+                        int H, int W, int Cin, int ncls, b200_stream_t stream);
+/* backward: dz fp32 NCHW -> da bf16 NHWC, dw fp32 [ncls][Cin], db fp32 [ncls]. partial: workspace. */
+int64_t b200unet_head_bwd_workspace_floats(int N, int H, int W, int Cin, int ncls);
+int b200unet_head_bwd(const float* dz_nchw, const void* a, int a_cs, const float* w, void* da, int da_cs,
+                      float* partial, float* dw, float* db, int N, int H, int W, int Cin, int ncls,
+                      b200_stream_t stream);
+
+/* ---- BatchNorm2d + ReLU (+ MaxPool2d(2)) bandwidth kernels (Model.py:17-18,21-22,36,42) ------------------- */
+/* Reduce the per-tile partials of the conv epilogue into batch statistics and the affine (scale, shift):
+ *   sums[0..C)   = sum y, sums[C..2C) = sum y^2 (fp64, so SyncBN can all-reduce them between the two calls). */
+int b200unet_bn_reduce_partials(const float* stats_partial, int64_t mtiles, int C, double* sums,
+                                b200_stream_t stream);
+/* count = number of elements per channel behind `sums` (global count under SyncBN). Writes mean/rstd (saved for
+ * backward), scale = gamma*rstd, shift = beta - mean*scale; if running_mean != NULL also
+ * running_mean = (1-mom)*rm + mom*mean, running_var = (1-mom)*rv + mom*var*count/(count-1). */
+int b200unet_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
+                         float* scale, float* shift, int C, b200_stream_t stream);
+/* eval mode: scale/shift from running statistics. */
+int b200unet_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
+                            const float* running_var, float eps, float* scale, float* shift, int C,
+                            b200_stream_t stream);
+/* a = relu(scale*y + shift) written with pitch a_cs (possibly into the concat buffer). If pooled != NULL also
+ * writes the 2x2/2 max-pooled tensor [N][H/2][W/2][C] (pitch C) and, if pool_idx != NULL, the window position
+ * 0..3 (= 2*dh + dw, first maximum in row-major order, NaN wins: nn.MaxPool2d semantics) as uint8. */
+int b200unet_bn_relu_fwd(const void* y, int y_cs, const float* scale, const float* shift, void* a, int a_cs,
+                         void* pooled, uint8_t* pool_idx, int N, int H, int W, int C, b200_stream_t stream);
+/* Backward of (BN -> ReLU [-> skip + pool]). g1 = gradient w.r.t. a arriving with pitch g1_cs (may be NULL if
+ * pooled-only); g_pool/pool_idx = gradient w.r.t. the pooled tensor (NULL if the layer is not pooled).
+ * Pass 1 (reduce): per-block partial sums of da and da*xhat where da = (g1 + unpool(g_pool)) * [a > 0]. */
+int64_t b200unet_bn_bwd_workspace_floats(int N, int H, int W, int C);
+int b200unet_bn_relu_bwd_reduce(const void* g1, int g1_cs, const void* g_pool, const uint8_t* pool_idx,
+                                const void* y, int y_cs, const float* scale, const float* shift, const float* mean,
+                                const float* rstd, float* partial, double* sums, int N, int H, int W, int C,
+                                b200_stream_t stream);
+/* Pass 2 (apply): dy = gamma*rstd*(da - sum(da)/count - xhat*sum(da*xhat)/count); also dgamma = sums[C..2C),
+ * dbeta = sums[0..C) (local sums; `sums` may have been all-reduced for SyncBN, then pass local copies in
+ * sums_local for the parameter gradients). */
+int b200unet_bn_relu_bwd_apply(const void* g1, int g1_cs, const void* g_pool, const uint8_t* pool_idx,
+                               const void* y, int y_cs, const float* gamma, const float* scale, const float* shift,
+                               const float* mean, const float* rstd, const double* sums, double count,
+                               const double* sums_local, void* dy, int dy_cs, float* dgamma, float* dbeta, int N,
+                               int H, int W, int C, b200_stream_t stream);
+/* per-channel sum over pixels of a bf16 NHWC tensor (ConvTranspose2d bias gradient). */
+int64_t b200unet_channel_sum_workspace_floats(int C);
+int b200unet_channel_sum(const void* x, int x_cs, float* workspace, float* out, int64_t pixels, int C,
+                         b200_stream_t stream);
+
+/* ---- losses (loss.py:442-516) ----------------------------------------------------------------------------- */
+/* 'dice_bce_mc' (loss.py:488-500) and 'CE' (loss.py:468-469) forward. logits fp32 NCHW, target fp32 [N][H][W]
+ * (class index stored as float, as the reference DataLoader produces). sums (fp64, 1+3*ncls): [sum CE,
+ * I_c, Z_c, Y_c]. loss_out[0] = total loss, [1] = CE, [2] = Dice. mode: 0 = 0.5*CE+0.5*Dice, 1 = CE only.
+ * err_flag: set to 1 if a target is outside [0, ncls) (the reference raises). */
+int b200unet_loss_ce_dice_fwd(const float* logits, const float* target, double* sums, float* loss_out,
+                              int* err_flag, int N, int ncls, int64_t HW, int mode, b200_stream_t stream);
+/* dlogits = grad_out[0] * dL/dlogits. */
+int b200unet_loss_ce_dice_bwd(const float* logits, const float* target, const double* sums, const float* grad_out,
+                              float* dlogits, int N, int ncls, int64_t HW, int mode, b200_stream_t stream);
+/* 'mse' / 'mseMC' (loss.py:473-476): mean((pred - target)^2) over n elements; relu_input != 0 fuses the
+ * Trainer's F.relu (Trainer.py:709-710) when the caller wants it (pred = max(o, 0)). */
+int b200unet_mse_fwd(const float* pred, const float* target, double* sum, float* loss_out, int64_t n,
+                     int relu_input, b200_stream_t stream);
+int b200unet_mse_bwd(const float* pred, const float* target, const float* grad_out, float* dpred, int64_t n,
+                     int relu_input, b200_stream_t stream);
+
+/* ---- inference head (test_mc3serousv5.py:880-881): fp32 softmax over classes, then first-maximum argmax --- */
+int b200unet_softmax_argmax(const float* logits, int64_t* mask, int N, int ncls, int64_t HW, b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200UNET_H_ */

@@ -1,0 +1,177 @@
+"""ORACLE (test infrastructure, not product code): CPU restatement of the hot path of caki35/UNet-Torch.
+
+The reference's arithmetic lives in PyTorch library ops (third-party, unpinned by the reference: no requirements
+file; this image has torch 2.11.0). Each function below restates, as explicit tensor algebra on plain torch CPU
+tensors (fp32 or fp64), what the reference call site computes, citing reference file:line. The restatement
+deliberately avoids nn.Module / cuDNN dispatch: convolutions are written as unfold + matmul, BatchNorm, pooling,
+the transposed convolution and the losses as their closed forms.
+
+Pinning: the reference has NO tests, golden vectors or fixtures for this path, so the
+oracle is pinned against outputs of the reference itself: oracle/make_golden.py imports /root/reference/Model.py
+and loss.py in the build container, runs them on seeded inputs and commits the results under tests/golden/;
+tests/test_oracle.py checks this file against those vectors (and, when /root/reference is present, live).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+EPS_BN = 1e-5
+MOMENTUM = 0.1
+
+
+# ------------------------------------------------------------------------------------------------ operators
+def conv3x3(x, w):
+    """nn.Conv2d(k=3, padding=1, bias=False) (Model.py:15-16,19-20): cross-correlation with zero padding.
+    x [N,C,H,W], w [K,C,3,3] -> [N,K,H,W]."""
+    n, c, h, wd = x.shape
+    cols = F.unfold(x, kernel_size=3, padding=1)            # [N, C*9, H*W], ordered (c, r, s)
+    y = w.reshape(w.shape[0], c * 9) @ cols                # [N, K, H*W]
+    return y.reshape(n, w.shape[0], h, wd)
+
+
+def batchnorm_train(y, gamma, beta, running_mean=None, running_var=None, count_scale=1):
+    """nn.BatchNorm2d in training mode (Model.py:17,21): biased variance for normalisation, unbiased for the
+    running estimate, momentum 0.1, eps 1e-5. Returns (out, new_running_mean, new_running_var)."""
+    m = y.shape[0] * y.shape[2] * y.shape[3] * count_scale
+    mu = y.mean(dim=(0, 2, 3))
+    var = y.var(dim=(0, 2, 3), unbiased=False)
+    out = (y - mu[None, :, None, None]) * torch.rsqrt(var + EPS_BN)[None, :, None, None]
+    out = out * gamma[None, :, None, None] + beta[None, :, None, None]
+    nrm = nrv = None
+    if running_mean is not None:
+        nrm = (1 - MOMENTUM) * running_mean + MOMENTUM * mu
+        nrv = (1 - MOMENTUM) * running_var + MOMENTUM * var * m / (m - 1)
+    return out, nrm, nrv
+
+
+def batchnorm_eval(y, gamma, beta, running_mean, running_var):
+    s = gamma * torch.rsqrt(running_var + EPS_BN)
+    return y * s[None, :, None, None] + (beta - running_mean * s)[None, :, None, None]
+
+
+def relu(x):
+    """nn.ReLU (Model.py:18,22)."""
+    return torch.clamp_min(x, 0)
+
+
+def maxpool2x2(x):
+    """nn.MaxPool2d(2) (Model.py:36,42): floor mode, first maximum in row-major window order.
+    Returns (pooled, window position 0..3 = 2*dh+dw, flat int64 index h*W+w as torch reports it)."""
+    n, c, h, w = x.shape
+    hp, wp = h // 2, w // 2
+    win = x[:, :, : 2 * hp, : 2 * wp].reshape(n, c, hp, 2, wp, 2).permute(0, 1, 2, 4, 3, 5).reshape(n, c, hp, wp, 4)
+    best = win[..., 0].clone()
+    pos = torch.zeros_like(best, dtype=torch.int64)
+    for k in range(1, 4):
+        v = win[..., k]
+        take = (v > best) | torch.isnan(v)
+        best = torch.where(take, v, best)
+        pos = torch.where(take, torch.full_like(pos, k), pos)
+    hh = torch.arange(hp).view(1, 1, hp, 1) * 2 + pos // 2
+    ww = torch.arange(wp).view(1, 1, 1, wp) * 2 + pos % 2
+    return best, pos, hh * w + ww
+
+
+def conv_transpose2x2(x, w, b):
+    """nn.ConvTranspose2d(C, C/2, kernel_size=2, stride=2) (Model.py:56-57): non-overlapping upsample.
+    x [N,C,H,W], w [C,D,2,2], b [D] -> [N,D,2H,2W]."""
+    n, c, h, wd = x.shape
+    out = torch.einsum("nchw,cdij->ndhiwj", x, w).reshape(n, w.shape[1], 2 * h, 2 * wd)
+    return out + b[None, :, None, None]
+
+
+def pad_and_cat(skip, up):
+    """F.pad + torch.cat([x2, x1], dim=1) (Model.py:69-79): centre pad, skip channels first."""
+    dy, dx = skip.shape[2] - up.shape[2], skip.shape[3] - up.shape[3]
+    up = F.pad(up, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+    return torch.cat([skip, up], dim=1)
+
+
+def conv1x1(x, w, b):
+    """OutConv (Model.py:86-92)."""
+    return torch.einsum("nchw,kc->nkhw", x, w.reshape(w.shape[0], -1)) + b[None, :, None, None]
+
+
+# ------------------------------------------------------------------------------------------------ network
+def _double_conv(sd, prefix, x, training, new_buffers):
+    for ci, bi in ((0, 1), (3, 4)):
+        y = conv3x3(x, sd[f"{prefix}.{ci}.weight"])
+        g, b = sd[f"{prefix}.{bi}.weight"], sd[f"{prefix}.{bi}.bias"]
+        rm, rv = sd[f"{prefix}.{bi}.running_mean"], sd[f"{prefix}.{bi}.running_var"]
+        if training:
+            y, nrm, nrv = batchnorm_train(y, g, b, rm, rv)
+            new_buffers[f"{prefix}.{bi}.running_mean"] = nrm.detach()
+            new_buffers[f"{prefix}.{bi}.running_var"] = nrv.detach()
+            new_buffers[f"{prefix}.{bi}.num_batches_tracked"] = sd[f"{prefix}.{bi}.num_batches_tracked"] + 1
+        else:
+            y = batchnorm_eval(y, g, b, rm, rv)
+        x = relu(y)
+    return x
+
+
+def unet_forward(sd, x, training=True):
+    """UNet.forward (Model.py:142-153) as a pure function of a reference-format state_dict (dropout=False).
+    Returns (logits, dict of updated BatchNorm buffers)."""
+    nb = {}
+    x1 = _double_conv(sd, "inc.double_conv", x, training, nb)
+    skips = [x1]
+    cur = x1
+    for i in range(1, 5):
+        cur, _, _ = maxpool2x2(cur)
+        cur = _double_conv(sd, f"down{i}.maxpool_conv.1.double_conv", cur, training, nb)
+        skips.append(cur)
+    for i in range(1, 5):
+        up = conv_transpose2x2(cur, sd[f"up{i}.up.weight"], sd[f"up{i}.up.bias"])
+        cur = _double_conv(sd, f"up{i}.conv.double_conv", pad_and_cat(skips[4 - i], up), training, nb)
+    return conv1x1(cur, sd["outc.conv.weight"], sd["outc.conv.bias"]), nb
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def softmax_ce(logits, target):
+    """nn.CrossEntropyLoss()(pred, target.long()) (loss.py:469,498): mean over N*H*W of -log softmax[target]."""
+    lse = torch.logsumexp(logits, dim=1)
+    zt = torch.gather(logits, 1, target.long().unsqueeze(1)).squeeze(1)
+    return (lse - zt).mean()
+
+
+def dice_softmax(logits, target, n_classes):
+    """DiceLoss(n_classes)(pred, target, softmax=True) (loss.py:238-251): sums over the WHOLE batch per class."""
+    p = torch.softmax(logits, dim=1)
+    total = 0.0
+    for c in range(n_classes):
+        t = (target == c).to(p.dtype)
+        inter, y, z = (p[:, c] * t).sum(), (t * t).sum(), (p[:, c] * p[:, c]).sum()
+        total = total + (1 - (2 * inter + 1e-5) / (z + y + 1e-5))
+    return total / n_classes
+
+
+def calc_loss(pred, target, loss_type, n_classes=None):
+    """The hot branches of calc_loss (loss.py:442-516)."""
+    if loss_type == "dice_bce_mc":
+        return 0.5 * softmax_ce(pred, target) + 0.5 * dice_softmax(pred, target, n_classes or pred.shape[1])
+    if loss_type == "CE":
+        return softmax_ce(pred, target)
+    if loss_type == "mse":
+        return ((pred.squeeze(1) - target) ** 2).mean()
+    if loss_type == "mseMC":
+        return ((pred - target) ** 2).mean()
+    raise ValueError(loss_type)
+
+
+def softmax_argmax(logits):
+    """F.softmax(outputs, 1) then torch.argmax(probs, 1) (test_mc3serousv5.py:880-881) in the logits' dtype:
+    p_j = exp(z_j - max) / sum_j exp(z_j - max); first maximum wins."""
+    m = logits.max(dim=1, keepdim=True).values
+    e = torch.exp(logits - m)
+    s = e[:, 0:1].clone()
+    for j in range(1, logits.shape[1]):
+        s = s + e[:, j:j + 1]
+    p = e / s
+    best = p[:, 0].clone()
+    idx = torch.zeros_like(best, dtype=torch.int64)
+    for j in range(1, logits.shape[1]):
+        take = p[:, j] > best
+        best = torch.where(take, p[:, j], best)
+        idx = torch.where(take, torch.full_like(idx, j), idx)
+    return idx

@@ -1,0 +1,107 @@
+"""CPU: the oracle (oracle/unet_oracle.py) against the golden vectors produced by the UNMODIFIED reference
+(oracle/make_golden.py), and - when /root/reference is mounted - against the live reference."""
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("case", ["w4_c1_k2_dicebce", "w4_c3_k5_dicebce", "w4_c3_k3_ce", "w4_c3_k2_msemc"])
+def test_small_net_forward_backward_matches_reference(golden, case):
+    g = golden("ref_small_nets.pt")[case]
+    ch, ncls, width, n, h, w, seed = g["cfg"]
+    sd = {k: (v.double() if v.is_floating_point() else v) for k, v in g["sd0"].items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    sd_req = dict(sd)
+    sd_req.update(params)
+    logits, new_buf = O.unet_forward(sd_req, g["x"].double(), training=True)
+    pred = O.relu(logits) if g["loss_type"].startswith("mse") else logits
+    loss = O.calc_loss(pred, g["y"].double(), g["loss_type"], ncls)
+    loss.backward()
+    # fp64 oracle vs fp64 reference: tight; vs the fp32 reference: fp32 round-off
+    assert rel(logits, g["logits64"]) < 2e-6
+    assert abs(float(loss) - float(g["loss64"])) < 1e-9 * max(1.0, abs(float(g["loss64"])))
+    assert rel(logits, g["logits"]) < 1e-4
+    for k, p in params.items():
+        assert rel(p.grad, g["grads64"][k]) < 1e-5, k
+    for k, v in g["buffers1"].items():
+        if "num_batches" in k:
+            assert int(new_buf[k]) == int(v)
+        else:
+            assert rel(new_buf[k], v) < 1e-5, k
+    # eval mode uses the updated running statistics
+    sd_eval = dict(sd)
+    sd_eval.update({k: v.double() if v.is_floating_point() else v for k, v in g["buffers1"].items()})
+    le, _ = O.unet_forward(sd_eval, g["x"].double(), training=False)
+    assert rel(le, g["logits_eval"]) < 1e-4
+
+
+def test_pool_semantics(golden):
+    ops = golden("ref_ops.pt")
+    for key in ("pool", "pool_odd"):
+        v, pos, idx = O.maxpool2x2(ops[key]["x"])
+        assert torch.equal(idx, ops[key]["idx"])
+        assert torch.equal(torch.nan_to_num(v, nan=7.0), torch.nan_to_num(ops[key]["out"], nan=7.0))
+
+
+def test_softmax_argmax_semantics(golden):
+    ops = golden("ref_ops.pt")
+    for key in ("argmax_small_logits", "argmax_ties"):
+        assert torch.equal(O.softmax_argmax(ops[key]["z"]), ops[key]["mask"])
+
+
+@pytest.mark.parametrize("ncls", [2, 5])
+@pytest.mark.parametrize("lt", ["dice_bce_mc", "CE"])
+def test_loss_closed_form(golden, ncls, lt):
+    g = golden("ref_ops.pt")[f"loss_{lt}_{ncls}"]
+    z = g["z"].clone().requires_grad_(True)
+    l = O.calc_loss(z, g["t"], lt, ncls)
+    (gr,) = torch.autograd.grad(l, z)
+    assert abs(float(l) - float(g["loss"])) < 2e-6
+    assert rel(gr, g["grad"]) < 1e-5
+
+
+def test_mse_losses(golden):
+    ops = golden("ref_ops.pt")
+    g = ops["loss_relu_mseMC"]
+    o = g["o"].clone().requires_grad_(True)
+    l = O.calc_loss(O.relu(o), g["t"], "mseMC")
+    (gr,) = torch.autograd.grad(l, o)
+    assert abs(float(l) - float(g["loss"])) < 1e-6 and rel(gr, g["grad"]) < 1e-6
+    g = ops["loss_mse"]
+    o = g["o"].clone().requires_grad_(True)
+    l = O.calc_loss(o, g["t"], "mse")
+    (gr,) = torch.autograd.grad(l, o)
+    assert abs(float(l) - float(g["loss"])) < 1e-6 and rel(gr, g["grad"]) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Model.py"), reason="reference not mounted")
+def test_live_reference_agrees():
+    sys.dont_write_bytecode = True
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_ref_model", "/root/reference/Model.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    torch.manual_seed(3)
+    net = ref.UNet(2, 3, 4).double()
+    x = torch.randn(2, 2, 32, 32, dtype=torch.float64)
+    net.train()
+    want = net(x)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    # the training forward above already updated the running stats; recompute from the pre-update buffers
+    for k in sd:
+        if k.endswith("running_mean"):
+            sd[k] = torch.zeros_like(sd[k])
+        if k.endswith("running_var"):
+            sd[k] = torch.ones_like(sd[k])
+    got, _ = O.unet_forward(sd, x, training=True)
+    assert rel(got, want) < 1e-10

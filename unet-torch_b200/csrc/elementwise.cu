@@ -1,0 +1,480 @@
+// Bandwidth-bound kernels around the convolutions: BatchNorm2d statistics/affine, BN-apply + ReLU (+ 2x2 max
+// pool with argmax position, + write-into-concat-buffer), their backward (reduce + apply, with the skip/pool
+// gradient merge), and per-channel sums. Reference: Model.py:17-18,21-22 (BatchNorm2d, ReLU), :36,42 (MaxPool2d),
+// :79 (torch.cat). All activation traffic is 128-bit (8 x bf16) per thread, channel-innermost (NHWC).
+#include "../../include/b200unet.h"
+#include "host_common.h"
+
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+constexpr int EW_MAX_BLOCKS = 148 * 8;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+int ew_blocks(long long work_items) {
+  long long b = (work_items + EW_THREADS - 1) / EW_THREADS;
+  if (b > EW_MAX_BLOCKS) b = EW_MAX_BLOCKS;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+// ------------------------------------------------------------------------------------------ statistics
+// partial [rows][ncols] fp32 -> sums[ncols] fp64 (+=). 32 columns x 8 row-lanes per block.
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, long long rows, int ncols,
+                                       double* __restrict__ sums) {
+  __shared__ double sh[8][32];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  double acc = 0.0;
+  if (col < ncols) {
+    for (long long r = static_cast<long long>(blockIdx.y) * 8 + rl; r < rows; r += static_cast<long long>(gridDim.y) * 8)
+      acc += static_cast<double>(partial[r * ncols + col]);
+  }
+  sh[rl][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rl == 0 && col < ncols) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    atomicAdd(sums + col, t);
+  }
+}
+
+int launch_reduce_partials(const float* partial, long long rows, int ncols, double* sums, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * ncols, st);
+  if (e != cudaSuccess) {
+    b2h::set_error("reduce_partials memset: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  long long gy = (rows + 63) / 64;
+  if (gy > 64) gy = 64;
+  if (gy < 1) gy = 1;
+  dim3 grid((ncols + 31) / 32, static_cast<unsigned>(gy));
+  reduce_partials_kernel<<<grid, 256, 0, st>>>(partial, rows, ncols, sums);
+  return b2h::check_launch("reduce_partials");
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                                   float* running_var, float* mean, float* rstd, float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[c] / count;
+  double var = sums[C + c] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const float mf = static_cast<float>(m);
+  const float rs = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  mean[c] = mf;
+  rstd[c] = rs;
+  const float sc = gamma[c] * rs;
+  scale[c] = sc;
+  shift[c] = beta[c] - mf * sc;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mf;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+__global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                                      float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * (1.0f / sqrtf(rv[c] + eps));
+  scale[c] = sc;
+  shift[c] = beta[c] - rm[c] * sc;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+template <bool POOL>
+__global__ void __launch_bounds__(EW_THREADS) bn_relu_fwd_kernel(const __nv_bfloat16* __restrict__ y, int y_cs,
+                                                                 const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift,
+                                                                 __nv_bfloat16* __restrict__ a, int a_cs,
+                                                                 __nv_bfloat16* __restrict__ pooled,
+                                                                 uint8_t* __restrict__ pool_idx, int N, int H, int W,
+                                                                 int C) {
+  const int cgs = C >> 3;  // 8-channel groups; divides blockDim, so a thread keeps its group across the loop
+  const int cg = threadIdx.x % cgs;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = scale[cg * 8 + i];
+    sh[i] = shift[cg * 8 + i];
+  }
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  if (!POOL) {
+    const long long total = static_cast<long long>(N) * H * W * cgs;
+    for (long long i = tid; i < total; i += stride) {
+      const long long pix = i / cgs;
+      float f[8];
+      unpack8(ldg128(y + pix * y_cs + cg * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(sc[j], f[j], sh[j]), 0.f);
+      *reinterpret_cast<uint4*>(a + pix * a_cs + cg * 8) = pack8(f);
+    }
+  } else {
+    const int Hp = H >> 1, Wp = W >> 1;
+    const long long total = static_cast<long long>(N) * Hp * Wp * cgs;
+    for (long long i = tid; i < total; i += stride) {
+      const long long pp = i / cgs;  // pooled pixel
+      const int wp = static_cast<int>(pp % Wp);
+      const int hp = static_cast<int>((pp / Wp) % Hp);
+      const long long n = pp / (static_cast<long long>(Wp) * Hp);
+      const long long p00 = (n * H + 2 * hp) * W + 2 * wp;
+      float best[8];
+      uint32_t bidx[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long pix = p00 + (k >> 1) * W + (k & 1);
+        float f[8];
+        unpack8(ldg128(y + pix * y_cs + cg * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = bf16_round(fmaxf(fmaf(sc[j], f[j], sh[j]), 0.f));
+        *reinterpret_cast<uint4*>(a + pix * a_cs + cg * 8) = pack8(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // nn.MaxPool2d: keep the first maximum in row-major window order; NaN wins
+          if (k == 0 || f[j] > best[j] || f[j] != f[j]) {
+            best[j] = f[j];
+            bidx[j] = k;
+          }
+        }
+      }
+      *reinterpret_cast<uint4*>(pooled + pp * C + cg * 8) = pack8(best);
+      if (pool_idx != nullptr) {
+        uint2 pk;
+        pk.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+        pk.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+        *reinterpret_cast<uint2*>(pool_idx + pp * C + cg * 8) = pk;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// da for one pixel / channel group: (g1 + unpool(g_pool)) * [bn(y) > 0]
+struct BwdSrc {
+  const __nv_bfloat16* g1;
+  int g1_cs;
+  const __nv_bfloat16* gp;
+  const uint8_t* pidx;
+  const __nv_bfloat16* y;
+  int y_cs;
+};
+
+template <bool POOL>
+__device__ __forceinline__ void load_da_window(const BwdSrc& s, long long item, int cg, int C, int H, int W,
+                                               const float (&sc)[8], const float (&sh)[8], float (&da)[POOL ? 4 : 1][8],
+                                               float (&yv)[POOL ? 4 : 1][8], long long (&pix)[POOL ? 4 : 1]) {
+  if (!POOL) {
+    pix[0] = item;
+    unpack8(ldg128(s.y + item * s.y_cs + cg * 8), yv[0]);
+    if (s.g1 != nullptr) {
+      unpack8(ldg128(s.g1 + item * s.g1_cs + cg * 8), da[0]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) da[0][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!(fmaf(sc[j], yv[0][j], sh[j]) > 0.f)) da[0][j] = 0.f;
+  } else {
+    const int Hp = H >> 1, Wp = W >> 1;
+    const int wp = static_cast<int>(item % Wp);
+    const int hp = static_cast<int>((item / Wp) % Hp);
+    const long long n = item / (static_cast<long long>(Wp) * Hp);
+    const long long p00 = (n * H + 2 * hp) * W + 2 * wp;
+    float gp[8];
+    unpack8(ldg128(s.gp + item * C + cg * 8), gp);
+    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(s.pidx + item * C + cg * 8));
+    uint32_t bidx[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bidx[j] = (pk.x >> (8 * j)) & 0xff;
+      bidx[4 + j] = (pk.y >> (8 * j)) & 0xff;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      pix[k] = p00 + (k >> 1) * W + (k & 1);
+      unpack8(ldg128(s.y + pix[k] * s.y_cs + cg * 8), yv[k]);
+      if (s.g1 != nullptr) {
+        unpack8(ldg128(s.g1 + pix[k] * s.g1_cs + cg * 8), da[k]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) da[k][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (bidx[j] == static_cast<uint32_t>(k)) da[k][j] += gp[j];
+        if (!(fmaf(sc[j], yv[k][j], sh[j]) > 0.f)) da[k][j] = 0.f;
+      }
+    }
+  }
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(BwdSrc s, const float* __restrict__ scale,
+                                                                   const float* __restrict__ shift,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd,
+                                                                   float* __restrict__ partial, int N, int H, int W,
+                                                                   int C) {
+  constexpr int NP = POOL ? 4 : 1;
+  const int cgs = C >> 3;
+  const int cg = threadIdx.x % cgs;
+  float sc[8], sh[8], mu[8], rs[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = scale[cg * 8 + i];
+    sh[i] = shift[cg * 8 + i];
+    mu[i] = mean[cg * 8 + i];
+    rs[i] = rstd[cg * 8 + i];
+    s1[i] = 0.f;
+    s2[i] = 0.f;
+  }
+  const long long items = POOL ? static_cast<long long>(N) * (H >> 1) * (W >> 1) : static_cast<long long>(N) * H * W;
+  const long long total = items * cgs;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float da[NP][8], yv[NP][8];
+    long long pix[NP];
+    load_da_window<POOL>(s, i / cgs, cg, C, H, W, sc, sh, da, yv, pix);
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += da[k][j];
+        s2[j] = fmaf(da[k][j], (yv[k][j] - mu[j]) * rs[j], s2[j]);
+      }
+  }
+  // block reduction across the threads that share a channel group
+  __shared__ float sh_red[EW_THREADS][17];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sh_red[threadIdx.x][j] = s1[j];
+    sh_red[threadIdx.x][8 + j] = s2[j];
+  }
+  __syncthreads();
+  // thread t < 2*C handles (which = t / C, channel = t % C)
+  for (int t = threadIdx.x; t < 2 * C; t += blockDim.x) {
+    const int which = t / C, ch = t % C;
+    const int g = ch >> 3, j = ch & 7;
+    float acc = 0.f;
+    for (int th = g; th < EW_THREADS; th += cgs) acc += sh_red[th][which * 8 + j];
+    partial[static_cast<size_t>(blockIdx.x) * 2 * C + t] = acc;
+  }
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(BwdSrc s, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd,
+                                                                  const double* __restrict__ sums, double count,
+                                                                  const double* __restrict__ sums_local,
+                                                                  __nv_bfloat16* __restrict__ dy, int dy_cs,
+                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                  int N, int H, int W, int C) {
+  constexpr int NP = POOL ? 4 : 1;
+  const int cgs = C >> 3;
+  const int cg = threadIdx.x % cgs;
+  float sc[8], sh[8], k1[8], k2[8], k3[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cg * 8 + i;
+    sc[i] = scale[c];
+    sh[i] = shift[c];
+    const double g = gamma[c], r = rstd[c], m = mean[c];
+    const double sda = sums[c] / count, sdx = sums[C + c] / count;
+    // dy = g*r*(da - sda - xhat*sdx), xhat = (y - m)*r
+    k1[i] = static_cast<float>(g * r);
+    k2[i] = static_cast<float>(-g * r * r * sdx);
+    k3[i] = static_cast<float>(-g * r * sda + g * r * r * m * sdx);
+  }
+  if (blockIdx.x == 0 && dgamma != nullptr) {
+    const double* sl = sums_local != nullptr ? sums_local : sums;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dbeta[c] = static_cast<float>(sl[c]);
+      dgamma[c] = static_cast<float>(sl[C + c]);
+    }
+  }
+  const long long items = POOL ? static_cast<long long>(N) * (H >> 1) * (W >> 1) : static_cast<long long>(N) * H * W;
+  const long long total = items * cgs;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float da[NP][8], yv[NP][8];
+    long long pix[NP];
+    load_da_window<POOL>(s, i / cgs, cg, C, H, W, sc, sh, da, yv, pix);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(k1[j], da[k][j], fmaf(k2[j], yv[k][j], k3[j]));
+      *reinterpret_cast<uint4*>(dy + pix[k] * dy_cs + cg * 8) = pack8(o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) channel_sum_kernel(const __nv_bfloat16* __restrict__ x, int x_cs,
+                                                                 float* __restrict__ partial, long long pixels, int C) {
+  const int cgs = C >> 3;
+  const int cg = threadIdx.x % cgs;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long total = pixels * cgs;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float f[8];
+    unpack8(ldg128(x + (i / cgs) * x_cs + cg * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] += f[j];
+  }
+  __shared__ float sh_red[EW_THREADS][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh_red[threadIdx.x][j] = s1[j];
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const int g = ch >> 3, j = ch & 7;
+    float acc = 0.f;
+    for (int th = g; th < EW_THREADS; th += cgs) acc += sh_red[th][j];
+    partial[static_cast<size_t>(blockIdx.x) * C + ch] = acc;
+  }
+}
+
+__global__ void double_to_float_kernel(const double* in, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<float>(in[i]);
+}
+
+bool ok_channels(int C) { return C >= 64 && C <= 2048 && (C & (C - 1)) == 0; }
+
+int bwd_blocks(int N, int H, int W, int C, bool pool) {
+  const long long items = pool ? static_cast<long long>(N) * (H / 2) * (W / 2) : static_cast<long long>(N) * H * W;
+  return ew_blocks(items * (C / 8));
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200unet_bn_reduce_partials(const float* stats_partial, int64_t mtiles, int C, double* sums, b200_stream_t stream) {
+  return launch_reduce_partials(stats_partial, mtiles, 2 * C, sums, static_cast<cudaStream_t>(stream));
+}
+
+int b200unet_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, float* mean, float* rstd, float* scale,
+                         float* shift, int C, b200_stream_t stream) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, count, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift, C);
+  return b2h::check_launch("bn_finalize");
+}
+
+int b200unet_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                            float eps, float* scale, float* shift, int C, b200_stream_t stream) {
+  bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma, beta, running_mean,
+                                                                                      running_var, eps, scale, shift, C);
+  return b2h::check_launch("bn_eval_affine");
+}
+
+int b200unet_bn_relu_fwd(const void* y, int y_cs, const float* scale, const float* shift, void* a, int a_cs, void* pooled,
+                         uint8_t* pool_idx, int N, int H, int W, int C, b200_stream_t stream) {
+  B2_REQUIRE(ok_channels(C), "bn_relu_fwd: C=%d must be a power of two in [64, 2048]", C);
+  B2_REQUIRE(y_cs % 8 == 0 && a_cs % 8 == 0, "bn_relu_fwd: pitches must be multiples of 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const auto* yy = static_cast<const __nv_bfloat16*>(y);
+  auto* aa = static_cast<__nv_bfloat16*>(a);
+  if (pooled == nullptr) {
+    const int blocks = ew_blocks(static_cast<long long>(N) * H * W * (C / 8));
+    bn_relu_fwd_kernel<false><<<blocks, EW_THREADS, 0, st>>>(yy, y_cs, scale, shift, aa, a_cs, nullptr, nullptr, N, H, W, C);
+  } else {
+    B2_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_fwd(pool): H=%d W=%d must be even", H, W);
+    const int blocks = ew_blocks(static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8));
+    bn_relu_fwd_kernel<true><<<blocks, EW_THREADS, 0, st>>>(yy, y_cs, scale, shift, aa, a_cs,
+                                                            static_cast<__nv_bfloat16*>(pooled), pool_idx, N, H, W, C);
+  }
+  return b2h::check_launch("bn_relu_fwd");
+}
+
+int64_t b200unet_bn_bwd_workspace_floats(int N, int H, int W, int C) {
+  (void)N; (void)H; (void)W;
+  return static_cast<int64_t>(EW_MAX_BLOCKS) * 2 * C;
+}
+
+int b200unet_bn_relu_bwd_reduce(const void* g1, int g1_cs, const void* g_pool, const uint8_t* pool_idx, const void* y,
+                                int y_cs, const float* scale, const float* shift, const float* mean, const float* rstd,
+                                float* partial, double* sums, int N, int H, int W, int C, b200_stream_t stream) {
+  B2_REQUIRE(ok_channels(C), "bn_relu_bwd_reduce: C=%d must be a power of two in [64, 2048]", C);
+  B2_REQUIRE(g1 != nullptr || g_pool != nullptr, "bn_relu_bwd_reduce: no gradient source");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BwdSrc s{static_cast<const __nv_bfloat16*>(g1), g1_cs, static_cast<const __nv_bfloat16*>(g_pool), pool_idx,
+           static_cast<const __nv_bfloat16*>(y), y_cs};
+  const bool pool = g_pool != nullptr;
+  if (pool) B2_REQUIRE(H % 2 == 0 && W % 2 == 0 && pool_idx != nullptr, "bn_relu_bwd_reduce(pool): bad arguments");
+  const int blocks = bwd_blocks(N, H, W, C, pool);
+  if (pool)
+    bn_bwd_reduce_kernel<true><<<blocks, EW_THREADS, 0, st>>>(s, scale, shift, mean, rstd, partial, N, H, W, C);
+  else
+    bn_bwd_reduce_kernel<false><<<blocks, EW_THREADS, 0, st>>>(s, scale, shift, mean, rstd, partial, N, H, W, C);
+  if (int e = b2h::check_launch("bn_relu_bwd_reduce")) return e;
+  return launch_reduce_partials(partial, blocks, 2 * C, sums, st);
+}
+
+int b200unet_bn_relu_bwd_apply(const void* g1, int g1_cs, const void* g_pool, const uint8_t* pool_idx, const void* y,
+                               int y_cs, const float* gamma, const float* scale, const float* shift, const float* mean,
+                               const float* rstd, const double* sums, double count, const double* sums_local, void* dy,
+                               int dy_cs, float* dgamma, float* dbeta, int N, int H, int W, int C, b200_stream_t stream) {
+  B2_REQUIRE(ok_channels(C), "bn_relu_bwd_apply: C=%d must be a power of two in [64, 2048]", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BwdSrc s{static_cast<const __nv_bfloat16*>(g1), g1_cs, static_cast<const __nv_bfloat16*>(g_pool), pool_idx,
+           static_cast<const __nv_bfloat16*>(y), y_cs};
+  const bool pool = g_pool != nullptr;
+  const int blocks = bwd_blocks(N, H, W, C, pool);
+  if (pool)
+    bn_bwd_apply_kernel<true><<<blocks, EW_THREADS, 0, st>>>(s, gamma, scale, shift, mean, rstd, sums, count, sums_local,
+                                                             static_cast<__nv_bfloat16*>(dy), dy_cs, dgamma, dbeta, N, H,
+                                                             W, C);
+  else
+    bn_bwd_apply_kernel<false><<<blocks, EW_THREADS, 0, st>>>(s, gamma, scale, shift, mean, rstd, sums, count, sums_local,
+                                                              static_cast<__nv_bfloat16*>(dy), dy_cs, dgamma, dbeta, N,
+                                                              H, W, C);
+  return b2h::check_launch("bn_relu_bwd_apply");
+}
+
+int64_t b200unet_channel_sum_workspace_floats(int C) { return static_cast<int64_t>(EW_MAX_BLOCKS) * C + 2 * C; }
+
+int b200unet_channel_sum(const void* x, int x_cs, float* workspace, float* out, int64_t pixels, int C,
+                         b200_stream_t stream) {
+  B2_REQUIRE(ok_channels(C), "channel_sum: C=%d must be a power of two in [64, 2048]", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = ew_blocks(pixels * (C / 8));
+  channel_sum_kernel<<<blocks, EW_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_cs, workspace, pixels, C);
+  if (int e = b2h::check_launch("channel_sum")) return e;
+  // fp64 accumulator lives at the (8-byte aligned) tail of the workspace
+  double* acc = reinterpret_cast<double*>(workspace + static_cast<size_t>(EW_MAX_BLOCKS) * C);
+  if (int e = launch_reduce_partials(workspace, blocks, C, acc, st)) return e;
+  double_to_float_kernel<<<(C + 127) / 128, 128, 0, st>>>(acc, out, C);
+  return b2h::check_launch("channel_sum_cast");
+}
+
+}  // extern "C"

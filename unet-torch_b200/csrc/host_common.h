@@ -1,0 +1,32 @@
+// Host-side helpers shared by the launchers: error reporting, launch counting, TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace b2h {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);  // cudaGetLastError -> 0 / error code (+ message)
+
+// 4-D NHWC-style bf16 tensor map, 128B swizzle. dims/strides listed innermost first; strides in BYTES for
+// dims 1..3 (dim 0 is contiguous). box = {64 channels, box_w, box_h, 1}.
+int make_tmap_4d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                 uint64_t s1, uint64_t s2, uint64_t s3, uint32_t box_w, uint32_t box_h);
+// 2-D K-major bf16 matrix [rows][k] (pitch k elements), box = {64, box_rows}, 128B swizzle.
+int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t k, uint64_t rows, uint32_t box_rows);
+
+#define B2_REQUIRE(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      b2h::set_error(__VA_ARGS__);   \
+      return 1;                      \
+    }                                \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace b2h

@@ -1,0 +1,371 @@
+// CUDA-core kernels for the two layers whose channel counts are too small for the tensor-core path:
+//   inc.conv1  nn.Conv2d(n_channels<=4, 64, 3, padding=1, bias=False)   (reference Model.py:15-16 via :111)
+//   outc       nn.Conv2d(64, n_classes, 1) + bias                        (reference Model.py:86-92)
+// Both are bound by the 64-channel bf16 activation they write / read (128 B per pixel), not by arithmetic.
+#include "../../include/b200unet.h"
+#include "host_common.h"
+
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int MAX_BLOCKS = 148 * 8;
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- inc.conv1 fprop
+// Block = 128 consecutive pixels (linear over N*H*W) x one 64-channel group; thread = one pixel.
+// The bf16 tile is staged in smem (16-byte chunks XOR-swizzled by row) for a coalesced store and for the
+// per-channel sum / sum of squares that feed BatchNorm.
+template <int CIN>
+__global__ void __launch_bounds__(128) first_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          __nv_bfloat16* __restrict__ y, int y_cs,
+                                                          float* __restrict__ stats, int N, int H, int W, int Cout) {
+  __shared__ float ws[CIN * 9][64];          // [c*9+rs][k]
+  __shared__ __align__(16) uint8_t tile[128 * 128];
+  __shared__ float red[2][2][64];
+  const int kg = blockIdx.y;                 // 64-channel group
+  for (int i = threadIdx.x; i < CIN * 9 * 64; i += 128) {
+    const int k = i & 63, j = i >> 6;
+    ws[j][k] = w[(static_cast<size_t>(kg * 64 + k) * CIN) * 9 + j];
+  }
+  __syncthreads();
+  const long long P = static_cast<long long>(N) * H * W;
+  const long long p = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
+  const bool valid = p < P;
+  float acc[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) acc[k] = 0.f;
+  if (valid) {
+    const int wq = static_cast<int>(p % W);
+    const int hq = static_cast<int>((p / W) % H);
+    const long long n = p / (static_cast<long long>(W) * H);
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      const float* xc = x + (n * CIN + c) * static_cast<long long>(H) * W;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = hq + r - 1;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int ww = wq + s - 1;
+          float xv = 0.f;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W) xv = __ldg(xc + static_cast<long long>(hh) * W + ww);
+          const float4* wr = reinterpret_cast<const float4*>(ws[c * 9 + r * 3 + s]);
+#pragma unroll
+          for (int k4 = 0; k4 < 16; ++k4) {
+            const float4 wv = wr[k4];
+            acc[4 * k4 + 0] = fmaf(xv, wv.x, acc[4 * k4 + 0]);
+            acc[4 * k4 + 1] = fmaf(xv, wv.y, acc[4 * k4 + 1]);
+            acc[4 * k4 + 2] = fmaf(xv, wv.z, acc[4 * k4 + 2]);
+            acc[4 * k4 + 3] = fmaf(xv, wv.w, acc[4 * k4 + 3]);
+          }
+        }
+      }
+    }
+  }
+  const int r = threadIdx.x;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    uint4 pk = make_uint4(pack2(acc[8 * t], acc[8 * t + 1]), pack2(acc[8 * t + 2], acc[8 * t + 3]),
+                          pack2(acc[8 * t + 4], acc[8 * t + 5]), pack2(acc[8 * t + 6], acc[8 * t + 7]));
+    *reinterpret_cast<uint4*>(tile + r * 128 + ((t ^ (r & 7)) << 4)) = pk;
+  }
+  __syncthreads();
+  // coalesced copy-out: 8 threads per pixel row
+  for (int i = threadIdx.x; i < 128 * 8; i += 128) {
+    const int rr = i >> 3, ch = i & 7;
+    const long long pp = static_cast<long long>(blockIdx.x) * 128 + rr;
+    if (pp < P)
+      *reinterpret_cast<uint4*>(y + pp * y_cs + kg * 64 + ch * 8) =
+          *reinterpret_cast<const uint4*>(tile + rr * 128 + ((ch ^ (rr & 7)) << 4));
+  }
+  if (stats != nullptr) {
+    const int c = threadIdx.x & 63, hf = threadIdx.x >> 6;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < 64; ++i) {
+      const int rr = hf * 64 + i;
+      const long long pp = static_cast<long long>(blockIdx.x) * 128 + rr;
+      const uint16_t u = *reinterpret_cast<const uint16_t*>(tile + rr * 128 + (((c >> 3) ^ (rr & 7)) << 4) + (c & 7) * 2);
+      const float v = (pp < P) ? __uint_as_float(static_cast<uint32_t>(u) << 16) : 0.f;
+      s1 += v;
+      s2 = fmaf(v, v, s2);
+    }
+    red[hf][0][c] = s1;
+    red[hf][1][c] = s2;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float* dst = stats + static_cast<size_t>(blockIdx.x) * 2 * Cout + kg * 64;
+      dst[threadIdx.x] = red[0][0][threadIdx.x] + red[1][0][threadIdx.x];
+      dst[Cout + threadIdx.x] = red[0][1][threadIdx.x] + red[1][1][threadIdx.x];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- inc.conv1 wgrad
+// thread = (pixel lane pl in 0..15, 4-channel group cq in 0..15) of one 64-channel group; 4 x CIN*9 accumulators.
+template <int CIN>
+__global__ void __launch_bounds__(256) first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                          int dy_cs, float* __restrict__ partial, int N, int H, int W,
+                                                          int Cout) {
+  constexpr int T = CIN * 9;
+  __shared__ float sh[256][T + 1];
+  const int kg = blockIdx.y;
+  const int cq = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  float acc[4][T];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < T; ++j) acc[i][j] = 0.f;
+  const long long P = static_cast<long long>(N) * H * W;
+  for (long long p = static_cast<long long>(blockIdx.x) * 16 + pl; p < P; p += static_cast<long long>(gridDim.x) * 16) {
+    const int wq = static_cast<int>(p % W);
+    const int hq = static_cast<int>((p / W) % H);
+    const long long n = p / (static_cast<long long>(W) * H);
+    const uint2 d = __ldg(reinterpret_cast<const uint2*>(dy + p * dy_cs + kg * 64 + cq * 4));
+    const float g[4] = {__uint_as_float(d.x << 16), __uint_as_float(d.x & 0xffff0000u), __uint_as_float(d.y << 16),
+                        __uint_as_float(d.y & 0xffff0000u)};
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      const float* xc = x + (n * CIN + c) * static_cast<long long>(H) * W;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = hq + r - 1;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int ww = wq + s - 1;
+          float xv = 0.f;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W) xv = __ldg(xc + static_cast<long long>(hh) * W + ww);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i][c * 9 + r * 3 + s] = fmaf(g[i], xv, acc[i][c * 9 + r * 3 + s]);
+        }
+      }
+    }
+  }
+  // reduce over the 16 pixel lanes, one output channel (of the 4) at a time
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < T; ++j) sh[threadIdx.x][j] = acc[i][j];
+    __syncthreads();
+    for (int o = threadIdx.x; o < 16 * T; o += 256) {
+      const int q = o / T, j = o % T;
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < 16; ++l) t += sh[l * 16 + q][j];
+      const int k = kg * 64 + q * 4 + i;
+      partial[(static_cast<size_t>(blockIdx.x) * Cout + k) * T + j] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- head
+__global__ void __launch_bounds__(256) head_fprop_kernel(const __nv_bfloat16* __restrict__ a, int a_cs,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         float* __restrict__ z, long long P, long long HW, int Cin,
+                                                         int ncls) {
+  extern __shared__ float wsm[];  // [ncls][Cin]
+  for (int i = threadIdx.x; i < ncls * Cin; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = (j < ncls) ? bias[j] : 0.f;
+    for (int c8 = 0; c8 < Cin / 8; ++c8) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a + p * a_cs + c8 * 8)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < ncls) {
+          const float* wr = wsm + j * Cin + c8 * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[j] = fmaf(f[i], wr[i], acc[j]);
+        }
+      }
+    }
+    const long long n = p / HW, hw = p % HW;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < ncls) z[(n * ncls + j) * HW + hw] = acc[j];
+  }
+}
+
+// thread = (pixel lane, 8-channel group); block = 256 threads = (256/cgs) pixels x cgs groups
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dz, const __nv_bfloat16* __restrict__ a,
+                                                       int a_cs, const float* __restrict__ w,
+                                                       __nv_bfloat16* __restrict__ da, int da_cs,
+                                                       float* __restrict__ partial, long long P, long long HW, int Cin,
+                                                       int ncls) {
+  __shared__ float sh[256][9];
+  const int cgs = Cin >> 3;
+  const int cg = threadIdx.x % cgs, pl = threadIdx.x / cgs, ppb = 256 / cgs;
+  float wr[8][8], dwacc[8][8], dbacc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    dbacc[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      wr[j][i] = (j < ncls) ? w[j * Cin + cg * 8 + i] : 0.f;
+      dwacc[j][i] = 0.f;
+    }
+  }
+  for (long long p = static_cast<long long>(blockIdx.x) * ppb + pl; p < P; p += static_cast<long long>(gridDim.x) * ppb) {
+    const long long n = p / HW, hw = p % HW;
+    float f[8], o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a + p * a_cs + cg * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < ncls) {
+        const float g = __ldg(dz + (n * ncls + j) * HW + hw);
+        dbacc[j] += g;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = fmaf(g, wr[j][i], o[i]);
+          dwacc[j][i] = fmaf(g, f[i], dwacc[j][i]);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(da + p * da_cs + cg * 8) =
+        make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+  }
+  // partial layout: [block][ncls][Cin + 1], last column = bias gradient
+  for (int j = 0; j < ncls; ++j) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sh[threadIdx.x][i] = dwacc[j][i];
+    sh[threadIdx.x][8] = (cg == 0) ? dbacc[j] : 0.f;
+    __syncthreads();
+    float* dst = partial + (static_cast<size_t>(blockIdx.x) * ncls + j) * (Cin + 1);
+    for (int c = threadIdx.x; c <= Cin; c += blockDim.x) {
+      float t = 0.f;
+      if (c < Cin) {
+        const int g = c >> 3, i = c & 7;
+        for (int l = 0; l < ppb; ++l) t += sh[l * cgs + g][i];
+      } else {
+        for (int l = 0; l < 256; ++l) t += sh[l][8];
+      }
+      dst[c] = t;
+    }
+  }
+}
+
+// column sums of partial [rows][ncols] (fp64 accumulate), optional split into (dw [ncls][Cin], db [ncls])
+__global__ void colsum_kernel(const float* __restrict__ partial, int rows, int ncols, float* __restrict__ out,
+                              float* __restrict__ out2, int split_stride) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  double acc = 0.0;
+  for (int r = 0; r < rows; ++r) acc += static_cast<double>(partial[static_cast<size_t>(r) * ncols + col]);
+  if (split_stride == 0) {
+    out[col] = static_cast<float>(acc);
+  } else {
+    const int j = col / split_stride, c = col % split_stride;
+    if (c < split_stride - 1) out[j * (split_stride - 1) + c] = static_cast<float>(acc);
+    else out2[j] = static_cast<float>(acc);
+  }
+}
+
+int first_wgrad_blocks(long long P) {
+  long long b = (P + 15) / 16;
+  if (b > 148 * 4) b = 148 * 4;
+  return static_cast<int>(b < 1 ? 1 : b);
+}
+int head_bwd_blocks(long long P, int Cin) {
+  const int ppb = 256 / (Cin / 8);
+  long long b = (P + ppb - 1) / ppb;
+  if (b > MAX_BLOCKS) b = MAX_BLOCKS;
+  return static_cast<int>(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200unet_conv3x3_first_fprop(const float* x_nchw, const float* w_oihw, void* y, int y_cs, float* stats_partial,
+                                 int N, int H, int W, int Cin, int Cout, b200_stream_t stream) {
+  B2_REQUIRE(Cin >= 1 && Cin <= 4, "conv3x3_first_fprop: Cin=%d must be in [1,4]", Cin);
+  B2_REQUIRE(Cout % 64 == 0 && y_cs % 8 == 0, "conv3x3_first_fprop: Cout=%d must be a multiple of 64", Cout);
+  const long long P = static_cast<long long>(N) * H * W;
+  dim3 grid(static_cast<unsigned>((P + 127) / 128), Cout / 64);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto* yy = static_cast<__nv_bfloat16*>(y);
+  switch (Cin) {
+    case 1: first_fprop_kernel<1><<<grid, 128, 0, st>>>(x_nchw, w_oihw, yy, y_cs, stats_partial, N, H, W, Cout); break;
+    case 2: first_fprop_kernel<2><<<grid, 128, 0, st>>>(x_nchw, w_oihw, yy, y_cs, stats_partial, N, H, W, Cout); break;
+    case 3: first_fprop_kernel<3><<<grid, 128, 0, st>>>(x_nchw, w_oihw, yy, y_cs, stats_partial, N, H, W, Cout); break;
+    default: first_fprop_kernel<4><<<grid, 128, 0, st>>>(x_nchw, w_oihw, yy, y_cs, stats_partial, N, H, W, Cout); break;
+  }
+  return b2h::check_launch("conv3x3_first_fprop");
+}
+
+int64_t b200unet_conv3x3_first_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout) {
+  return static_cast<int64_t>(first_wgrad_blocks(static_cast<long long>(N) * H * W)) * Cout * Cin * 9;
+}
+
+int b200unet_conv3x3_first_wgrad(const float* x_nchw, const void* dy, int dy_cs, float* partial, float* dw_oihw, int N,
+                                 int H, int W, int Cin, int Cout, b200_stream_t stream) {
+  B2_REQUIRE(Cin >= 1 && Cin <= 4, "conv3x3_first_wgrad: Cin=%d must be in [1,4]", Cin);
+  B2_REQUIRE(Cout % 64 == 0 && dy_cs % 8 == 0, "conv3x3_first_wgrad: Cout=%d must be a multiple of 64", Cout);
+  const long long P = static_cast<long long>(N) * H * W;
+  const int blocks = first_wgrad_blocks(P);
+  dim3 grid(blocks, Cout / 64);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const auto* dd = static_cast<const __nv_bfloat16*>(dy);
+  switch (Cin) {
+    case 1: first_wgrad_kernel<1><<<grid, 256, 0, st>>>(x_nchw, dd, dy_cs, partial, N, H, W, Cout); break;
+    case 2: first_wgrad_kernel<2><<<grid, 256, 0, st>>>(x_nchw, dd, dy_cs, partial, N, H, W, Cout); break;
+    case 3: first_wgrad_kernel<3><<<grid, 256, 0, st>>>(x_nchw, dd, dy_cs, partial, N, H, W, Cout); break;
+    default: first_wgrad_kernel<4><<<grid, 256, 0, st>>>(x_nchw, dd, dy_cs, partial, N, H, W, Cout); break;
+  }
+  if (int e = b2h::check_launch("conv3x3_first_wgrad")) return e;
+  const int ncols = Cout * Cin * 9;
+  colsum_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(partial, blocks, ncols, dw_oihw, nullptr, 0);
+  return b2h::check_launch("conv3x3_first_wgrad_reduce");
+}
+
+int b200unet_head_fprop(const void* a, int a_cs, const float* w, const float* bias, float* logits_nchw, int N, int H,
+                        int W, int Cin, int ncls, b200_stream_t stream) {
+  B2_REQUIRE(ncls >= 1 && ncls <= 8, "head_fprop: n_classes=%d must be in [1,8]", ncls);
+  B2_REQUIRE(Cin % 8 == 0 && a_cs % 8 == 0, "head_fprop: Cin=%d must be a multiple of 8", Cin);
+  const long long P = static_cast<long long>(N) * H * W;
+  long long blocks = (P + 255) / 256;
+  if (blocks > MAX_BLOCKS) blocks = MAX_BLOCKS;
+  head_fprop_kernel<<<static_cast<int>(blocks), 256, ncls * Cin * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), a_cs, w, bias, logits_nchw, P, static_cast<long long>(H) * W, Cin, ncls);
+  return b2h::check_launch("head_fprop");
+}
+
+int64_t b200unet_head_bwd_workspace_floats(int N, int H, int W, int Cin, int ncls) {
+  return static_cast<int64_t>(head_bwd_blocks(static_cast<long long>(N) * H * W, Cin)) * ncls * (Cin + 1);
+}
+
+int b200unet_head_bwd(const float* dz_nchw, const void* a, int a_cs, const float* w, void* da, int da_cs, float* partial,
+                      float* dw, float* db, int N, int H, int W, int Cin, int ncls, b200_stream_t stream) {
+  B2_REQUIRE(ncls >= 1 && ncls <= 8, "head_bwd: n_classes=%d must be in [1,8]", ncls);
+  B2_REQUIRE(Cin % 8 == 0 && 256 % (Cin / 8) == 0 && a_cs % 8 == 0 && da_cs % 8 == 0, "head_bwd: unsupported Cin=%d", Cin);
+  const long long P = static_cast<long long>(N) * H * W;
+  const int blocks = head_bwd_blocks(P, Cin);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  head_bwd_kernel<<<blocks, 256, 0, st>>>(dz_nchw, static_cast<const __nv_bfloat16*>(a), a_cs, w,
+                                          static_cast<__nv_bfloat16*>(da), da_cs, partial, P,
+                                          static_cast<long long>(H) * W, Cin, ncls);
+  if (int e = b2h::check_launch("head_bwd")) return e;
+  const int ncols = ncls * (Cin + 1);
+  colsum_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(partial, blocks, ncols, dw, db, Cin + 1);
+  return b2h::check_launch("head_bwd_reduce");
+}
+
+}  // extern "C"

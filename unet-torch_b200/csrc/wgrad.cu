@@ -1,0 +1,361 @@
+// tcgen05 weight-gradient kernels: the reduction runs over PIXELS, so both operands are MN-major in smem
+// (NHWC tiles: pixels are rows = K, channels contiguous = M / N).
+//   KIND_CONV3  dW[k][r][s][c] = sum_{n,h,w} dy[n,h,w,k] * x[n,h+r-1,w+s-1,c]     (nn.Conv2d backward-weight)
+//   KIND_UP     dW[ci][d][i][j] = sum_{n,h,w} x[n,h,w,ci] * du[n,2h+i,2w+j,d]      (nn.ConvTranspose2d k2 s2)
+// A CTA owns a 128 (A-side channels) x BNC (B-side channels) x TAPS accumulator set in TMEM and streams a
+// contiguous range of 8x16 pixel tiles through a TMA ring (split-K over pixels across CTAs). For the 3x3 case
+// a CTA handles one horizontal tap s; its x tile carries two halo rows and the three vertical taps r are
+// descriptor offsets of r*16 pixel rows. fp32 partials go to a workspace and a second kernel reduces the splits
+// in a fixed order (deterministic) into the parameter's own layout.
+#include "../../include/b200unet.h"
+#include "host_common.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace b2;
+
+constexpr int TH = 8, TW = 16, BM = TH * TW;
+enum { KIND_CONV3 = 0, KIND_UP = 1 };
+
+struct WgradArgs {
+  CUtensorMap tmA;     // A-side activations (conv3: dy, up: x)
+  CUtensorMap tmB[4];  // B-side (conv3: x [0]; up: du, one strided map per (i,j))
+  int tiles_w, tiles_h, tiles_total;
+  int mtiles, ntiles, splits;
+  int Ca, Cb;          // channel counts of the A and B side
+  float* partial;      // [splits][Ca][TAPS_TOTAL][Cb]
+};
+
+template <int KIND, int BNC>
+struct WPlan {
+  static constexpr int TAPS = (KIND == KIND_CONV3) ? 3 : 4;        // accumulators per CTA
+  static constexpr int TAPS_TOTAL = (KIND == KIND_CONV3) ? 9 : 4;  // taps in the partial layout
+  static constexpr int A_BYTES = 2 * BM * 128;                     // two 64-channel boxes
+  static constexpr int B_BOX = (KIND == KIND_CONV3) ? (TH + 2) * TW * 128 : BM * 128;
+  static constexpr int B_BYTES = (KIND == KIND_CONV3 ? 1 : 4) * (BNC / 64) * B_BOX;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NS = (227 * 1024 - 2048) / STAGE_BYTES;
+  static constexpr int BAR_OFF = NS * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int TMEM_COLS = (TAPS * BNC <= 256) ? 256 : 512;
+  static_assert(TAPS * BNC <= 512, "accumulators exceed TMEM");
+  static_assert(NS >= 2, "need at least a double buffer");
+};
+
+template <int KIND, int BNC>
+__global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradArgs args) {
+  using P = WPlan<KIND, BNC>;
+  constexpr int NS = P::NS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + P::BAR_OFF;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (NS + i); };
+  const uint32_t acc_full = bars + 8u * (2 * NS);
+  const uint32_t tmem_slot = acc_full + 8;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + P::BAR_OFF + 8 * (2 * NS) + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // CTA -> (m tile, n tile, horizontal tap, split)
+  int b = blockIdx.x;
+  const int mt = b % args.mtiles; b /= args.mtiles;
+  const int nt = b % args.ntiles; b /= args.ntiles;
+  int s = 0;
+  if (KIND == KIND_CONV3) { s = b % 3; b /= 3; }
+  const int z = b;
+  const int m0 = mt * 128, n0 = nt * BNC;
+  const int t_begin = static_cast<int>(static_cast<long long>(args.tiles_total) * z / args.splits);
+  const int t_end = static_cast<int>(static_cast<long long>(args.tiles_total) * (z + 1) / args.splits);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&args.tmA);
+    prefetch_tmap(&args.tmB[0]);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(full(i), 1);
+      mbar_init(empty(i), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, P::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0, ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int twi = t % args.tiles_w;
+        const int thi = (t / args.tiles_w) % args.tiles_h;
+        const int img = t / (args.tiles_w * args.tiles_h);
+        const int h0 = thi * TH, w0 = twi * TW;
+        mbar_wait(empty(st), ph ^ 1);
+        mbar_arrive_expect_tx(full(st), P::STAGE_BYTES);
+        const uint32_t sA = smem_base + st * P::STAGE_BYTES;
+        const uint32_t sB = sA + P::A_BYTES;
+        tma_load_4d(sA, &args.tmA, full(st), m0, w0, h0, img);
+        tma_load_4d(sA + BM * 128, &args.tmA, full(st), m0 + 64, w0, h0, img);
+        if (KIND == KIND_CONV3) {
+#pragma unroll
+          for (int j = 0; j < BNC / 64; ++j)
+            tma_load_4d(sB + j * P::B_BOX, &args.tmB[0], full(st), n0 + 64 * j, w0 + s - 1, h0 - 1, img);
+        } else {
+#pragma unroll
+          for (int ij = 0; ij < 4; ++ij)
+#pragma unroll
+            for (int j = 0; j < BNC / 64; ++j)
+              tma_load_4d(sB + (ij * (BNC / 64) + j) * P::B_BOX, &args.tmB[ij], full(st), n0 + 64 * j, w0, h0, img);
+        }
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BNC, 1, 1);
+      int st = 0, ph = 0;
+      uint32_t acc = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(full(st), ph);
+        tc_fence_after();
+        const uint32_t sA = smem_base + st * P::STAGE_BYTES;
+        const uint32_t sB = sA + P::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BM / 16; ++k) {
+          const uint64_t adesc = umma_desc_sw128(sA + k * 2048, BM * 128, 1024);
+#pragma unroll
+          for (int tap = 0; tap < P::TAPS; ++tap) {
+            uint32_t bb;
+            if (KIND == KIND_CONV3) bb = sB + (k * 16 + tap * TW) * 128;
+            else bb = sB + tap * (BNC / 64) * P::B_BOX + k * 2048;
+            umma_bf16(tmem_base + tap * BNC, adesc, umma_desc_sw128(bb, P::B_BOX, 1024), idesc, acc);
+          }
+          acc = 1;
+        }
+        umma_commit(empty(st));
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int ka = m0 + row;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int tap = 0; tap < P::TAPS; ++tap) {
+      const int tapidx = (KIND == KIND_CONV3) ? tap * 3 + s : tap;
+      float* dst = args.partial +
+                   ((static_cast<size_t>(z) * args.Ca + ka) * P::TAPS_TOTAL + tapidx) * static_cast<size_t>(args.Cb) + n0;
+#pragma unroll 1
+      for (int c = 0; c < BNC / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + tap * BNC + c * 32, v);
+        tmem_ld_wait();
+        if (ka < args.Ca) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P::TMEM_COLS);
+}
+
+// partial [Z][K][9][C] -> dw OIHW [K][C][3][3]
+__global__ void reduce_conv3_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Z, int K, int C) {
+  const size_t total = static_cast<size_t>(K) * 9 * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int z = 0; z < Z; ++z) acc += partial[z * total + i];
+    const int c = static_cast<int>(i % C);
+    const int rs = static_cast<int>((i / C) % 9);
+    const size_t k = i / (static_cast<size_t>(C) * 9);
+    dw[(k * C + c) * 9 + rs] = acc;
+  }
+}
+// partial [Z][Cin][4][Cup] -> dw [Cin][Cup][2][2]
+__global__ void reduce_up_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Z, int Cin, int Cup) {
+  const size_t total = static_cast<size_t>(Cin) * 4 * Cup;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int z = 0; z < Z; ++z) acc += partial[z * total + i];
+    const int d = static_cast<int>(i % Cup);
+    const int ij = static_cast<int>((i / Cup) % 4);
+    const size_t ci = i / (static_cast<size_t>(Cup) * 4);
+    dw[(ci * Cup + d) * 4 + ij] = acc;
+  }
+}
+
+// ---- weight preparation (fp32 parameter -> bf16 GEMM operands)
+__global__ void prep_conv3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                  __nv_bfloat16* __restrict__ wd, int K, int C) {
+  const size_t total = static_cast<size_t>(K) * C * 9;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // i indexes the fprop operand [k][rs][c]
+    const int c = static_cast<int>(i % C);
+    const int rs = static_cast<int>((i / C) % 9);
+    const size_t k = i / (static_cast<size_t>(C) * 9);
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[(k * C + c) * 9 + rs]);
+    if (wf) wf[i] = v;
+    if (wd) wd[(static_cast<size_t>(c) * 9 + (8 - rs)) * K + k] = v;
+  }
+}
+__global__ void prep_up_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                               __nv_bfloat16* __restrict__ wd, int Cin, int Cup) {
+  const size_t total = static_cast<size_t>(Cin) * Cup * 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // i indexes the fprop operand [(ij, d)][ci]
+    const int ci = static_cast<int>(i % Cin);
+    const int d = static_cast<int>((i / Cin) % Cup);
+    const int ij = static_cast<int>(i / (static_cast<size_t>(Cin) * Cup));
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[(static_cast<size_t>(ci) * Cup + d) * 4 + ij]);
+    if (wf) wf[i] = v;
+    if (wd) wd[static_cast<size_t>(ci) * 4 * Cup + static_cast<size_t>(ij) * Cup + d] = v;
+  }
+}
+
+int conv3_bnc(int Cin) { return (Cin % 128 == 0) ? 128 : 64; }
+
+int pick_splits(int base_ctas, int tiles_total) {
+  int z = 148 / base_ctas;
+  if (z < 1) z = 1;
+  if (z > tiles_total) z = tiles_total;
+  return z;
+}
+
+template <int KIND, int BNC>
+int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
+  using P = WPlan<KIND, BNC>;
+  static bool configured = false;
+  auto kern = wgrad_kernel<KIND, BNC>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
+    if (e != cudaSuccess) {
+      b2h::set_error("wgrad: cudaFuncSetAttribute(smem=%d): %s", P::TOTAL, cudaGetErrorString(e));
+      return 2;
+    }
+    configured = true;
+  }
+  const int grid = a.mtiles * a.ntiles * (KIND == KIND_CONV3 ? 3 : 1) * a.splits;
+  kern<<<grid, 192, P::TOTAL, st>>>(a);
+  return b2h::check_launch("wgrad");
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200unet_prep_conv3x3_weight(const float* w_oihw, void* w_fprop, void* w_dgrad, int K, int C, b200_stream_t stream) {
+  const size_t total = static_cast<size_t>(K) * C * 9;
+  const int blocks = static_cast<int>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  prep_conv3_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oihw, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), K, C);
+  return b2h::check_launch("prep_conv3x3_weight");
+}
+
+int b200unet_prep_convt2x2_weight(const float* w, void* w_fprop, void* w_dgrad, int Cin, int Cup, b200_stream_t stream) {
+  const size_t total = static_cast<size_t>(Cin) * Cup * 4;
+  const int blocks = static_cast<int>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  prep_up_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), Cin, Cup);
+  return b2h::check_launch("prep_convt2x2_weight");
+}
+
+static void conv3_wgrad_geometry(int N, int H, int W, int Cin, int Cout, int* bnc, int* mtiles, int* ntiles, int* tiles,
+                                 int* splits) {
+  *bnc = conv3_bnc(Cin);
+  *mtiles = b2h::ceil_div(Cout, 128);
+  *ntiles = Cin / *bnc;
+  *tiles = N * b2h::ceil_div(H, TH) * b2h::ceil_div(W, TW);
+  *splits = pick_splits(*mtiles * *ntiles * 3, *tiles);
+}
+
+int64_t b200unet_conv3x3_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout) {
+  int bnc, mt, nt, tiles, z;
+  conv3_wgrad_geometry(N, H, W, Cin, Cout, &bnc, &mt, &nt, &tiles, &z);
+  return static_cast<int64_t>(z) * Cout * 9 * Cin;
+}
+
+int b200unet_conv3x3_wgrad(const void* x, int x_cs, const void* dy, int dy_cs, float* partial, float* dw_oihw, int N,
+                           int H, int W, int Cin, int Cout, b200_stream_t stream) {
+  B2_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv3x3_wgrad: Cin (%d) and Cout (%d) must be multiples of 64", Cin, Cout);
+  B2_REQUIRE(x_cs % 8 == 0 && dy_cs % 8 == 0, "conv3x3_wgrad: pitches must be multiples of 8");
+  WgradArgs a;
+  int bnc;
+  conv3_wgrad_geometry(N, H, W, Cin, Cout, &bnc, &a.mtiles, &a.ntiles, &a.tiles_total, &a.splits);
+  a.tiles_w = b2h::ceil_div(W, TW);
+  a.tiles_h = b2h::ceil_div(H, TH);
+  a.Ca = Cout;
+  a.Cb = Cin;
+  a.partial = partial;
+  const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(dy_cs) * 2;
+  if (int e = b2h::make_tmap_4d(&a.tmA, dy, Cout, W, H, N, ys, ys * W, ys * W * H, TW, TH)) return e;
+  if (int e = b2h::make_tmap_4d(&a.tmB[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TW, TH + 2)) return e;
+  for (int i = 1; i < 4; ++i) a.tmB[i] = a.tmB[0];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int e = (bnc == 128) ? launch_wgrad<KIND_CONV3, 128>(a, st) : launch_wgrad<KIND_CONV3, 64>(a, st);
+  if (e) return e;
+  const size_t total = static_cast<size_t>(Cout) * 9 * Cin;
+  const int blocks = static_cast<int>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  reduce_conv3_kernel<<<blocks, 256, 0, st>>>(partial, dw_oihw, a.splits, Cout, Cin);
+  return b2h::check_launch("conv3x3_wgrad_reduce");
+}
+
+static void up_wgrad_geometry(int N, int H, int W, int Cin, int Cup, int* mtiles, int* ntiles, int* tiles, int* splits) {
+  *mtiles = b2h::ceil_div(Cin, 128);
+  *ntiles = Cup / 64;
+  *tiles = N * b2h::ceil_div(H, TH) * b2h::ceil_div(W, TW);
+  *splits = pick_splits(*mtiles * *ntiles, *tiles);
+}
+
+int64_t b200unet_convt2x2_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cup) {
+  int mt, nt, tiles, z;
+  up_wgrad_geometry(N, H, W, Cin, Cup, &mt, &nt, &tiles, &z);
+  return static_cast<int64_t>(z) * Cin * 4 * Cup;
+}
+
+int b200unet_convt2x2_wgrad(const void* x, int x_cs, const void* du, int du_cs, float* partial, float* dw, int N, int H,
+                            int W, int Cin, int Cup, int H2, int W2, int pad_top, int pad_left, b200_stream_t stream) {
+  B2_REQUIRE(Cin % 64 == 0 && Cup % 64 == 0, "convt2x2_wgrad: Cin (%d) and Cup (%d) must be multiples of 64", Cin, Cup);
+  B2_REQUIRE(pad_top >= 0 && pad_left >= 0 && 2 * H + pad_top <= H2 && 2 * W + pad_left <= W2, "convt2x2_wgrad: bad canvas");
+  B2_REQUIRE(x_cs % 8 == 0 && du_cs % 8 == 0, "convt2x2_wgrad: pitches must be multiples of 8");
+  WgradArgs a;
+  up_wgrad_geometry(N, H, W, Cin, Cup, &a.mtiles, &a.ntiles, &a.tiles_total, &a.splits);
+  a.tiles_w = b2h::ceil_div(W, TW);
+  a.tiles_h = b2h::ceil_div(H, TH);
+  a.Ca = Cin;
+  a.Cb = Cup;
+  a.partial = partial;
+  const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, us = static_cast<uint64_t>(du_cs) * 2;
+  if (int e = b2h::make_tmap_4d(&a.tmA, x, Cin, W, H, N, xs, xs * W, xs * W * H, TW, TH)) return e;
+  for (int ij = 0; ij < 4; ++ij) {
+    const int i = ij >> 1, j = ij & 1;
+    const uint8_t* base = static_cast<const uint8_t*>(du) + (static_cast<uint64_t>(pad_top + i) * W2 + pad_left + j) * us;
+    if (int e = b2h::make_tmap_4d(&a.tmB[ij], base, Cup, W, H, N, 2 * us, 2 * us * W2, us * W2 * H2, TW, TH)) return e;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = launch_wgrad<KIND_UP, 64>(a, st)) return e;
+  const size_t total = static_cast<size_t>(Cin) * 4 * Cup;
+  const int blocks = static_cast<int>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  reduce_up_kernel<<<blocks, 256, 0, st>>>(partial, dw, a.splits, Cin, Cup);
+  return b2h::check_launch("convt2x2_wgrad_reduce");
+}
+
+}  // extern "C"

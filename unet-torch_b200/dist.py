@@ -1,0 +1,153 @@
+"""Data-parallel plumbing for the U-Net hot path (one process per GPU, torch.distributed over NCCL/NVLink).
+
+The reference is single-GPU (train.py:304 `device = "cuda:0"`); batch sharding is the path's natural partition:
+each rank runs forward/backward on its own images, and only two things cross ranks
+  (i)  BatchNorm statistics (SyncBN): the fp64 [sum, sum^2] (forward) and [sum da, sum da*xhat] (backward) vectors
+       are all-reduced between the reduce and the apply kernels, so every rank normalises with global-batch
+       statistics (torch.nn.SyncBatchNorm semantics);
+  (ii) parameter gradients: written by backward straight into ONE flat fp32 buffer laid out in backward order and
+       all-reduced (mean) bucket by bucket on a side stream while backward keeps running.
+Works with the gloo backend on CPU tensors for the world_size-2 unit tests of the bucketing logic.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGrads:
+    def __init__(self, ctx: "DataParallelContext", params):
+        self.ctx = ctx
+        self.params = list(params)
+        self.offsets = {}
+        total = 0
+        for p in self.params:
+            self.offsets[p] = total
+            total += (p.numel() + 63) // 64 * 64  # keep every view 256-byte aligned
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.total = total
+        # buckets: contiguous ranges in backward order, closed when >= bucket_bytes
+        self.buckets = []
+        start, size = 0, 0
+        limit = ctx.bucket_bytes // 4
+        for p in self.params:
+            size += (p.numel() + 63) // 64 * 64
+            if size >= limit:
+                self.buckets.append((start, start + size))
+                start, size = start + size, 0
+        if size:
+            self.buckets.append((start, start + size))
+        self.ready_upto = 0
+        self.next_bucket = 0
+        self.works = []
+        self._pending = set(self.params)
+        self._order = list(self.params)
+        self._pos = 0
+
+    def view_for(self, p):
+        o = self.offsets[p]
+        return self.flat[o:o + p.numel()].view(p.shape)
+
+    def mark_ready(self, ps):
+        for p in ps:
+            self._pending.discard(p)
+        # advance the contiguous ready prefix (parameters are produced in the declared order)
+        while self._pos < len(self._order) and self._order[self._pos] not in self._pending:
+            p = self._order[self._pos]
+            self.ready_upto = self.offsets[p] + (p.numel() + 63) // 64 * 64
+            self._pos += 1
+        while self.next_bucket < len(self.buckets) and self.buckets[self.next_bucket][1] <= self.ready_upto:
+            self._launch(self.buckets[self.next_bucket])
+            self.next_bucket += 1
+
+    def _launch(self, rng):
+        self.ctx.all_reduce_mean_async(self.flat[rng[0]:rng[1]], self.works)
+
+    def finish(self):
+        while self.next_bucket < len(self.buckets):
+            self._launch(self.buckets[self.next_bucket])
+            self.next_bucket += 1
+        self.ctx.wait_all(self.works)
+
+
+class DataParallelContext:
+    """Process-wide switch: `enable()` once after init_process_group; UNet picks it up in training mode."""
+
+    _current = None
+
+    def __init__(self, sync_bn=True, bucket_mb=25.0, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.sync_bn = sync_bn and self.world_size > 1
+        self.bucket_bytes = int(bucket_mb * (1 << 20))
+        self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+
+    # ---- global registration
+    @classmethod
+    def enable(cls, **kw):
+        cls._current = cls(**kw)
+        return cls._current
+
+    @classmethod
+    def disable(cls):
+        cls._current = None
+
+    @classmethod
+    def current(cls):
+        c = cls._current
+        if c is None or c.world_size == 1:
+            return None
+        return c
+
+    # ---- collectives
+    def all_reduce_sum(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def make_flat_grads(self, params):
+        return FlatGrads(self, params)
+
+    def all_reduce_mean_async(self, t, works):
+        if t.is_cuda:
+            # run the collective on a side stream so the backward kernels that follow keep the SMs busy
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                t.mul_(1.0 / self.world_size)
+            works.append(None)
+        else:
+            w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            works.append((w, t))
+
+    def wait_all(self, works):
+        if self.comm_stream is not None and any(w is None for w in works):
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        for w in works:
+            if w is not None:
+                w[0].wait()
+                w[1].mul_(1.0 / self.world_size)
+        works.clear()
+
+
+def init_from_env(sync_bn=True, bucket_mb=25.0):
+    """torchrun-style bring-up: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return None
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+        backend = "nccl"
+    else:
+        backend = "gloo"
+    if not dist.is_initialized():
+        kw = {"device_id": torch.device("cuda", local)} if backend == "nccl" else {}
+        dist.init_process_group(backend=backend, **kw)
+    return DataParallelContext.enable(sync_bn=sync_bn, bucket_mb=bucket_mb)

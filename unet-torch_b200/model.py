@@ -1,0 +1,411 @@
+"""Drop-in `UNet` for the reference's Model.py:95-169, executed by hand-written sm_100a kernels.
+
+The module tree (inc / down1-4 / up1-4 / outc and their children) only HOLDS parameters and buffers so that the
+118 state_dict keys, their shapes/dtypes (fp32) and the constructor's RNG consumption match the reference
+(Model.py:7-92, 96-140, 167-169). `UNet.forward` never calls those children: the whole encoder-decoder runs as ONE
+torch.autograd.Function whose forward/backward are chains of C-ABI launches on NHWC bf16 buffers
+(see include/b200unet.h). There is no PyTorch/cuDNN fallback for this model.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .dist import DataParallelContext
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------ containers
+def _double_conv(cin, cout):
+    # keys: double_conv.{0,1,3,4}.*  (Model.py:14-23)
+    return nn.Sequential(
+        nn.Conv2d(cin, cout, kernel_size=3, padding=1, bias=False),
+        nn.BatchNorm2d(cout),
+        nn.ReLU(inplace=True),
+        nn.Conv2d(cout, cout, kernel_size=3, padding=1, bias=False),
+        nn.BatchNorm2d(cout),
+        nn.ReLU(inplace=True),
+    )
+
+
+class _Holder(nn.Module):
+    """Parameter container: its forward is never the product path."""
+
+    def forward(self, *a, **k):  # pragma: no cover - guard
+        raise RuntimeError(
+            f"{type(self).__name__} is a parameter container of the B200 UNet; call UNet.forward(x) "
+            "(sub-blocks are executed by fused sm_100a kernels, not module by module)"
+        )
+
+
+class DoubleConv(_Holder):
+    def __init__(self, in_channels, out_channels, mid_channels=None):
+        super().__init__()
+        if mid_channels not in (None, out_channels):
+            raise ValueError("mid_channels != out_channels is not used by UNet and not supported")
+        self.double_conv = _double_conv(in_channels, out_channels)
+
+
+class Down(_Holder):
+    def __init__(self, in_channels, out_channels, dropout=False, dropout_p=0.5):
+        super().__init__()
+        mods = [nn.MaxPool2d(2)]
+        if dropout:
+            mods.append(nn.Dropout(p=dropout_p))  # shifts DoubleConv to index 2, as in Model.py:34-39
+        mods.append(DoubleConv(in_channels, out_channels))
+        self.maxpool_conv = nn.Sequential(*mods)
+
+
+class Up(_Holder):
+    def __init__(self, in_channels, out_channels, dropout_flag=False, dropout_p=0.5):
+        super().__init__()
+        self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+        self.conv = DoubleConv(in_channels, out_channels)
+        self.dropout_flag = dropout_flag
+        if dropout_flag:
+            self.dropout = nn.Dropout(p=dropout_p)
+
+
+class OutConv(_Holder):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+
+
+# ------------------------------------------------------------------------------------------------ engine
+class _ConvBN:
+    """One conv3x3 + BatchNorm2d pair: fp32 master parameters and cached bf16 GEMM operands."""
+
+    def __init__(self, conv: nn.Conv2d, bn: nn.BatchNorm2d, first: bool):
+        self.conv, self.bn, self.first = conv, bn, first
+        self._ver = None
+        self.wf = self.wd = None
+
+    def operands(self):
+        w = self.conv.weight
+        key = (w._version, w.data_ptr())
+        if key != self._ver:
+            with torch.no_grad():
+                self.wf, self.wd = ops.prep_conv3x3_weight(w.detach())
+            self._ver = key
+        return self.wf, self.wd
+
+
+class _UpOp:
+    def __init__(self, up: nn.ConvTranspose2d):
+        self.up = up
+        self._ver = None
+        self.wf = self.wd = None
+
+    def operands(self):
+        w = self.up.weight
+        key = (w._version, w.data_ptr())
+        if key != self._ver:
+            with torch.no_grad():
+                self.wf, self.wd = ops.prep_convt2x2_weight(w.detach())
+            self._ver = key
+        return self.wf, self.wd
+
+
+class _Saved:
+    __slots__ = ("x", "enc", "dec", "head_in", "shapes", "dp")
+
+
+def _dc(mod) -> nn.Sequential:
+    return mod.double_conv
+
+
+class UNetEngine:
+    """Executes the forward and backward of the whole network as chains of C-ABI launches."""
+
+    def __init__(self, net: "UNet"):
+        self.net = net
+        downs = [net.down1, net.down2, net.down3, net.down4]
+        ups = [net.up1, net.up2, net.up3, net.up4]
+        enc_dc = [_dc(net.inc)] + [_dc(d.maxpool_conv[-1]) for d in downs]
+        self.enc = [(_ConvBN(s[0], s[1], first=(i == 0)), _ConvBN(s[3], s[4], first=False)) for i, s in enumerate(enc_dc)]
+        # decoder index j = 0..3 <-> up1..up4, operates at level 3-j
+        self.ups = [_UpOp(u.up) for u in ups]
+        self.dec = [(_ConvBN(_dc(u.conv)[0], _dc(u.conv)[1], False), _ConvBN(_dc(u.conv)[3], _dc(u.conv)[4], False)) for u in ups]
+        self.head = net.outc.conv
+
+    # parameters in the order their gradients are produced by backward (used for DP bucketing)
+    def params_in_backward_order(self):
+        out = [self.head.weight, self.head.bias]
+        for j in (3, 2, 1, 0):
+            c1, c2 = self.dec[j]
+            out += [c2.bn.weight, c2.bn.bias, c2.conv.weight, c1.bn.weight, c1.bn.bias, c1.conv.weight,
+                    self.ups[j].up.bias, self.ups[j].up.weight]
+        for l in (4, 3, 2, 1, 0):
+            c1, c2 = self.enc[l]
+            out += [c2.bn.weight, c2.bn.bias, c2.conv.weight, c1.bn.weight, c1.bn.bias, c1.conv.weight]
+        return out
+
+    # ------------------------------------------------------------------ BN helpers
+    def _bn_affine(self, cb: _ConvBN, stats_partial, rows, count, training, dp):
+        bn = cb.bn
+        c = bn.num_features
+        dev = bn.weight.device
+        scale = torch.empty(c, dtype=torch.float32, device=dev)
+        shift = torch.empty(c, dtype=torch.float32, device=dev)
+        if not training:
+            ops.bn_eval_affine(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, scale, shift)
+            return scale, shift, None, None, count
+        sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
+        ops.bn_reduce_partials(stats_partial, rows, c, sums)
+        if dp is not None and dp.sync_bn:
+            dp.all_reduce_sum(sums)
+            count = count * dp.world_size
+        mean = torch.empty(c, dtype=torch.float32, device=dev)
+        rstd = torch.empty(c, dtype=torch.float32, device=dev)
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        track = bn.track_running_stats and bn.running_mean is not None
+        ops.bn_finalize(sums, count, bn.weight, bn.bias, bn.eps, mom, bn.running_mean if track else None,
+                        bn.running_var if track else None, mean, rstd, scale, shift)
+        if track:
+            bn.num_batches_tracked += 1
+        return scale, shift, mean, rstd, count
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, training: bool, save: bool):
+        net = self.net
+        if x.dim() != 4 or x.shape[1] != net.n_channels:
+            raise ValueError(f"UNet expects [B,{net.n_channels},H,W] input, got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("the B200 UNet runs on CUDA (sm_100a) only; there is no CPU fallback")
+        n, _, h, w = x.shape
+        if h % 16 or w % 16:
+            raise ValueError(f"H and W must be multiples of 16 (got {h}x{w}); odd-size F.pad path not implemented")
+        x = x.contiguous().float()
+        dev = x.device
+        dp = DataParallelContext.current() if training else None
+        f = net.initial_feature_map
+        ch = [f * (1 << l) for l in range(5)]
+        hs = [h >> l for l in range(5)]
+        wsz = [w >> l for l in range(5)]
+        # concat buffers of decoder levels 0..3: [skip | upsampled]
+        cat = [torch.empty((n, hs[l], wsz[l], 2 * ch[l]), dtype=BF16, device=dev) for l in range(4)]
+        saved = _Saved() if save else None
+        enc_rec, dec_rec = [], []
+
+        def conv_bn_relu(cb: _ConvBN, inp, c_out, hh, ww, a_out, pooled=None, pool_idx=None):
+            y = torch.empty((n, hh, ww, c_out), dtype=BF16, device=dev)
+            stats = None
+            if cb.first:
+                rows = ops.first_conv_stat_rows(n, hh, ww)
+                if training:
+                    stats = torch.empty(rows * 2 * c_out, dtype=torch.float32, device=dev)
+                ops.conv3x3_first(inp, cb.conv.weight.detach(), y, stats)
+            else:
+                rows = ops.num_pixel_tiles(n, hh, ww)
+                if training:
+                    stats = torch.empty(rows * 2 * c_out, dtype=torch.float32, device=dev)
+                wf, _ = cb.operands()
+                ops.conv3x3(inp, wf, y, stats)
+            scale, shift, mean, rstd, count = self._bn_affine(cb, stats, rows, n * hh * ww, training, dp)
+            ops.bn_relu_fwd(y, scale, shift, a_out, pooled, pool_idx)
+            return (inp, y, scale, shift, mean, rstd, count)
+
+        # ---- encoder
+        inp = x
+        for l in range(5):
+            c1, c2 = self.enc[l]
+            a1 = torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
+            r1 = conv_bn_relu(c1, inp, ch[l], hs[l], wsz[l], a1)
+            if l < 4:
+                a2 = cat[l][..., : ch[l]]
+                pooled = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l]), dtype=BF16, device=dev)
+                idx = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l]), dtype=torch.uint8, device=dev) if save else None
+                r2 = conv_bn_relu(c2, a1, ch[l], hs[l], wsz[l], a2, pooled, idx)
+                inp = pooled
+            else:
+                a2 = torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
+                idx = None
+                r2 = conv_bn_relu(c2, a1, ch[l], hs[l], wsz[l], a2)
+            enc_rec.append((r1, r2, a2, idx))
+        # ---- decoder
+        d_in = enc_rec[4][2]
+        for j in range(4):
+            l = 3 - j
+            upo = self.ups[j]
+            wf, _ = upo.operands()
+            ops.convt2x2(d_in, wf, upo.up.bias.detach(), cat[l][..., ch[l]:])
+            c1, c2 = self.dec[j]
+            a1 = torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
+            r1 = conv_bn_relu(c1, cat[l], ch[l], hs[l], wsz[l], a1)
+            a2 = torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
+            r2 = conv_bn_relu(c2, a1, ch[l], hs[l], wsz[l], a2)
+            dec_rec.append((d_in, r1, r2, a2))
+            d_in = a2
+        # ---- head
+        logits = torch.empty((n, net.n_classes, h, w), dtype=torch.float32, device=dev)
+        ops.head_fprop(d_in, self.head.weight.detach(), self.head.bias.detach(), logits)
+        if save:
+            saved.x, saved.enc, saved.dec, saved.head_in = x, enc_rec, dec_rec, d_in
+            saved.shapes = (n, ch, hs, wsz)
+            saved.dp = dp
+        return logits, saved
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, saved: _Saved, dlogits: torch.Tensor):
+        n, ch, hs, wsz = saved.shapes
+        dev = dlogits.device
+        dp = saved.dp
+        grads = {}
+        flat = dp.make_flat_grads(self.params_in_backward_order()) if dp is not None else None
+
+        def gbuf(p):
+            if flat is not None:
+                return flat.view_for(p)
+            return torch.empty_like(p, memory_format=torch.contiguous_format)
+
+        def done(*ps):
+            if flat is not None:
+                flat.mark_ready(ps)
+
+        sync = (lambda s: dp.all_reduce_sum(s)) if (dp is not None and dp.sync_bn) else None
+
+        def bn_conv_bwd(cb: _ConvBN, rec, g1, g_pool, pool_idx, hh, ww, need_dx):
+            inp, y, scale, shift, mean, rstd, count = rec
+            bn = cb.bn
+            dgamma, dbeta = gbuf(bn.weight), gbuf(bn.bias)
+            ops.bn_relu_bwd(g1, g_pool, pool_idx, y, bn.weight.detach(), scale, shift, mean, rstd, y, dgamma, dbeta,
+                            count=count, allreduce=sync)
+            dy = y  # dy overwrote y in place
+            dw = gbuf(cb.conv.weight)
+            if cb.first:
+                ops.conv3x3_first_wgrad(inp, dy, dw)
+            else:
+                ops.conv3x3_wgrad(inp, dy, dw)
+            grads[bn.weight], grads[bn.bias], grads[cb.conv.weight] = dgamma, dbeta, dw
+            done(bn.weight, bn.bias, cb.conv.weight)
+            if not need_dx:
+                return None
+            _, wd = cb.operands()
+            dx = torch.empty((n, hh, ww, wd.shape[0]), dtype=BF16, device=dev)
+            ops.conv3x3(dy, wd, dx)
+            return dx
+
+        # ---- head
+        dlogits = dlogits.contiguous().float()
+        hw_, hb_ = self.head.weight, self.head.bias
+        g = torch.empty((n, hs[0], wsz[0], ch[0]), dtype=BF16, device=dev)
+        dwh, dbh = gbuf(hw_), gbuf(hb_)
+        ops.head_bwd(dlogits, saved.head_in, hw_.detach(), g, dwh, dbh)
+        grads[hw_], grads[hb_] = dwh, dbh
+        done(hw_, hb_)
+        # ---- decoder, up4 -> up1
+        skip_grads = [None] * 4
+        for j in (3, 2, 1, 0):
+            l = 3 - j
+            d_in, r1, r2, _ = saved.dec[j]
+            c1, c2 = self.dec[j]
+            g = bn_conv_bwd(c2, r2, g, None, None, hs[l], wsz[l], True)
+            dcat = bn_conv_bwd(c1, r1, g, None, None, hs[l], wsz[l], True)
+            skip_grads[l] = dcat[..., : ch[l]]
+            du = dcat[..., ch[l]:]
+            upo = self.ups[j]
+            db, dwu = gbuf(upo.up.bias), gbuf(upo.up.weight)
+            ops.channel_sum(du, db)
+            ops.convt2x2_wgrad(d_in, du, dwu)
+            grads[upo.up.bias], grads[upo.up.weight] = db, dwu
+            done(upo.up.bias, upo.up.weight)
+            _, wd = upo.operands()
+            g = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l + 1]), dtype=BF16, device=dev)
+            ops.convt2x2_dgrad(du, wd, g)
+        # ---- encoder, level 4 -> 0
+        g_pool = None
+        for l in (4, 3, 2, 1, 0):
+            r1, r2, _, idx = saved.enc[l]
+            c1, c2 = self.enc[l]
+            if l == 4:
+                g1 = bn_conv_bwd(c2, r2, g, None, None, hs[l], wsz[l], True)
+            else:
+                g1 = bn_conv_bwd(c2, r2, skip_grads[l], g_pool, idx, hs[l], wsz[l], True)
+            g_pool = bn_conv_bwd(c1, r1, g1, None, None, hs[l], wsz[l], need_dx=(l > 0))
+        if flat is not None:
+            flat.finish()
+        return grads
+
+
+class _UNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine: UNetEngine, x, *params):
+        logits, saved = engine.forward(x, training=engine.net.training, save=True)
+        ctx.engine, ctx.saved, ctx.params = engine, saved, params
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        if ctx.saved is None:
+            raise RuntimeError("UNet backward called twice: activations are consumed in place")
+        grads = ctx.engine.backward(ctx.saved, dlogits)
+        ctx.saved = None
+        return (None, None) + tuple(grads.get(p) for p in ctx.params)
+
+
+# ------------------------------------------------------------------------------------------------ public module
+class UNet(nn.Module):
+    """Same constructor and forward(x) as the reference (Model.py:96, :142)."""
+
+    def __init__(self, n_channels, n_classes, initial_feature_map=64, usa_cuda=True, dropout=False, dropout_p=0.5):
+        super().__init__()
+        self.usa_cuda = usa_cuda
+        self.n_channels = {-2: 3, -1: 1}.get(n_channels, n_channels)  # Model.py:99-104
+        self.n_classes = n_classes
+        self.initial_feature_map = initial_feature_map
+        self.dropout = dropout
+        self.dropout_p = dropout_p
+        f = initial_feature_map
+        # creation + init order fixes the RNG stream (Model.py:107-140): build a block, then re-init its Conv2d's
+        blocks = [("inc", lambda: DoubleConv(self.n_channels, f))]
+        for i in range(4):
+            blocks.append((f"down{i + 1}", lambda i=i: Down(f << i, f << (i + 1), dropout, dropout_p)))
+        for i in range(4):
+            blocks.append((f"up{i + 1}", lambda i=i: Up(f << (4 - i), f << (3 - i), dropout, dropout_p)))
+        blocks.append(("outc", lambda: OutConv(f, n_classes)))
+        for name, make in blocks:
+            mod = make()
+            setattr(self, name, mod)
+            mod.apply(self.weights_init)
+        self._engine = None
+
+    def weights_init(self, m):
+        if isinstance(m, nn.Conv2d):  # Model.py:167-169: ConvTranspose2d keeps torch's default init
+            nn.init.kaiming_normal_(m.weight)
+
+    def _get_engine(self) -> UNetEngine:
+        if self._engine is None:
+            if self.initial_feature_map % 64 != 0:
+                raise ValueError("initial_feature_map must be a multiple of 64 for the tensor-core path")
+            if self.n_channels > 4 or self.n_classes > 8:
+                raise ValueError("n_channels <= 4 and n_classes <= 8 are supported")
+            if self.dropout:
+                raise NotImplementedError("dropout=True variant is not implemented in the B200 path")
+            object.__setattr__(self, "_engine", UNetEngine(self))
+        return self._engine
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        object.__setattr__(self, "_engine", None)  # parameters may have been re-created (.to / .half / ...)
+        return out
+
+    def forward(self, x):
+        eng = self._get_engine()
+        params = eng.params_in_backward_order()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _UNetFn.apply(eng, x, *params)
+        logits, _ = eng.forward(x, training=self.training, save=False)
+        return logits
+
+    def use_checkpointing(self):
+        raise NotImplementedError("activation checkpointing is not needed: bf16 activations fit in HBM3e")
+
+
+def predict_mask(logits: torch.Tensor) -> torch.Tensor:
+    """softmax(dim=1) -> argmax(dim=1) of test_mc3serousv5.py:880-881, fused."""
+    return ops.softmax_argmax(logits.contiguous().float())

@@ -1,0 +1,266 @@
+"""Tensor-level wrappers over the C ABI: each function takes torch CUDA tensors (device memory + stream plumbing
+only) and launches the hand-written sm_100a kernels on the current stream. Activations are NHWC bf16 tensors of
+shape [N, H, W, C]; a tensor may be a channel slice of a wider buffer (stride(2) = pixel pitch).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _nhwc(t: torch.Tensor):
+    """Validate an NHWC bf16 (possibly channel-sliced) tensor and return (ptr, pitch, N, H, W, C)."""
+    if t.dtype != BF16 or t.dim() != 4 or not t.is_cuda:
+        raise ValueError(f"expected a CUDA bf16 [N,H,W,C] tensor, got {t.dtype} {tuple(t.shape)} {t.device}")
+    n, h, w, c = t.shape
+    cs = t.stride(2)
+    if t.stride(3) != 1 or t.stride(1) != w * cs or t.stride(0) != h * w * cs:
+        raise ValueError(f"tensor is not NHWC with a uniform pixel pitch: shape {tuple(t.shape)} strides {t.stride()}")
+    return t.data_ptr(), cs, n, h, w, c
+
+
+def _f32(t: torch.Tensor):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"expected a contiguous CUDA fp32 tensor, got {t.dtype} {t.device} contiguous={t.is_contiguous()}")
+    return t.data_ptr()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def tile_hw():
+    return _lib.query("b200unet_tile_h"), _lib.query("b200unet_tile_w")
+
+
+def num_pixel_tiles(n, h, w):
+    th, tw = tile_hw()
+    return n * ((h + th - 1) // th) * ((w + tw - 1) // tw)
+
+
+# --------------------------------------------------------------------------------------------- weights
+def prep_conv3x3_weight(w: torch.Tensor, want_dgrad=True):
+    """fp32 OIHW [K,C,3,3] -> (fprop operand [K,3,3,C] bf16, dgrad operand [C,3,3,K] bf16 with rotated taps)."""
+    k, c = w.shape[0], w.shape[1]
+    wf = torch.empty((k, 3, 3, c), dtype=BF16, device=w.device)
+    wd = torch.empty((c, 3, 3, k), dtype=BF16, device=w.device) if want_dgrad else None
+    _lib.call("b200unet_prep_conv3x3_weight", _f32(w), wf.data_ptr(), _ptr(wd), k, c, _stream())
+    return wf, wd
+
+
+def prep_convt2x2_weight(w: torch.Tensor):
+    """fp32 [Cin,Cup,2,2] -> (fprop operand [4*Cup, Cin] bf16, dgrad operand [Cin, 4*Cup] bf16)."""
+    cin, cup = w.shape[0], w.shape[1]
+    wf = torch.empty((4 * cup, cin), dtype=BF16, device=w.device)
+    wd = torch.empty((cin, 4 * cup), dtype=BF16, device=w.device)
+    _lib.call("b200unet_prep_convt2x2_weight", _f32(w), wf.data_ptr(), wd.data_ptr(), cin, cup, _stream())
+    return wf, wd
+
+
+# --------------------------------------------------------------------------------------------- tensor-core ops
+def conv3x3(x: torch.Tensor, w_op: torch.Tensor, out: torch.Tensor, stats_partial: torch.Tensor | None = None):
+    """out = conv3x3(x) with a prepared [Cout,3,3,Cin] bf16 operand (fprop or dgrad operand)."""
+    xp, xcs, n, h, w, cin = _nhwc(x)
+    op, ocs, n2, h2, w2, cout = _nhwc(out)
+    if (n, h, w) != (n2, h2, w2) or tuple(w_op.shape) != (cout, 3, 3, cin) or w_op.dtype != BF16:
+        raise ValueError(f"conv3x3: shape mismatch x{tuple(x.shape)} w{tuple(w_op.shape)} out{tuple(out.shape)}")
+    if stats_partial is not None and stats_partial.numel() < num_pixel_tiles(n, h, w) * 2 * cout:
+        raise ValueError("conv3x3: stats_partial too small")
+    _lib.call("b200unet_conv3x3_igemm", xp, xcs, w_op.data_ptr(), op, ocs, _f32(stats_partial), n, h, w, cin, cout,
+              _stream())
+    return out
+
+
+def convt2x2(x, w_fprop, bias, out_canvas_slice, pad_top=0, pad_left=0):
+    """ConvTranspose2d(k=2,s=2)+bias of x [N,H,W,Cin] written into out_canvas_slice [N,H2,W2,Cup] (a channel slice
+    of the concat buffer) at offset (pad_top, pad_left)."""
+    xp, xcs, n, h, w, cin = _nhwc(x)
+    op, ocs, n2, h2, w2, cup = _nhwc(out_canvas_slice)
+    if tuple(w_fprop.shape) != (4 * cup, cin) or n != n2:
+        raise ValueError("convt2x2: shape mismatch")
+    _lib.call("b200unet_convt2x2_fprop", xp, xcs, w_fprop.data_ptr(), _f32(bias), op, ocs, n, h, w, cin, cup, h2, w2,
+              pad_top, pad_left, _stream())
+
+
+def convt2x2_dgrad(du_canvas_slice, w_dgrad, dx, pad_top=0, pad_left=0):
+    up, ucs, n, h2, w2, cup = _nhwc(du_canvas_slice)
+    xp, xcs, n2, h, w, cin = _nhwc(dx)
+    if tuple(w_dgrad.shape) != (cin, 4 * cup) or n != n2:
+        raise ValueError("convt2x2_dgrad: shape mismatch")
+    _lib.call("b200unet_convt2x2_dgrad", up, ucs, w_dgrad.data_ptr(), xp, xcs, n, h, w, cin, cup, h2, w2, pad_top,
+              pad_left, _stream())
+    return dx
+
+
+def _workspace(nfloats, device):
+    return torch.empty((max(int(nfloats), 1),), dtype=torch.float32, device=device)
+
+
+def conv3x3_wgrad(x, dy, dw_out: torch.Tensor):
+    """dw_out (fp32 OIHW [Cout,Cin,3,3]) = weight gradient of conv3x3(x) given dy. Overwrites dw_out."""
+    xp, xcs, n, h, w, cin = _nhwc(x)
+    yp, ycs, n2, h2, w2, cout = _nhwc(dy)
+    if (n, h, w) != (n2, h2, w2) or tuple(dw_out.shape) != (cout, cin, 3, 3):
+        raise ValueError("conv3x3_wgrad: shape mismatch")
+    ws = _workspace(_lib.query("b200unet_conv3x3_wgrad_workspace_floats", n, h, w, cin, cout), x.device)
+    _lib.call("b200unet_conv3x3_wgrad", xp, xcs, yp, ycs, ws.data_ptr(), _f32(dw_out), n, h, w, cin, cout, _stream())
+    return dw_out
+
+
+def convt2x2_wgrad(x, du_canvas_slice, dw_out, pad_top=0, pad_left=0):
+    xp, xcs, n, h, w, cin = _nhwc(x)
+    up, ucs, n2, h2, w2, cup = _nhwc(du_canvas_slice)
+    if tuple(dw_out.shape) != (cin, cup, 2, 2) or n != n2:
+        raise ValueError("convt2x2_wgrad: shape mismatch")
+    ws = _workspace(_lib.query("b200unet_convt2x2_wgrad_workspace_floats", n, h, w, cin, cup), x.device)
+    _lib.call("b200unet_convt2x2_wgrad", xp, xcs, up, ucs, ws.data_ptr(), _f32(dw_out), n, h, w, cin, cup, h2, w2,
+              pad_top, pad_left, _stream())
+    return dw_out
+
+
+# --------------------------------------------------------------------------------------------- first layer / head
+def conv3x3_first(x_nchw: torch.Tensor, w_oihw: torch.Tensor, out, stats_partial=None):
+    n, cin, h, w = x_nchw.shape
+    op, ocs, n2, h2, w2, cout = _nhwc(out)
+    if (n, h, w) != (n2, h2, w2) or tuple(w_oihw.shape) != (cout, cin, 3, 3):
+        raise ValueError("conv3x3_first: shape mismatch")
+    if stats_partial is not None and stats_partial.numel() < first_conv_stat_rows(n, h, w) * 2 * cout:
+        raise ValueError("conv3x3_first: stats_partial too small")
+    _lib.call("b200unet_conv3x3_first_fprop", _f32(x_nchw), _f32(w_oihw), op, ocs, _f32(stats_partial), n, h, w, cin,
+              cout, _stream())
+    return out
+
+
+def first_conv_stat_rows(n, h, w):
+    return (n * h * w + 127) // 128
+
+
+def conv3x3_first_wgrad(x_nchw, dy, dw_out):
+    n, cin, h, w = x_nchw.shape
+    yp, ycs, n2, h2, w2, cout = _nhwc(dy)
+    ws = _workspace(_lib.query("b200unet_conv3x3_first_wgrad_workspace_floats", n, h, w, cin, cout), dy.device)
+    _lib.call("b200unet_conv3x3_first_wgrad", _f32(x_nchw), yp, ycs, ws.data_ptr(), _f32(dw_out), n, h, w, cin, cout,
+              _stream())
+    return dw_out
+
+
+def head_fprop(a, w, bias, logits_nchw):
+    ap, acs, n, h, wd, cin = _nhwc(a)
+    ncls = w.shape[0]
+    _lib.call("b200unet_head_fprop", ap, acs, _f32(w.view(ncls, cin)), _f32(bias), _f32(logits_nchw), n, h, wd, cin,
+              ncls, _stream())
+    return logits_nchw
+
+
+def head_bwd(dz_nchw, a, w, da, dw, db):
+    ap, acs, n, h, wd, cin = _nhwc(a)
+    dp, dcs, *_ = _nhwc(da)
+    ncls = w.shape[0]
+    ws = _workspace(_lib.query("b200unet_head_bwd_workspace_floats", n, h, wd, cin, ncls), a.device)
+    _lib.call("b200unet_head_bwd", _f32(dz_nchw), ap, acs, _f32(w.view(ncls, cin)), dp, dcs, ws.data_ptr(), _f32(dw),
+              _f32(db), n, h, wd, cin, ncls, _stream())
+
+
+# --------------------------------------------------------------------------------------------- BN / ReLU / pool
+def bn_reduce_partials(stats_partial, rows, c, sums_f64):
+    _lib.call("b200unet_bn_reduce_partials", _f32(stats_partial), rows, c, sums_f64.data_ptr(), _stream())
+
+
+def bn_finalize(sums_f64, count, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift):
+    c = gamma.numel()
+    _lib.call("b200unet_bn_finalize", sums_f64.data_ptr(), float(count), _f32(gamma), _f32(beta), eps, momentum,
+              _ptr(running_mean), _ptr(running_var), _f32(mean), _f32(rstd), _f32(scale), _f32(shift), c, _stream())
+
+
+def bn_eval_affine(gamma, beta, running_mean, running_var, eps, scale, shift):
+    _lib.call("b200unet_bn_eval_affine", _f32(gamma), _f32(beta), _f32(running_mean), _f32(running_var), eps,
+              _f32(scale), _f32(shift), gamma.numel(), _stream())
+
+
+def bn_relu_fwd(y, scale, shift, a, pooled=None, pool_idx=None):
+    yp, ycs, n, h, w, c = _nhwc(y)
+    ap, acs, *_ = _nhwc(a)
+    _lib.call("b200unet_bn_relu_fwd", yp, ycs, _f32(scale), _f32(shift), ap, acs, _ptr(pooled), _ptr(pool_idx), n, h, w,
+              c, _stream())
+
+
+def bn_relu_bwd(g1, g_pool, pool_idx, y, gamma, scale, shift, mean, rstd, dy, dgamma, dbeta, count=None,
+                allreduce=None):
+    """Backward of BN->ReLU(->skip+pool). g1: gradient w.r.t. the activation (may be a channel slice, or None);
+    g_pool/pool_idx: gradient through the 2x2 max pool (or None). Writes dy (may alias y), dgamma, dbeta.
+    allreduce: optional callable(sums_f64) applied between the two passes (SyncBN)."""
+    yp, ycs, n, h, w, c = _nhwc(y)
+    g1p, g1cs = (None, 0)
+    if g1 is not None:
+        g1p, g1cs, *_ = _nhwc(g1)
+    dp, dcs, *_ = _nhwc(dy)
+    ws = _workspace(_lib.query("b200unet_bn_bwd_workspace_floats", n, h, w, c), y.device)
+    sums = torch.empty((2 * c,), dtype=torch.float64, device=y.device)
+    _lib.call("b200unet_bn_relu_bwd_reduce", g1p, g1cs, _ptr(g_pool), _ptr(pool_idx), yp, ycs, _f32(scale), _f32(shift),
+              _f32(mean), _f32(rstd), ws.data_ptr(), sums.data_ptr(), n, h, w, c, _stream())
+    sums_local = None
+    if count is None:
+        count = n * h * w
+    if allreduce is not None:
+        sums_local = sums.clone()
+        allreduce(sums)
+    _lib.call("b200unet_bn_relu_bwd_apply", g1p, g1cs, _ptr(g_pool), _ptr(pool_idx), yp, ycs, _f32(gamma), _f32(scale),
+              _f32(shift), _f32(mean), _f32(rstd), sums.data_ptr(), float(count), _ptr(sums_local), dp, dcs,
+              _f32(dgamma), _f32(dbeta), n, h, w, c, _stream())
+
+
+def channel_sum(x, out):
+    xp, xcs, n, h, w, c = _nhwc(x)
+    ws = _workspace(_lib.query("b200unet_channel_sum_workspace_floats", c), x.device)
+    _lib.call("b200unet_channel_sum", xp, xcs, ws.data_ptr(), _f32(out), n * h * w, c, _stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------- losses / inference
+def loss_ce_dice_fwd(logits, target, mode):
+    n, ncls, h, w = logits.shape
+    sums = torch.empty((25,), dtype=torch.float64, device=logits.device)
+    out = torch.empty((3,), dtype=torch.float32, device=logits.device)
+    err = torch.empty((1,), dtype=torch.int32, device=logits.device)
+    _lib.call("b200unet_loss_ce_dice_fwd", _f32(logits), _f32(target), sums.data_ptr(), out.data_ptr(), err.data_ptr(),
+              n, ncls, h * w, mode, _stream())
+    return out, sums, err
+
+
+def loss_ce_dice_bwd(logits, target, sums, grad_out, mode):
+    n, ncls, h, w = logits.shape
+    dz = torch.empty_like(logits)
+    _lib.call("b200unet_loss_ce_dice_bwd", _f32(logits), _f32(target), sums.data_ptr(), _f32(grad_out), dz.data_ptr(),
+              n, ncls, h * w, mode, _stream())
+    return dz
+
+
+def mse_fwd(pred, target, relu_input=False):
+    s = torch.empty((1,), dtype=torch.float64, device=pred.device)
+    out = torch.empty((1,), dtype=torch.float32, device=pred.device)
+    _lib.call("b200unet_mse_fwd", _f32(pred), _f32(target), s.data_ptr(), out.data_ptr(), pred.numel(),
+              int(relu_input), _stream())
+    return out
+
+
+def mse_bwd(pred, target, grad_out, relu_input=False):
+    d = torch.empty_like(pred)
+    _lib.call("b200unet_mse_bwd", _f32(pred), _f32(target), _f32(grad_out), d.data_ptr(), pred.numel(),
+              int(relu_input), _stream())
+    return d
+
+
+def softmax_argmax(logits):
+    n, ncls, h, w = logits.shape
+    mask = torch.empty((n, h, w), dtype=torch.int64, device=logits.device)
+    _lib.call("b200unet_softmax_argmax", _f32(logits), mask.data_ptr(), n, ncls, h * w, _stream())
+    return mask
