@@ -1,0 +1,83 @@
+"""ORACLE / CPU BASELINE (test and measurement infrastructure, not product code).
+
+The reference's CPU path for the hot path is `Model.UNet(...)(x)` + `loss.calc_loss(..., 'dice_bce_mc')` +
+`.backward()` in fp32. /root/reference cannot travel to the GPU box, so this port issues the
+SAME torch CPU library ops the reference modules dispatch to (F.conv2d / F.batch_norm / F.relu / F.max_pool2d /
+F.conv_transpose2d / F.pad / torch.cat: Model.py:15-22, 36, 56-57, 69-79, 89) in the same order with the same
+shapes, so its host-core throughput is the reference's. tests/test_oracle.py checks it against the explicit-algebra
+oracle (unet_oracle.py), which is itself pinned to the reference's golden vectors.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import unet_oracle as O
+
+
+def _double_conv(p, prefix, x, training=True):
+    for ci, bi in ((0, 1), (3, 4)):
+        x = F.conv2d(x, p[f"{prefix}.{ci}.weight"], None, padding=1)
+        x = F.batch_norm(x, p[f"{prefix}.{bi}.running_mean"], p[f"{prefix}.{bi}.running_var"], p[f"{prefix}.{bi}.weight"],
+                         p[f"{prefix}.{bi}.bias"], training, O.MOMENTUM, O.EPS_BN)
+        x = F.relu(x)
+    return x
+
+
+def unet_forward_torchops(p, x, training=True):
+    x1 = _double_conv(p, "inc.double_conv", x, training)
+    skips, cur = [x1], x1
+    for i in range(1, 5):
+        cur = _double_conv(p, f"down{i}.maxpool_conv.1.double_conv", F.max_pool2d(cur, 2), training)
+        skips.append(cur)
+    for i in range(1, 5):
+        up = F.conv_transpose2d(cur, p[f"up{i}.up.weight"], p[f"up{i}.up.bias"], stride=2)
+        cur = _double_conv(p, f"up{i}.conv.double_conv", O.pad_and_cat(skips[4 - i], up), training)
+    return F.conv2d(cur, p["outc.conv.weight"], p["outc.conv.bias"])
+
+
+def init_state(n_channels, n_classes, width=64, seed=0):
+    """Random-init state in the reference's state_dict format (kaiming-normal 3x3 / 1x1 convs, Model.py:167-169)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def dc(prefix, cin, cout):
+        for ci, bi, a, b in ((0, 1, cin, cout), (3, 4, cout, cout)):
+            sd[f"{prefix}.{ci}.weight"] = torch.randn(b, a, 3, 3, generator=g) * (2.0 / (a * 9)) ** 0.5
+            sd[f"{prefix}.{bi}.weight"] = torch.ones(b)
+            sd[f"{prefix}.{bi}.bias"] = torch.zeros(b)
+            sd[f"{prefix}.{bi}.running_mean"] = torch.zeros(b)
+            sd[f"{prefix}.{bi}.running_var"] = torch.ones(b)
+            sd[f"{prefix}.{bi}.num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+
+    dc("inc.double_conv", n_channels, width)
+    for i in range(1, 5):
+        dc(f"down{i}.maxpool_conv.1.double_conv", width << (i - 1), width << i)
+    for i in range(1, 5):
+        cin = width << (5 - i)
+        bound = (1.0 / (cin // 2 * 4)) ** 0.5
+        sd[f"up{i}.up.weight"] = (torch.rand(cin, cin // 2, 2, 2, generator=g) * 2 - 1) * bound
+        sd[f"up{i}.up.bias"] = (torch.rand(cin // 2, generator=g) * 2 - 1) * bound
+        dc(f"up{i}.conv.double_conv", cin, cin // 2)
+    sd["outc.conv.weight"] = torch.randn(n_classes, width, 1, 1, generator=g) * (2.0 / width) ** 0.5
+    sd["outc.conv.bias"] = torch.zeros(n_classes)
+    return sd
+
+
+def make_step(n_channels, n_classes, batch, h, w, seed=0):
+    """Returns step() = one forward + dice_bce_mc loss + backward of the reference path on the host CPU."""
+    sd = init_state(n_channels, n_classes, 64, seed)
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(batch, n_channels, h, w, generator=g)
+    y = torch.randint(0, n_classes, (batch, h, w), generator=g).float()
+
+    def step():
+        for p in params.values():
+            p.grad = None
+        out = unet_forward_torchops(sd, x, True)
+        loss = 0.5 * F.cross_entropy(out, y.long()) + 0.5 * O.dice_softmax(out, y, n_classes)
+        loss.backward()
+        return float(loss)
+
+    return step

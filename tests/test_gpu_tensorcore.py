@@ -1,0 +1,119 @@
+"""-m gpu: tcgen05 implicit-GEMM kernels (conv3x3 fprop / dgrad / wgrad, ConvTranspose2d fprop / dgrad / wgrad)
+against the oracle on identical bf16-rounded inputs. Tolerance: 1e-2 relative (north_star, bf16); observed error
+is the bf16 rounding of the output (~2e-3)."""
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+from gpu_util import BF16, bf16_round, from_nhwc, rel_l2, to_nhwc_bf16
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import unet_torch_b200
+    from unet_torch_b200 import ops as _ops
+
+    return _ops
+
+
+CONV_SHAPES = [
+    # n, h, w, cin, cout
+    (1, 8, 16, 64, 64),       # exactly one tile
+    (2, 16, 32, 64, 64),
+    (1, 24, 40, 128, 128),    # ragged tiles (h, w not multiples of 8 / 16)
+    (2, 8, 16, 256, 256),
+    (1, 16, 16, 128, 64),     # decoder-style Cin > Cout
+    (1, 4, 4, 64, 128),       # image smaller than a tile
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", CONV_SHAPES)
+def test_conv3x3_fprop_and_stats(ops, n, h, w, cin, cout):
+    g = torch.Generator().manual_seed(11)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+    wf, wd = ops.prep_conv3x3_weight(wt.cuda())
+    assert torch.equal(wf.float().cpu(), wt.permute(0, 2, 3, 1).contiguous())
+    y = torch.empty(n, h, w, cout, dtype=BF16, device="cuda")
+    rows = ops.num_pixel_tiles(n, h, w)
+    st = torch.zeros(rows * 2 * cout, device="cuda")
+    ops.conv3x3(to_nhwc_bf16(x), wf, y, st)
+    torch.cuda.synchronize()
+    want = O.conv3x3(x, wt)
+    assert rel_l2(from_nhwc(y), want) < TOL
+    yb = from_nhwc(y)
+    s = st.view(rows, 2, cout).sum(0).cpu()
+    assert rel_l2(s[0], yb.sum((0, 2, 3))) < 1e-3 + 1e-4
+    assert rel_l2(s[1], (yb * yb).sum((0, 2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", CONV_SHAPES[:5])
+def test_conv3x3_dgrad(ops, n, h, w, cin, cout):
+    g = torch.Generator().manual_seed(12)
+    xv = torch.randn(n, cin, h, w, generator=g).requires_grad_(True)
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+    dy = bf16_round(torch.randn(n, cout, h, w, generator=g))
+    (O.conv3x3(xv, wt) * dy).sum().backward()
+    _, wd = ops.prep_conv3x3_weight(wt.cuda())
+    dx = torch.empty(n, h, w, cin, dtype=BF16, device="cuda")
+    ops.conv3x3(to_nhwc_bf16(dy), wd, dx)
+    assert rel_l2(from_nhwc(dx), xv.grad) < TOL
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", CONV_SHAPES)
+def test_conv3x3_wgrad(ops, n, h, w, cin, cout):
+    g = torch.Generator().manual_seed(13)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wv = torch.zeros(cout, cin, 3, 3, requires_grad=True)
+    dy = bf16_round(torch.randn(n, cout, h, w, generator=g))
+    (O.conv3x3(x, wv) * dy).sum().backward()
+    dw = torch.empty(cout, cin, 3, 3, device="cuda")
+    ops.conv3x3_wgrad(to_nhwc_bf16(x), to_nhwc_bf16(dy), dw)
+    assert rel_l2(dw, wv.grad) < 1e-4  # fp32 accumulation of exact bf16 products
+
+
+def test_conv3x3_reads_and_writes_channel_slices(ops):
+    """The decoder reads the concat buffer and the encoder writes into it: pitches larger than the channel count."""
+    g = torch.Generator().manual_seed(14)
+    n, h, w, c = 1, 16, 16, 64
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    wt = bf16_round(torch.randn(c, c, 3, 3, generator=g) * 0.06)
+    wf, _ = ops.prep_conv3x3_weight(wt.cuda())
+    xin = torch.full((n, h, w, 3 * c), 7.0, dtype=BF16, device="cuda")
+    xin[..., c:2 * c] = to_nhwc_bf16(x)
+    yout = torch.zeros(n, h, w, 2 * c, dtype=BF16, device="cuda")
+    ops.conv3x3(xin[..., c:2 * c], wf, yout[..., c:])
+    assert rel_l2(from_nhwc(yout[..., c:]), O.conv3x3(x, wt)) < TOL
+    assert float(yout[..., :c].float().abs().max()) == 0.0
+
+
+UP_SHAPES = [(1, 8, 16, 128, 64), (2, 4, 8, 256, 128), (1, 12, 20, 128, 64)]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cup", UP_SHAPES)
+def test_conv_transpose_fprop_dgrad_wgrad(ops, n, h, w, cin, cup):
+    g = torch.Generator().manual_seed(15)
+    xv = bf16_round(torch.randn(n, cin, h, w, generator=g)).requires_grad_(True)
+    wv = bf16_round(torch.randn(cin, cup, 2, 2, generator=g) * (1.0 / cin) ** 0.5).requires_grad_(True)
+    b = torch.randn(cup, generator=g)
+    want = O.conv_transpose2x2(xv, wv, b)
+    du = bf16_round(torch.randn(want.shape, generator=g))
+    (want * du).sum().backward()
+    wf, wd = ops.prep_convt2x2_weight(wv.detach().cuda())
+    # forward into the right half of a concat buffer
+    cat = torch.zeros(n, 2 * h, 2 * w, 2 * cup, dtype=BF16, device="cuda")
+    ops.convt2x2(to_nhwc_bf16(xv.detach()), wf, b.cuda(), cat[..., cup:])
+    assert rel_l2(from_nhwc(cat[..., cup:]), want) < TOL
+    assert float(cat[..., :cup].float().abs().max()) == 0.0
+    # backward data / weights from a gradient that also lives in a concat-shaped buffer
+    dcat = torch.zeros(n, 2 * h, 2 * w, 2 * cup, dtype=BF16, device="cuda")
+    dcat[..., cup:] = to_nhwc_bf16(du)
+    dx = torch.empty(n, h, w, cin, dtype=BF16, device="cuda")
+    ops.convt2x2_dgrad(dcat[..., cup:], wd, dx)
+    assert rel_l2(from_nhwc(dx), xv.grad) < TOL
+    dw = torch.empty(cin, cup, 2, 2, device="cuda")
+    ops.convt2x2_wgrad(to_nhwc_bf16(xv.detach()), dcat[..., cup:], dw)
+    assert rel_l2(dw, wv.grad) < 1e-4

@@ -105,3 +105,14 @@ def test_live_reference_agrees():
             sd[k] = torch.ones_like(sd[k])
     got, _ = O.unet_forward(sd, x, training=True)
     assert rel(got, want) < 1e-10
+
+
+def test_cpu_baseline_port_matches_oracle():
+    """bench.py's CPU baseline issues the torch library ops the reference calls; it must agree with the oracle."""
+    from oracle import cpu_baseline as CB
+
+    sd = CB.init_state(3, 2, width=4, seed=5)
+    x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(6))
+    a = CB.unet_forward_torchops({k: v.clone() for k, v in sd.items()}, x, True)
+    b, _ = O.unet_forward(sd, x, True)
+    assert rel(a, b) < 1e-5
