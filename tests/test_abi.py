@@ -1,0 +1,62 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/b200unet.h declares, and the ctypes binding
+agrees with the header (argument count and kind). No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+
+    g.build()
+    from unet_torch_b200 import _lib
+
+    return _lib
+
+
+def header_decls():
+    h = open(os.path.join(ROOT, "include", "b200unet.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return re.findall(r"\b(?:int|int64_t|const char\*)\s+(b200unet_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S)
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    decls = header_decls()
+    assert len(decls) >= 30
+    cdll = ctypes.CDLL(lib.LIB_PATH)
+    for name, args in decls:
+        assert hasattr(cdll, name), f"{name} declared in include/b200unet.h but not exported"
+        assert name in lib.SIGNATURES, f"{name} has no ctypes binding"
+        arglist = [a.strip() for a in args.split(",") if a.strip() and a.strip() != "void"]
+        bound = lib.SIGNATURES[name][1]
+        assert len(arglist) == len(bound), name
+        for a, ct in zip(arglist, bound):
+            is_ptr = "*" in a or "b200_stream_t" in a
+            want = "c_void_p" if is_ptr else "c_double" if a.startswith("double") else "c_float" if a.startswith(
+                "float") else "c_long" if "int64_t" in a else "c_int"
+            assert ct.__name__ == want, (name, a, ct.__name__)
+    assert set(lib.SIGNATURES) == {n for n, _ in decls}
+
+
+def test_host_only_queries(lib):
+    assert lib.query("b200unet_version") >= 100
+    assert (lib.query("b200unet_tile_h"), lib.query("b200unet_tile_w")) == (8, 16)
+    # split-K workspace: splits * Cout * 9 * Cin floats, at least one split
+    ws = lib.query("b200unet_conv3x3_wgrad_workspace_floats", 16, 512, 512, 64, 64)
+    assert ws % (64 * 9 * 64) == 0 and ws >= 64 * 9 * 64
+    assert lib.query("b200unet_conv3x3_wgrad_workspace_floats", 16, 32, 32, 1024, 1024) == 1024 * 9 * 1024
+    assert lib.query("b200unet_launch_count") == 0
+
+
+def test_bad_shapes_are_errors_not_fallbacks(lib):
+    # no GPU needed: argument validation happens before anything touches the device
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        lib.call("b200unet_conv3x3_igemm", None, 48, None, None, 64, None, 1, 8, 16, 48, 64, None)
+    with pytest.raises(RuntimeError, match="n_classes"):
+        lib.call("b200unet_head_fprop", None, 64, None, None, None, 1, 8, 8, 64, 9, None)
+    assert "n_classes" in lib.last_error()

@@ -80,6 +80,8 @@ def test_bn_relu_backward(ops, pool):
     bet = beta.clone().requires_grad_(True)
     out, _, _ = O.batchnorm_train(yv, gam, bet)
     a = O.relu(out)
+    # the device stores `a` in bf16 and pools the stored values: give the oracle the identical pooling input
+    a = a + (bf16_round(a.detach()) - a.detach())
     g1 = bf16_round(torch.randn(n, c, h, w, generator=g))
     loss = (a * g1).sum()
     gp = None

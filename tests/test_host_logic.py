@@ -1,0 +1,76 @@
+"""CPU: the host-side mirror of the reference interface (module tree / state_dict ABI / init RNG order / loss
+dispatch) and the absence of any CPU fallback."""
+import copy
+
+import pytest
+import torch
+
+
+def checksum(v):
+    f = v.double().flatten()
+    return torch.tensor([f.sum(), f.abs().sum(), f[0], f[f.numel() // 2], f[-1]], dtype=torch.float64)
+
+
+def test_state_dict_keys_shapes_and_init_match_reference(golden):
+    import unet_torch_b200 as U
+
+    for case, g in golden("ref_full_nets.pt").items():
+        ch, ncls, width, n, h, w, seed = g["cfg"]
+        torch.manual_seed(seed)
+        net = U.UNet(ch, ncls, width)
+        sd = net.state_dict()
+        assert list(sd.keys()) == list(g["sd0_checksum"].keys()), case  # same keys, same order
+        for k, v in sd.items():
+            assert torch.allclose(checksum(v), g["sd0_checksum"][k], rtol=1e-12, atol=0), (case, k)
+            assert v.dtype in (torch.float32, torch.int64)
+
+
+def test_narrow_reference_checkpoint_loads(golden):
+    import unet_torch_b200 as U
+
+    g = golden("ref_small_nets.pt")["w4_c3_k5_dicebce"]
+    net = U.UNet(3, 5, 4)
+    missing = net.load_state_dict(g["sd0"], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    sd = copy.deepcopy(net.state_dict())  # Trainer.py:759 deep-copies the state_dict
+    assert torch.equal(sd["outc.conv.weight"], g["sd0"]["outc.conv.weight"])
+
+
+def test_constructor_contract():
+    import unet_torch_b200 as U
+
+    net = U.UNet(-2, 3, 64, True, False, 0.5)  # train.py:196-205 passes six positional arguments
+    assert (net.n_channels, net.n_classes, net.initial_feature_map, net.usa_cuda, net.dropout, net.dropout_p) == (
+        3, 3, 64, True, False, 0.5)
+    assert U.UNet(-1, 2).n_channels == 1
+    names = [n for n, _ in net.named_children()]
+    assert names == ["inc", "down1", "down2", "down3", "down4", "up1", "up2", "up3", "up4", "outc"]
+    d = U.UNet(3, 2, 64, True, True, 0.3)
+    assert "down1.maxpool_conv.2.double_conv.0.weight" in d.state_dict()  # Dropout shifts the index (Model.py:34-39)
+
+
+def test_no_cpu_fallback():
+    import unet_torch_b200 as U
+
+    net = U.UNet(3, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.randn(1, 3, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        U.calc_loss(torch.randn(1, 2, 8, 8, requires_grad=True), torch.zeros(1, 8, 8), loss_type="dice_bce_mc")
+    with pytest.raises(RuntimeError):
+        net.inc(torch.randn(1, 3, 32, 32))  # blocks are parameter containers, not a torch fallback
+
+
+def test_root_shims_mirror_reference_imports():
+    import Model
+    import loss
+    import unet_torch_b200 as U
+
+    assert Model.UNet is U.UNet
+    loss.CLASS_NUMBER = 5  # train.py:163
+    assert U.loss.CLASS_NUMBER == 5
+    assert callable(loss.calc_loss) and loss.DiceLoss is U.DiceLoss
+    with pytest.raises(NotImplementedError):
+        Model.UNet_multitask(3, 2)
+    with pytest.raises(NotImplementedError):
+        loss.calc_loss(torch.zeros(1, 1, 4, 4), torch.zeros(1, 4, 4), loss_type="HausdorffDTLoss")

@@ -125,13 +125,26 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_fwd_kernel(const __nv_bflo
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   if (!POOL) {
     const long long total = static_cast<long long>(N) * H * W * cgs;
-    for (long long i = tid; i < total; i += stride) {
-      const long long pix = i / cgs;
-      float f[8];
-      unpack8(ldg128(y + pix * y_cs + cg * 8), f);
+    constexpr int U = 4;  // independent 128-bit loads in flight per thread
+    for (long long i0 = tid; i0 < total; i0 += stride * U) {
+      uint4 raw[U];
+      long long pix[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(sc[j], f[j], sh[j]), 0.f);
-      *reinterpret_cast<uint4*>(a + pix * a_cs + cg * 8) = pack8(f);
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * stride;
+        pix[u] = i / cgs;
+        if (i < total) raw[u] = ldg128(y + pix[u] * y_cs + cg * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (i0 + u * stride < total) {
+          float f[8];
+          unpack8(raw[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(sc[j], f[j], sh[j]), 0.f);
+          *reinterpret_cast<uint4*>(a + pix[u] * a_cs + cg * 8) = pack8(f);
+        }
+      }
     }
   } else {
     const int Hp = H >> 1, Wp = W >> 1;
@@ -183,90 +196,100 @@ struct BwdSrc {
   int y_cs;
 };
 
+// Raw 128-bit loads of one work item (one pixel, or one 2x2 pooling window), issued before any arithmetic so
+// that several items' loads are in flight per thread.
 template <bool POOL>
-__device__ __forceinline__ void load_da_window(const BwdSrc& s, long long item, int cg, int C, int H, int W,
-                                               const float (&sc)[8], const float (&sh)[8], float (&da)[POOL ? 4 : 1][8],
-                                               float (&yv)[POOL ? 4 : 1][8], long long (&pix)[POOL ? 4 : 1]) {
+struct BwdRaw {
+  static constexpr int NP = POOL ? 4 : 1;
+  uint4 y[NP], g[NP], gp;
+  uint2 idx;
+  long long pix[NP];
+};
+
+template <bool POOL>
+__device__ __forceinline__ void bwd_load(const BwdSrc& s, long long item, int cg, int C, int H, int W, BwdRaw<POOL>& r) {
   if (!POOL) {
-    pix[0] = item;
-    unpack8(ldg128(s.y + item * s.y_cs + cg * 8), yv[0]);
-    if (s.g1 != nullptr) {
-      unpack8(ldg128(s.g1 + item * s.g1_cs + cg * 8), da[0]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) da[0][j] = 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (!(fmaf(sc[j], yv[0][j], sh[j]) > 0.f)) da[0][j] = 0.f;
+    r.pix[0] = item;
+    r.y[0] = ldg128(s.y + item * s.y_cs + cg * 8);
+    r.g[0] = s.g1 != nullptr ? ldg128(s.g1 + item * s.g1_cs + cg * 8) : make_uint4(0, 0, 0, 0);
   } else {
     const int Hp = H >> 1, Wp = W >> 1;
     const int wp = static_cast<int>(item % Wp);
     const int hp = static_cast<int>((item / Wp) % Hp);
     const long long n = item / (static_cast<long long>(Wp) * Hp);
     const long long p00 = (n * H + 2 * hp) * W + 2 * wp;
-    float gp[8];
-    unpack8(ldg128(s.gp + item * C + cg * 8), gp);
-    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(s.pidx + item * C + cg * 8));
-    uint32_t bidx[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      bidx[j] = (pk.x >> (8 * j)) & 0xff;
-      bidx[4 + j] = (pk.y >> (8 * j)) & 0xff;
-    }
+    r.gp = ldg128(s.gp + item * C + cg * 8);
+    r.idx = __ldg(reinterpret_cast<const uint2*>(s.pidx + item * C + cg * 8));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      pix[k] = p00 + (k >> 1) * W + (k & 1);
-      unpack8(ldg128(s.y + pix[k] * s.y_cs + cg * 8), yv[k]);
-      if (s.g1 != nullptr) {
-        unpack8(ldg128(s.g1 + pix[k] * s.g1_cs + cg * 8), da[k]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) da[k][j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (bidx[j] == static_cast<uint32_t>(k)) da[k][j] += gp[j];
-        if (!(fmaf(sc[j], yv[k][j], sh[j]) > 0.f)) da[k][j] = 0.f;
-      }
+      r.pix[k] = p00 + (k >> 1) * W + (k & 1);
+      r.y[k] = ldg128(s.y + r.pix[k] * s.y_cs + cg * 8);
+      r.g[k] = s.g1 != nullptr ? ldg128(s.g1 + r.pix[k] * s.g1_cs + cg * 8) : make_uint4(0, 0, 0, 0);
     }
   }
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(BwdSrc s, const float* __restrict__ scale,
-                                                                   const float* __restrict__ shift,
-                                                                   const float* __restrict__ mean,
-                                                                   const float* __restrict__ rstd,
-                                                                   float* __restrict__ partial, int N, int H, int W,
-                                                                   int C) {
+__device__ __forceinline__ void bwd_decode(const BwdRaw<POOL>& r, int k, const float (&sc)[8], const float (&sh)[8],
+                                           float (&da)[8], float (&yv)[8]) {
+  unpack8(r.y[k], yv);
+  unpack8(r.g[k], da);
+  if (POOL) {
+    float gp[8];
+    unpack8(r.gp, gp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t b = ((j < 4 ? r.idx.x : r.idx.y) >> (8 * (j & 3))) & 0xffu;
+      if (b == static_cast<uint32_t>(k)) da[j] += gp[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (!(fmaf(sc[j], yv[j], sh[j]) > 0.f)) da[j] = 0.f;
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(BwdSrc s, const float* __restrict__ scale,
+                                                                      const float* __restrict__ shift,
+                                                                      const float* __restrict__ mean,
+                                                                      const float* __restrict__ rstd,
+                                                                      float* __restrict__ partial, int N, int H, int W,
+                                                                      int C) {
   constexpr int NP = POOL ? 4 : 1;
+  constexpr int U = POOL ? 1 : 4;
   const int cgs = C >> 3;
   const int cg = threadIdx.x % cgs;
-  float sc[8], sh[8], mu[8], rs[8], s1[8], s2[8];
+  float sc[8], sh[8], s1[8], s2[8];  // s1 = sum da, s2 = sum da*y (turned into sum da*xhat at the end)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     sc[i] = scale[cg * 8 + i];
     sh[i] = shift[cg * 8 + i];
-    mu[i] = mean[cg * 8 + i];
-    rs[i] = rstd[cg * 8 + i];
     s1[i] = 0.f;
     s2[i] = 0.f;
   }
   const long long items = POOL ? static_cast<long long>(N) * (H >> 1) * (W >> 1) : static_cast<long long>(N) * H * W;
   const long long total = items * cgs;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    float da[NP][8], yv[NP][8];
-    long long pix[NP];
-    load_da_window<POOL>(s, i / cgs, cg, C, H, W, sc, sh, da, yv, pix);
+  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    BwdRaw<POOL> raw[U];
 #pragma unroll
-    for (int k = 0; k < NP; ++k)
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * stride < total) bwd_load<POOL>(s, (i0 + u * stride) / cgs, cg, C, H, W, raw[u]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += da[k][j];
-        s2[j] = fmaf(da[k][j], (yv[k][j] - mu[j]) * rs[j], s2[j]);
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride < total) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          float da[8], yv[8];
+          bwd_decode<POOL>(raw[u], k, sc, sh, da, yv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s1[j] += da[j];
+            s2[j] = fmaf(da[j], yv[j], s2[j]);
+          }
+        }
       }
+    }
   }
   // block reduction across the threads that share a channel group
   __shared__ float sh_red[EW_THREADS][17];
@@ -276,28 +299,34 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_reduce_kernel(BwdSrc s, con
     sh_red[threadIdx.x][8 + j] = s2[j];
   }
   __syncthreads();
-  // thread t < 2*C handles (which = t / C, channel = t % C)
-  for (int t = threadIdx.x; t < 2 * C; t += blockDim.x) {
-    const int which = t / C, ch = t % C;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     const int g = ch >> 3, j = ch & 7;
-    float acc = 0.f;
-    for (int th = g; th < EW_THREADS; th += cgs) acc += sh_red[th][which * 8 + j];
-    partial[static_cast<size_t>(blockIdx.x) * 2 * C + t] = acc;
+    double a1 = 0.0, a2 = 0.0;
+    for (int th = g; th < EW_THREADS; th += cgs) {
+      a1 += static_cast<double>(sh_red[th][j]);
+      a2 += static_cast<double>(sh_red[th][8 + j]);
+    }
+    // sum da*xhat = rstd * (sum da*y - mean * sum da)
+    const double sx = static_cast<double>(rstd[ch]) * (a2 - static_cast<double>(mean[ch]) * a1);
+    partial[static_cast<size_t>(blockIdx.x) * 2 * C + ch] = static_cast<float>(a1);
+    partial[static_cast<size_t>(blockIdx.x) * 2 * C + C + ch] = static_cast<float>(sx);
   }
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(BwdSrc s, const float* __restrict__ gamma,
-                                                                  const float* __restrict__ scale,
-                                                                  const float* __restrict__ shift,
-                                                                  const float* __restrict__ mean,
-                                                                  const float* __restrict__ rstd,
-                                                                  const double* __restrict__ sums, double count,
-                                                                  const double* __restrict__ sums_local,
-                                                                  __nv_bfloat16* __restrict__ dy, int dy_cs,
-                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                  int N, int H, int W, int C) {
+__global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(BwdSrc s, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ scale,
+                                                                     const float* __restrict__ shift,
+                                                                     const float* __restrict__ mean,
+                                                                     const float* __restrict__ rstd,
+                                                                     const double* __restrict__ sums, double count,
+                                                                     const double* __restrict__ sums_local,
+                                                                     __nv_bfloat16* __restrict__ dy, int dy_cs,
+                                                                     float* __restrict__ dgamma,
+                                                                     float* __restrict__ dbeta, int N, int H, int W,
+                                                                     int C) {
   constexpr int NP = POOL ? 4 : 1;
+  constexpr int U = POOL ? 1 : 4;
   const int cgs = C >> 3;
   const int cg = threadIdx.x % cgs;
   float sc[8], sh[8], k1[8], k2[8], k3[8];
@@ -323,16 +352,23 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(BwdSrc s, cons
   const long long items = POOL ? static_cast<long long>(N) * (H >> 1) * (W >> 1) : static_cast<long long>(N) * H * W;
   const long long total = items * cgs;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    float da[NP][8], yv[NP][8];
-    long long pix[NP];
-    load_da_window<POOL>(s, i / cgs, cg, C, H, W, sc, sh, da, yv, pix);
+  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    BwdRaw<POOL> raw[U];
 #pragma unroll
-    for (int k = 0; k < NP; ++k) {
-      float o[8];
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * stride < total) bwd_load<POOL>(s, (i0 + u * stride) / cgs, cg, C, H, W, raw[u]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(k1[j], da[k][j], fmaf(k2[j], yv[k][j], k3[j]));
-      *reinterpret_cast<uint4*>(dy + pix[k] * dy_cs + cg * 8) = pack8(o);
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride < total) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          float da[8], yv[8], o[8];
+          bwd_decode<POOL>(raw[u], k, sc, sh, da, yv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(k1[j], da[j], fmaf(k2[j], yv[j], k3[j]));
+          *reinterpret_cast<uint4*>(dy + raw[u].pix[k] * dy_cs + cg * 8) = pack8(o);
+        }
+      }
     }
   }
 }

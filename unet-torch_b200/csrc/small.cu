@@ -114,60 +114,98 @@ __global__ void __launch_bounds__(128) first_fprop_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------- inc.conv1 wgrad
-// thread = (pixel lane pl in 0..15, 4-channel group cq in 0..15) of one 64-channel group; 4 x CIN*9 accumulators.
+// dW[k][c][r][s] = sum_p dy[p][k] * x[p + (r-1, s-1)][c]: a [64 x pixels] x [pixels x CIN*9] product, FMA-bound.
+// Per 64-pixel tile the block stages dy (fp32) and the im2col row of every pixel in smem; thread
+// (stream q, 4-channel group kq, tap group jq) keeps a 4 x JG register tile and walks its stream's 16 pixels with
+// 3 LDS.128 per 28 FMAs. Streams are reduced through smem at the end; per-block partials go to the workspace.
 template <int CIN>
 __global__ void __launch_bounds__(256) first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                           int dy_cs, float* __restrict__ partial, int N, int H, int W,
                                                           int Cout) {
   constexpr int T = CIN * 9;
-  __shared__ float sh[256][T + 1];
+  constexpr int JG = (T + 3) / 4;          // taps per thread
+  constexpr int JGP = (JG + 3) / 4 * 4;    // padded to a multiple of 4 floats
+  constexpr int TP = 64;                   // pixels per tile
+  __shared__ __align__(16) float dys[TP][64];
+  __shared__ __align__(16) float xcol[TP][4 * JGP];
   const int kg = blockIdx.y;
-  const int cq = threadIdx.x & 15, pl = threadIdx.x >> 4;
-  float acc[4][T];
+  const int q = threadIdx.x >> 6, kq = (threadIdx.x & 63) >> 2, jq = threadIdx.x & 3;
+  float acc[4][JG];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < T; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < JG; ++j) acc[i][j] = 0.f;
   const long long P = static_cast<long long>(N) * H * W;
-  for (long long p = static_cast<long long>(blockIdx.x) * 16 + pl; p < P; p += static_cast<long long>(gridDim.x) * 16) {
-    const int wq = static_cast<int>(p % W);
-    const int hq = static_cast<int>((p / W) % H);
-    const long long n = p / (static_cast<long long>(W) * H);
-    const uint2 d = __ldg(reinterpret_cast<const uint2*>(dy + p * dy_cs + kg * 64 + cq * 4));
-    const float g[4] = {__uint_as_float(d.x << 16), __uint_as_float(d.x & 0xffff0000u), __uint_as_float(d.y << 16),
-                        __uint_as_float(d.y & 0xffff0000u)};
+  const long long ntiles = (P + TP - 1) / TP;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long p0 = tile * TP;
+    __syncthreads();  // previous tile fully consumed
+    // stage dy: 64 px x 64 ch bf16 = 512 uint4, two per thread
 #pragma unroll
-    for (int c = 0; c < CIN; ++c) {
-      const float* xc = x + (n * CIN + c) * static_cast<long long>(H) * W;
+    for (int it = 0; it < 2; ++it) {
+      const int v = threadIdx.x + it * 256;
+      const int pr = v >> 3, ch = v & 7;
+      float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (p0 + pr < P) unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (p0 + pr) * dy_cs + kg * 64 + ch * 8)), f);
+      *reinterpret_cast<float4*>(&dys[pr][ch * 8]) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(&dys[pr][ch * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    // stage the im2col rows: element (pixel pr, tap j) with j = c*9 + r*3 + s stored at [pr][(j / JG) * JGP + j % JG]
+    for (int v = threadIdx.x; v < TP * 4 * JGP; v += 256) {
+      const int pr = v / (4 * JGP), col = v % (4 * JGP);
+      const int grp = col / JGP, jj = col % JGP;
+      const int j = grp * JG + jj;
+      float xv = 0.f;
+      const long long p = p0 + pr;
+      if (jj < JG && j < T && p < P) {
+        const int wq = static_cast<int>(p % W);
+        const int hq = static_cast<int>((p / W) % H);
+        const long long n = p / (static_cast<long long>(W) * H);
+        const int c = j / 9, r = (j % 9) / 3, sx = j % 3;
+        const int hh = hq + r - 1, ww = wq + sx - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) xv = __ldg(x + ((n * CIN + c) * H + hh) * static_cast<long long>(W) + ww);
+      }
+      xcol[pr][col] = xv;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < TP / 4; ++i) {
+      const int pr = q * (TP / 4) + i;
+      const float4 d = *reinterpret_cast<const float4*>(&dys[pr][kq * 4]);
+      float xv[JGP];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int hh = hq + r - 1;
+      for (int j4 = 0; j4 < JGP / 4; ++j4) {
+        const float4 t = *reinterpret_cast<const float4*>(&xcol[pr][jq * JGP + j4 * 4]);
+        xv[4 * j4] = t.x; xv[4 * j4 + 1] = t.y; xv[4 * j4 + 2] = t.z; xv[4 * j4 + 3] = t.w;
+      }
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int ww = wq + s - 1;
-          float xv = 0.f;
-          if (hh >= 0 && hh < H && ww >= 0 && ww < W) xv = __ldg(xc + static_cast<long long>(hh) * W + ww);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i][c * 9 + r * 3 + s] = fmaf(g[i], xv, acc[i][c * 9 + r * 3 + s]);
-        }
+      for (int j = 0; j < JG; ++j) {
+        acc[0][j] = fmaf(d.x, xv[j], acc[0][j]);
+        acc[1][j] = fmaf(d.y, xv[j], acc[1][j]);
+        acc[2][j] = fmaf(d.z, xv[j], acc[2][j]);
+        acc[3][j] = fmaf(d.w, xv[j], acc[3][j]);
       }
     }
   }
-  // reduce over the 16 pixel lanes, one output channel (of the 4) at a time
+  // reduce the 4 pixel streams: reuse dys as [4 streams][64 k][T] would not fit; go tap by tap through xcol-sized scratch
+  __syncthreads();
+  float* scratch = &dys[0][0];  // 4096 floats >= 4 streams * 64 k * 4 (one tap slot per jq) * ... processed per j
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int j = 0; j < JG; ++j) {
+    // slot layout: [q][k = kq*4+i][jq]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) scratch[(q * 64 + kq * 4 + i) * 4 + jq] = acc[i][j];
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < T; ++j) sh[threadIdx.x][j] = acc[i][j];
-    __syncthreads();
-    for (int o = threadIdx.x; o < 16 * T; o += 256) {
-      const int q = o / T, j = o % T;
-      float t = 0.f;
-#pragma unroll
-      for (int l = 0; l < 16; ++l) t += sh[l * 16 + q][j];
-      const int k = kg * 64 + q * 4 + i;
-      partial[(static_cast<size_t>(blockIdx.x) * Cout + k) * T + j] = t;
+    {
+      const int k = threadIdx.x >> 2, g4 = threadIdx.x & 3;  // 64 k x 4 tap groups = 256 outputs per j
+      const int jt = g4 * JG + j;
+      if (jt < T) {
+        const float t = scratch[(0 * 64 + k) * 4 + g4] + scratch[(1 * 64 + k) * 4 + g4] + scratch[(2 * 64 + k) * 4 + g4] +
+                        scratch[(3 * 64 + k) * 4 + g4];
+        partial[(static_cast<size_t>(blockIdx.x) * Cout + kg * 64 + k) * T + jt] = t;
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -203,46 +241,74 @@ __global__ void __launch_bounds__(256) head_fprop_kernel(const __nv_bfloat16* __
   }
 }
 
-// thread = (pixel lane, 8-channel group); block = 256 threads = (256/cgs) pixels x cgs groups
+// Block = 256 threads walks tiles of 256 pixels: dz of the tile is staged (coalesced) in smem, then thread
+// (pixel lane pl, 8-channel group cg) handles the pixels pl, pl+ppb, ... of the tile with all its activation loads
+// issued up front. dW/db partial sums stay in registers across tiles and are reduced once per block.
+template <int NCLS>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dz, const __nv_bfloat16* __restrict__ a,
                                                        int a_cs, const float* __restrict__ w,
                                                        __nv_bfloat16* __restrict__ da, int da_cs,
-                                                       float* __restrict__ partial, long long P, long long HW, int Cin,
-                                                       int ncls) {
+                                                       float* __restrict__ partial, long long P, long long HW, int Cin) {
+  constexpr int ncls = NCLS;
+  __shared__ float dzs[NCLS][256];
   __shared__ float sh[256][9];
   const int cgs = Cin >> 3;
   const int cg = threadIdx.x % cgs, pl = threadIdx.x / cgs, ppb = 256 / cgs;
-  float wr[8][8], dwacc[8][8], dbacc[8];
+  float wr[NCLS][8], dwacc[NCLS][8], dbacc[NCLS];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < NCLS; ++j) {
     dbacc[j] = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      wr[j][i] = (j < ncls) ? w[j * Cin + cg * 8 + i] : 0.f;
+      wr[j][i] = w[j * Cin + cg * 8 + i];
       dwacc[j][i] = 0.f;
     }
   }
-  for (long long p = static_cast<long long>(blockIdx.x) * ppb + pl; p < P; p += static_cast<long long>(gridDim.x) * ppb) {
-    const long long n = p / HW, hw = p % HW;
-    float f[8], o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unpack8(__ldg(reinterpret_cast<const uint4*>(a + p * a_cs + cg * 8)), f);
+  const long long ntiles = (P + 255) / 256;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long p0 = tile * 256;
+    __syncthreads();
+    {
+      const long long p = p0 + threadIdx.x;
+      const long long n = p / HW, hw = p - n * HW;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < ncls) {
-        const float g = __ldg(dz + (n * ncls + j) * HW + hw);
-        dbacc[j] += g;
+      for (int j = 0; j < NCLS; ++j) dzs[j][threadIdx.x] = (p < P) ? __ldg(dz + (n * ncls + j) * HW + hw) : 0.f;
+    }
+    __syncthreads();
+    // cgs <= 32 -> ppb >= 8 pixels per pass, 256/ppb = cgs passes; process 4 passes per batch of loads
+    for (int it0 = 0; it0 < cgs; it0 += 4) {
+      uint4 raw[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          o[i] = fmaf(g, wr[j][i], o[i]);
-          dwacc[j][i] = fmaf(g, f[i], dwacc[j][i]);
+      for (int u = 0; u < 4; ++u) {
+        const long long p = p0 + (it0 + u) * ppb + pl;
+        raw[u] = (it0 + u < cgs && p < P) ? __ldg(reinterpret_cast<const uint4*>(a + p * a_cs + cg * 8)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int lp = (it0 + u) * ppb + pl;
+        const long long p = p0 + lp;
+        if (it0 + u < cgs && p < P) {
+          float f[8], o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          unpack8(raw[u], f);
+#pragma unroll
+          for (int j = 0; j < NCLS; ++j) {
+            const float g = dzs[j][lp];
+            dbacc[j] += g;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[i] = fmaf(g, wr[j][i], o[i]);
+              dwacc[j][i] = fmaf(g, f[i], dwacc[j][i]);
+            }
+          }
+          *reinterpret_cast<uint4*>(da + p * da_cs + cg * 8) =
+              make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
         }
       }
     }
-    *reinterpret_cast<uint4*>(da + p * da_cs + cg * 8) =
-        make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
   }
   // partial layout: [block][ncls][Cin + 1], last column = bias gradient
-  for (int j = 0; j < ncls; ++j) {
+#pragma unroll
+  for (int j = 0; j < NCLS; ++j) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 8; ++i) sh[threadIdx.x][i] = dwacc[j][i];
@@ -279,14 +345,14 @@ __global__ void colsum_kernel(const float* __restrict__ partial, int rows, int n
 }
 
 int first_wgrad_blocks(long long P) {
-  long long b = (P + 15) / 16;
+  long long b = (P + 63) / 64;
   if (b > 148 * 4) b = 148 * 4;
   return static_cast<int>(b < 1 ? 1 : b);
 }
 int head_bwd_blocks(long long P, int Cin) {
-  const int ppb = 256 / (Cin / 8);
-  long long b = (P + ppb - 1) / ppb;
-  if (b > MAX_BLOCKS) b = MAX_BLOCKS;
+  (void)Cin;
+  long long b = (P + 255) / 256;
+  if (b > 148 * 4) b = 148 * 4;
   return static_cast<int>(b < 1 ? 1 : b);
 }
 
@@ -359,9 +425,16 @@ int b200unet_head_bwd(const float* dz_nchw, const void* a, int a_cs, const float
   const long long P = static_cast<long long>(N) * H * W;
   const int blocks = head_bwd_blocks(P, Cin);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  head_bwd_kernel<<<blocks, 256, 0, st>>>(dz_nchw, static_cast<const __nv_bfloat16*>(a), a_cs, w,
-                                          static_cast<__nv_bfloat16*>(da), da_cs, partial, P,
-                                          static_cast<long long>(H) * W, Cin, ncls);
+#define B2_HEAD_BWD(NC)                                                                                          \
+  case NC:                                                                                                      \
+    head_bwd_kernel<NC><<<blocks, 256, 0, st>>>(dz_nchw, static_cast<const __nv_bfloat16*>(a), a_cs, w,          \
+                                                static_cast<__nv_bfloat16*>(da), da_cs, partial, P,             \
+                                                static_cast<long long>(H) * W, Cin);                            \
+    break;
+  switch (ncls) {
+    B2_HEAD_BWD(1) B2_HEAD_BWD(2) B2_HEAD_BWD(3) B2_HEAD_BWD(4) B2_HEAD_BWD(5) B2_HEAD_BWD(6) B2_HEAD_BWD(7) B2_HEAD_BWD(8)
+  }
+#undef B2_HEAD_BWD
   if (int e = b2h::check_launch("head_bwd")) return e;
   const int ncols = ncls * (Cin + 1);
   colsum_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(partial, blocks, ncols, dw, db, Cin + 1);
