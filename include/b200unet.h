@@ -150,6 +150,11 @@ int b200unet_mse_bwd(const float* pred, const float* target, const float* grad_o
 /* ---- inference head (test_mc3serousv5.py:880-881): fp32 softmax over classes, then first-maximum argmax --- */
 int b200unet_softmax_argmax(const float* logits, int64_t* mask, int N, int ncls, int64_t HW, b200_stream_t stream);
 
+/* ---- bring-up probe (test aid): UMMA operand whose start is offset by `shift` 128-byte rows inside a
+ * 128B-swizzled tile. out[128][64] = A[shift:shift+128][:] * B^T; A is 160x64 bf16, B is 64x64 bf16. */
+int b200unet_probe_shift(const void* a_160x64, const void* b_64x64, float* out_128x64, int shift,
+                         int use_base_offset, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

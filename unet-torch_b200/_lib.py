@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200unet_mse_fwd": (c_int, [_P, _P, _P, _P, _L, _I, _P]),
     "b200unet_mse_bwd": (c_int, [_P, _P, _P, _P, _L, _I, _P]),
     "b200unet_softmax_argmax": (c_int, [_P, _P, _I, _I, _L, _P]),
+    "b200unet_probe_shift": (c_int, [_P, _P, _P, _I, _I, _P]),
 }
 
 _lib = None

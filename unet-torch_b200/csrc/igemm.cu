@@ -222,9 +222,9 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ Igem
     if (et == 0) {
       for (int q = 0; q < BN / 64; ++q) {
         if (MODE == MODE_UP) {
-          const int ij = n0 / args.cup;
-          const int d0 = n0 - ij * args.cup;
-          tma_store_4d(&args.tmO[ij], stage + q * (BM * 128), d0 + q * 64, w0, h0, img);
+          const int col = n0 + q * 64;  // a tile may span several (i,j) sub-positions: one output map per chunk
+          const int ij = col / args.cup;
+          tma_store_4d(&args.tmO[ij], stage + q * (BM * 128), col - ij * args.cup, w0, h0, img);
         } else {
           tma_store_4d(&args.tmO[0], stage + q * (BM * 128), n0 + q * 64, w0, h0, img);
         }
@@ -363,7 +363,7 @@ int b200unet_convt2x2_fprop(const void* x, int x_cs, const void* w_fprop, const 
   a.cup = Cup;
   a.stats = nullptr;
   a.bias = bias;
-  const int bn = pick_bn(4 * Cup, Cup);
+  const int bn = (env_bn() == 0) ? 256 : pick_bn(4 * Cup, 256);  // all four (i,j) sub-positions of 64 channels per CTA
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, os = static_cast<uint64_t>(out_cs) * 2;
   if (int e = b2h::make_tmap_4d(&a.tmA[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TW, TH)) return e;
   for (int i = 1; i < 4; ++i) a.tmA[i] = a.tmA[0];

@@ -150,22 +150,26 @@ __global__ void __launch_bounds__(256) first_wgrad_kernel(const float* __restric
       *reinterpret_cast<float4*>(&dys[pr][ch * 8]) = make_float4(f[0], f[1], f[2], f[3]);
       *reinterpret_cast<float4*>(&dys[pr][ch * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
     }
-    // stage the im2col rows: element (pixel pr, tap j) with j = c*9 + r*3 + s stored at [pr][(j / JG) * JGP + j % JG]
-    for (int v = threadIdx.x; v < TP * 4 * JGP; v += 256) {
-      const int pr = v / (4 * JGP), col = v % (4 * JGP);
-      const int grp = col / JGP, jj = col % JGP;
-      const int j = grp * JG + jj;
-      float xv = 0.f;
+    // stage the im2col rows: element (pixel pr, tap j) with j = c*9 + r*3 + s stored at [pr][(j / JG) * JGP + j % JG];
+    // thread (pr = t/4, grp = t%4) fills the JG taps of its group: one coordinate decode, JG predicated loads
+    {
+      const int pr = threadIdx.x >> 2, grp = threadIdx.x & 3;
       const long long p = p0 + pr;
-      if (jj < JG && j < T && p < P) {
-        const int wq = static_cast<int>(p % W);
-        const int hq = static_cast<int>((p / W) % H);
-        const long long n = p / (static_cast<long long>(W) * H);
-        const int c = j / 9, r = (j % 9) / 3, sx = j % 3;
-        const int hh = hq + r - 1, ww = wq + sx - 1;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) xv = __ldg(x + ((n * CIN + c) * H + hh) * static_cast<long long>(W) + ww);
+      const int wq = static_cast<int>(p % W);
+      const int hq = static_cast<int>((p / W) % H);
+      const long long n = p / (static_cast<long long>(W) * H);
+      const float* xn = x + n * CIN * static_cast<long long>(H) * W;
+#pragma unroll
+      for (int jj = 0; jj < JGP; ++jj) {
+        const int j = grp * JG + jj;
+        float xv = 0.f;
+        if (jj < JG && j < T && p < P) {
+          const int c = j / 9, r = (j % 9) / 3, sx = j % 3;
+          const int hh = hq + r - 1, ww = wq + sx - 1;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W) xv = __ldg(xn + (static_cast<long long>(c) * H + hh) * W + ww);
+        }
+        xcol[pr][grp * JGP + jj] = xv;
       }
-      xcol[pr][col] = xv;
     }
     __syncthreads();
 #pragma unroll 4
