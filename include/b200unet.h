@@ -48,9 +48,11 @@ int b200unet_prep_convt2x2_weight(const float* w, void* w_fprop, void* w_dgrad, 
 /* ---- tensor-core implicit GEMMs (tcgen05 / TMEM / TMA) ---------------------------------------------------- */
 /* 3x3, pad 1, no bias (nn.Conv2d, Model.py:15-16,19-20). y[n,h,w,k] = sum_{r,s,c} x[n,h+r-1,w+s-1,c] w[k,r,s,c].
  * Used for fprop (w = fprop operand) and for dgrad (x = dy, w = dgrad operand, Cin/Cout swapped).
- * stats_partial: NULL or fp32 [mtiles][2][Cout] (per pixel-tile sum and sum of squares of the bf16 outputs),
- * mtiles = N * ceil(H/tile_h) * ceil(W/tile_w); feeds BatchNorm2d (Model.py:17,21).
+ * stats_partial: NULL or fp32 [rows][2][Cout] partial sums and sums of squares of the bf16 outputs, rows =
+ * b200unet_conv3x3_stat_rows(N,H,W,Cin,Cout) (one row per pixel tile, or per persistent CTA for the resident-weight
+ * kernel used when Cin <= 128); feeds BatchNorm2d (Model.py:17,21) through b200unet_bn_reduce_partials.
  * Requires Cin % 64 == 0 and Cout % 64 == 0. */
+int b200unet_conv3x3_stat_rows(int N, int H, int W, int Cin, int Cout);
 int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial,
                            int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
 /* ConvTranspose2d(Cin, Cup, 2, 2) + bias (Model.py:56-57,66): out[n,2h+i,2w+j,d] = b[d] + sum_c x[n,h,w,c] W[c,d,i,j],
@@ -152,8 +154,8 @@ int b200unet_softmax_argmax(const float* logits, int64_t* mask, int N, int ncls,
 
 /* ---- bring-up probe (test aid): UMMA operand whose start is offset by `shift` 128-byte rows inside a
  * 128B-swizzled tile. out[128][64] = A[shift:shift+128][:] * B^T; A is 160x64 bf16, B is 64x64 bf16. */
-int b200unet_probe_shift(const void* a_160x64, const void* b_64x64, float* out_128x64, int shift,
-                         int use_base_offset, b200_stream_t stream);
+int b200unet_probe_shift(const void* a_256x64, const void* b_64x64, float* out_128x64, int shift,
+                         int use_base_offset, int sbo_bytes, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

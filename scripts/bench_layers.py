@@ -68,7 +68,7 @@ for name, cin, cout, lvl in layers:
     wf, wd = ops.prep_conv3x3_weight(w)
     y = torch.empty(B, h, h, cout, dtype=BF16, device="cuda")
     dx = torch.empty(B, h, h, cin, dtype=BF16, device="cuda")
-    st = torch.empty(ops.num_pixel_tiles(B, h, h) * 2 * cout, device="cuda")
+    st = torch.empty(ops.conv3x3_stat_rows(B, h, h, cin, cout) * 2 * cout, device="cuda")
     dw = torch.empty(cout, cin, 3, 3, device="cuda")
     if want("fprop"):
         ms = timeit(lambda: ops.conv3x3(x, wf, y, st)); rec(f"fprop {name} {cin}->{cout} @{h}", ms, flops); tot["fprop"] += ms

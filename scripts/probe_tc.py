@@ -45,7 +45,7 @@ def conv_case(n, h, w, cin, cout, wt, tag):
     x = torch.randn(n, cin, h, w, generator=g).to(BF16).float()
     wf, wd = ops.prep_conv3x3_weight(wt.cuda())
     y = torch.zeros(n, h, w, cout, dtype=BF16, device="cuda")
-    rows = ops.num_pixel_tiles(n, h, w)
+    rows = ops.conv3x3_stat_rows(n, h, w, cin, cout)
     st = torch.zeros(rows * 2 * cout, device="cuda")
     ops.conv3x3(nhwc(x), wf, y, st)
     torch.cuda.synchronize()

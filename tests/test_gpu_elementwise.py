@@ -80,33 +80,38 @@ def test_bn_relu_backward(ops, pool):
     bet = beta.clone().requires_grad_(True)
     out, _, _ = O.batchnorm_train(yv, gam, bet)
     a = O.relu(out)
-    # the device stores `a` in bf16 and pools the stored values: give the oracle the identical pooling input
-    a = a + (bf16_round(a.detach()) - a.detach())
-    g1 = bf16_round(torch.randn(n, c, h, w, generator=g))
-    loss = (a * g1).sum()
-    gp = None
-    if pool:
-        pv, pos, flat = O.maxpool2x2(a)
-        gp = bf16_round(torch.randn(pv.shape, generator=g))
-        loss = loss + (pv * gp).sum()
-    loss.backward()
-    # device side
+    # device-side statistics and (for the pooled case) the forward kernel on the same data
     yd = to_nhwc_bf16(y)
     mu = y.mean((0, 2, 3))
     var = y.var((0, 2, 3), unbiased=False)
     rstd = torch.rsqrt(var + 1e-5)
     scale = (gamma * rstd).cuda()
     shift = (beta - mu * gamma * rstd).cuda()
-    dy = torch.empty_like(yd)
-    dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
     gpd = idx = None
     if pool:
-        # pool positions from the forward kernel on the same data
         tmp_a = torch.empty_like(yd)
         pooled = torch.empty(n, h // 2, w // 2, c, dtype=BF16, device="cuda")
         idx = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device="cuda")
         ops.bn_relu_fwd(yd, scale, shift, tmp_a, pooled, idx)
+        # the device pools the bf16 activation it stored: hand the oracle the IDENTICAL pooling input (straight-through
+        # for the rounding), so that near-ties pick the same window position on both sides
+        a_dev = from_nhwc(tmp_a)
+        assert rel_l2(a_dev, a.detach()) < 4e-3
+        a = a + (a_dev - a.detach())
+    else:
+        a = a + (bf16_round(a.detach()) - a.detach())
+    g1 = bf16_round(torch.randn(n, c, h, w, generator=g))
+    loss = (a * g1).sum()
+    gp = None
+    if pool:
+        pv, pos, flat = O.maxpool2x2(a)
+        assert torch.equal(idx.permute(0, 3, 1, 2).cpu().long(), pos)
+        gp = bf16_round(torch.randn(pv.shape, generator=g))
+        loss = loss + (pv * gp).sum()
         gpd = to_nhwc_bf16(gp)
+    loss.backward()
+    dy = torch.empty_like(yd)
+    dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
     ops.bn_relu_bwd(to_nhwc_bf16(g1), gpd, idx, yd, gamma.cuda(), scale, shift, mu.cuda(), rstd.cuda(), dy, dgamma, dbeta)
     assert rel_l2(from_nhwc(dy), yv.grad) < 1e-2
     assert rel_l2(dgamma, gam.grad) < 2e-3

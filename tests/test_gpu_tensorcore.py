@@ -27,6 +27,11 @@ CONV_SHAPES = [
     (2, 8, 16, 256, 256),
     (1, 16, 16, 128, 64),     # decoder-style Cin > Cout
     (1, 4, 4, 64, 128),       # image smaller than a tile
+    # persistent resident-weight kernel (Cin <= 128): several 16x8 tiles per CTA, every (BN, K-block) variant
+    (4, 64, 96, 64, 64),      # 192 tiles > 148 CTAs
+    (2, 40, 72, 64, 128),     # BN = 128, ragged rows
+    (3, 64, 64, 128, 64),     # two K blocks per tile
+    (2, 48, 64, 128, 256),    # four channel slices share each pixel tile
 ]
 
 
@@ -38,7 +43,7 @@ def test_conv3x3_fprop_and_stats(ops, n, h, w, cin, cout):
     wf, wd = ops.prep_conv3x3_weight(wt.cuda())
     assert torch.equal(wf.float().cpu(), wt.permute(0, 2, 3, 1).contiguous())
     y = torch.empty(n, h, w, cout, dtype=BF16, device="cuda")
-    rows = ops.num_pixel_tiles(n, h, w)
+    rows = ops.conv3x3_stat_rows(n, h, w, cin, cout)
     st = torch.zeros(rows * 2 * cout, device="cuda")
     ops.conv3x3(to_nhwc_bf16(x), wf, y, st)
     torch.cuda.synchronize()
@@ -50,7 +55,7 @@ def test_conv3x3_fprop_and_stats(ops, n, h, w, cin, cout):
     assert rel_l2(s[1], (yb * yb).sum((0, 2, 3))) < 1e-4
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout", CONV_SHAPES[:5])
+@pytest.mark.parametrize("n,h,w,cin,cout", CONV_SHAPES[:5] + CONV_SHAPES[6:])
 def test_conv3x3_dgrad(ops, n, h, w, cin, cout):
     g = torch.Generator().manual_seed(12)
     xv = torch.randn(n, cin, h, w, generator=g).requires_grad_(True)

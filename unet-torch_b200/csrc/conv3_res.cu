@@ -1,0 +1,350 @@
+// Persistent tcgen05 implicit-GEMM for the 3x3 convolutions with few input channels (Cin = 64 or 128), i.e. the
+// high-resolution levels of the U-Net where the reduction is short (K = 9*Cin <= 1152) and per-tile overheads and
+// operand re-fetches, not arithmetic, bound a one-tile-per-CTA kernel (nn.Conv2d fprop / dgrad, reference
+// Model.py:15-16,19-20: inc.conv2, down1.*, up3.conv2, up4.* and the matching backward-data passes).
+//
+//   * One CTA per SM, alive for the whole launch. Its BN-channel slice of the weights (all 9 taps, all of Cin:
+//     <= 144 KiB of bf16) is TMA-loaded into shared memory ONCE and stays resident.
+//   * Pixel tile = 16 rows x 8 columns = 128 pixels = UMMA M. Per 64-channel block ONE halo tile of 18 x 10 pixels
+//     (128 B per pixel, 128B-swizzled by TMA, out-of-bounds = conv zero padding) is loaded; the 9 taps are UMMA
+//     shared-memory descriptors into that tile: start = (r*10 + s) pixel rows, 8-row groups 10 pixels (1280 B) apart.
+//     The tensor core applies the swizzle on absolute smem address bits, so neither the start nor the group stride
+//     has to be a multiple of the 1024-byte swizzle atom (scripts/probe_shift.py checks this on the device).
+//     => 1.4 activation tile loads per K block instead of 9 (im2col) or 3.75 (igemm.cu).
+//   * Two accumulator buffers in TMEM: the MMA warp runs tile i+1 while the epilogue warps drain tile i
+//     (tcgen05.ld -> bf16 -> swizzled smem staging -> TMA store) and accumulate the BatchNorm statistics
+//     (Model.py:17,21) of the STORED bf16 values in registers; one partial row per CTA at the end.
+#include "../../include/b200unet.h"
+#include "host_common.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace b2;
+
+constexpr int RTH = 16, RTW = 8;                      // output pixel tile
+constexpr int HALO_H = RTH + 2, HALO_W = RTW + 2;     // input halo tile
+constexpr int A_BOX_BYTES = HALO_H * HALO_W * 128;    // 23040
+constexpr int A_STAGE = (A_BOX_BYTES + 1023) / 1024 * 1024;
+constexpr int OUT_CHUNK = 128 * 128;                  // 128 pixels x 64 channels bf16
+
+struct ResArgs {
+  CUtensorMap tmA, tmW, tmO;
+  int tiles_w, tiles_h, tiles_total;
+  int H, W;
+  int ncols;     // Cout
+  int ntiles_n;  // Cout / BN
+  int workers;   // CTAs per channel slice (grid = workers * ntiles_n)
+  float* stats;  // [workers][2][ncols] or null
+};
+
+template <int BN, int KB, int NA, int OB>
+struct ResPlan {
+  static constexpr int W_BYTES = 9 * KB * BN * 128;
+  static constexpr int A_OFF = W_BYTES;
+  static constexpr int OUT_OFF = A_OFF + NA * A_STAGE;
+  static constexpr int OUT_BYTES = OB * (BN / 64) * OUT_CHUNK;
+  static constexpr int BAR_OFF = OUT_OFF + OUT_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024 /* alignment slack */;
+  static_assert(TOTAL <= 227 * 1024, "shared memory plan exceeds 227 KiB");
+  static_assert(4 * 2 * BN * 4 <= OUT_BYTES, "final statistics reduction aliases the staging buffer");
+};
+
+template <int BN, int KB, int NA, int OB>
+__global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant__ ResArgs args) {
+  using P = ResPlan<BN, KB, NA, OB>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sW = smem_base;
+  const uint32_t sA = smem_base + P::A_OFF;
+  const uint32_t sO = smem_base + P::OUT_OFF;
+  const uint32_t bars = smem_base + P::BAR_OFF;
+  const uint32_t W_full = bars;
+  auto A_full = [&](int i) { return bars + 8u * (1 + i); };
+  auto A_empty = [&](int i) { return bars + 8u * (1 + NA + i); };
+  auto T_full = [&](int i) { return bars + 8u * (1 + 2 * NA + i); };
+  auto T_empty = [&](int i) { return bars + 8u * (3 + 2 * NA + i); };
+  const uint32_t tmem_slot = bars + 8u * (5 + 2 * NA);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + P::BAR_OFF + 8 * (5 + 2 * NA));
+
+  const int warp = warp_idx_uniform();
+  const int lane = threadIdx.x & 31;
+  const int nt = blockIdx.x % args.ntiles_n;
+  const int pw = blockIdx.x / args.ntiles_n;
+  const int n0 = nt * BN;
+  const int ntiles_mine = (args.tiles_total - pw + args.workers - 1) / args.workers;  // tiles pw, pw+workers, ...
+
+  if (warp == 0 && elect_one_sync()) {
+    prefetch_tmap(&args.tmA);
+    prefetch_tmap(&args.tmW);
+    prefetch_tmap(&args.tmO);
+    mbar_init(W_full, 1);
+    for (int i = 0; i < NA; ++i) {
+      mbar_init(A_full(i), 1);
+      mbar_init(A_empty(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(T_full(i), 1);
+      mbar_init(T_empty(i), 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  auto tile_coords = [&](int j, int& img, int& h0, int& w0) {
+    const int t = pw + j * args.workers;
+    const int twi = t % args.tiles_w;
+    const int thi = (t / args.tiles_w) % args.tiles_h;
+    img = t / (args.tiles_w * args.tiles_h);
+    h0 = thi * RTH;
+    w0 = twi * RTW;
+  };
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(W_full, P::W_BYTES);
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int cb = 0; cb < KB; ++cb)
+          tma_load_2d(sW + (tap * KB + cb) * (BN * 128), &args.tmW, W_full, (tap * KB + cb) * 64, n0);
+      int sa = 0, pa = 0;
+#pragma unroll 1
+      for (int j = 0; j < ntiles_mine; ++j) {
+        int img, h0, w0;
+        tile_coords(j, img, h0, w0);
+#pragma unroll
+        for (int cb = 0; cb < KB; ++cb) {
+          mbar_wait(A_empty(sa), pa ^ 1);
+          mbar_arrive_expect_tx(A_full(sa), A_BOX_BYTES);
+          tma_load_4d(sA + sa * A_STAGE, &args.tmA, A_full(sa), cb * 64, w0 - 1, h0 - 1, img);
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t a_hi = umma_desc_hi_sw128(HALO_W * 128), b_hi = umma_desc_hi_sw128(1024);
+      const uint32_t w_lo = umma_desc_lo(sW, 16);
+      mbar_wait(W_full, 0);
+      tc_fence_after();
+      int sa = 0, pa = 0;
+#pragma unroll 1
+      for (int j = 0; j < ntiles_mine; ++j) {
+        const int buf = j & 1;
+        mbar_wait(T_empty(buf), ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int cb = 0; cb < KB; ++cb) {
+          mbar_wait(A_full(sa), pa);
+          tc_fence_after();
+          const uint32_t a_lo = umma_desc_lo(sA + sa * A_STAGE, 16);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            // descriptor low words step in 16-byte units: tap (r,s) = (r*10+s) pixel rows of 128 B, K step = 32 B
+            const uint32_t a_tap = a_lo + ((tap / 3) * HALO_W + (tap % 3)) * 8;
+            const uint32_t b_tap = w_lo + (tap * KB + cb) * (BN * 8);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16_lh(d_tmem, a_tap + 2 * k, a_hi, b_tap + 2 * k, b_hi, idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(A_empty(sa));
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(T_full(buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================= epilogue (4 warps, 128 threads)
+    const int quad = warp & 3;          // TMEM lanes [32*quad, 32*quad+32)
+    const int row = quad * 32 + lane;   // pixel of the tile: (row >> 3, row & 7)
+    const int et = threadIdx.x - 64;    // 0..127
+    const int cp = et & 31, rq = et >> 5;  // statistics: channel pair within a 64-channel chunk, 32-row quarter
+    const bool want_stats = args.stats != nullptr;
+    float s1[BN / 64][2], s2[BN / 64][2];
+#pragma unroll
+    for (int q = 0; q < BN / 64; ++q) s1[q][0] = s1[q][1] = s2[q][0] = s2[q][1] = 0.f;
+
+#pragma unroll 1
+    for (int j = 0; j < ntiles_mine; ++j) {
+      const int buf = j & 1;
+      const uint32_t stage = sO + (OB == 1 ? 0 : (j & 1)) * ((BN / 64) * OUT_CHUNK);
+      int img, h0, w0;
+      tile_coords(j, img, h0, w0);
+      mbar_wait(T_full(buf), (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < BN / 64; ++q) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN + q * 64 + half * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * t + 0]), __uint_as_float(v[8 * t + 1]));
+            const uint32_t p1 = pack_bf16x2(__uint_as_float(v[8 * t + 2]), __uint_as_float(v[8 * t + 3]));
+            const uint32_t p2 = pack_bf16x2(__uint_as_float(v[8 * t + 4]), __uint_as_float(v[8 * t + 5]));
+            const uint32_t p3 = pack_bf16x2(__uint_as_float(v[8 * t + 6]), __uint_as_float(v[8 * t + 7]));
+            const uint32_t chunk = static_cast<uint32_t>(half * 4 + t) ^ (row & 7);
+            const uint32_t addr = stage + q * OUT_CHUNK + row * 128 + chunk * 16;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(p0), "r"(p1), "r"(p2), "r"(p3)
+                         : "memory");
+          }
+        }
+      }
+      // accumulator buffer drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(T_empty(buf));
+      fence_proxy_async_smem();
+      if (OB == 2 && et == 0) tma_store_wait_read0();  // the store issued one tile ago (other buffer) has read its smem
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+#pragma unroll
+        for (int q = 0; q < BN / 64; ++q) tma_store_4d(&args.tmO, stage + q * OUT_CHUNK, n0 + q * 64, w0, h0, img);
+        tma_store_commit();
+      }
+      if (want_stats) {
+        const bool full = (h0 + RTH <= args.H) && (w0 + RTW <= args.W);
+#pragma unroll
+        for (int q = 0; q < BN / 64; ++q) {
+          const uint32_t base = stage + q * OUT_CHUNK + (cp & 3) * 4;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int r = rq * 32 + i;
+            uint32_t u;
+            asm volatile("ld.shared.b32 %0, [%1];"
+                         : "=r"(u)
+                         : "r"(base + r * 128 + ((static_cast<uint32_t>(cp >> 2) ^ (r & 7)) << 4)));
+            float x0 = __uint_as_float(u << 16), x1 = __uint_as_float(u & 0xffff0000u);
+            if (!full && !((h0 + (r >> 3) < args.H) && (w0 + (r & 7) < args.W))) x0 = x1 = 0.f;
+            s1[q][0] += x0;
+            s1[q][1] += x1;
+            s2[q][0] = fmaf(x0, x0, s2[q][0]);
+            s2[q][1] = fmaf(x1, x1, s2[q][1]);
+          }
+        }
+      }
+      if (OB == 1) {
+        if (et == 0) tma_store_wait_read0();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+    if (et == 0) tma_store_wait_read0();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (want_stats) {
+      // cross-quarter reduction through the (now idle) staging buffer: red[rq][stat][BN]
+      float* red = reinterpret_cast<float*>(smem_gen + P::OUT_OFF);
+#pragma unroll
+      for (int q = 0; q < BN / 64; ++q) {
+        red[(rq * 2 + 0) * BN + q * 64 + cp * 2 + 0] = s1[q][0];
+        red[(rq * 2 + 0) * BN + q * 64 + cp * 2 + 1] = s1[q][1];
+        red[(rq * 2 + 1) * BN + q * 64 + cp * 2 + 0] = s2[q][0];
+        red[(rq * 2 + 1) * BN + q * 64 + cp * 2 + 1] = s2[q][1];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* dst = args.stats + static_cast<size_t>(pw) * 2 * args.ncols + n0;
+      for (int i = et; i < 2 * BN; i += 128) {
+        const int stat = i / BN, ch = i - stat * BN;
+        dst[stat * args.ncols + ch] = red[(0 * 2 + stat) * BN + ch] + red[(1 * 2 + stat) * BN + ch] +
+                                      red[(2 * 2 + stat) * BN + ch] + red[(3 * 2 + stat) * BN + ch];
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+template <int BN, int KB, int NA, int OB>
+int launch_res(const ResArgs& a, cudaStream_t st) {
+  using P = ResPlan<BN, KB, NA, OB>;
+  static bool configured = false;
+  auto kern = conv3_res_kernel<BN, KB, NA, OB>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
+    if (e != cudaSuccess) {
+      b2h::set_error("conv3_res: cudaFuncSetAttribute(smem=%d): %s", P::TOTAL, cudaGetErrorString(e));
+      return 2;
+    }
+    configured = true;
+  }
+  kern<<<a.workers * a.ntiles_n, 192, P::TOTAL, st>>>(a);
+  return b2h::check_launch("conv3_res");
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+namespace b2h {
+
+bool conv3_res_applicable(int Cin, int Cout) {
+  return (Cin == 64 || Cin == 128) && Cout % 64 == 0;
+}
+
+static int res_bn(int Cin, int Cout) { return (Cin == 64 && Cout % 128 == 0) ? 128 : 64; }
+
+// geometry shared by the launcher and the statistics-row query
+static void res_geometry(int N, int H, int W, int Cin, int Cout, int* bn, int* ntn, int* workers, int* tiles) {
+  *bn = res_bn(Cin, Cout);
+  *ntn = Cout / *bn;
+  *tiles = N * ceil_div(H, RTH) * ceil_div(W, RTW);
+  int w = num_sms() / *ntn;
+  if (w < 1) w = 1;
+  if (w > *tiles) w = *tiles;
+  *workers = w;
+}
+
+int conv3_res_stat_rows(int N, int H, int W, int Cin, int Cout) {
+  int bn, ntn, workers, tiles;
+  res_geometry(N, H, W, Cin, Cout, &bn, &ntn, &workers, &tiles);
+  return workers;
+}
+
+int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
+                     int W, int Cin, int Cout, cudaStream_t st) {
+  ResArgs a;
+  int bn, tiles;
+  res_geometry(N, H, W, Cin, Cout, &bn, &a.ntiles_n, &a.workers, &tiles);
+  a.tiles_total = tiles;
+  a.tiles_w = ceil_div(W, RTW);
+  a.tiles_h = ceil_div(H, RTH);
+  a.H = H;
+  a.W = W;
+  a.ncols = Cout;
+  a.stats = stats_partial;
+  const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
+  if (int e = make_tmap_4d(&a.tmA, x, Cin, W, H, N, xs, xs * W, xs * W * H, HALO_W, HALO_H)) return e;
+  if (int e = make_tmap_2d(&a.tmW, w, static_cast<uint64_t>(9) * Cin, Cout, bn)) return e;
+  if (int e = make_tmap_4d(&a.tmO, y, Cout, W, H, N, ys, ys * W, ys * W * H, RTW, RTH)) return e;
+  if (Cin == 64 && bn == 64) return launch_res<64, 1, 4, 2>(a, st);
+  if (Cin == 64 && bn == 128) return launch_res<128, 1, 2, 1>(a, st);
+  return launch_res<64, 2, 2, 2>(a, st);
+}
+
+}  // namespace b2h

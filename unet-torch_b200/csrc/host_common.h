@@ -29,4 +29,10 @@ int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t k, uint64_t rows, ui
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// conv3_res.cu: persistent resident-weight 3x3 kernel for Cin in {64, 128}
+bool conv3_res_applicable(int Cin, int Cout);
+int conv3_res_stat_rows(int N, int H, int W, int Cin, int Cout);
+int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
+                     int W, int Cin, int Cout, cudaStream_t st);
+
 }  // namespace b2h

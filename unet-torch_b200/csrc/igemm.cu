@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ Igem
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Plan::BAR_OFF + 8 * (2 * NA + 2 * NB) + 8);
   float* red = reinterpret_cast<float*>(smem_gen + Plan::RED_OFF);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
 
   // ---- tile coordinates
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ Igem
   const int ngroups = (MODE == MODE_CONV3) ? args.kblocks * 3 : (MODE == MODE_GATHER4 ? args.kblocks * 4 : args.kblocks);
 
   // ---- one-time setup
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     prefetch_tmap(&args.tmA[0]);
     prefetch_tmap(&args.tmB);
     prefetch_tmap(&args.tmO[0]);
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ Igem
 
   if (warp == 0) {
     // ================================================================= TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int sa = 0, pa = 0, sb = 0, pb = 0;
       for (int g = 0; g < ngroups; ++g) {
         int cb, s = 0, ij = 0;
@@ -154,8 +154,9 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ Igem
     __syncwarp();
   } else if (warp == 1) {
     // ================================================================= MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t d_hi = umma_desc_hi_sw128(1024);
       int sa = 0, pa = 0, sb = 0, pb = 0;
       uint32_t acc = 0;
       for (int g = 0; g < ngroups; ++g) {
@@ -165,12 +166,11 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ Igem
         for (int t = 0; t < TAPS; ++t) {
           mbar_wait(B_full(sb), pb);
           tc_fence_after();
-          const uint32_t a_base = sA + sa * A_BYTES + (MODE == MODE_CONV3 ? t * TW * 128 : 0);
-          const uint32_t b_base = sB + sb * B_BYTES;
+          const uint32_t a_lo = umma_desc_lo(sA + sa * A_BYTES + (MODE == MODE_CONV3 ? t * TW * 128 : 0), 16);
+          const uint32_t b_lo = umma_desc_lo(sB + sb * B_BYTES, 16);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_bf16(tmem_base, umma_desc_sw128(a_base + k * 32, 16, 1024), umma_desc_sw128(b_base + k * 32, 16, 1024),
-                      idesc, acc);
+            umma_bf16_lh(tmem_base, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, acc);
             acc = 1;
           }
           umma_commit(B_empty(sb));
@@ -307,6 +307,15 @@ int launch_mode(IgemmArgs& a, int bn, int mtiles, cudaStream_t st) {
   return 1;
 }
 
+bool use_resident(int Cin, int Cout) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("B200UNET_NO_RES");
+    off = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return !off && b2h::conv3_res_applicable(Cin, Cout);
+}
+
 int pick_bn(int ncols, int limit) {
   int want = env_bn();
   if (want != 64 && want != 128 && want != 256) want = 128;
@@ -324,6 +333,8 @@ int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int 
   B2_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv3x3_igemm: Cin (%d) and Cout (%d) must be multiples of 64", Cin, Cout);
   B2_REQUIRE(N > 0 && H > 0 && W > 0, "conv3x3_igemm: empty tensor");
   B2_REQUIRE(x_cs >= Cin && y_cs >= Cout && x_cs % 8 == 0 && y_cs % 8 == 0, "conv3x3_igemm: bad pitches %d %d", x_cs, y_cs);
+  if (use_resident(Cin, Cout))
+    return b2h::conv3_res_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream));
   IgemmArgs a;
   a.tiles_w = b2h::ceil_div(W, TW);
   a.tiles_h = b2h::ceil_div(H, TH);
@@ -343,6 +354,11 @@ int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int 
   if (int e = b2h::make_tmap_4d(&a.tmO[0], y, Cout, W, H, N, ys, ys * W, ys * W * H, TW, TH)) return e;
   for (int i = 1; i < 4; ++i) a.tmO[i] = a.tmO[0];
   return launch_mode<MODE_CONV3>(a, bn, N * a.tiles_w * a.tiles_h, static_cast<cudaStream_t>(stream));
+}
+
+int b200unet_conv3x3_stat_rows(int N, int H, int W, int Cin, int Cout) {
+  if (use_resident(Cin, Cout)) return b2h::conv3_res_stat_rows(N, H, W, Cin, Cout);
+  return N * b2h::ceil_div(H, TH) * b2h::ceil_div(W, TW);
 }
 
 int b200unet_convt2x2_fprop(const void* x, int x_cs, const void* w_fprop, const float* bias, void* out, int out_cs,

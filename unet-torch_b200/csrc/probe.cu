@@ -1,6 +1,8 @@
 // Hardware probe (bring-up / test aid, not on the product path): does a 128B-swizzled K-major UMMA operand work
 // when its start address is offset by a whole number of 128-byte rows that is NOT a multiple of the 8-row
-// swizzle atom? D[128 x 64] = A[shift : shift+128][0:64] * B[64 x 64]^T, A tile = 160 rows loaded by TMA.
+// swizzle atom, and when its 8-row groups are `sbo` bytes apart with sbo NOT a multiple of 1024 (the 16x8-pixel
+// tile inside an 18x10 halo tile of conv3_res.cu uses sbo = 1280)?
+// D[m = 8g + i][0:64] = A[shift + g * sbo/128 + i][0:64] * B[64 x 64]^T, A tile = 256 rows loaded by TMA.
 #include "../../include/b200unet.h"
 #include "host_common.h"
 #include "tc_common.cuh"
@@ -10,12 +12,12 @@ using namespace b2;
 
 __global__ void __launch_bounds__(128) probe_shift_kernel(const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB, float* out, int shift,
-                                                          int use_base_offset) {
+                                                          int use_base_offset, int sbo) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sA = base, sB = base + 160 * 128, bar = sB + 64 * 128, bar2 = bar + 8, slot = bar + 16;
-  volatile uint32_t* slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 160 * 128 + 64 * 128 + 16);
+  const uint32_t sA = base, sB = base + 256 * 128, bar = sB + 64 * 128, bar2 = bar + 8, slot = bar + 16;
+  volatile uint32_t* slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 256 * 128 + 64 * 128 + 16);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
@@ -28,7 +30,7 @@ __global__ void __launch_bounds__(128) probe_shift_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *slot_gen;
   if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar, 160 * 128 + 64 * 128);
+    mbar_arrive_expect_tx(bar, 256 * 128 + 64 * 128);
     tma_load_2d(sA, &tmA, bar, 0, 0);
     tma_load_2d(sB, &tmB, bar, 0, 0);
     mbar_wait(bar, 0);
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(128) probe_shift_kernel(const __grid_constant_
     constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
     for (int k = 0; k < 4; ++k) {
       const uint32_t a_addr = sA + shift * 128 + k * 32;
-      uint64_t ad = umma_desc_sw128(a_addr, 16, 1024);
+      uint64_t ad = umma_desc_sw128(a_addr, 16, sbo);
       if (use_base_offset) ad |= static_cast<uint64_t>((a_addr >> 7) & 7) << 49;
       umma_bf16(tmem, ad, umma_desc_sw128(sB + k * 32, 16, 1024), idesc, k > 0);
     }
@@ -58,12 +60,12 @@ __global__ void __launch_bounds__(128) probe_shift_kernel(const __grid_constant_
 }
 }  // namespace
 
-extern "C" int b200unet_probe_shift(const void* a_160x64, const void* b_64x64, float* out_128x64, int shift,
-                                    int use_base_offset, b200_stream_t stream) {
+extern "C" int b200unet_probe_shift(const void* a_256x64, const void* b_64x64, float* out_128x64, int shift,
+                                    int use_base_offset, int sbo_bytes, b200_stream_t stream) {
   CUtensorMap ta, tb;
-  if (int e = b2h::make_tmap_2d(&ta, a_160x64, 64, 160, 160)) return e;
+  if (int e = b2h::make_tmap_2d(&ta, a_256x64, 64, 256, 256)) return e;
   if (int e = b2h::make_tmap_2d(&tb, b_64x64, 64, 64, 64)) return e;
-  const int smem = 160 * 128 + 64 * 128 + 64 + 1024;
-  probe_shift_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, out_128x64, shift, use_base_offset);
+  const int smem = 256 * 128 + 64 * 128 + 64 + 1024;
+  probe_shift_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, out_128x64, shift, use_base_offset, sbo_bytes);
   return b2h::check_launch("probe_shift");
 }

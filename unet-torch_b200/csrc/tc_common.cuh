@@ -13,6 +13,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+// Warp index the compiler can PROVE warp-uniform (shfl broadcast), so role branches on it are not treated as
+// divergent. Together with elect_one_sync() this lets ptxas emit the uniform-datapath instructions (UTCHMMA,
+// UTMALDG, ...) back to back; a plain `if (lane == 0)` wraps each of them in an ELECT / BRA.U.ANY loop
+// (5 extra instructions per MMA, which made the single issuing thread the bottleneck for N = 64 tiles).
+__device__ __forceinline__ uint32_t warp_idx_uniform() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{ .reg .pred P; .reg .b32 r; elect.sync r|P, 0xffffffff; selp.u32 %0, 1, 0, P; }" : "=r"(pred));
+  return pred != 0;
+}
 
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -135,6 +145,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= 1ull << 46;  // descriptor version (Blackwell)
   d |= 2ull << 61;  // SWIZZLE_128B
   return d;
+}
+// The same descriptor split into its 32-bit halves: the high word is a compile-time constant of the layout, the low
+// word carries the start address (and LBO), so stepping along K or between conv taps is ONE 32-bit add of
+// (byte offset >> 4) on the low word.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3ffffu) >> 4) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) /* version */ | (2u << 29) /* SWIZZLE_128B */;
+}
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{ .reg .pred p; .reg .b64 da, db; mov.b64 da, {%1, %2}; mov.b64 db, {%3, %4}; setp.ne.b32 p, %6, 0; "
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p; }" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // Instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn_major,

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   const uint32_t tmem_slot = acc_full + 8;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + P::BAR_OFF + 8 * (2 * NS) + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
 
   // CTA -> (m tile, n tile, horizontal tap, split)
   int b = blockIdx.x;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   const int t_begin = static_cast<int>(static_cast<long long>(args.tiles_total) * z / args.splits);
   const int t_end = static_cast<int>(static_cast<long long>(args.tiles_total) * (z + 1) / args.splits);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     prefetch_tmap(&args.tmA);
     prefetch_tmap(&args.tmB[0]);
     for (int i = 0; i < NS; ++i) {
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int st = 0, ph = 0;
       for (int t = t_begin; t < t_end; ++t) {
         const int twi = t % args.tiles_w;
@@ -116,8 +116,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BNC, 1, 1);
+      constexpr uint32_t d_hi = umma_desc_hi_sw128(1024);
       int st = 0, ph = 0;
       uint32_t acc = 0;
       for (int t = t_begin; t < t_end; ++t) {
@@ -127,13 +128,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         const uint32_t sB = sA + P::A_BYTES;
 #pragma unroll
         for (int k = 0; k < BM / 16; ++k) {
-          const uint64_t adesc = umma_desc_sw128(sA + k * 2048, BM * 128, 1024);
+          const uint32_t a_lo = umma_desc_lo(sA + k * 2048, BM * 128);
 #pragma unroll
           for (int tap = 0; tap < P::TAPS; ++tap) {
             uint32_t bb;
             if (KIND == KIND_CONV3) bb = sB + (k * 16 + tap * TW) * 128;
             else bb = sB + tap * (BNC / 64) * P::B_BOX + k * 2048;
-            umma_bf16(tmem_base + tap * BNC, adesc, umma_desc_sw128(bb, P::B_BOX, 1024), idesc, acc);
+            umma_bf16_lh(tmem_base + tap * BNC, a_lo, d_hi, umma_desc_lo(bb, P::B_BOX), d_hi, idesc, acc);
           }
           acc = 1;
         }

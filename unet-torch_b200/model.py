@@ -201,7 +201,7 @@ class UNetEngine:
                     stats = torch.empty(rows * 2 * c_out, dtype=torch.float32, device=dev)
                 ops.conv3x3_first(inp, cb.conv.weight.detach(), y, stats)
             else:
-                rows = ops.num_pixel_tiles(n, hh, ww)
+                rows = ops.conv3x3_stat_rows(n, hh, ww, inp.shape[3], c_out)
                 if training:
                     stats = torch.empty(rows * 2 * c_out, dtype=torch.float32, device=dev)
                 wf, _ = cb.operands()

@@ -47,6 +47,11 @@ def num_pixel_tiles(n, h, w):
     return n * ((h + th - 1) // th) * ((w + tw - 1) // tw)
 
 
+def conv3x3_stat_rows(n, h, w, cin, cout):
+    """Rows of the BatchNorm partial-statistics buffer conv3x3() fills for this shape."""
+    return _lib.query("b200unet_conv3x3_stat_rows", n, h, w, cin, cout)
+
+
 # --------------------------------------------------------------------------------------------- weights
 def prep_conv3x3_weight(w: torch.Tensor, want_dgrad=True):
     """fp32 OIHW [K,C,3,3] -> (fprop operand [K,3,3,C] bf16, dgrad operand [C,3,3,K] bf16 with rotated taps)."""
@@ -73,7 +78,7 @@ def conv3x3(x: torch.Tensor, w_op: torch.Tensor, out: torch.Tensor, stats_partia
     op, ocs, n2, h2, w2, cout = _nhwc(out)
     if (n, h, w) != (n2, h2, w2) or tuple(w_op.shape) != (cout, 3, 3, cin) or w_op.dtype != BF16:
         raise ValueError(f"conv3x3: shape mismatch x{tuple(x.shape)} w{tuple(w_op.shape)} out{tuple(out.shape)}")
-    if stats_partial is not None and stats_partial.numel() < num_pixel_tiles(n, h, w) * 2 * cout:
+    if stats_partial is not None and stats_partial.numel() < conv3x3_stat_rows(n, h, w, cin, cout) * 2 * cout:
         raise ValueError("conv3x3: stats_partial too small")
     _lib.call("b200unet_conv3x3_igemm", xp, xcs, w_op.data_ptr(), op, ocs, _f32(stats_partial), n, h, w, cin, cout,
               _stream())
