@@ -75,6 +75,24 @@ int b200unet_convt2x2_wgrad(const void* x, int x_cs, const void* du, int du_cs, 
                             int N, int H, int W, int Cin, int Cup, int H2, int W2, int pad_top, int pad_left,
                             b200_stream_t stream);
 
+/* ---- inc.conv1 on the tensor cores (Model.py:111 -> :15-16 with Cin = n_channels <= 7) ------------------- */
+/* x fp32 NCHW [N][Cin][H][W] -> col bf16 NHWC [N][H][W][64] (pitch col_cs): col[..., c*9+r*3+s] = x[n,c,h+r-1,w+s-1],
+ * zero outside the image and in columns >= 9*Cin. */
+int b200unet_first_im2col(const float* x_nchw, void* col, int col_cs, int N, int H, int W, int Cin,
+                          b200_stream_t stream);
+/* nn.Conv2d weight OIHW fp32 [Cout][Cin][3][3] -> bf16 [Cout][64] operand matching the im2col columns. */
+int b200unet_prep_first_weight(const float* w_oihw, void* w1, int Cout, int Cin, b200_stream_t stream);
+/* y[n,h,w,k] = sum_j x[n,h,w,j] w[k,j], j < 64 (1x1 convolution of a 64-channel tensor; tcgen05, persistent CTAs,
+ * weights resident). stats_partial as for b200unet_conv3x3_igemm with rows = b200unet_conv1x1_c64_stat_rows(). */
+int b200unet_conv1x1_c64_stat_rows(int N, int H, int W, int Cout);
+int b200unet_conv1x1_c64_igemm(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial,
+                               int N, int H, int W, int Cout, b200_stream_t stream);
+/* dw[k][j] = sum_{n,h,w} dy[n,h,w,k] col[n,h,w,j] for j < T (T = 9*Cin): inc.conv1's weight gradient, written as
+ * fp32 OIHW [Cout][Cin][3][3] (= [Cout][T]). partial: b200unet_conv1x1_c64_wgrad_workspace_floats() floats. */
+int64_t b200unet_conv1x1_c64_wgrad_workspace_floats(int N, int H, int W, int Cout);
+int b200unet_conv1x1_c64_wgrad(const void* col, int col_cs, const void* dy, int dy_cs, float* partial, float* dw,
+                               int N, int H, int W, int T, int Cout, b200_stream_t stream);
+
 /* ---- first layer and head (tiny channel counts: bandwidth-bound CUDA-core kernels) ------------------------ */
 /* inc.conv1: x fp32 NCHW [N][Cin<=4][H][W] (Trainer.py:700-702 hands fp32 NCHW) -> y bf16 NHWC [..][Cout] + stats. */
 int b200unet_conv3x3_first_fprop(const float* x_nchw, const float* w_oihw, void* y, int y_cs, float* stats_partial,

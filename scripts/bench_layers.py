@@ -127,6 +127,12 @@ if want("edge"):
     dw = torch.empty_like(w)
     rec("first_fprop 3->64", timeit(lambda: ops.conv3x3_first(x, w, y, st)), bytes_=B * h * h * (128.0 + 12))
     rec("first_wgrad 3->64", timeit(lambda: ops.conv3x3_first_wgrad(x, y, dw)), bytes_=B * h * h * (128.0 + 12))
+    col = torch.empty(B, h, h, 64, dtype=BF16, device="cuda")
+    w1 = ops.prep_first_weight(w)
+    st2 = torch.empty(ops.conv1x1_c64_stat_rows(B, h, h, 64) * 128, device="cuda")
+    rec("first_im2col 3->64col", timeit(lambda: ops.first_im2col(x, col)), bytes_=B * h * h * (128.0 + 12))
+    rec("first_gemm 64col->64 (+stats)", timeit(lambda: ops.conv1x1_c64(col, w1, y, st2)), bytes_=B * h * h * 256.0)
+    rec("first_wgrad_tc", timeit(lambda: ops.conv1x1_c64_wgrad(col, y, dw)), bytes_=B * h * h * 256.0)
     hw_ = torch.randn(2, 64, 1, 1, device="cuda")
     hb = torch.zeros(2, device="cuda")
     z = torch.empty(B, 2, h, h, device="cuda")

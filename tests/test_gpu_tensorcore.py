@@ -95,6 +95,40 @@ def test_conv3x3_reads_and_writes_channel_slices(ops):
     assert float(yout[..., :c].float().abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 24, 1, 64), (3, 64, 72, 3, 64), (1, 40, 24, 4, 128)])
+def test_first_layer_im2col_gemm_and_wgrad(ops, n, h, w, cin, cout):
+    """inc.conv1 (Model.py:111): fp32 NCHW input -> bf16 im2col -> 1x1 tcgen05 GEMM (+ BN statistics), and its wgrad."""
+    g = torch.Generator().manual_seed(16)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    col = torch.full((n, h, w, 64), 9.0, dtype=BF16, device="cuda")
+    ops.first_im2col(x.cuda(), col)
+    # im2col itself is exact: bf16-rounded input taps, zero padding, zero tail columns
+    xb = bf16_round(x)
+    want_col = torch.nn.functional.unfold(xb, 3, padding=1).view(n, cin * 9, h, w).permute(0, 2, 3, 1)
+    assert torch.equal(col[..., : cin * 9].float().cpu(), want_col)
+    assert float(col[..., cin * 9:].float().abs().max()) == 0.0
+    w1 = ops.prep_first_weight(wt.cuda())
+    y = torch.empty(n, h, w, cout, dtype=BF16, device="cuda")
+    rows = ops.conv1x1_c64_stat_rows(n, h, w, cout)
+    st = torch.zeros(rows * 2 * cout, device="cuda")
+    ops.conv1x1_c64(col, w1, y, st)
+    want = O.conv3x3(xb, bf16_round(wt))
+    assert rel_l2(from_nhwc(y), want) < TOL
+    assert rel_l2(from_nhwc(y), O.conv3x3(x, wt)) < 6e-3  # vs the unrounded fp32 conv: input + weight + output rounding
+    yb = from_nhwc(y)
+    s = st.view(rows, 2, cout).sum(0).cpu()
+    assert rel_l2(s[0], yb.sum((0, 2, 3))) < 1e-3 + 1e-4
+    assert rel_l2(s[1], (yb * yb).sum((0, 2, 3))) < 1e-4
+    # weight gradient
+    dy = bf16_round(torch.randn(n, cout, h, w, generator=g))
+    wv = wt.clone().requires_grad_(True)
+    (O.conv3x3(xb, wv) * dy).sum().backward()
+    dw = torch.empty(cout, cin, 3, 3, device="cuda")
+    ops.conv1x1_c64_wgrad(col, to_nhwc_bf16(dy), dw)
+    assert rel_l2(dw, wv.grad) < 1e-4
+
+
 UP_SHAPES = [(1, 8, 16, 128, 64), (2, 4, 8, 256, 128), (1, 12, 20, 128, 64)]
 
 

@@ -23,10 +23,17 @@ namespace {
 using namespace b2;
 
 constexpr int RTH = 16, RTW = 8;                      // output pixel tile
-constexpr int HALO_H = RTH + 2, HALO_W = RTW + 2;     // input halo tile
-constexpr int A_BOX_BYTES = HALO_H * HALO_W * 128;    // 23040
-constexpr int A_STAGE = (A_BOX_BYTES + 1023) / 1024 * 1024;
 constexpr int OUT_CHUNK = 128 * 128;                  // 128 pixels x 64 channels bf16
+
+// TAPS = 9: 3x3 conv, input tile carries a one-pixel halo. TAPS = 1: 1x1 conv (plain GEMM over pixels), used for
+// inc.conv1 on its im2col'ed input (first_layer.cu).
+template <int TAPS>
+struct TileGeom {
+  static constexpr int HALO = (TAPS == 9) ? 1 : 0;
+  static constexpr int IN_H = RTH + 2 * HALO, IN_W = RTW + 2 * HALO;
+  static constexpr int A_BOX_BYTES = IN_H * IN_W * 128;  // 23040 for 3x3
+  static constexpr int A_STAGE = (A_BOX_BYTES + 1023) / 1024 * 1024;
+};
 
 struct ResArgs {
   CUtensorMap tmA, tmW, tmO;
@@ -38,9 +45,10 @@ struct ResArgs {
   float* stats;  // [workers][2][ncols] or null
 };
 
-template <int BN, int KB, int NA, int OB>
+template <int BN, int KB, int NA, int OB, int TAPS>
 struct ResPlan {
-  static constexpr int W_BYTES = 9 * KB * BN * 128;
+  static constexpr int A_STAGE = TileGeom<TAPS>::A_STAGE;
+  static constexpr int W_BYTES = TAPS * KB * BN * 128;
   static constexpr int A_OFF = W_BYTES;
   static constexpr int OUT_OFF = A_OFF + NA * A_STAGE;
   static constexpr int OUT_BYTES = OB * (BN / 64) * OUT_CHUNK;
@@ -50,9 +58,11 @@ struct ResPlan {
   static_assert(4 * 2 * BN * 4 <= OUT_BYTES, "final statistics reduction aliases the staging buffer");
 };
 
-template <int BN, int KB, int NA, int OB>
+template <int BN, int KB, int NA, int OB, int TAPS>
 __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant__ ResArgs args) {
-  using P = ResPlan<BN, KB, NA, OB>;
+  using P = ResPlan<BN, KB, NA, OB, TAPS>;
+  using G = TileGeom<TAPS>;
+  constexpr int A_STAGE = G::A_STAGE, A_BOX_BYTES = G::A_BOX_BYTES, IN_W = G::IN_W;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -110,7 +120,7 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(W_full, P::W_BYTES);
 #pragma unroll 1
-      for (int tap = 0; tap < 9; ++tap)
+      for (int tap = 0; tap < TAPS; ++tap)
 #pragma unroll
         for (int cb = 0; cb < KB; ++cb)
           tma_load_2d(sW + (tap * KB + cb) * (BN * 128), &args.tmW, W_full, (tap * KB + cb) * 64, n0);
@@ -123,7 +133,7 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
         for (int cb = 0; cb < KB; ++cb) {
           mbar_wait(A_empty(sa), pa ^ 1);
           mbar_arrive_expect_tx(A_full(sa), A_BOX_BYTES);
-          tma_load_4d(sA + sa * A_STAGE, &args.tmA, A_full(sa), cb * 64, w0 - 1, h0 - 1, img);
+          tma_load_4d(sA + sa * A_STAGE, &args.tmA, A_full(sa), cb * 64, w0 - G::HALO, h0 - G::HALO, img);
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
       }
@@ -133,7 +143,7 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
     // ================================================================= MMA issuer
     if (elect_one_sync()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      constexpr uint32_t a_hi = umma_desc_hi_sw128(HALO_W * 128), b_hi = umma_desc_hi_sw128(1024);
+      constexpr uint32_t a_hi = umma_desc_hi_sw128(IN_W * 128), b_hi = umma_desc_hi_sw128(1024);
       const uint32_t w_lo = umma_desc_lo(sW, 16);
       mbar_wait(W_full, 0);
       tc_fence_after();
@@ -151,9 +161,9 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
           tc_fence_after();
           const uint32_t a_lo = umma_desc_lo(sA + sa * A_STAGE, 16);
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < TAPS; ++tap) {
             // descriptor low words step in 16-byte units: tap (r,s) = (r*10+s) pixel rows of 128 B, K step = 32 B
-            const uint32_t a_tap = a_lo + ((tap / 3) * HALO_W + (tap % 3)) * 8;
+            const uint32_t a_tap = a_lo + ((tap / 3) * IN_W + (tap % 3)) * 8;
             const uint32_t b_tap = w_lo + (tap * KB + cb) * (BN * 8);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -272,11 +282,11 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-template <int BN, int KB, int NA, int OB>
+template <int BN, int KB, int NA, int OB, int TAPS>
 int launch_res(const ResArgs& a, cudaStream_t st) {
-  using P = ResPlan<BN, KB, NA, OB>;
+  using P = ResPlan<BN, KB, NA, OB, TAPS>;
   static bool configured = false;
-  auto kern = conv3_res_kernel<BN, KB, NA, OB>;
+  auto kern = conv3_res_kernel<BN, KB, NA, OB, TAPS>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) {
@@ -309,10 +319,9 @@ bool conv3_res_applicable(int Cin, int Cout) {
 
 static int res_bn(int Cin, int Cout) { return (Cin == 64 && Cout % 128 == 0) ? 128 : 64; }
 
-// geometry shared by the launcher and the statistics-row query
-static void res_geometry(int N, int H, int W, int Cin, int Cout, int* bn, int* ntn, int* workers, int* tiles) {
-  *bn = res_bn(Cin, Cout);
-  *ntn = Cout / *bn;
+// geometry shared by the launchers and the statistics-row queries
+static void res_geometry(int N, int H, int W, int bn, int Cout, int* ntn, int* workers, int* tiles) {
+  *ntn = Cout / bn;
   *tiles = N * ceil_div(H, RTH) * ceil_div(W, RTW);
   int w = num_sms() / *ntn;
   if (w < 1) w = 1;
@@ -321,17 +330,16 @@ static void res_geometry(int N, int H, int W, int Cin, int Cout, int* bn, int* n
 }
 
 int conv3_res_stat_rows(int N, int H, int W, int Cin, int Cout) {
-  int bn, ntn, workers, tiles;
-  res_geometry(N, H, W, Cin, Cout, &bn, &ntn, &workers, &tiles);
+  int ntn, workers, tiles;
+  res_geometry(N, H, W, res_bn(Cin, Cout), Cout, &ntn, &workers, &tiles);
   return workers;
 }
 
 int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
                      int W, int Cin, int Cout, cudaStream_t st) {
   ResArgs a;
-  int bn, tiles;
-  res_geometry(N, H, W, Cin, Cout, &bn, &a.ntiles_n, &a.workers, &tiles);
-  a.tiles_total = tiles;
+  const int bn = res_bn(Cin, Cout);
+  res_geometry(N, H, W, bn, Cout, &a.ntiles_n, &a.workers, &a.tiles_total);
   a.tiles_w = ceil_div(W, RTW);
   a.tiles_h = ceil_div(H, RTH);
   a.H = H;
@@ -339,12 +347,36 @@ int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, 
   a.ncols = Cout;
   a.stats = stats_partial;
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
-  if (int e = make_tmap_4d(&a.tmA, x, Cin, W, H, N, xs, xs * W, xs * W * H, HALO_W, HALO_H)) return e;
+  if (int e = make_tmap_4d(&a.tmA, x, Cin, W, H, N, xs, xs * W, xs * W * H, TileGeom<9>::IN_W, TileGeom<9>::IN_H)) return e;
   if (int e = make_tmap_2d(&a.tmW, w, static_cast<uint64_t>(9) * Cin, Cout, bn)) return e;
   if (int e = make_tmap_4d(&a.tmO, y, Cout, W, H, N, ys, ys * W, ys * W * H, RTW, RTH)) return e;
-  if (Cin == 64 && bn == 64) return launch_res<64, 1, 4, 2>(a, st);
-  if (Cin == 64 && bn == 128) return launch_res<128, 1, 2, 1>(a, st);
-  return launch_res<64, 2, 2, 2>(a, st);
+  if (Cin == 64 && bn == 64) return launch_res<64, 1, 4, 2, 9>(a, st);
+  if (Cin == 64 && bn == 128) return launch_res<128, 1, 2, 1, 9>(a, st);
+  return launch_res<64, 2, 2, 2, 9>(a, st);
+}
+
+// 1x1 convolution of a 64-channel NHWC tensor (the im2col'ed network input) with a [Cout][64] bf16 operand.
+int conv1x1_c64_stat_rows(int N, int H, int W, int Cout) {
+  int ntn, workers, tiles;
+  res_geometry(N, H, W, 64, Cout, &ntn, &workers, &tiles);
+  return workers;
+}
+
+int conv1x1_c64_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
+                       int W, int Cout, cudaStream_t st) {
+  ResArgs a;
+  res_geometry(N, H, W, 64, Cout, &a.ntiles_n, &a.workers, &a.tiles_total);
+  a.tiles_w = ceil_div(W, RTW);
+  a.tiles_h = ceil_div(H, RTH);
+  a.H = H;
+  a.W = W;
+  a.ncols = Cout;
+  a.stats = stats_partial;
+  const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
+  if (int e = make_tmap_4d(&a.tmA, x, 64, W, H, N, xs, xs * W, xs * W * H, RTW, RTH)) return e;
+  if (int e = make_tmap_2d(&a.tmW, w, 64, Cout, 64)) return e;
+  if (int e = make_tmap_4d(&a.tmO, y, Cout, W, H, N, ys, ys * W, ys * W * H, RTW, RTH)) return e;
+  return launch_res<64, 1, 4, 2, 1>(a, st);
 }
 
 }  // namespace b2h

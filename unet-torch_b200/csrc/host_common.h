@@ -34,5 +34,9 @@ bool conv3_res_applicable(int Cin, int Cout);
 int conv3_res_stat_rows(int N, int H, int W, int Cin, int Cout);
 int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
                      int W, int Cin, int Cout, cudaStream_t st);
+// the same kernel as a 1x1 convolution over a 64-channel input (inc.conv1 on its im2col'ed input, first_layer.cu)
+int conv1x1_c64_stat_rows(int N, int H, int W, int Cout);
+int conv1x1_c64_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
+                       int W, int Cout, cudaStream_t st);
 
 }  // namespace b2h

@@ -2,6 +2,7 @@
 // (NHWC tiles: pixels are rows = K, channels contiguous = M / N).
 //   KIND_CONV3  dW[k][r][s][c] = sum_{n,h,w} dy[n,h,w,k] * x[n,h+r-1,w+s-1,c]     (nn.Conv2d backward-weight)
 //   KIND_UP     dW[ci][d][i][j] = sum_{n,h,w} x[n,h,w,ci] * du[n,2h+i,2w+j,d]      (nn.ConvTranspose2d k2 s2)
+//   KIND_PLAIN  dW[k][j]        = sum_{n,h,w} dy[n,h,w,k] * col[n,h,w,j]            (inc.conv1 on its im2col'ed input)
 // A CTA owns a 128 (A-side channels) x BNC (B-side channels) x TAPS accumulator set in TMEM and streams a
 // contiguous range of 8x16 pixel tiles through a TMA ring (split-K over pixels across CTAs). For the 3x3 case
 // a CTA handles one horizontal tap s; its x tile carries two halo rows and the three vertical taps r are
@@ -16,7 +17,7 @@ namespace {
 using namespace b2;
 
 constexpr int TH = 8, TW = 16, BM = TH * TW;
-enum { KIND_CONV3 = 0, KIND_UP = 1 };
+enum { KIND_CONV3 = 0, KIND_UP = 1, KIND_PLAIN = 2 };
 
 struct WgradArgs {
   CUtensorMap tmA;     // A-side activations (conv3: dy, up: x)
@@ -29,11 +30,11 @@ struct WgradArgs {
 
 template <int KIND, int BNC>
 struct WPlan {
-  static constexpr int TAPS = (KIND == KIND_CONV3) ? 3 : 4;        // accumulators per CTA
-  static constexpr int TAPS_TOTAL = (KIND == KIND_CONV3) ? 9 : 4;  // taps in the partial layout
+  static constexpr int TAPS = (KIND == KIND_CONV3) ? 3 : (KIND == KIND_UP ? 4 : 1);        // accumulators per CTA
+  static constexpr int TAPS_TOTAL = (KIND == KIND_CONV3) ? 9 : (KIND == KIND_UP ? 4 : 1);  // taps in the partial layout
   static constexpr int A_BYTES = 2 * BM * 128;                     // two 64-channel boxes
   static constexpr int B_BOX = (KIND == KIND_CONV3) ? (TH + 2) * TW * 128 : BM * 128;
-  static constexpr int B_BYTES = (KIND == KIND_CONV3 ? 1 : 4) * (BNC / 64) * B_BOX;
+  static constexpr int B_BYTES = (KIND == KIND_UP ? 4 : 1) * (BNC / 64) * B_BOX;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NS = (227 * 1024 - 2048) / STAGE_BYTES;
   static constexpr int BAR_OFF = NS * STAGE_BYTES;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
             tma_load_4d(sB + j * P::B_BOX, &args.tmB[0], full(st), n0 + 64 * j, w0 + s - 1, h0 - 1, img);
         } else {
 #pragma unroll
-          for (int ij = 0; ij < 4; ++ij)
+          for (int ij = 0; ij < P::TAPS; ++ij)
 #pragma unroll
             for (int j = 0; j < BNC / 64; ++j)
               tma_load_4d(sB + (ij * (BNC / 64) + j) * P::B_BOX, &args.tmB[ij], full(st), n0 + 64 * j, w0, h0, img);
@@ -202,6 +203,17 @@ __global__ void reduce_up_kernel(const float* __restrict__ partial, float* __res
   }
 }
 
+// partial [Z][K][64] -> dw [K][T] (T <= 64 real columns: inc.conv1's OIHW gradient flattened as [k][c*9 + r*3 + s])
+__global__ void reduce_plain_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Z, int K, int T) {
+  const int total = K * T;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i / T, j = i - k * T;
+    float acc = 0.f;
+    for (int z = 0; z < Z; ++z) acc += partial[(static_cast<size_t>(z) * K + k) * 64 + j];
+    dw[i] = acc;
+  }
+}
+
 // ---- weight preparation (fp32 parameter -> bf16 GEMM operands)
 __global__ void prep_conv3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                   __nv_bfloat16* __restrict__ wd, int K, int C) {
@@ -234,11 +246,24 @@ __global__ void prep_up_kernel(const float* __restrict__ w, __nv_bfloat16* __res
 
 int conv3_bnc(int Cin) { return (Cin % 128 == 0) ? 128 : 64; }
 
+// Split-K factor over the pixel tiles. One CTA per SM (the TMA ring takes ~200 KB), so the launch runs in
+// ceil(ctas / 148) waves: pick the split whose last wave is fullest (e.g. 96 base CTAs -> z = 3 -> 288 CTAs = 1.95
+// waves instead of 0.65), preferring fewer splits (less partial traffic) on ties.
 int pick_splits(int base_ctas, int tiles_total) {
-  int z = 148 / base_ctas;
-  if (z < 1) z = 1;
-  if (z > tiles_total) z = tiles_total;
-  return z;
+  const int sms = 148;
+  int best_z = 1;
+  double best_eff = 0.0;
+  for (int z = 1; z <= tiles_total; ++z) {
+    const int ctas = base_ctas * z;
+    if (z > 1 && ctas > 4 * sms) break;
+    const int waves = (ctas + sms - 1) / sms;
+    const double eff = static_cast<double>(ctas) / (waves * sms);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best_z = z;
+    }
+  }
+  return best_z;
 }
 
 template <int KIND, int BNC>
@@ -357,6 +382,40 @@ int b200unet_convt2x2_wgrad(const void* x, int x_cs, const void* du, int du_cs, 
   const int blocks = static_cast<int>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   reduce_up_kernel<<<blocks, 256, 0, st>>>(partial, dw, a.splits, Cin, Cup);
   return b2h::check_launch("convt2x2_wgrad_reduce");
+}
+
+static void plain_wgrad_geometry(int N, int H, int W, int Cout, int* mtiles, int* tiles, int* splits) {
+  *mtiles = b2h::ceil_div(Cout, 128);
+  *tiles = N * b2h::ceil_div(H, TH) * b2h::ceil_div(W, TW);
+  *splits = pick_splits(*mtiles, *tiles);
+}
+
+int64_t b200unet_conv1x1_c64_wgrad_workspace_floats(int N, int H, int W, int Cout) {
+  int mt, tiles, z;
+  plain_wgrad_geometry(N, H, W, Cout, &mt, &tiles, &z);
+  return static_cast<int64_t>(z) * Cout * 64;
+}
+
+int b200unet_conv1x1_c64_wgrad(const void* col, int col_cs, const void* dy, int dy_cs, float* partial, float* dw, int N,
+                               int H, int W, int T, int Cout, b200_stream_t stream) {
+  B2_REQUIRE(Cout % 64 == 0 && T >= 1 && T <= 64, "conv1x1_c64_wgrad: Cout=%d must be a multiple of 64 and T=%d in [1,64]", Cout, T);
+  B2_REQUIRE(col_cs % 8 == 0 && dy_cs % 8 == 0 && col_cs >= 64, "conv1x1_c64_wgrad: bad pitches");
+  WgradArgs a;
+  plain_wgrad_geometry(N, H, W, Cout, &a.mtiles, &a.tiles_total, &a.splits);
+  a.ntiles = 1;
+  a.tiles_w = b2h::ceil_div(W, TW);
+  a.tiles_h = b2h::ceil_div(H, TH);
+  a.Ca = Cout;
+  a.Cb = 64;
+  a.partial = partial;
+  const uint64_t cs = static_cast<uint64_t>(col_cs) * 2, ys = static_cast<uint64_t>(dy_cs) * 2;
+  if (int e = b2h::make_tmap_4d(&a.tmA, dy, Cout, W, H, N, ys, ys * W, ys * W * H, TW, TH)) return e;
+  if (int e = b2h::make_tmap_4d(&a.tmB[0], col, 64, W, H, N, cs, cs * W, cs * W * H, TW, TH)) return e;
+  for (int i = 1; i < 4; ++i) a.tmB[i] = a.tmB[0];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = launch_wgrad<KIND_PLAIN, 64>(a, st)) return e;
+  reduce_plain_kernel<<<b2h::ceil_div(Cout * T, 256), 256, 0, st>>>(partial, dw, a.splits, Cout, T);
+  return b2h::check_launch("conv1x1_c64_wgrad_reduce");
 }
 
 }  // extern "C"

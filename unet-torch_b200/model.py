@@ -90,7 +90,10 @@ class _ConvBN:
         key = (w._version, w.data_ptr())
         if key != self._ver:
             with torch.no_grad():
-                self.wf, self.wd = ops.prep_conv3x3_weight(w.detach())
+                if self.first:  # inc.conv1 runs as a 1x1 GEMM over the im2col'ed input: [Cout, 64] operand, no dgrad
+                    self.wf, self.wd = ops.prep_first_weight(w.detach()), None
+                else:
+                    self.wf, self.wd = ops.prep_conv3x3_weight(w.detach())
             self._ver = key
         return self.wf, self.wd
 
@@ -196,10 +199,14 @@ class UNetEngine:
             y = torch.empty((n, hh, ww, c_out), dtype=BF16, device=dev)
             stats = None
             if cb.first:
-                rows = ops.first_conv_stat_rows(n, hh, ww)
+                col = torch.empty((n, hh, ww, 64), dtype=BF16, device=dev)
+                ops.first_im2col(inp, col)
+                inp = col  # saved for the weight gradient
+                rows = ops.conv1x1_c64_stat_rows(n, hh, ww, c_out)
                 if training:
                     stats = torch.empty(rows * 2 * c_out, dtype=torch.float32, device=dev)
-                ops.conv3x3_first(inp, cb.conv.weight.detach(), y, stats)
+                w1, _ = cb.operands()
+                ops.conv1x1_c64(col, w1, y, stats)
             else:
                 rows = ops.conv3x3_stat_rows(n, hh, ww, inp.shape[3], c_out)
                 if training:
@@ -278,7 +285,7 @@ class UNetEngine:
             dy = y  # dy overwrote y in place
             dw = gbuf(cb.conv.weight)
             if cb.first:
-                ops.conv3x3_first_wgrad(inp, dy, dw)
+                ops.conv1x1_c64_wgrad(inp, dy, dw)
             else:
                 ops.conv3x3_wgrad(inp, dy, dw)
             grads[bn.weight], grads[bn.bias], grads[cb.conv.weight] = dgamma, dbeta, dw
@@ -382,8 +389,8 @@ class UNet(nn.Module):
         if self._engine is None:
             if self.initial_feature_map % 64 != 0:
                 raise ValueError("initial_feature_map must be a multiple of 64 for the tensor-core path")
-            if self.n_channels > 4 or self.n_classes > 8:
-                raise ValueError("n_channels <= 4 and n_classes <= 8 are supported")
+            if self.n_channels > 7 or self.n_classes > 8:
+                raise ValueError("n_channels <= 7 and n_classes <= 8 are supported")
             if self.dropout:
                 raise NotImplementedError("dropout=True variant is not implemented in the B200 path")
             object.__setattr__(self, "_engine", UNetEngine(self))

@@ -132,6 +132,55 @@ def convt2x2_wgrad(x, du_canvas_slice, dw_out, pad_top=0, pad_left=0):
     return dw_out
 
 
+# --------------------------------------------------------------------------------------------- inc.conv1 (tensor cores)
+def first_im2col(x_nchw: torch.Tensor, col: torch.Tensor):
+    """fp32 NCHW network input -> 64-column bf16 im2col tensor [N,H,W,64] (column c*9+r*3+s, zero padded)."""
+    if x_nchw.dtype != torch.float32 or not x_nchw.is_cuda or not x_nchw.is_contiguous() or x_nchw.dim() != 4:
+        raise ValueError("first_im2col: expected a contiguous CUDA fp32 NCHW tensor")
+    n, cin, h, w = x_nchw.shape
+    cp, ccs, n2, h2, w2, c64 = _nhwc(col)
+    if (n, h, w) != (n2, h2, w2) or c64 != 64:
+        raise ValueError("first_im2col: shape mismatch")
+    _lib.call("b200unet_first_im2col", x_nchw.data_ptr(), cp, ccs, n, h, w, cin, _stream())
+    return col
+
+
+def prep_first_weight(w: torch.Tensor):
+    """fp32 OIHW [K,Cin,3,3] -> bf16 [K,64] operand matching first_im2col's columns."""
+    k, cin = w.shape[0], w.shape[1]
+    w1 = torch.empty((k, 64), dtype=BF16, device=w.device)
+    _lib.call("b200unet_prep_first_weight", _f32(w), w1.data_ptr(), k, cin, _stream())
+    return w1
+
+
+def conv1x1_c64_stat_rows(n, h, w, cout):
+    return _lib.query("b200unet_conv1x1_c64_stat_rows", n, h, w, cout)
+
+
+def conv1x1_c64(x, w1, out, stats_partial=None):
+    """out[n,h,w,k] = sum_j x[n,h,w,j] w1[k,j] over a 64-channel input (+ BatchNorm partial statistics)."""
+    xp, xcs, n, h, w, c = _nhwc(x)
+    op, ocs, n2, h2, w2, cout = _nhwc(out)
+    if (n, h, w) != (n2, h2, w2) or c != 64 or tuple(w1.shape) != (cout, 64) or w1.dtype != BF16:
+        raise ValueError("conv1x1_c64: shape mismatch")
+    if stats_partial is not None and stats_partial.numel() < conv1x1_c64_stat_rows(n, h, w, cout) * 2 * cout:
+        raise ValueError("conv1x1_c64: stats_partial too small")
+    _lib.call("b200unet_conv1x1_c64_igemm", xp, xcs, w1.data_ptr(), op, ocs, _f32(stats_partial), n, h, w, cout, _stream())
+    return out
+
+
+def conv1x1_c64_wgrad(col, dy, dw_out):
+    """dw_out (fp32 OIHW [Cout,Cin,3,3]) = weight gradient of inc.conv1 from its im2col'ed input and dy."""
+    cp, ccs, n, h, w, c = _nhwc(col)
+    yp, ycs, n2, h2, w2, cout = _nhwc(dy)
+    if (n, h, w) != (n2, h2, w2) or c != 64 or dw_out.shape[0] != cout or dw_out[0].numel() > 64:
+        raise ValueError("conv1x1_c64_wgrad: shape mismatch")
+    ws = _workspace(_lib.query("b200unet_conv1x1_c64_wgrad_workspace_floats", n, h, w, cout), dy.device)
+    _lib.call("b200unet_conv1x1_c64_wgrad", cp, ccs, yp, ycs, ws.data_ptr(), _f32(dw_out), n, h, w, dw_out[0].numel(),
+              cout, _stream())
+    return dw_out
+
+
 # --------------------------------------------------------------------------------------------- first layer / head
 def conv3x3_first(x_nchw: torch.Tensor, w_oihw: torch.Tensor, out, stats_partial=None):
     n, cin, h, w = x_nchw.shape
