@@ -1,19 +1,28 @@
 #!/bin/bash
-# ncu evidence for one bench command: (1) launch list with device time per launch, (2) --set full capture of the
-# kernels named in $KERNELS (regex). Each ncu pass only after the same command exited 0 without ncu.
-# usage: TAG=r1a KERNELS='igemm_kernel|wgrad_kernel' bash scripts/gpu_profile.sh
+# ncu evidence for the bench command (1 GPU): (1) launch list with the device time of every launch of ~2 steps,
+# (2) --set full captures of the dominant kernels. Every ncu pass directly follows a plain run that exited 0.
+# usage: TAG=r1 bash scripts/gpu_profile.sh        (outputs under gpurun_out/, summaries are made on the CPU box)
 mkdir -p gpurun_out
 TAG=${TAG:-prof}
-KERNELS=${KERNELS:-igemm_kernel}
-SKIP=${SKIP:-4800}     # launches of the 3 warm-up steps + setup
-COUNT=${COUNT:-1400}   # a little over one step
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $COUNT --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-900} -c ${COUNT:-700} --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
-$CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k "regex:$KERNELS" -s ${FULL_SKIP:-120} -c ${FULL_COUNT:-12} \
-    -f -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
-echo "full capture rc=$?"
+full() {  # name, kernel regex, skip (matching launches), count, extra flags
+  $CMD > gpurun_out/${TAG}_plain_$1.log 2>&1 &&
+  ncu --set full --clock-control none $5 -k "regex:$2" -s $3 -c $4 -f -o gpurun_out/${TAG}_$1 $CMD \
+      > gpurun_out/${TAG}_ncu_$1.log 2>&1
+  echo "full capture $1 rc=$?"
+}
+for what in ${FULL:-res igemm wgrad bn}; do
+  case $what in
+    res)   full res   'conv3_res_kernel' 45 8 "" ;;
+    igemm) full igemm 'igemm_kernel' 84 6 "" ;;
+    wgrad) full wgrad 'wgrad_kernel' 66 5 "" ;;
+    bn)    full bn    'bn_bwd_apply_kernel|bn_bwd_reduce_kernel|bn_relu_fwd_kernel' 162 5 "" ;;
+  esac
+done
+# gpurun copies back at most 64 MiB: drop the largest reports until the directory fits
+while [ $(du -sm gpurun_out | cut -f1) -gt 58 ]; do big=$(ls -S gpurun_out/*.ncu-rep | head -1); echo "dropping $big"; rm -f $big; done
 ls -la gpurun_out | tail -20

@@ -7,7 +7,8 @@ import sys
 
 METRICS = [
     ("gpu__time_duration.sum", "dur_us", 1e-3),
-    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor_pipe_%", 1),
+    ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_active_%", 1),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum", "l2_to_sm_MB", 1e-6),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_thr_%", 1),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_%", 1),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_%", 1),
