@@ -1,0 +1,73 @@
+"""torchrun worker for tests/test_gpu_dist.py: data-parallel UNet step (NCCL, SyncBN, bucketed gradient all-reduce)
+against the same global batch run on one GPU (per-rank Dice, as under DDP: SURVEY.md section 8e)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import unet_torch_b200 as U  # noqa: E402
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    ctx = U.init_from_env(sync_bn=True, bucket_mb=4.0)
+    assert ctx is not None and ctx.world_size == world
+    dev = torch.device("cuda", local)
+    per, hw = 2, 48
+    torch.manual_seed(0)
+    net = U.UNet(3, 2).to(dev).train()
+    U.loss.CLASS_NUMBER = 2
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(per * world, 3, hw, hw, generator=g)
+    y = torch.randint(0, 2, (per * world, hw, hw), generator=g).float()
+    sl = slice(rank * per, (rank + 1) * per)
+    # ---- data parallel step on this rank's shard
+    out = net(x[sl].to(dev))
+    loss = U.calc_loss(out, y[sl].to(dev), loss_type="dice_bce_mc")
+    loss.backward()
+    torch.cuda.synchronize()
+    dp_out = out.detach().clone()
+    dp_grads = {n: p.grad.detach().clone() for n, p in net.named_parameters()}
+    dp_rm = net.inc.double_conv[1].running_mean.detach().clone()
+    # every rank must hold identical (averaged) gradients
+    for n, gr in dp_grads.items():
+        ref = gr.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref, gr), f"rank {rank}: gradient of {n} differs from rank 0 after the all-reduce"
+    # ---- the same global batch on one GPU, no data parallelism
+    U.DataParallelContext.disable()
+    torch.manual_seed(0)
+    net1 = U.UNet(3, 2).to(dev).train()
+    out1 = net1(x.to(dev))
+    losses = [U.calc_loss(out1[r * per:(r + 1) * per], y[r * per:(r + 1) * per].to(dev), loss_type="dice_bce_mc")
+              for r in range(world)]
+    (sum(losses) / world).backward()
+    torch.cuda.synchronize()
+    e_out = rel(dp_out, out1.detach()[sl])
+    worst, worst_n = 0.0, ""
+    for n, p in net1.named_parameters():
+        e = rel(dp_grads[n], p.grad)
+        if e > worst:
+            worst, worst_n = e, n
+    e_rm = rel(dp_rm, net1.inc.double_conv[1].running_mean)
+    print(f"rank {rank}: logits rel {e_out:.3e}, worst grad rel {worst:.3e} ({worst_n}), running_mean rel {e_rm:.3e}", flush=True)
+    assert e_out < 2e-3, e_out
+    assert worst < 2e-2, (worst, worst_n)
+    assert e_rm < 1e-5, e_rm
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DP_OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()

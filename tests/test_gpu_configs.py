@@ -1,0 +1,102 @@
+"""-m gpu: the other BASELINE.json configs as parity cases (they are not bench lines).
+
+configs[3]  5-class inference on large tiles (test_mc3serousv5.py:878-881): eval-mode forward (running statistics) and
+            the fused softmax->argmax mask, against the CPU oracle at a size it finishes in seconds, and at the full
+            tile size through properties (determinism, mask == first-maximum of fp32 softmax of the same logits).
+configs[4]  regression head, relu + 'mseMC' (Trainer.py:709-712, loss.py:476) at 768^2: loss equals the closed form on
+            the device logits, gradients finite, one SGD step lowers the loss.
+"""
+import pytest
+import torch
+
+from gpu_util import rel_l2
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _trained_buffers(net):
+    """Make the running statistics non-trivial (as after training) without running a training loop."""
+    g = torch.Generator().manual_seed(99)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+
+
+def test_config4_eval_forward_and_mask_against_oracle():
+    import unet_torch_b200 as U
+
+    torch.manual_seed(35)
+    net = U.UNet(3, 5)
+    with torch.no_grad():
+        _trained_buffers(net)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda().eval()
+    x = torch.randn(1, 3, 96, 128, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        out = net(x.cuda())
+    want, _ = O.unet_forward(sd, x, training=False)
+    e = rel_l2(out, want)
+    print(f"config4 eval logits rel-L2 vs oracle {e:.3e}")
+    assert e < 3e-2
+    # eval must not touch the buffers
+    for k, v in net.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+    # mask: bit-exact against the oracle's softmax->argmax on the SAME (device) logits
+    mask = U.predict_mask(out)
+    assert mask.dtype == torch.int64 and mask.shape == (1, 96, 128)
+    assert torch.equal(mask.cpu(), O.softmax_argmax(out.cpu()))
+    # and close to the oracle's own mask (differences only where bf16 noise flips a near-tie)
+    agree = float((mask.cpu() == O.softmax_argmax(want)).float().mean())
+    print(f"config4 mask agreement with the fp32 oracle end to end: {agree:.4f}")
+    assert agree > 0.93
+
+
+def test_config4_full_tile_properties():
+    import unet_torch_b200 as U
+
+    torch.manual_seed(1063)
+    net = U.UNet(3, 5).cuda().eval()
+    x = torch.randn(2, 3, 1024, 1024, device="cuda")
+    with torch.no_grad():
+        a = net(x)
+        b = net(x)
+    assert a.shape == (2, 5, 1024, 1024) and torch.isfinite(a).all()
+    assert torch.equal(a, b)  # deterministic: no atomics on the path
+    mask = U.predict_mask(a)
+    p = torch.softmax(a, dim=1)
+    assert torch.equal(mask, torch.argmax(p, dim=1))
+    assert int(mask.min()) >= 0 and int(mask.max()) < 5
+    # images are independent in eval mode: batch of 2 == two batches of 1
+    with torch.no_grad():
+        a0 = net(x[:1])
+    assert torch.equal(a0, a[:1])
+
+
+def test_config5_regression_mse_768():
+    import unet_torch_b200 as U
+
+    torch.manual_seed(0)
+    net = U.UNet(3, 2).cuda().train()
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 3, 768, 768, generator=g).cuda()
+    t = (torch.rand(2, 2, 768, 768, generator=g) * 200.0 * (torch.rand(2, 2, 768, 768, generator=g) > 0.9)).cuda()
+    losses = []
+    for it in range(3):
+        out = net(x)
+        pred = torch.relu(out)
+        loss = U.calc_loss(pred, t, loss_type="mseMC")
+        if it == 0:
+            want = torch.mean((torch.relu(out.detach().double()) - t.double()) ** 2)
+            assert abs(float(loss) - float(want)) <= 1e-5 * abs(float(want))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+        opt.step()
+        losses.append(float(loss))
+    print("config5 losses:", losses)
+    assert losses[-1] < losses[0]

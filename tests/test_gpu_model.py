@@ -75,6 +75,11 @@ def test_forward_backward_against_reference_golden(golden, case):
     with torch.no_grad():
         oe = net(x)
     assert oe.shape == g["logits_eval"].shape
+    # running statistics after ONE momentum-0.1 update are still close to their init, so eval logits are large-ish
+    # and well conditioned: compare values, not only shapes (reference: eval forward right after its own first step)
+    e_eval = rel_l2(oe, g["logits_eval"])
+    print(f"{case}: eval logits rel {e_eval:.3e}")
+    assert e_eval < 3e-2
 
 
 def test_module_interface_matches_reference():
