@@ -138,14 +138,17 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n_gpus, batch_override=None):
+def workload_config(n_gpus, batch_override=None, graphs=False, torch_optim=False):
     b = batch_override or CFG["batch_per_gpu"]
     return {
         "workload": "BASELINE configs[1]: UNet(3,2) training step (fwd + dice_bce_mc loss + bwd + SGD), 3x512x512, "
                     f"batch {b} per GPU" + (", data parallel + SyncBN (configs[2] per-GPU batch)" if n_gpus > 1 else ""),
         "global_batch": b * n_gpus, "image": [CFG["n_channels"], CFG["H"], CFG["W"]], "loss": CFG["loss"],
-        "optimizer": "SGD(lr=0.01, momentum=0.9, weight_decay=1e-4)",
+        "optimizer": "SGD(lr=0.01, momentum=0.9, weight_decay=1e-4)" + ("" if torch_optim else
+                     " as unet_torch_b200.FusedSGD (torch.optim.SGD arithmetic fused with the bf16 operand re-cast)"),
         "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
+        "cuda_graphs": "forward and backward of the network replayed as captured CUDA graphs (single GPU); loss and "
+                       "optimizer eager" if (n_gpus == 1 and graphs) else "off",
         "l2": "per-step working set (~10 GB of bf16 activations) is far larger than the 126 MB L2; no explicit flush",
     }
 
@@ -172,7 +175,8 @@ def run_ours(args):
 
         for p in list(net.parameters()) + list(net.buffers()):
             dist.broadcast(p.data, 0)
-    opt = torch.optim.SGD(net.parameters(), lr=CFG["lr"], momentum=CFG["momentum"], weight_decay=CFG["weight_decay"])
+    okw = dict(lr=CFG["lr"], momentum=CFG["momentum"], weight_decay=CFG["weight_decay"])
+    opt = torch.optim.SGD(net.parameters(), **okw) if args.torch_optim else U.FusedSGD(net, **okw)
     B, H, W = CFG["batch_per_gpu"], CFG["H"], CFG["W"]
     gen = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.randn(B, CFG["n_channels"], H, W, generator=gen).pin_memory()
@@ -206,12 +210,17 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # one eager step: configures the kernels and counts OUR launches per step (graph replays bypass the counter)
+    l0 = _lib.query("b200unet_launch_count")
+    step(x_dev, y_dev)
+    launches_per_step = _lib.query("b200unet_launch_count") - l0
+    use_graphs = not args.no_graphs
+    net.enable_cuda_graphs(use_graphs)
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
     # ---- device-resident timing
     barrier()
     sampler.mark_begin()
-    launches0 = _lib.query("b200unet_launch_count")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -219,7 +228,7 @@ def run_ours(args):
     e1.record()
     barrier()
     sampler.mark_end()
-    launches = _lib.query("b200unet_launch_count") - launches0
+    launches = launches_per_step * args.steps
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
@@ -228,18 +237,38 @@ def run_ours(args):
     # ---- end to end: host buffers in, loss out, every step
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    copy_stream = torch.cuda.Stream()
+    cur = torch.cuda.current_stream()
+
+    def fetch():
+        """Pinned host batch -> device on the copy stream (what a pin_memory DataLoader + non_blocking .to() does)."""
+        with torch.cuda.stream(copy_stream):
+            xd = x_host.to(dev, non_blocking=True)
+            yd = y_host.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return xd, yd, ev
+
     e0.record()
+    copy_stream.wait_stream(cur)
     last = None
-    for _ in range(args.steps):
-        xd = x_host.to(dev, non_blocking=True)
-        yd = y_host.to(dev, non_blocking=True)
-        last = step(xd, yd).item()
+    nxt = fetch()
+    for i in range(args.steps):
+        xd, yd, ev = nxt
+        cur.wait_event(ev)
+        xd.record_stream(cur)
+        yd.record_stream(cur)
+        loss = step(xd, yd)
+        if i + 1 < args.steps:
+            nxt = fetch()  # the next step's copy overlaps this step's kernels; every step's inputs cross PCIe in the region
+        last = loss.item()  # device -> host read of the step's result, every step
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
 
     # ---- roofline of the dominant kernel class (tcgen05 conv3x3 implicit GEMM), CUDA events around each launch
+    net.enable_cuda_graphs(False)  # per-launch CUDA events need the eager launch path
     prof = []
     orig = ops.conv3x3
 
@@ -273,10 +302,11 @@ def run_ours(args):
     line = {
         "metric": "unet_train_img_per_s_512", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world, graphs=use_graphs, torch_optim=args.torch_optim),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4),
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last,
+                "how": "pinned host batch -> device on a copy stream one step ahead, loss.item() every step"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "model_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3 / world,
@@ -285,6 +315,16 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_baseline_leg()
     print(json.dumps(line), flush=True)
     return 0
+
+
+def _shutdown_dist():
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 def cpu_baseline_leg():
@@ -309,10 +349,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-optim", action="store_true", help="step with stock torch.optim.SGD instead of FusedSGD")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    return run_ours(args)
+    try:
+        return run_ours(args)
+    finally:
+        _shutdown_dist()
 
 
 if __name__ == "__main__":

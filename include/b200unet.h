@@ -145,6 +145,11 @@ int b200unet_bn_relu_bwd_apply(const void* g1, int g1_cs, const void* g_pool, co
                                const float* mean, const float* rstd, const double* sums, double count,
                                const double* sums_local, void* dy, int dy_cs, float* dgamma, float* dbeta, int N,
                                int H, int W, int C, b200_stream_t stream);
+/* out[c] = sum_r partial[r][col_lo + c], c < n: per-channel sums from the [rows][row_pitch] statistics rows a conv
+ * epilogue wrote (row_pitch = 2*Cout; columns [0,Cout) hold the sums). Used for the ConvTranspose2d bias gradient
+ * (Model.py:56): db = sum over pixels of the upsampled half of the concat gradient. */
+int b200unet_partial_colsum(const float* partial, int64_t rows, int row_pitch, int col_lo, int n, float* out,
+                            b200_stream_t stream);
 /* per-channel sum over pixels of a bf16 NHWC tensor (ConvTranspose2d bias gradient). */
 int64_t b200unet_channel_sum_workspace_floats(int C);
 int b200unet_channel_sum(const void* x, int x_cs, float* workspace, float* out, int64_t pixels, int C,
@@ -169,6 +174,22 @@ int b200unet_mse_bwd(const float* pred, const float* target, const float* grad_o
 
 /* ---- inference head (test_mc3serousv5.py:880-881): fp32 softmax over classes, then first-maximum argmax --- */
 int b200unet_softmax_argmax(const float* logits, int64_t* mask, int N, int ncls, int64_t HW, b200_stream_t stream);
+
+/* ---- fused optimizer step (reference: torch.optim.SGD built in train.py:341-347, stepped in
+ * Trainer.py:719-725). torch.optim.SGD arithmetic on the fp32 master parameter (weight decay, momentum, dampening,
+ * nesterov; first_step = the momentum buffer is initialised with the gradient) fused with the bf16 re-cast of the
+ * two GEMM operands. grad == NULL only refreshes the operands. momentum_buf may be NULL when momentum == 0. */
+int b200unet_sgd_conv3x3_weight(float* w_oihw, const float* grad, float* momentum_buf, void* w_fprop, void* w_dgrad,
+                                int K, int C, float lr, float momentum, float dampening, float weight_decay,
+                                int nesterov, int first_step, b200_stream_t stream);
+int b200unet_sgd_convt2x2_weight(float* w, const float* grad, float* momentum_buf, void* w_fprop, void* w_dgrad,
+                                 int Cin, int Cup, float lr, float momentum, float dampening, float weight_decay,
+                                 int nesterov, int first_step, b200_stream_t stream);
+/* the same update for `count` small fp32 tensors (HOST arrays of device pointers / element counts) in one launch
+ * per 48 tensors: BatchNorm affine parameters, biases, the 1x1 head, inc.conv1. */
+int b200unet_sgd_small(float* const* w, const float* const* grad, float* const* momentum_buf, const int* numel,
+                       int count, float lr, float momentum, float dampening, float weight_decay, int nesterov,
+                       int first_step, b200_stream_t stream);
 
 /* ---- bring-up probe (test aid): UMMA operand whose start is offset by `shift` 128-byte rows inside a
  * 128B-swizzled tile. out[128][64] = A[shift:shift+128][:] * B^T; A is 160x64 bf16, B is 64x64 bf16. */

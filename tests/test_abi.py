@@ -49,7 +49,11 @@ def test_host_only_queries(lib):
     # split-K workspace: splits * Cout * 9 * Cin floats, at least one split
     ws = lib.query("b200unet_conv3x3_wgrad_workspace_floats", 16, 512, 512, 64, 64)
     assert ws % (64 * 9 * 64) == 0 and ws >= 64 * 9 * 64
-    assert lib.query("b200unet_conv3x3_wgrad_workspace_floats", 16, 32, 32, 1024, 1024) == 1024 * 9 * 1024
+    # deep layer: 192 base CTAs -> 3 pixel splits fill 3.9 waves of 148 SMs instead of 1.3
+    assert lib.query("b200unet_conv3x3_wgrad_workspace_floats", 16, 32, 32, 1024, 1024) == 3 * 1024 * 9 * 1024
+    # statistics rows: one per persistent CTA for the resident-weight kernel (Cin <= 128), one per 8x16 tile otherwise
+    assert lib.query("b200unet_conv3x3_stat_rows", 16, 512, 512, 64, 64) == 148
+    assert lib.query("b200unet_conv3x3_stat_rows", 16, 64, 64, 512, 512) == 16 * 8 * 4
     assert lib.query("b200unet_launch_count") == 0
 
 

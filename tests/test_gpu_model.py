@@ -110,3 +110,102 @@ def test_module_interface_matches_reference():
         losses.append(l.item())
     assert losses[-1] < losses[0]  # training on one batch makes progress
     net.load_state_dict({k: v.clone() for k, v in net.state_dict().items()})
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager():
+    """enable_cuda_graphs(): the captured forward/backward must produce the same bits as the eager launches, across
+    optimizer steps (weights change -> operands refreshed in place), and refuse a stale backward."""
+    import unet_torch_b200 as U
+
+    U.loss.CLASS_NUMBER = 2
+    x = torch.randn(2, 3, 64, 48, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    y = torch.randint(0, 2, (2, 64, 48), device="cuda", generator=torch.Generator("cuda").manual_seed(4)).float()
+
+    def run(graphs):
+        torch.manual_seed(11)
+        net = U.UNet(3, 2).cuda().train().enable_cuda_graphs(graphs)
+        opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9)
+        outs = []
+        for _ in range(4):
+            out = net(x)
+            loss = U.calc_loss(out, y, loss_type="dice_bce_mc")
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            outs.append((out.detach().clone(), float(loss), net.up1.up.weight.grad.clone(),
+                         net.inc.double_conv[0].weight.grad.clone()))
+            opt.step()
+        net.eval()
+        with torch.no_grad():
+            e1 = net(x).clone()
+            e2 = net(x).clone()  # second eval call of this shape replays the captured eval graph
+        return net, outs, e1, e2
+
+    net_e, eager, ee1, ee2 = run(False)
+    net_g, graph, ge1, ge2 = run(True)
+    assert net_g._engine._graphs, "no graph was captured"
+    for (o1, l1, g1, h1), (o2, l2, g2, h2) in zip(eager, graph):
+        assert torch.equal(o1, o2) and l1 == l2 and torch.equal(g1, g2) and torch.equal(h1, h2)
+    assert torch.equal(ee1, ge1) and torch.equal(ee2, ge2) and torch.equal(ge1, ge2)
+    for (k, a), (_, b) in zip(net_e.state_dict().items(), net_g.state_dict().items()):
+        assert torch.equal(a, b), k
+    # stale backward: two forwards of the same shape, then backward of the first
+    net_g.train()
+    o1 = net_g(x)
+    o2 = net_g(x)
+    with pytest.raises(RuntimeError, match="ONE set of saved activations"):
+        o1.sum().backward()
+    o2.sum().backward()
+
+
+@pytest.mark.parametrize("nesterov,damp,wd", [(False, 0.0, 1e-4), (True, 0.0, 0.0), (False, 0.1, 1e-3)])
+def test_fused_sgd_matches_torch_sgd(nesterov, damp, wd):
+    """FusedSGD (one pass: update + bf16 operand re-cast) against torch.optim.SGD on identical gradients: parameters
+    and momentum buffers to fp32 rounding, operands exactly the bf16 cast of the updated parameter, and the next
+    forward identical to one that re-casts lazily."""
+    import unet_torch_b200 as U
+    from unet_torch_b200 import ops
+
+    U.loss.CLASS_NUMBER = 2
+    x = torch.randn(2, 3, 32, 32, device="cuda", generator=torch.Generator("cuda").manual_seed(7))
+    y = torch.randint(0, 2, (2, 32, 32), device="cuda", generator=torch.Generator("cuda").manual_seed(8)).float()
+    torch.manual_seed(5)
+    net_a = U.UNet(3, 2).cuda().train()
+    torch.manual_seed(5)
+    net_b = U.UNet(3, 2).cuda().train()
+    kw = dict(lr=0.05, momentum=0.9, dampening=damp, weight_decay=wd, nesterov=nesterov)
+    opt_a = torch.optim.SGD(net_a.parameters(), **kw)
+    opt_b = U.FusedSGD(net_b, **kw)
+    for it in range(3):
+        for net, opt in ((net_a, opt_a), (net_b, opt_b)):
+            loss = U.calc_loss(net(x), y, loss_type="dice_bce_mc")
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+        # identical gradients go into both optimizers (isolates the optimizer arithmetic from bf16 chaos upstream)
+        for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+            pb.grad.copy_(pa.grad)
+        opt_a.step()
+        opt_b.step()
+        for (k, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+            assert torch.allclose(pa, pb, rtol=2e-6, atol=1e-8), (it, k, float((pa - pb).abs().max()))
+            ba, bb = opt_a.state[pa]["momentum_buffer"], opt_b.state[pb]["momentum_buffer"]
+            assert torch.allclose(ba, bb, rtol=2e-6, atol=1e-8), (it, k)
+            pb.data.copy_(pa.data)  # keep the two runs on identical weights ...
+        net_b._engine = None        # ... and let the next forward re-derive b's operands from them
+    # operands written by the fused step == lazy re-cast of the same parameter
+    torch.manual_seed(5)
+    net_c = U.UNet(3, 2).cuda().train()
+    opt_c = U.FusedSGD(net_c, **kw)
+    loss = U.calc_loss(net_c(x), y, loss_type="dice_bce_mc")
+    loss.backward()
+    opt_c.step()
+    eng = net_c._get_engine()
+    for c1, c2 in eng.enc + eng.dec:
+        for cb in (c1, c2):
+            if cb.first:
+                continue
+            wf, wd_ = ops.prep_conv3x3_weight(cb.conv.weight.detach())
+            assert cb._ver == (cb.conv.weight._version, cb.conv.weight.data_ptr())
+            assert torch.equal(wf, cb.wf) and torch.equal(wd_, cb.wd)
+    for u in eng.ups:
+        wf, wd_ = ops.prep_convt2x2_weight(u.up.weight.detach())
+        assert torch.equal(wf, u.wf) and torch.equal(wd_, u.wd)

@@ -8,6 +8,7 @@ from . import _lib  # noqa: F401
 from .model import UNet, DoubleConv, Down, Up, OutConv, predict_mask  # noqa: F401
 from .loss import calc_loss, DiceLoss, ce_dice_loss, relu_mse_loss  # noqa: F401
 from .dist import DataParallelContext, init_from_env  # noqa: F401
+from .optim import FusedSGD  # noqa: F401
 
 __all__ = ["UNet", "DoubleConv", "Down", "Up", "OutConv", "calc_loss", "DiceLoss", "ce_dice_loss", "relu_mse_loss",
-           "predict_mask", "DataParallelContext", "init_from_env"]
+           "predict_mask", "DataParallelContext", "init_from_env", "FusedSGD"]

@@ -57,6 +57,7 @@ SIGNATURES = {
         c_int,
         [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _D, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     ),
+    "b200unet_partial_colsum": (c_int, [_P, _L, _I, _I, _I, _P, _P]),
     "b200unet_channel_sum_workspace_floats": (c_int64, [_I]),
     "b200unet_channel_sum": (c_int, [_P, _I, _P, _P, _L, _I, _P]),
     "b200unet_loss_ce_dice_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _P]),
@@ -64,6 +65,9 @@ SIGNATURES = {
     "b200unet_mse_fwd": (c_int, [_P, _P, _P, _P, _L, _I, _P]),
     "b200unet_mse_bwd": (c_int, [_P, _P, _P, _P, _L, _I, _P]),
     "b200unet_softmax_argmax": (c_int, [_P, _P, _I, _I, _L, _P]),
+    "b200unet_sgd_conv3x3_weight": (c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _I, _P]),
+    "b200unet_sgd_convt2x2_weight": (c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _I, _P]),
+    "b200unet_sgd_small": (c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_probe_shift": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
 }
 

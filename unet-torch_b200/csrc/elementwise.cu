@@ -398,6 +398,26 @@ __global__ void __launch_bounds__(EW_THREADS) channel_sum_kernel(const __nv_bflo
   }
 }
 
+// out[c] = sum over rows of partial[r][col_lo + c] (fp64 accumulation, fixed order): per-channel sums taken from the
+// statistics rows a convolution epilogue already produced (ConvTranspose2d bias gradient, Model.py:56).
+__global__ void partial_colsum_kernel(const float* __restrict__ partial, long long rows, int row_pitch, int col_lo, int n,
+                                      float* __restrict__ out) {
+  __shared__ double sh[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  double acc = 0.0;
+  if (c < n)
+    for (long long r = rl; r < rows; r += 8) acc += static_cast<double>(partial[r * row_pitch + col_lo + c]);
+  sh[rl][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rl == 0 && c < n) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    out[c] = static_cast<float>(t);
+  }
+}
+
 __global__ void double_to_float_kernel(const double* in, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = static_cast<float>(in[i]);
@@ -495,6 +515,13 @@ int b200unet_bn_relu_bwd_apply(const void* g1, int g1_cs, const void* g_pool, co
                                                               static_cast<__nv_bfloat16*>(dy), dy_cs, dgamma, dbeta, N,
                                                               H, W, C);
   return b2h::check_launch("bn_relu_bwd_apply");
+}
+
+int b200unet_partial_colsum(const float* partial, int64_t rows, int row_pitch, int col_lo, int n, float* out,
+                            b200_stream_t stream) {
+  B2_REQUIRE(rows > 0 && n > 0 && col_lo >= 0 && col_lo + n <= row_pitch, "partial_colsum: bad column range");
+  partial_colsum_kernel<<<(n + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, rows, row_pitch, col_lo, n, out);
+  return b2h::check_launch("partial_colsum");
 }
 
 int64_t b200unet_channel_sum_workspace_floats(int C) { return static_cast<int64_t>(EW_MAX_BLOCKS) * C + 2 * C; }

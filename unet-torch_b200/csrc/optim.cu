@@ -1,0 +1,151 @@
+// Fused optimizer step for the U-Net parameters (reference: train.py:341-347 builds
+// torch.optim.SGD, Trainer.py:719-725 steps it every iteration). One pass over a conv / convT weight does
+//   g' = g + wd*w ;  buf = mom*buf + (1-damp)*g'  (buf = g' on the first step) ;  w -= lr * (nesterov ? g' + mom*buf : buf)
+// in fp32 on the master parameter AND writes the two bf16 GEMM operands the tensor-core kernels consume (fprop and
+// dgrad layouts), so the separate re-cast pass (prep_conv3_kernel) and torch's foreach kernels disappear.
+// All global accesses are coalesced: the fp32 tensors are walked in their own order, the bf16 tile is transposed
+// through shared memory and written as 128-byte rows (operand 1) and 32-byte runs (operand 2).
+#include "../../include/b200unet.h"
+#include "host_common.h"
+
+#include <cuda_bf16.h>
+
+namespace {
+
+struct SgdHyper {
+  float lr, momentum, dampening, weight_decay;
+  int nesterov, first_step;
+};
+
+__device__ __forceinline__ float sgd_update(float& w, float g, float& buf, const SgdHyper& h) {
+  g = fmaf(h.weight_decay, w, g);
+  if (h.momentum != 0.f) {
+    buf = h.first_step ? g : fmaf(h.momentum, buf, (1.f - h.dampening) * g);
+    g = h.nesterov ? fmaf(h.momentum, buf, g) : buf;
+  }
+  w = fmaf(-h.lr, g, w);
+  return w;
+}
+
+// Parameter tensor w[A][B][TAPS] (fp32). Tile = 16 a x 64 b x TAPS.
+//   op1[a][tap][b]                                   (conv3: fprop operand [K][rs][C]; convT: dgrad operand [ci][ij][d])
+//   ROT ? op2[b][TAPS-1-tap][a] : op2[tap][b][a]     (conv3: dgrad operand [C][8-rs][K]; convT: fprop operand [ij][d][ci])
+template <int TAPS, bool ROT>
+__global__ void __launch_bounds__(256) sgd_weight_kernel(float* __restrict__ w, const float* __restrict__ g,
+                                                         float* __restrict__ buf, __nv_bfloat16* __restrict__ op1,
+                                                         __nv_bfloat16* __restrict__ op2, int A, int B, SgdHyper h) {
+  constexpr int TA = 16, TB = 64;
+  __shared__ __align__(16) __nv_bfloat16 sm[TA][TAPS][TB];
+  const int b0 = blockIdx.x * TB, a0 = blockIdx.y * TA;
+  for (int idx = threadIdx.x; idx < TA * TB * TAPS; idx += 256) {
+    const int aa = idx / (TB * TAPS), r = idx - aa * (TB * TAPS);
+    const int bb = r / TAPS, tap = r - bb * TAPS;
+    const size_t gi = (static_cast<size_t>(a0 + aa) * B + b0) * TAPS + r;
+    float wv = w[gi], bv = (buf != nullptr && !h.first_step) ? buf[gi] : 0.f;
+    if (g != nullptr) {
+      sgd_update(wv, g[gi], bv, h);
+      w[gi] = wv;
+      if (buf != nullptr) buf[gi] = bv;
+    }
+    sm[aa][tap][bb] = __float2bfloat16_rn(wv);
+  }
+  __syncthreads();
+  // operand 1: rows of 64 b (128 B), 8 threads per row
+  for (int idx = threadIdx.x; idx < TA * TAPS * 8; idx += 256) {
+    const int row = idx >> 3, ch = idx & 7;
+    const int aa = row / TAPS, tap = row - aa * TAPS;
+    *reinterpret_cast<uint4*>(op1 + (static_cast<size_t>(a0 + aa) * TAPS + tap) * B + b0 + ch * 8) =
+        *reinterpret_cast<const uint4*>(&sm[aa][tap][ch * 8]);
+  }
+  // operand 2: runs of 16 a (32 B) per (b, tap)
+  if (op2 != nullptr) {
+    for (int idx = threadIdx.x; idx < TB * TAPS * 2; idx += 256) {
+      const int half = idx & 1, pr = idx >> 1;
+      const int bb = pr % TB, tap = pr / TB;
+      __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = sm[half * 8 + i][tap][bb];
+      const size_t row = ROT ? (static_cast<size_t>(b0 + bb) * TAPS + (TAPS - 1 - tap))
+                             : (static_cast<size_t>(tap) * B + b0 + bb);
+      *reinterpret_cast<uint4*>(op2 + row * A + a0 + half * 8) = *reinterpret_cast<const uint4*>(v);
+    }
+  }
+}
+
+// small tensors (BatchNorm affine, biases, head, inc.conv1): up to 48 per launch, one block column per tensor
+struct SmallTable {
+  float* w[48];
+  const float* g[48];
+  float* buf[48];
+  int n[48];
+  int count;
+};
+
+__global__ void __launch_bounds__(256) sgd_small_kernel(SmallTable t, SgdHyper h) {
+  const int ti = blockIdx.y;
+  if (ti >= t.count) return;
+  float* w = t.w[ti];
+  const float* g = t.g[ti];
+  float* buf = t.buf[ti];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t.n[ti]; i += gridDim.x * blockDim.x) {
+    float wv = w[i], bv = (buf != nullptr && !h.first_step) ? buf[i] : 0.f;
+    sgd_update(wv, g[i], bv, h);
+    w[i] = wv;
+    if (buf != nullptr) buf[i] = bv;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200unet_sgd_conv3x3_weight(float* w_oihw, const float* grad, float* momentum_buf, void* w_fprop, void* w_dgrad,
+                                int K, int C, float lr, float momentum, float dampening, float weight_decay,
+                                int nesterov, int first_step, b200_stream_t stream) {
+  B2_REQUIRE(K % 16 == 0 && C % 64 == 0, "sgd_conv3x3_weight: K=%d must be a multiple of 16 and C=%d of 64", K, C);
+  B2_REQUIRE(w_oihw != nullptr && w_fprop != nullptr, "sgd_conv3x3_weight: null parameter / operand");
+  SgdHyper h{lr, momentum, dampening, weight_decay, nesterov, first_step};
+  dim3 grid(C / 64, K / 16);
+  sgd_weight_kernel<9, true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oihw, grad, momentum_buf, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), K, C, h);
+  return b2h::check_launch("sgd_conv3x3_weight");
+}
+
+int b200unet_sgd_convt2x2_weight(float* w, const float* grad, float* momentum_buf, void* w_fprop, void* w_dgrad,
+                                 int Cin, int Cup, float lr, float momentum, float dampening, float weight_decay,
+                                 int nesterov, int first_step, b200_stream_t stream) {
+  B2_REQUIRE(Cin % 16 == 0 && Cup % 64 == 0, "sgd_convt2x2_weight: Cin=%d must be a multiple of 16 and Cup=%d of 64", Cin, Cup);
+  B2_REQUIRE(w != nullptr && w_dgrad != nullptr, "sgd_convt2x2_weight: null parameter / operand");
+  SgdHyper h{lr, momentum, dampening, weight_decay, nesterov, first_step};
+  dim3 grid(Cup / 64, Cin / 16);
+  // parameter [Cin][Cup][4]: operand 1 = dgrad operand [ci][ij][d], operand 2 = fprop operand [ij][d][ci]
+  sgd_weight_kernel<4, false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, grad, momentum_buf, static_cast<__nv_bfloat16*>(w_dgrad), static_cast<__nv_bfloat16*>(w_fprop), Cin, Cup, h);
+  return b2h::check_launch("sgd_convt2x2_weight");
+}
+
+int b200unet_sgd_small(float* const* w, const float* const* grad, float* const* momentum_buf, const int* numel,
+                       int count, float lr, float momentum, float dampening, float weight_decay, int nesterov,
+                       int first_step, b200_stream_t stream) {
+  B2_REQUIRE(count >= 0, "sgd_small: negative count");
+  SgdHyper h{lr, momentum, dampening, weight_decay, nesterov, first_step};
+  for (int base = 0; base < count; base += 48) {
+    SmallTable t;
+    t.count = count - base < 48 ? count - base : 48;
+    int maxn = 1;
+    for (int i = 0; i < t.count; ++i) {
+      t.w[i] = w[base + i];
+      t.g[i] = grad[base + i];
+      t.buf[i] = momentum_buf ? momentum_buf[base + i] : nullptr;
+      t.n[i] = numel[base + i];
+      if (t.n[i] > maxn) maxn = t.n[i];
+    }
+    int bx = (maxn + 255) / 256;
+    if (bx > 64) bx = 64;
+    sgd_small_kernel<<<dim3(bx, t.count), 256, 0, static_cast<cudaStream_t>(stream)>>>(t, h);
+    if (int e = b2h::check_launch("sgd_small")) return e;
+  }
+  return 0;
+}
+
+}  // extern "C"

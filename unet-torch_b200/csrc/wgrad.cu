@@ -12,6 +12,8 @@
 #include "host_common.h"
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 using namespace b2;
@@ -284,6 +286,181 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   return b2h::check_launch("wgrad");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Cout = 64 layers (inc.conv2, up4.conv1, up4.conv2 at 512^2: 20 % of the wgrad FLOPs). With dy on the M side half of
+// every 128-row MMA would be idle, so the roles are swapped: M = x channels, N = the 64 dy channels.
+//   CB = 2 (Cin = 128): M = 128 x channels; one MMA per vertical tap r (A start = halo row k + r).
+//   CB = 1 (Cin = 64) : two vertical taps are STACKED in M: the second 64-row block of the MN-major A descriptor is
+//                       "the same 64 channels one image row further down" (LBO = one tile row = 2048 B), so taps
+//                       (0,1) are one M = 128 MMA and tap 2 rides in a second one (its upper half is discarded).
+// One CTA = one horizontal tap s and one split of the pixel tiles. Partials: [z][tap][Cin][64].
+template <int CB>
+struct WSPlan {
+  static constexpr int X_BOX = (TH + 2) * TW * 128;  // 20480
+  static constexpr int Y_BOX = BM * 128;             // 16384
+  static constexpr int STAGE = CB * X_BOX + Y_BOX;
+  static constexpr int NS_MAX = (227 * 1024 - 2048) / STAGE;
+  static constexpr int NS = NS_MAX > 6 ? 6 : NS_MAX;
+  static constexpr int NACC = (CB == 1) ? 2 : 3;
+  static constexpr int TMEM_COLS = (CB == 1) ? 128 : 256;
+  static constexpr int BAR_OFF = NS * STAGE;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int CB>
+__global__ void __launch_bounds__(192, 1) wgrad_swap_kernel(const __grid_constant__ WgradArgs args) {
+  using P = WSPlan<CB>;
+  constexpr int NS = P::NS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + P::BAR_OFF;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (NS + i); };
+  const uint32_t acc_full = bars + 8u * (2 * NS);
+  const uint32_t tmem_slot = acc_full + 8;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + P::BAR_OFF + 8 * (2 * NS) + 8);
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  const int s = blockIdx.x % 3, z = blockIdx.x / 3;
+  const int t_begin = static_cast<int>(static_cast<long long>(args.tiles_total) * z / args.splits);
+  const int t_end = static_cast<int>(static_cast<long long>(args.tiles_total) * (z + 1) / args.splits);
+
+  if (warp == 0 && elect_one_sync()) {
+    prefetch_tmap(&args.tmA);
+    prefetch_tmap(&args.tmB[0]);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(full(i), 1);
+      mbar_init(empty(i), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, P::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int st = 0, ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int twi = t % args.tiles_w;
+        const int thi = (t / args.tiles_w) % args.tiles_h;
+        const int img = t / (args.tiles_w * args.tiles_h);
+        const int h0 = thi * TH, w0 = twi * TW;
+        mbar_wait(empty(st), ph ^ 1);
+        mbar_arrive_expect_tx(full(st), P::STAGE);
+        const uint32_t sX = smem_base + st * P::STAGE;
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb)
+          tma_load_4d(sX + cb * P::X_BOX, &args.tmB[0], full(st), cb * 64, w0 + s - 1, h0 - 1, img);  // x, with halo
+        tma_load_4d(sX + CB * P::X_BOX, &args.tmA, full(st), 0, w0, h0, img);                          // dy
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t d_hi = umma_desc_hi_sw128(1024);
+      int st = 0, ph = 0;
+      uint32_t acc = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(full(st), ph);
+        tc_fence_after();
+        const uint32_t sX = smem_base + st * P::STAGE;
+        const uint32_t sY = sX + CB * P::X_BOX;
+#pragma unroll
+        for (int k = 0; k < BM / 16; ++k) {  // 16 pixels (one tile row) per MMA
+          const uint32_t b_lo = umma_desc_lo(sY + k * 2048, P::Y_BOX);
+          if (CB == 2) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              umma_bf16_lh(tmem_base + r * 64, umma_desc_lo(sX + (k + r) * 2048, P::X_BOX), d_hi, b_lo, d_hi, idesc, acc);
+          } else {
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr)
+              umma_bf16_lh(tmem_base + pr * 64, umma_desc_lo(sX + (k + 2 * pr) * 2048, 2048), d_hi, b_lo, d_hi, idesc, acc);
+          }
+          acc = 1;
+        }
+        umma_commit(empty(st));
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int Cin = args.Cb;
+#pragma unroll 1
+    for (int a = 0; a < P::NACC; ++a) {
+      int r, c;
+      if (CB == 2) { r = a; c = row; }
+      else { r = 2 * a + (row >> 6); c = row & 63; }
+      float* dst = args.partial + ((static_cast<size_t>(z) * 9 + (r * 3 + s)) * Cin + c) * 64;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + a * 64 + h * 32, v);
+        tmem_ld_wait();
+        if (r < 3) {
+          float4* d4 = reinterpret_cast<float4*>(dst + h * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, P::TMEM_COLS);
+}
+
+// partial [Z][9][C][64] -> dw OIHW [64][C][3][3]
+__global__ void reduce_conv3_swapped_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Z, int C) {
+  const int total = 9 * C * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int z = 0; z < Z; ++z) acc += partial[static_cast<size_t>(z) * total + i];
+    const int k = i & 63, c = (i >> 6) % C, rs = i / (64 * C);
+    dw[(static_cast<size_t>(k) * C + c) * 9 + rs] = acc;
+  }
+}
+
+template <int CB>
+int launch_wgrad_swap(const WgradArgs& a, cudaStream_t st) {
+  using P = WSPlan<CB>;
+  static bool configured = false;
+  auto kern = wgrad_swap_kernel<CB>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
+    if (e != cudaSuccess) {
+      b2h::set_error("wgrad_swap: cudaFuncSetAttribute(smem=%d): %s", P::TOTAL, cudaGetErrorString(e));
+      return 2;
+    }
+    configured = true;
+  }
+  kern<<<3 * a.splits, 192, P::TOTAL, st>>>(a);
+  return b2h::check_launch("wgrad_swap");
+}
+
+bool use_swap(int Cin, int Cout) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("B200UNET_NO_WGRAD_SWAP");
+    off = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return !off && Cout == 64 && (Cin == 64 || Cin == 128);
+}
+
 }  // namespace
 
 extern "C" {
@@ -310,6 +487,10 @@ static void conv3_wgrad_geometry(int N, int H, int W, int Cin, int Cout, int* bn
   *mtiles = b2h::ceil_div(Cout, 128);
   *ntiles = Cin / *bnc;
   *tiles = N * b2h::ceil_div(H, TH) * b2h::ceil_div(W, TW);
+  if (use_swap(Cin, Cout)) {
+    *mtiles = 1;
+    *ntiles = 1;
+  }
   *splits = pick_splits(*mtiles * *ntiles * 3, *tiles);
 }
 
@@ -336,6 +517,11 @@ int b200unet_conv3x3_wgrad(const void* x, int x_cs, const void* dy, int dy_cs, f
   if (int e = b2h::make_tmap_4d(&a.tmB[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TW, TH + 2)) return e;
   for (int i = 1; i < 4; ++i) a.tmB[i] = a.tmB[0];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_swap(Cin, Cout)) {
+    if (int e = (Cin == 64) ? launch_wgrad_swap<1>(a, st) : launch_wgrad_swap<2>(a, st)) return e;
+    reduce_conv3_swapped_kernel<<<b2h::ceil_div(9 * Cin * 64, 256), 256, 0, st>>>(partial, dw_oihw, a.splits, Cin);
+    return b2h::check_launch("conv3x3_wgrad_reduce");
+  }
   int e = (bnc == 128) ? launch_wgrad<KIND_CONV3, 128>(a, st) : launch_wgrad<KIND_CONV3, 64>(a, st);
   if (e) return e;
   const size_t total = static_cast<size_t>(Cout) * 9 * Cin;

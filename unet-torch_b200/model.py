@@ -90,10 +90,11 @@ class _ConvBN:
         key = (w._version, w.data_ptr())
         if key != self._ver:
             with torch.no_grad():
+                # the operand tensors are re-filled IN PLACE once they exist (captured CUDA graphs hold their addresses)
                 if self.first:  # inc.conv1 runs as a 1x1 GEMM over the im2col'ed input: [Cout, 64] operand, no dgrad
-                    self.wf, self.wd = ops.prep_first_weight(w.detach()), None
+                    self.wf, self.wd = ops.prep_first_weight(w.detach(), self.wf), None
                 else:
-                    self.wf, self.wd = ops.prep_conv3x3_weight(w.detach())
+                    self.wf, self.wd = ops.prep_conv3x3_weight(w.detach(), out=(self.wf, self.wd))
             self._ver = key
         return self.wf, self.wd
 
@@ -109,7 +110,7 @@ class _UpOp:
         key = (w._version, w.data_ptr())
         if key != self._ver:
             with torch.no_grad():
-                self.wf, self.wd = ops.prep_convt2x2_weight(w.detach())
+                self.wf, self.wd = ops.prep_convt2x2_weight(w.detach(), out=(self.wf, self.wd))
             self._ver = key
         return self.wf, self.wd
 
@@ -135,6 +136,35 @@ class UNetEngine:
         self.ups = [_UpOp(u.up) for u in ups]
         self.dec = [(_ConvBN(_dc(u.conv)[0], _dc(u.conv)[1], False), _ConvBN(_dc(u.conv)[3], _dc(u.conv)[4], False)) for u in ups]
         self.head = net.outc.conv
+        self._graphs = {}     # (shape, device, training, save) -> _GraphedStep
+        self._seen = set()    # keys that already ran once eagerly (kernel attributes configured, allocator warm)
+
+    def graphed_step(self, x, training, save):
+        """The captured step for this input, or None when the call must run eagerly: graphs disabled, data parallel
+        active (NCCL collectives are issued eagerly), or first call for this shape (eager warm-up)."""
+        net = self.net
+        if not net._cuda_graphs or not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+            return None
+        if training and DataParallelContext.current() is not None:
+            return None
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        key = (tuple(x.shape), x.device.index, bool(training), bool(save))
+        st = self._graphs.get(key)
+        if st is None:
+            if key not in self._seen:
+                self._seen.add(key)
+                return None
+            st = self._graphs[key] = _GraphedStep(self, x, training, save)
+        return st
+
+    def refresh_operands(self):
+        """Re-derive the bf16 GEMM operands of every parameter whose version changed (no-op otherwise)."""
+        for c1, c2 in self.enc + self.dec:
+            c1.operands()
+            c2.operands()
+        for u in self.ups:
+            u.operands()
 
     # parameters in the order their gradients are produced by backward (used for DP bucketing)
     def params_in_backward_order(self):
@@ -276,7 +306,7 @@ class UNetEngine:
 
         sync = (lambda s: dp.all_reduce_sum(s)) if (dp is not None and dp.sync_bn) else None
 
-        def bn_conv_bwd(cb: _ConvBN, rec, g1, g_pool, pool_idx, hh, ww, need_dx):
+        def bn_conv_bwd(cb: _ConvBN, rec, g1, g_pool, pool_idx, hh, ww, need_dx, dx_colsum=None):
             inp, y, scale, shift, mean, rstd, count = rec
             bn = cb.bn
             dgamma, dbeta = gbuf(bn.weight), gbuf(bn.bias)
@@ -293,8 +323,17 @@ class UNetEngine:
             if not need_dx:
                 return None
             _, wd = cb.operands()
-            dx = torch.empty((n, hh, ww, wd.shape[0]), dtype=BF16, device=dev)
-            ops.conv3x3(dy, wd, dx)
+            cdx = wd.shape[0]
+            dx = torch.empty((n, hh, ww, cdx), dtype=BF16, device=dev)
+            if dx_colsum is None:
+                ops.conv3x3(dy, wd, dx)
+            else:
+                # per-channel pixel sums of dx[..., lo:] from the conv epilogue's statistics rows (convT bias gradient)
+                lo, out = dx_colsum
+                rows = ops.conv3x3_stat_rows(n, hh, ww, dy.shape[3], cdx)
+                part = torch.empty(rows * 2 * cdx, dtype=torch.float32, device=dev)
+                ops.conv3x3(dy, wd, dx, part)
+                ops.partial_colsum(part, rows, 2 * cdx, lo, cdx - lo, out)
             return dx
 
         # ---- head
@@ -312,12 +351,11 @@ class UNetEngine:
             d_in, r1, r2, _ = saved.dec[j]
             c1, c2 = self.dec[j]
             g = bn_conv_bwd(c2, r2, g, None, None, hs[l], wsz[l], True)
-            dcat = bn_conv_bwd(c1, r1, g, None, None, hs[l], wsz[l], True)
-            skip_grads[l] = dcat[..., : ch[l]]
-            du = dcat[..., ch[l]:]
             upo = self.ups[j]
             db, dwu = gbuf(upo.up.bias), gbuf(upo.up.weight)
-            ops.channel_sum(du, db)
+            dcat = bn_conv_bwd(c1, r1, g, None, None, hs[l], wsz[l], True, dx_colsum=(ch[l], db))
+            skip_grads[l] = dcat[..., : ch[l]]
+            du = dcat[..., ch[l]:]
             ops.convt2x2_wgrad(d_in, du, dwu)
             grads[upo.up.bias], grads[upo.up.weight] = db, dwu
             done(upo.up.bias, upo.up.weight)
@@ -339,15 +377,76 @@ class UNetEngine:
         return grads
 
 
+class _GraphedStep:
+    """Forward (and backward) of one (input shape, mode) captured as CUDA graphs that share a private memory pool.
+
+    The ~270 launches of a step are mostly short; replaying them as a graph removes the host launch path and the
+    inter-kernel gaps. Everything a graph touches is static: the input is copied into `x`, activations / saved
+    tensors / gradients live in the pool, the bf16 weight operands are refreshed in place OUTSIDE the graph
+    (UNetEngine.refresh_operands) before each replay. One forward may be in flight per shape: a second forward
+    overwrites the saved activations of the first, so its backward is refused."""
+
+    def __init__(self, engine: "UNetEngine", x: torch.Tensor, training: bool, save: bool):
+        self.engine, self.training, self.save = engine, training, save
+        self.x = torch.empty_like(x)
+        self.pool = torch.cuda.graph_pool_handle()
+        self.fwd = self.bwd = None
+        self.logits = self.saved = self.dlogits = self.grads = None
+        self.epoch = 0
+        self.bwd_done_epoch = 0
+
+    def forward(self, x):
+        self.engine.refresh_operands()
+        self.x.copy_(x)
+        if self.fwd is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.pool):
+                self.logits, self.saved = self.engine.forward(self.x, self.training, self.save)
+            self.fwd = g
+        self.fwd.replay()
+        self.epoch += 1
+        return self.logits.clone()  # the caller may keep its logits across the next replay
+
+    def backward(self, epoch, dlogits):
+        if epoch != self.epoch:
+            raise RuntimeError("CUDA-graph mode keeps ONE set of saved activations per input shape: backward of an "
+                               "older forward was requested after a newer forward ran (disable graphs with "
+                               "net.enable_cuda_graphs(False) for this pattern)")
+        if self.bwd_done_epoch == epoch:
+            raise RuntimeError("UNet backward called twice: activations are consumed in place")
+        if self.dlogits is None:
+            self.dlogits = torch.empty_like(self.logits)
+        self.dlogits.copy_(dlogits)
+        if self.bwd is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.pool):
+                self.grads = self.engine.backward(self.saved, self.dlogits)
+            self.bwd = g
+        self.bwd.replay()
+        self.bwd_done_epoch = epoch
+        # the static gradient tensors stay referenced here, so autograd copies them into .grad instead of adopting them
+        return self.grads
+
+
 class _UNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine: UNetEngine, x, *params):
-        logits, saved = engine.forward(x, training=engine.net.training, save=True)
-        ctx.engine, ctx.saved, ctx.params = engine, saved, params
+        training = engine.net.training
+        step = engine.graphed_step(x, training, save=True)
+        if step is not None:
+            logits = step.forward(x)
+            ctx.step, ctx.epoch, ctx.saved = step, step.epoch, None
+        else:
+            logits, saved = engine.forward(x, training=training, save=True)
+            ctx.step, ctx.saved = None, saved
+        ctx.engine, ctx.params = engine, params
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
+        if ctx.step is not None:
+            grads = ctx.step.backward(ctx.epoch, dlogits.contiguous().float())
+            return (None, None) + tuple(grads.get(p) for p in ctx.params)
         if ctx.saved is None:
             raise RuntimeError("UNet backward called twice: activations are consumed in place")
         grads = ctx.engine.backward(ctx.saved, dlogits)
@@ -380,6 +479,15 @@ class UNet(nn.Module):
             setattr(self, name, mod)
             mod.apply(self.weights_init)
         self._engine = None
+        self._cuda_graphs = os.environ.get("B200UNET_CUDA_GRAPHS", "0") not in ("", "0")
+
+    def enable_cuda_graphs(self, flag: bool = True):
+        """Replay forward/backward as captured CUDA graphs (per input shape; first call of a shape runs eagerly).
+        Off by default: outputs are copies of static buffers and one forward per shape may be in flight."""
+        self._cuda_graphs = bool(flag)
+        if self._engine is not None:
+            self._engine._graphs.clear()
+        return self
 
     def weights_init(self, m):
         if isinstance(m, nn.Conv2d):  # Model.py:167-169: ConvTranspose2d keeps torch's default init
@@ -406,6 +514,9 @@ class UNet(nn.Module):
         params = eng.params_in_backward_order()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _UNetFn.apply(eng, x, *params)
+        step = eng.graphed_step(x, self.training, save=False)
+        if step is not None:
+            return step.forward(x)
         logits, _ = eng.forward(x, training=self.training, save=False)
         return logits
 

@@ -53,20 +53,25 @@ def conv3x3_stat_rows(n, h, w, cin, cout):
 
 
 # --------------------------------------------------------------------------------------------- weights
-def prep_conv3x3_weight(w: torch.Tensor, want_dgrad=True):
-    """fp32 OIHW [K,C,3,3] -> (fprop operand [K,3,3,C] bf16, dgrad operand [C,3,3,K] bf16 with rotated taps)."""
+def prep_conv3x3_weight(w: torch.Tensor, want_dgrad=True, out=(None, None)):
+    """fp32 OIHW [K,C,3,3] -> (fprop operand [K,3,3,C] bf16, dgrad operand [C,3,3,K] bf16 with rotated taps).
+    `out`: operand tensors of a previous call to refill in place."""
     k, c = w.shape[0], w.shape[1]
-    wf = torch.empty((k, 3, 3, c), dtype=BF16, device=w.device)
-    wd = torch.empty((c, 3, 3, k), dtype=BF16, device=w.device) if want_dgrad else None
+    wf, wd = out
+    if wf is None or wf.device != w.device:
+        wf = torch.empty((k, 3, 3, c), dtype=BF16, device=w.device)
+        wd = torch.empty((c, 3, 3, k), dtype=BF16, device=w.device) if want_dgrad else None
     _lib.call("b200unet_prep_conv3x3_weight", _f32(w), wf.data_ptr(), _ptr(wd), k, c, _stream())
     return wf, wd
 
 
-def prep_convt2x2_weight(w: torch.Tensor):
+def prep_convt2x2_weight(w: torch.Tensor, out=(None, None)):
     """fp32 [Cin,Cup,2,2] -> (fprop operand [4*Cup, Cin] bf16, dgrad operand [Cin, 4*Cup] bf16)."""
     cin, cup = w.shape[0], w.shape[1]
-    wf = torch.empty((4 * cup, cin), dtype=BF16, device=w.device)
-    wd = torch.empty((cin, 4 * cup), dtype=BF16, device=w.device)
+    wf, wd = out
+    if wf is None or wf.device != w.device:
+        wf = torch.empty((4 * cup, cin), dtype=BF16, device=w.device)
+        wd = torch.empty((cin, 4 * cup), dtype=BF16, device=w.device)
     _lib.call("b200unet_prep_convt2x2_weight", _f32(w), wf.data_ptr(), wd.data_ptr(), cin, cup, _stream())
     return wf, wd
 
@@ -145,10 +150,10 @@ def first_im2col(x_nchw: torch.Tensor, col: torch.Tensor):
     return col
 
 
-def prep_first_weight(w: torch.Tensor):
+def prep_first_weight(w: torch.Tensor, out=None):
     """fp32 OIHW [K,Cin,3,3] -> bf16 [K,64] operand matching first_im2col's columns."""
     k, cin = w.shape[0], w.shape[1]
-    w1 = torch.empty((k, 64), dtype=BF16, device=w.device)
+    w1 = out if (out is not None and out.device == w.device) else torch.empty((k, 64), dtype=BF16, device=w.device)
     _lib.call("b200unet_prep_first_weight", _f32(w), w1.data_ptr(), k, cin, _stream())
     return w1
 
@@ -270,6 +275,12 @@ def bn_relu_bwd(g1, g_pool, pool_idx, y, gamma, scale, shift, mean, rstd, dy, dg
     _lib.call("b200unet_bn_relu_bwd_apply", g1p, g1cs, _ptr(g_pool), _ptr(pool_idx), yp, ycs, _f32(gamma), _f32(scale),
               _f32(shift), _f32(mean), _f32(rstd), sums.data_ptr(), float(count), _ptr(sums_local), dp, dcs,
               _f32(dgamma), _f32(dbeta), n, h, w, c, _stream())
+
+
+def partial_colsum(stats_partial, rows, row_pitch, col_lo, n, out):
+    """out[c] = sum over the statistics rows of column col_lo + c (see conv3x3(stats_partial=...))."""
+    _lib.call("b200unet_partial_colsum", _f32(stats_partial), rows, row_pitch, col_lo, n, _f32(out), _stream())
+    return out
 
 
 def channel_sum(x, out):
