@@ -129,7 +129,9 @@ def test_first_layer_im2col_gemm_and_wgrad(ops, n, h, w, cin, cout):
     assert rel_l2(dw, wv.grad) < 1e-4
 
 
-UP_SHAPES = [(1, 8, 16, 128, 64), (2, 4, 8, 256, 128), (1, 12, 20, 128, 64)]
+UP_SHAPES = [(1, 8, 16, 128, 64), (2, 4, 8, 256, 128), (1, 12, 20, 128, 64),
+             # resident-weight variants with several tiles per CTA / the streaming kernel (Cin = 1024)
+             (3, 64, 72, 128, 64), (2, 32, 40, 256, 128), (1, 16, 24, 512, 256), (1, 8, 8, 1024, 512)]
 
 
 @pytest.mark.parametrize("n,h,w,cin,cup", UP_SHAPES)

@@ -36,16 +36,26 @@ struct TileGeom {
 };
 
 struct ResArgs {
-  CUtensorMap tmA, tmW, tmO;
+  CUtensorMap tmA[4];  // activations; [1..3] only for the 4-map gather (ConvTranspose2d backward-data)
+  CUtensorMap tmW;
+  CUtensorMap tmO[4];  // output; [1..3] only for the pixel-shuffle scatter (ConvTranspose2d forward)
   int tiles_w, tiles_h, tiles_total;
   int H, W;
-  int ncols;     // Cout
-  int ntiles_n;  // Cout / BN
-  int workers;   // CTAs per channel slice (grid = workers * ntiles_n)
-  float* stats;  // [workers][2][ncols] or null
+  int ncols;          // GEMM N (all output columns)
+  int ntiles_n;       // ncols / BN
+  int workers;        // CTAs per channel slice (grid = workers * ntiles_n)
+  int cup;            // UP: output channels per (i,j) sub-position
+  float* stats;       // [workers][2][ncols] or null
+  const float* bias;  // UP: [cup] or null
 };
 
-template <int BN, int KB, int NA, int OB, int TAPS>
+// What the GEMM is:            A operand per K block                      epilogue
+//   RES_CONV (TAPS 9 or 1)      tmA[0], channel block cb                   one output map, BN statistics
+//   RES_UP     (TAPS 1)         tmA[0], channel block cb                   + bias, one strided output map per (i,j)
+//   RES_GATHER (TAPS 1)         tmA[ij], K block kb = ij * (KB/4) + cb     one output map
+enum { RES_CONV = 0, RES_UP = 1, RES_GATHER = 2 };
+
+template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV>
 struct ResPlan {
   static constexpr int A_STAGE = TileGeom<TAPS>::A_STAGE;
   static constexpr int W_BYTES = TAPS * KB * BN * 128;
@@ -58,9 +68,11 @@ struct ResPlan {
   static_assert(4 * 2 * BN * 4 <= OUT_BYTES, "final statistics reduction aliases the staging buffer");
 };
 
-template <int BN, int KB, int NA, int OB, int TAPS>
+template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV>
 __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant__ ResArgs args) {
-  using P = ResPlan<BN, KB, NA, OB, TAPS>;
+  using P = ResPlan<BN, KB, NA, OB, TAPS, KIND>;
+  static_assert(KIND == RES_CONV || TAPS == 1, "the transposed-convolution GEMMs have no spatial taps");
+  static_assert(KIND != RES_GATHER || KB % 4 == 0, "gather: K blocks split evenly over the four (i,j) maps");
   using G = TileGeom<TAPS>;
   constexpr int A_STAGE = G::A_STAGE, A_BOX_BYTES = G::A_BOX_BYTES, IN_W = G::IN_W;
   extern __shared__ uint8_t smem_raw[];
@@ -86,9 +98,9 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
   const int ntiles_mine = (args.tiles_total - pw + args.workers - 1) / args.workers;  // tiles pw, pw+workers, ...
 
   if (warp == 0 && elect_one_sync()) {
-    prefetch_tmap(&args.tmA);
+    prefetch_tmap(&args.tmA[0]);
     prefetch_tmap(&args.tmW);
-    prefetch_tmap(&args.tmO);
+    prefetch_tmap(&args.tmO[0]);
     mbar_init(W_full, 1);
     for (int i = 0; i < NA; ++i) {
       mbar_init(A_full(i), 1);
@@ -129,11 +141,14 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
       for (int j = 0; j < ntiles_mine; ++j) {
         int img, h0, w0;
         tile_coords(j, img, h0, w0);
-#pragma unroll
+#pragma unroll 1
         for (int cb = 0; cb < KB; ++cb) {
           mbar_wait(A_empty(sa), pa ^ 1);
           mbar_arrive_expect_tx(A_full(sa), A_BOX_BYTES);
-          tma_load_4d(sA + sa * A_STAGE, &args.tmA, A_full(sa), cb * 64, w0 - G::HALO, h0 - G::HALO, img);
+          if (KIND == RES_GATHER)
+            tma_load_4d(sA + sa * A_STAGE, &args.tmA[cb / (KB / 4)], A_full(sa), (cb % (KB / 4)) * 64, w0, h0, img);
+          else
+            tma_load_4d(sA + sa * A_STAGE, &args.tmA[0], A_full(sa), cb * 64, w0 - G::HALO, h0 - G::HALO, img);
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
       }
@@ -155,7 +170,7 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         uint32_t acc = 0;
-#pragma unroll
+#pragma unroll(KB <= 2 ? KB : 1)
         for (int cb = 0; cb < KB; ++cb) {
           mbar_wait(A_full(sa), pa);
           tc_fence_after();
@@ -204,6 +219,11 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
           uint32_t v[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN + q * 64 + half * 32, v);
           tmem_ld_wait();
+          if (KIND == RES_UP && args.bias != nullptr) {
+            const float* bp = args.bias + (n0 + q * 64 + half * 32) % args.cup;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __ldg(bp + jj));
+          }
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * t + 0]), __uint_as_float(v[8 * t + 1]));
@@ -226,7 +246,14 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et == 0) {
 #pragma unroll
-        for (int q = 0; q < BN / 64; ++q) tma_store_4d(&args.tmO, stage + q * OUT_CHUNK, n0 + q * 64, w0, h0, img);
+        for (int q = 0; q < BN / 64; ++q) {
+          if (KIND == RES_UP) {  // column block -> (i,j) sub-position -> its strided (pixel-shuffle) output map
+            const int col = n0 + q * 64, ij = col / args.cup;
+            tma_store_4d(&args.tmO[ij], stage + q * OUT_CHUNK, col - ij * args.cup, w0, h0, img);
+          } else {
+            tma_store_4d(&args.tmO[0], stage + q * OUT_CHUNK, n0 + q * 64, w0, h0, img);
+          }
+        }
         tma_store_commit();
       }
       if (want_stats) {
@@ -282,11 +309,11 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-template <int BN, int KB, int NA, int OB, int TAPS>
+template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV>
 int launch_res(const ResArgs& a, cudaStream_t st) {
-  using P = ResPlan<BN, KB, NA, OB, TAPS>;
+  using P = ResPlan<BN, KB, NA, OB, TAPS, KIND>;
   static bool configured = false;
-  auto kern = conv3_res_kernel<BN, KB, NA, OB, TAPS>;
+  auto kern = conv3_res_kernel<BN, KB, NA, OB, TAPS, KIND>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) {
@@ -347,9 +374,12 @@ int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, 
   a.ncols = Cout;
   a.stats = stats_partial;
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
-  if (int e = make_tmap_4d(&a.tmA, x, Cin, W, H, N, xs, xs * W, xs * W * H, TileGeom<9>::IN_W, TileGeom<9>::IN_H)) return e;
+  a.cup = Cout;
+  a.bias = nullptr;
+  if (int e = make_tmap_4d(&a.tmA[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TileGeom<9>::IN_W, TileGeom<9>::IN_H)) return e;
   if (int e = make_tmap_2d(&a.tmW, w, static_cast<uint64_t>(9) * Cin, Cout, bn)) return e;
-  if (int e = make_tmap_4d(&a.tmO, y, Cout, W, H, N, ys, ys * W, ys * W * H, RTW, RTH)) return e;
+  if (int e = make_tmap_4d(&a.tmO[0], y, Cout, W, H, N, ys, ys * W, ys * W * H, RTW, RTH)) return e;
+  for (int i = 1; i < 4; ++i) { a.tmA[i] = a.tmA[0]; a.tmO[i] = a.tmO[0]; }
   if (Cin == 64 && bn == 64) return launch_res<64, 1, 4, 2, 9>(a, st);
   if (Cin == 64 && bn == 128) return launch_res<128, 1, 2, 1, 9>(a, st);
   return launch_res<64, 2, 2, 2, 9>(a, st);
@@ -373,10 +403,73 @@ int conv1x1_c64_launch(const void* x, int x_cs, const void* w, void* y, int y_cs
   a.ncols = Cout;
   a.stats = stats_partial;
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
-  if (int e = make_tmap_4d(&a.tmA, x, 64, W, H, N, xs, xs * W, xs * W * H, RTW, RTH)) return e;
+  a.cup = Cout;
+  a.bias = nullptr;
+  if (int e = make_tmap_4d(&a.tmA[0], x, 64, W, H, N, xs, xs * W, xs * W * H, RTW, RTH)) return e;
   if (int e = make_tmap_2d(&a.tmW, w, 64, Cout, 64)) return e;
-  if (int e = make_tmap_4d(&a.tmO, y, Cout, W, H, N, ys, ys * W, ys * W * H, RTW, RTH)) return e;
+  if (int e = make_tmap_4d(&a.tmO[0], y, Cout, W, H, N, ys, ys * W, ys * W * H, RTW, RTH)) return e;
+  for (int i = 1; i < 4; ++i) { a.tmA[i] = a.tmA[0]; a.tmO[i] = a.tmO[0]; }
   return launch_res<64, 1, 4, 2, 1>(a, st);
+}
+
+// ---- ConvTranspose2d(k2,s2) forward as a resident-weight GEMM with the pixel-shuffle scatter epilogue.
+// Applicable while a BN-column slice of the [4*Cup][Cin] operand fits next to the activation ring and every CTA's
+// activation re-reads stay cheap: Cin <= 512 (up2/up3/up4 of the U-Net; up1 streams through igemm.cu).
+bool convt_res_applicable(int Cin, int Cup) { return (Cin == 128 || Cin == 256 || Cin == 512) && Cup == Cin / 2; }
+
+int convt_res_fprop_launch(const void* x, int x_cs, const void* w_fprop, const float* bias, void* out, int out_cs, int N,
+                           int H, int W, int Cin, int Cup, int H2, int W2, int pad_top, int pad_left, cudaStream_t st) {
+  ResArgs a;
+  const int bn = (Cin == 128) ? 256 : 128;
+  res_geometry(N, H, W, bn, 4 * Cup, &a.ntiles_n, &a.workers, &a.tiles_total);
+  a.tiles_w = ceil_div(W, RTW);
+  a.tiles_h = ceil_div(H, RTH);
+  a.H = H;
+  a.W = W;
+  a.ncols = 4 * Cup;
+  a.cup = Cup;
+  a.stats = nullptr;
+  a.bias = bias;
+  const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, os = static_cast<uint64_t>(out_cs) * 2;
+  if (int e = make_tmap_4d(&a.tmA[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, RTW, RTH)) return e;
+  for (int i = 1; i < 4; ++i) a.tmA[i] = a.tmA[0];
+  if (int e = make_tmap_2d(&a.tmW, w_fprop, Cin, static_cast<uint64_t>(4) * Cup, bn)) return e;
+  for (int ij = 0; ij < 4; ++ij) {
+    const int i = ij >> 1, j = ij & 1;
+    const uint8_t* base = static_cast<const uint8_t*>(out) + (static_cast<uint64_t>(pad_top + i) * W2 + pad_left + j) * os;
+    if (int e = make_tmap_4d(&a.tmO[ij], base, Cup, W, H, N, 2 * os, 2 * os * W2, os * W2 * H2, RTW, RTH)) return e;
+  }
+  if (Cin == 128) return launch_res<256, 2, 4, 1, 1, RES_UP>(a, st);
+  if (Cin == 256) return launch_res<128, 4, 4, 1, 1, RES_UP>(a, st);
+  return launch_res<128, 8, 3, 1, 1, RES_UP>(a, st);
+}
+
+// ---- its backward-data: dx[p][ci] = sum_{ij,d} du[2h+i, 2w+j][d] W[ci][ij*Cup + d]; four strided gathers on the A side.
+bool convt_res_dgrad_applicable(int Cin, int Cup) { return (Cin == 128 || Cin == 256) && Cup == Cin / 2; }
+
+int convt_res_dgrad_launch(const void* du, int du_cs, const void* w_dgrad, void* dx, int dx_cs, int N, int H, int W,
+                           int Cin, int Cup, int H2, int W2, int pad_top, int pad_left, cudaStream_t st) {
+  ResArgs a;
+  res_geometry(N, H, W, 128, Cin, &a.ntiles_n, &a.workers, &a.tiles_total);
+  a.tiles_w = ceil_div(W, RTW);
+  a.tiles_h = ceil_div(H, RTH);
+  a.H = H;
+  a.W = W;
+  a.ncols = Cin;
+  a.cup = Cin;
+  a.stats = nullptr;
+  a.bias = nullptr;
+  const uint64_t us = static_cast<uint64_t>(du_cs) * 2, xs = static_cast<uint64_t>(dx_cs) * 2;
+  for (int ij = 0; ij < 4; ++ij) {
+    const int i = ij >> 1, j = ij & 1;
+    const uint8_t* base = static_cast<const uint8_t*>(du) + (static_cast<uint64_t>(pad_top + i) * W2 + pad_left + j) * us;
+    if (int e = make_tmap_4d(&a.tmA[ij], base, Cup, W, H, N, 2 * us, 2 * us * W2, us * W2 * H2, RTW, RTH)) return e;
+  }
+  if (int e = make_tmap_2d(&a.tmW, w_dgrad, static_cast<uint64_t>(4) * Cup, Cin, 128)) return e;
+  if (int e = make_tmap_4d(&a.tmO[0], dx, Cin, W, H, N, xs, xs * W, xs * W * H, RTW, RTH)) return e;
+  for (int i = 1; i < 4; ++i) a.tmO[i] = a.tmO[0];
+  if (Cin == 128) return launch_res<128, 4, 4, 1, 1, RES_GATHER>(a, st);
+  return launch_res<128, 8, 3, 1, 1, RES_GATHER>(a, st);
 }
 
 }  // namespace b2h

@@ -34,6 +34,13 @@ bool conv3_res_applicable(int Cin, int Cout);
 int conv3_res_stat_rows(int N, int H, int W, int Cin, int Cout);
 int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
                      int W, int Cin, int Cout, cudaStream_t st);
+// ... as ConvTranspose2d(k2,s2) forward (scatter epilogue) and backward-data (4-map gather) for the shallow levels
+bool convt_res_applicable(int Cin, int Cup);
+int convt_res_fprop_launch(const void* x, int x_cs, const void* w_fprop, const float* bias, void* out, int out_cs, int N,
+                           int H, int W, int Cin, int Cup, int H2, int W2, int pad_top, int pad_left, cudaStream_t st);
+bool convt_res_dgrad_applicable(int Cin, int Cup);
+int convt_res_dgrad_launch(const void* du, int du_cs, const void* w_dgrad, void* dx, int dx_cs, int N, int H, int W,
+                           int Cin, int Cup, int H2, int W2, int pad_top, int pad_left, cudaStream_t st);
 // the same kernel as a 1x1 convolution over a 64-channel input (inc.conv1 on its im2col'ed input, first_layer.cu)
 int conv1x1_c64_stat_rows(int N, int H, int W, int Cout);
 int conv1x1_c64_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,

@@ -368,6 +368,9 @@ int b200unet_convt2x2_fprop(const void* x, int x_cs, const void* w_fprop, const 
   B2_REQUIRE(pad_top >= 0 && pad_left >= 0 && 2 * H + pad_top <= H2 && 2 * W + pad_left <= W2,
              "convt2x2_fprop: upsampled map (%dx%d)+pad(%d,%d) does not fit canvas %dx%d", 2 * H, 2 * W, pad_top, pad_left, H2, W2);
   B2_REQUIRE(x_cs % 8 == 0 && out_cs % 8 == 0, "convt2x2_fprop: pitches must be multiples of 8");
+  if (use_resident(64, 64) && b2h::convt_res_applicable(Cin, Cup))
+    return b2h::convt_res_fprop_launch(x, x_cs, w_fprop, bias, out, out_cs, N, H, W, Cin, Cup, H2, W2, pad_top, pad_left,
+                                       static_cast<cudaStream_t>(stream));
   IgemmArgs a;
   a.tiles_w = b2h::ceil_div(W, TW);
   a.tiles_h = b2h::ceil_div(H, TH);
@@ -397,6 +400,9 @@ int b200unet_convt2x2_dgrad(const void* du, int du_cs, const void* w_dgrad, void
   B2_REQUIRE(Cin % 64 == 0 && Cup % 64 == 0, "convt2x2_dgrad: Cin (%d) and Cup (%d) must be multiples of 64", Cin, Cup);
   B2_REQUIRE(pad_top >= 0 && pad_left >= 0 && 2 * H + pad_top <= H2 && 2 * W + pad_left <= W2, "convt2x2_dgrad: bad canvas");
   B2_REQUIRE(du_cs % 8 == 0 && dx_cs % 8 == 0, "convt2x2_dgrad: pitches must be multiples of 8");
+  if (use_resident(64, 64) && b2h::convt_res_dgrad_applicable(Cin, Cup))
+    return b2h::convt_res_dgrad_launch(du, du_cs, w_dgrad, dx, dx_cs, N, H, W, Cin, Cup, H2, W2, pad_top, pad_left,
+                                       static_cast<cudaStream_t>(stream));
   IgemmArgs a;
   a.tiles_w = b2h::ceil_div(W, TW);
   a.tiles_h = b2h::ceil_div(H, TH);
