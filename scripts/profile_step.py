@@ -12,7 +12,7 @@ S = int(os.environ.get("S", 512))
 torch.manual_seed(0)
 net = U.UNet(3, 2).cuda().train()
 U.loss.CLASS_NUMBER = 2
-opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+opt = U.FusedSGD(net, lr=0.01, momentum=0.9, weight_decay=1e-4)
 x = torch.randn(B, 3, S, S, device="cuda")
 y = torch.randint(0, 2, (B, S, S), device="cuda").float()
 
