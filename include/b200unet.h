@@ -175,6 +175,42 @@ int b200unet_mse_bwd(const float* pred, const float* target, const float* grad_o
 /* ---- inference head (test_mc3serousv5.py:880-881): fp32 softmax over classes, then first-maximum argmax --- */
 int b200unet_softmax_argmax(const float* logits, int64_t* mask, int N, int ncls, int64_t HW, b200_stream_t stream);
 
+/* ---- generic fp32 path (generic_f32.cu): check mode and the slow-but-correct route for shapes outside the
+ * tensor-core path (H, W not divisible by 16 -> F.pad branch Model.py:69-73 and floor-mode pooling; widths that are not
+ * multiples of 64; dropout variants Model.py:34-39,81-82). NCHW fp32 like the reference; `*_ns` = batch stride in
+ * elements so that a channel range of the concat tensor is a valid view. One thread per output, fp64 reductions. */
+int b200unet_gen_conv3x3(const float* in, int64_t in_ns, const float* w, float* out, int64_t out_ns, int N, int Ci,
+    int Co, int H, int W, int transposed, b200_stream_t stream);
+int b200unet_gen_conv3x3_wgrad(const float* x, int64_t x_ns, const float* dy, int64_t dy_ns, float* dw, int N, int
+    Ci, int Co, int H, int W, b200_stream_t stream);
+int b200unet_gen_channel_stats(const float* y, int64_t y_ns, double* sums, int N, int C, int HW, b200_stream_t
+    stream);
+int b200unet_gen_bn_relu_fwd(const float* y, int64_t y_ns, const float* scale, const float* shift, float* a,
+    int64_t a_ns, int N, int C, int HW, b200_stream_t stream);
+int b200unet_gen_maxpool2x2(const float* a, int64_t a_ns, float* pooled, uint8_t* idx, int N, int C, int H, int W,
+    b200_stream_t stream);
+int b200unet_gen_unpool_add(const float* g_pooled, const uint8_t* idx, float* g, int64_t g_ns, int N, int C, int H,
+    int W, b200_stream_t stream);
+int b200unet_gen_bn_relu_bwd_reduce(const float* g, int64_t g_ns, const float* y, int64_t y_ns, const float* scale,
+    const float* shift, const float* mean, const float* rstd, double* sums, int N, int C, int HW, b200_stream_t
+    stream);
+int b200unet_gen_bn_relu_bwd_apply(const float* g, int64_t g_ns, const float* y, int64_t y_ns, const float* gamma,
+    const float* scale, const float* shift, const float* mean, const float* rstd, const double* sums, double count,
+    const double* sums_local, float* dy, int64_t dy_ns, float* dgamma, float* dbeta, int N, int C, int HW,
+    b200_stream_t stream);
+int b200unet_gen_convt2x2_fprop(const float* x, int64_t x_ns, const float* w, const float* bias, float* out,
+    int64_t out_ns, int N, int Cin, int Cup, int H, int W, int H2, int W2, int pad_top, int pad_left, b200_stream_t
+    stream);
+int b200unet_gen_convt2x2_dgrad(const float* du, int64_t du_ns, const float* w, float* dx, int64_t dx_ns, int N,
+    int Cin, int Cup, int H, int W, int H2, int W2, int pad_top, int pad_left, b200_stream_t stream);
+int b200unet_gen_convt2x2_wgrad(const float* x, int64_t x_ns, const float* du, int64_t du_ns, float* dw, float* db,
+    int N, int Cin, int Cup, int H, int W, int H2, int W2, int pad_top, int pad_left, b200_stream_t stream);
+int b200unet_gen_conv1x1_fwd(const float* a, int64_t a_ns, const float* w, const float* bias, float* z, int N, int
+    C, int J, int64_t HW, b200_stream_t stream);
+int b200unet_gen_conv1x1_bwd(const float* dz, const float* a, int64_t a_ns, const float* w, float* da, int64_t
+    da_ns, float* dw, float* db, int N, int C, int J, int64_t HW, b200_stream_t stream);
+int b200unet_gen_mul(float* x, int64_t x_ns, const float* mask, int N, int64_t CHW, b200_stream_t stream);
+
 /* ---- fused optimizer step (reference: torch.optim.SGD built in train.py:341-347, stepped in
  * Trainer.py:719-725). torch.optim.SGD arithmetic on the fp32 master parameter (weight decay, momentum, dampening,
  * nesterov; first_step = the momentum buffer is initialised with the gradient) fused with the bf16 re-cast of the

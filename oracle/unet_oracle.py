@@ -110,21 +110,40 @@ def _double_conv(sd, prefix, x, training, new_buffers):
     return x
 
 
-def unet_forward(sd, x, training=True):
-    """UNet.forward (Model.py:142-153) as a pure function of a reference-format state_dict (dropout=False).
+def unet_forward(sd, x, training=True, dropout_masks=None):
+    """UNet.forward (Model.py:142-153) as a pure function of a reference-format state_dict.
+    dropout_masks: None (dropout=False, or eval), or {"down1".."down4", "up1".."up4": multiplier tensors} applied where
+    the reference applies nn.Dropout: after the pooling of Down (Model.py:34-39) and after the concat of Up (:81-82).
     Returns (logits, dict of updated BatchNorm buffers)."""
     nb = {}
+    dci = 2 if "down1.maxpool_conv.2.double_conv.0.weight" in sd else 1  # dropout=True shifts the DoubleConv index
     x1 = _double_conv(sd, "inc.double_conv", x, training, nb)
     skips = [x1]
     cur = x1
     for i in range(1, 5):
         cur, _, _ = maxpool2x2(cur)
-        cur = _double_conv(sd, f"down{i}.maxpool_conv.1.double_conv", cur, training, nb)
+        if dropout_masks is not None:
+            cur = cur * dropout_masks[f"down{i}"]
+        cur = _double_conv(sd, f"down{i}.maxpool_conv.{dci}.double_conv", cur, training, nb)
         skips.append(cur)
     for i in range(1, 5):
         up = conv_transpose2x2(cur, sd[f"up{i}.up.weight"], sd[f"up{i}.up.bias"])
-        cur = _double_conv(sd, f"up{i}.conv.double_conv", pad_and_cat(skips[4 - i], up), training, nb)
+        cat = pad_and_cat(skips[4 - i], up)
+        if dropout_masks is not None:
+            cat = cat * dropout_masks[f"up{i}"]
+        cur = _double_conv(sd, f"up{i}.conv.double_conv", cat, training, nb)
     return conv1x1(cur, sd["outc.conv.weight"], sd["outc.conv.bias"]), nb
+
+
+def dropout_mask_shapes(n, h, w, width=64):
+    """Shapes of the tensors nn.Dropout sees, in the order the reference draws its masks (down1-4, then up1-4)."""
+    hs, ws = [h], [w]
+    for _ in range(4):
+        hs.append(hs[-1] // 2)
+        ws.append(ws[-1] // 2)
+    out = [(f"down{i}", (n, width << (i - 1), hs[i], ws[i])) for i in range(1, 5)]
+    out += [(f"up{i}", (n, width << (5 - i), hs[4 - i], ws[4 - i])) for i in range(1, 5)]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ losses

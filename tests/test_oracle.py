@@ -107,6 +107,36 @@ def test_live_reference_agrees():
     assert rel(got, want) < 1e-10
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/Model.py"), reason="reference not mounted")
+@pytest.mark.parametrize("h,w,dropout", [(37, 45, False), (32, 32, True), (50, 35, True)])
+def test_live_reference_odd_sizes_and_dropout(h, w, dropout):
+    """Pins the oracle's floor-mode pooling, the F.pad branch (Model.py:69-73) and the dropout placement
+    (Model.py:34-39, 81-82) to the unmodified reference: same seed -> same masks (CPU generator, same draw order)."""
+    sys.dont_write_bytecode = True
+    import importlib.util
+
+    import torch.nn.functional as F
+
+    spec = importlib.util.spec_from_file_location("_ref_model2", "/root/reference/Model.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    torch.manual_seed(4)
+    net = ref.UNet(3, 2, 4, dropout=dropout, dropout_p=0.3).double()
+    x = torch.randn(2, 3, h, w, dtype=torch.float64)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net.train()
+    torch.manual_seed(77)
+    want = net(x)
+    masks = None
+    if dropout:
+        torch.manual_seed(77)
+        masks = {name: F.dropout(torch.ones(shape, dtype=torch.float64), 0.3, True)
+                 for name, shape in O.dropout_mask_shapes(2, h, w, 4)}
+    got, _ = O.unet_forward(sd, x, training=True, dropout_masks=masks)
+    assert got.shape == want.shape == (2, 2, h, w)
+    assert rel(got, want) < 1e-10
+
+
 def test_cpu_baseline_port_matches_oracle():
     """bench.py's CPU baseline issues the torch library ops the reference calls; it must agree with the oracle."""
     from oracle import cpu_baseline as CB

@@ -65,6 +65,20 @@ SIGNATURES = {
     "b200unet_mse_fwd": (c_int, [_P, _P, _P, _P, _L, _I, _P]),
     "b200unet_mse_bwd": (c_int, [_P, _P, _P, _P, _L, _I, _P]),
     "b200unet_softmax_argmax": (c_int, [_P, _P, _I, _I, _L, _P]),
+    "b200unet_gen_conv3x3": (c_int, [_P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
+    "b200unet_gen_conv3x3_wgrad": (c_int, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _P]),
+    "b200unet_gen_channel_stats": (c_int, [_P, _L, _P, _I, _I, _I, _P]),
+    "b200unet_gen_bn_relu_fwd": (c_int, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _P]),
+    "b200unet_gen_maxpool2x2": (c_int, [_P, _L, _P, _P, _I, _I, _I, _I, _P]),
+    "b200unet_gen_unpool_add": (c_int, [_P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "b200unet_gen_bn_relu_bwd_reduce": (c_int, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200unet_gen_bn_relu_bwd_apply": (c_int, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _D, _P, _P, _L, _P, _P, _I, _I, _I, _P]),
+    "b200unet_gen_convt2x2_fprop": (c_int, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "b200unet_gen_convt2x2_dgrad": (c_int, [_P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "b200unet_gen_convt2x2_wgrad": (c_int, [_P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "b200unet_gen_conv1x1_fwd": (c_int, [_P, _L, _P, _P, _P, _I, _I, _I, _L, _P]),
+    "b200unet_gen_conv1x1_bwd": (c_int, [_P, _P, _L, _P, _P, _L, _P, _P, _I, _I, _I, _L, _P]),
+    "b200unet_gen_mul": (c_int, [_P, _L, _P, _I, _L, _P]),
     "b200unet_sgd_conv3x3_weight": (c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_sgd_convt2x2_weight": (c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_sgd_small": (c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _P]),

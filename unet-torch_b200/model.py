@@ -212,7 +212,8 @@ class UNetEngine:
             raise RuntimeError("the B200 UNet runs on CUDA (sm_100a) only; there is no CPU fallback")
         n, _, h, w = x.shape
         if h % 16 or w % 16:
-            raise ValueError(f"H and W must be multiples of 16 (got {h}x{w}); odd-size F.pad path not implemented")
+            raise ValueError(f"tensor-core engine: H and W must be multiples of 16 (got {h}x{w}); the generic engine "
+                             "takes other sizes")
         x = x.contiguous().float()
         dev = x.device
         dp = DataParallelContext.current() if training else None
@@ -430,7 +431,7 @@ class _GraphedStep:
 
 class _UNetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, engine: UNetEngine, x, *params):
+    def forward(ctx, engine, x, *params):
         training = engine.net.training
         step = engine.graphed_step(x, training, save=True)
         if step is not None:
@@ -479,6 +480,8 @@ class UNet(nn.Module):
             setattr(self, name, mod)
             mod.apply(self.weights_init)
         self._engine = None
+        self._generic = None
+        self._check_fp32 = os.environ.get("B200UNET_CHECK_FP32", "0") not in ("", "0")
         self._cuda_graphs = os.environ.get("B200UNET_CUDA_GRAPHS", "0") not in ("", "0")
 
     def enable_cuda_graphs(self, flag: bool = True):
@@ -493,24 +496,45 @@ class UNet(nn.Module):
         if isinstance(m, nn.Conv2d):  # Model.py:167-169: ConvTranspose2d keeps torch's default init
             nn.init.kaiming_normal_(m.weight)
 
+    def set_check_mode(self, flag: bool = True):
+        """fp32 check mode: run every operator with the generic fp32 CUDA-core kernels (reference precision)."""
+        self._check_fp32 = bool(flag)
+        return self
+
+    def _fast_supported(self) -> bool:
+        """Can the tensor-core engine run this architecture at all (input size is checked per call)?"""
+        return (self.initial_feature_map % 64 == 0 and self.n_channels <= 7 and self.n_classes <= 8 and not self.dropout)
+
     def _get_engine(self) -> UNetEngine:
+        """The tensor-core engine; raises if the architecture is outside its envelope."""
         if self._engine is None:
-            if self.initial_feature_map % 64 != 0:
-                raise ValueError("initial_feature_map must be a multiple of 64 for the tensor-core path")
-            if self.n_channels > 7 or self.n_classes > 8:
-                raise ValueError("n_channels <= 7 and n_classes <= 8 are supported")
-            if self.dropout:
-                raise NotImplementedError("dropout=True variant is not implemented in the B200 path")
+            if not self._fast_supported():
+                raise ValueError("tensor-core engine needs initial_feature_map % 64 == 0, n_channels <= 7, "
+                                 "n_classes <= 8 and dropout=False; other variants run on the generic fp32 engine")
             object.__setattr__(self, "_engine", UNetEngine(self))
         return self._engine
+
+    def _engine_for(self, x):
+        """Tensor-core engine when the architecture and this input fit it, otherwise (or in check mode) the generic
+        fp32 engine. Both are CUDA kernels of this library; there is no PyTorch / CPU fallback."""
+        fast = (not self._check_fp32 and self._fast_supported() and x.dim() == 4 and x.shape[2] % 16 == 0
+                and x.shape[3] % 16 == 0)
+        if fast:
+            return self._get_engine()
+        if self._generic is None:
+            from .generic import GenericEngine
+
+            object.__setattr__(self, "_generic", GenericEngine(self))
+        return self._generic
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         object.__setattr__(self, "_engine", None)  # parameters may have been re-created (.to / .half / ...)
+        object.__setattr__(self, "_generic", None)
         return out
 
     def forward(self, x):
-        eng = self._get_engine()
+        eng = self._engine_for(x)
         params = eng.params_in_backward_order()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _UNetFn.apply(eng, x, *params)

@@ -30,8 +30,10 @@ class FusedSGD(torch.optim.Optimizer):
 
     def _plan(self):
         """(big, small): big = [(param, holder, kind)] for tensor-core operands, small = every other parameter."""
-        eng = self.net._get_engine()
         big = {}
+        if not self.net._fast_supported() or self.net._check_fp32:
+            return big  # generic fp32 engine: no bf16 operands to maintain, every tensor takes the plain update
+        eng = self.net._get_engine()
         for c1, c2 in eng.enc + eng.dec:
             for cb in (c1, c2):
                 if not cb.first:
