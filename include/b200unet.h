@@ -175,6 +175,19 @@ int b200unet_mse_bwd(const float* pred, const float* target, const float* grad_o
 /* ---- inference head (test_mc3serousv5.py:880-881): fp32 softmax over classes, then first-maximum argmax --- */
 int b200unet_softmax_argmax(const float* logits, int64_t* mask, int N, int ncls, int64_t HW, b200_stream_t stream);
 
+/* ---- SyncBN over NVLink peer memory (nvl_sync.cu): one-shot all-reduce of a small fp64 vector through
+ * symmetric buffers mapped into every rank (peer_bufs = HOST array of `world` device pointers, index = rank; each
+ * buffer b200unet_nvl_buffer_bytes() bytes, zeroed once before first use), optionally fused with the BatchNorm
+ * finalisation of b200unet_bn_finalize. `seq` = 1, 2, 3, ... must advance identically on all ranks. One kernel per
+ * rank; it spins (bounded) until every peer has published, so each rank must run on its own GPU. */
+int64_t b200unet_nvl_buffer_bytes(void);
+int b200unet_nvl_allreduce_f64(const double* local, double* out, int n, void* const* peer_bufs, int world, int rank,
+                               int64_t seq, b200_stream_t stream);
+int b200unet_nvl_bn_sync_finalize(const double* local_sums, double* global_sums, void* const* peer_bufs, int world,
+                                  int rank, int64_t seq, double global_count, const float* gamma, const float* beta,
+                                  float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                                  float* rstd, float* scale, float* shift, int C, b200_stream_t stream);
+
 /* ---- generic fp32 path (generic_f32.cu): check mode and the slow-but-correct route for shapes outside the
  * tensor-core path (H, W not divisible by 16 -> F.pad branch Model.py:69-73 and floor-mode pooling; widths that are not
  * multiples of 64; dropout variants Model.py:34-39,81-82). NCHW fp32 like the reference; `*_ns` = batch stride in

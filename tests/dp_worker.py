@@ -22,6 +22,15 @@ def main():
     ctx = U.init_from_env(sync_bn=True, bucket_mb=4.0)
     assert ctx is not None and ctx.world_size == world
     dev = torch.device("cuda", local)
+    # ---- NVLink one-shot all-reduce (csrc/nvl_sync.cu) against NCCL, several rounds (both slots, growing sequence)
+    want_nvl = os.environ.get("B200UNET_NVL_SYNCBN", "1") not in ("", "0")
+    assert ctx.has_nvl == want_nvl, f"NVLink SyncBN path: has_nvl={ctx.has_nvl}, expected {want_nvl}"
+    for it, nel in enumerate((2048, 128, 2, 1000, 2048)):
+        v = (torch.arange(nel, dtype=torch.float64, device=dev) * 1e-3 + rank * 1000.5 + it) ** 2
+        ref = v.clone()
+        dist.all_reduce(ref)
+        ctx.all_reduce_sum(v)  # fp64, <= 2048 elements: NVLink kernel when available
+        assert torch.equal(v, ref) or float((v - ref).abs().max() / ref.abs().max()) < 1e-15, (it, nel)
     per, hw = 2, 48
     torch.manual_seed(0)
     net = U.UNet(3, 2).to(dev).train()

@@ -1,0 +1,165 @@
+// Synchronised BatchNorm over NVLink / NVSwitch peer memory: one-shot all-reduce of the per-channel fp64 statistics
+// fused with the BatchNorm finalisation, in ONE kernel per rank (SURVEY.md section 8e ii/iii; reference semantics:
+// torch.nn.SyncBatchNorm over nn.BatchNorm2d, Model.py:17,21).
+//
+// A step issues 36 of these reductions (18 forward, 18 backward), each <= 16 KB and on the critical path, so they are
+// latency-bound: a NCCL call costs ~20-30 us of stream time, this kernel a few us. Every rank owns a symmetric buffer
+// (torch.distributed._symmetric_memory, mapped into all peers). Protocol for reduction number `seq` (slot = seq & 1):
+//   1. write my vector into slot[seq&1][my_rank] of EVERY rank's buffer (plain stores to mapped peer memory),
+//      __threadfence_system, then store-release `seq` into flag[slot][my_rank] of every rank;
+//   2. spin (acquire loads, bounded) until my own flag[slot][r] == seq for all r;
+//   3. sum the `world` vectors in rank order (bit-identical on all ranks), optionally finalise BatchNorm.
+// Two slots suffice: a rank can only reach reduction seq+2 after every peer has published seq+1, i.e. after every peer
+// has finished reading seq. Sequence numbers never repeat, so flags are never reset.
+#include "../../include/b200unet.h"
+#include "host_common.h"
+
+namespace {
+
+constexpr int MAX_WORLD = 8;
+constexpr int SLOT_DOUBLES = 2048;                                   // 2 * Cmax
+constexpr size_t FLAG_OFFSET = size_t(2) * MAX_WORLD * SLOT_DOUBLES * 8;  // bytes: data region first, then flags
+constexpr size_t BUFFER_BYTES = FLAG_OFFSET + 2 * MAX_WORLD * 8;
+
+struct PeerTable {
+  unsigned char* buf[MAX_WORLD];
+};
+
+struct FinalizeArgs {
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* mean;
+  float* rstd;
+  float* scale;
+  float* shift;
+  double count;  // GLOBAL element count per channel
+  float eps, momentum;
+  int C;         // 0 = plain all-reduce
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) nvl_allreduce_kernel(const double* __restrict__ local, double* __restrict__ out, int n,
+                                                           PeerTable peers, int world, int rank,
+                                                           unsigned long long seq, FinalizeArgs fin) {
+  const int slot = static_cast<int>(seq & 1ull);
+  const size_t my_off = (static_cast<size_t>(slot) * MAX_WORLD + rank) * SLOT_DOUBLES;
+  // 1. publish
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = local[i];
+    for (int p = 0; p < world; ++p) reinterpret_cast<double*>(peers.buf[p])[my_off + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world)
+    st_release_sys(reinterpret_cast<unsigned long long*>(peers.buf[threadIdx.x] + FLAG_OFFSET) + slot * MAX_WORLD + rank, seq);
+  // 2. wait for every rank's vector of this sequence number
+  if (threadIdx.x < world) {
+    const unsigned long long* f =
+        reinterpret_cast<const unsigned long long*>(peers.buf[rank] + FLAG_OFFSET) + slot * MAX_WORLD + threadIdx.x;
+    unsigned long long t0 = 0;
+    unsigned int it = 0;
+    while (ld_acquire_sys(f) != seq) {
+      if ((++it & 0xfffu) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) __trap();  // 20 s: a peer died; surface an error instead of hanging
+      }
+    }
+  }
+  __syncthreads();
+  // 3. reduce in rank order
+  const double* mine = reinterpret_cast<const double*>(peers.buf[rank]) + static_cast<size_t>(slot) * MAX_WORLD * SLOT_DOUBLES;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += ld_volatile_f64(mine + static_cast<size_t>(r) * SLOT_DOUBLES + i);
+    out[i] = s;
+  }
+  if (fin.C > 0) {
+    __syncthreads();  // out[] written by this block is read back below (same block: visible after the barrier)
+    const int C = fin.C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double m = out[c] / fin.count;
+      double var = out[C + c] / fin.count - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mf = static_cast<float>(m);
+      const float rs = static_cast<float>(1.0 / sqrt(var + static_cast<double>(fin.eps)));
+      fin.mean[c] = mf;
+      fin.rstd[c] = rs;
+      const float sc = fin.gamma[c] * rs;
+      fin.scale[c] = sc;
+      fin.shift[c] = fin.beta[c] - mf * sc;
+      if (fin.running_mean != nullptr) {
+        const double unbiased = fin.count > 1.0 ? var * fin.count / (fin.count - 1.0) : var;
+        fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * mf;
+        fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * static_cast<float>(unbiased);
+      }
+    }
+  }
+}
+
+int fill_table(PeerTable* t, void* const* peer_bufs, int world, int rank, int n) {
+  if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) {
+    b2h::set_error("nvl: world %d / rank %d out of range (max %d ranks)", world, rank, MAX_WORLD);
+    return 1;
+  }
+  if (n < 1 || n > SLOT_DOUBLES) {
+    b2h::set_error("nvl: vector length %d out of range (max %d doubles)", n, SLOT_DOUBLES);
+    return 1;
+  }
+  for (int i = 0; i < MAX_WORLD; ++i) t->buf[i] = i < world ? static_cast<unsigned char*>(peer_bufs[i]) : nullptr;
+  for (int i = 0; i < world; ++i)
+    if (t->buf[i] == nullptr) {
+      b2h::set_error("nvl: null peer buffer %d", i);
+      return 1;
+    }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t b200unet_nvl_buffer_bytes(void) { return static_cast<int64_t>(BUFFER_BYTES); }
+
+int b200unet_nvl_allreduce_f64(const double* local, double* out, int n, void* const* peer_bufs, int world, int rank,
+                               int64_t seq, b200_stream_t stream) {
+  PeerTable t;
+  if (int e = fill_table(&t, peer_bufs, world, rank, n)) return e;
+  B2_REQUIRE(seq > 0, "nvl_allreduce_f64: sequence numbers start at 1");
+  FinalizeArgs fin{};
+  fin.C = 0;
+  nvl_allreduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(local, out, n, t, world, rank,
+                                                                        static_cast<unsigned long long>(seq), fin);
+  return b2h::check_launch("nvl_allreduce_f64");
+}
+
+int b200unet_nvl_bn_sync_finalize(const double* local_sums, double* global_sums, void* const* peer_bufs, int world,
+                                  int rank, int64_t seq, double global_count, const float* gamma, const float* beta,
+                                  float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                                  float* rstd, float* scale, float* shift, int C, b200_stream_t stream) {
+  PeerTable t;
+  if (int e = fill_table(&t, peer_bufs, world, rank, 2 * C)) return e;
+  B2_REQUIRE(seq > 0 && C > 0, "nvl_bn_sync_finalize: bad arguments");
+  FinalizeArgs fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, global_count, eps, momentum, C};
+  nvl_allreduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(local_sums, global_sums, 2 * C, t, world, rank,
+                                                                        static_cast<unsigned long long>(seq), fin);
+  return b2h::check_launch("nvl_bn_sync_finalize");
+}
+
+}  // extern "C"

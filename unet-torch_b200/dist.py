@@ -11,7 +11,9 @@ Works with the gloo backend on CPU tensors for the world_size-2 unit tests of th
 """
 from __future__ import annotations
 
+import ctypes
 import os
+import warnings
 
 import torch
 import torch.distributed as dist
@@ -87,6 +89,56 @@ class DataParallelContext:
         self.sync_bn = sync_bn and self.world_size > 1
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+        # SyncBN statistics over NVLink peer memory (csrc/nvl_sync.cu): symmetric buffer + peer pointer table
+        self._nvl = None
+        self._seq = 0
+        if (self.sync_bn and torch.cuda.is_available() and group is None and self.world_size <= 8
+                and dist.get_backend() == "nccl" and os.environ.get("B200UNET_NVL_SYNCBN", "1") not in ("", "0")):
+            self._setup_nvl()
+
+    def _setup_nvl(self):
+        """Allocate the symmetric buffer and exchange peer pointers. Any failure (no P2P, older torch) leaves the NCCL
+        path in place; the decision is made collectively so that all ranks take the same path."""
+        ok = 1
+        state = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            from . import _lib
+
+            nbytes = int(_lib.query("b200unet_nvl_buffer_bytes"))
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != self.world_size or any(p == 0 for p in ptrs):
+                raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+            state = (buf, hdl, (ctypes.c_void_p * self.world_size)(*ptrs))
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            warnings.warn(f"NVLink SyncBN path unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        torch.cuda.synchronize()  # buffers are zeroed everywhere before any peer can write
+        dist.barrier()
+        if int(flag.item()) == 1:
+            self._nvl = state
+
+    @property
+    def has_nvl(self):
+        return self._nvl is not None
+
+    def bn_sync_finalize(self, sums, global_count, bn, eps, momentum, track, mean, rstd, scale, shift):
+        """All-reduce the fp64 [sum, sum^2] vector over NVLink and finalise BatchNorm in the same kernel."""
+        from . import _lib
+
+        self._seq += 1
+        c = bn.num_features
+        _lib.call("b200unet_nvl_bn_sync_finalize", sums.data_ptr(), sums.data_ptr(), self._nvl[2], self.world_size,
+                  self.rank, self._seq, float(global_count), bn.weight.data_ptr(), bn.bias.data_ptr(), float(eps),
+                  float(momentum), bn.running_mean.data_ptr() if track else None,
+                  bn.running_var.data_ptr() if track else None, mean.data_ptr(), rstd.data_ptr(), scale.data_ptr(),
+                  shift.data_ptr(), c, torch.cuda.current_stream().cuda_stream)
 
     # ---- global registration
     @classmethod
@@ -107,6 +159,14 @@ class DataParallelContext:
 
     # ---- collectives
     def all_reduce_sum(self, t):
+        if (self._nvl is not None and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+                and 0 < t.numel() <= 2048):
+            from . import _lib
+
+            self._seq += 1
+            _lib.call("b200unet_nvl_allreduce_f64", t.data_ptr(), t.data_ptr(), t.numel(), self._nvl[2], self.world_size,
+                      self.rank, self._seq, torch.cuda.current_stream().cuda_stream)
+            return
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def make_flat_grads(self, params):

@@ -190,13 +190,18 @@ class UNetEngine:
             return scale, shift, None, None, count
         sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
         ops.bn_reduce_partials(stats_partial, rows, c, sums)
-        if dp is not None and dp.sync_bn:
-            dp.all_reduce_sum(sums)
-            count = count * dp.world_size
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         rstd = torch.empty(c, dtype=torch.float32, device=dev)
         mom = bn.momentum if bn.momentum is not None else 0.1
         track = bn.track_running_stats and bn.running_mean is not None
+        if dp is not None and dp.sync_bn:
+            count = count * dp.world_size
+            if dp.has_nvl:  # one kernel: NVLink one-shot all-reduce of [sum, sum^2] + finalisation
+                dp.bn_sync_finalize(sums, count, bn, bn.eps, mom, track, mean, rstd, scale, shift)
+                if track:
+                    bn.num_batches_tracked += 1
+                return scale, shift, mean, rstd, count
+            dp.all_reduce_sum(sums)
         ops.bn_finalize(sums, count, bn.weight, bn.bias, bn.eps, mom, bn.running_mean if track else None,
                         bn.running_var if track else None, mean, rstd, scale, shift)
         if track:
