@@ -157,9 +157,11 @@ int b200unet_channel_sum(const void* x, int x_cs, float* workspace, float* out, 
 
 /* ---- losses (loss.py:442-516) ----------------------------------------------------------------------------- */
 /* 'dice_bce_mc' (loss.py:488-500) and 'CE' (loss.py:468-469) forward. logits fp32 NCHW, target fp32 [N][H][W]
- * (class index stored as float, as the reference DataLoader produces). sums (fp64, 1+3*ncls): [sum CE,
- * I_c, Z_c, Y_c]. loss_out[0] = total loss, [1] = CE, [2] = Dice. mode: 0 = 0.5*CE+0.5*Dice, 1 = CE only.
+ * (class index stored as float, as the reference DataLoader produces). sums: fp64 scratch of
+ * b200unet_loss_sums_doubles() doubles ([sum CE, I_c, Z_c, Y_c], one scalar per 128-byte line), handed unchanged to
+ * the backward. loss_out[0] = total loss, [1] = CE, [2] = Dice. mode: 0 = 0.5*CE+0.5*Dice, 1 = CE only.
  * err_flag: set to 1 if a target is outside [0, ncls) (the reference raises). */
+int b200unet_loss_sums_doubles(void);
 int b200unet_loss_ce_dice_fwd(const float* logits, const float* target, double* sums, float* loss_out,
                               int* err_flag, int N, int ncls, int64_t HW, int mode, b200_stream_t stream);
 /* dlogits = grad_out[0] * dL/dlogits. */

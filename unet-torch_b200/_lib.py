@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200unet_partial_colsum": (c_int, [_P, _L, _I, _I, _I, _P, _P]),
     "b200unet_channel_sum_workspace_floats": (c_int64, [_I]),
     "b200unet_channel_sum": (c_int, [_P, _I, _P, _P, _L, _I, _P]),
+    "b200unet_loss_sums_doubles": (c_int, []),
     "b200unet_loss_ce_dice_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _P]),
     "b200unet_loss_ce_dice_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _P]),
     "b200unet_mse_fwd": (c_int, [_P, _P, _P, _P, _L, _I, _P]),

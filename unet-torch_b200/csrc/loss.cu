@@ -10,6 +10,10 @@
 namespace {
 
 constexpr int MAXC = 8;
+// every accumulated scalar lives in its own 128-byte line: fp64 atomics from ~1200 blocks to the SAME line serialise
+// (25 scalars in 2 lines cost ~100 us), spread over 25 lines they take a few us
+constexpr int SUM_STRIDE = 16;
+constexpr int SUM_SLOTS = 1 + 3 * MAXC;
 constexpr int LOSS_THREADS = 256;
 constexpr int LOSS_MAX_BLOCKS = 148 * 8;
 
@@ -29,7 +33,7 @@ __device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], int nv, doub
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < LOSS_THREADS / 32; ++w) t += static_cast<double>(sh[w][threadIdx.x]);
-    atomicAdd(dst + threadIdx.x, t);
+    atomicAdd(dst + threadIdx.x * SUM_STRIDE, t);
   }
 }
 
@@ -99,9 +103,9 @@ __global__ void ce_dice_finalize_kernel(const double* __restrict__ sums, float* 
   const double s = 1e-5;
   for (int j = 0; j < ncls; ++j) {
     // reference arithmetic is fp32; reproduce its rounding points on the large sums
-    const float I = static_cast<float>(sums[1 + j]);
-    const float Z = static_cast<float>(sums[1 + MAXC + j]);
-    const float Y = static_cast<float>(sums[1 + 2 * MAXC + j]);
+    const float I = static_cast<float>(sums[(1 + j) * SUM_STRIDE]);
+    const float Z = static_cast<float>(sums[(1 + MAXC + j) * SUM_STRIDE]);
+    const float Y = static_cast<float>(sums[(1 + 2 * MAXC + j) * SUM_STRIDE]);
     const float d = 1.f - (2.f * I + static_cast<float>(s)) / (Z + Y + static_cast<float>(s));
     dice += static_cast<double>(d);
   }
@@ -126,8 +130,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) ce_dice_bwd_kernel(const float* 
     cN[j] = 0.f;
     cD[j] = 0.f;
     if (j < ncls) {
-      const double N = 2.0 * sums[1 + j] + 1e-5;
-      const double D = sums[1 + MAXC + j] + sums[1 + 2 * MAXC + j] + 1e-5;
+      const double N = 2.0 * sums[(1 + j) * SUM_STRIDE] + 1e-5;
+      const double D = sums[(1 + MAXC + j) * SUM_STRIDE] + sums[(1 + 2 * MAXC + j) * SUM_STRIDE] + 1e-5;
       cN[j] = static_cast<float>(-(2.0 / ncls) / D);
       cD[j] = static_cast<float>((2.0 / ncls) * N / (D * D));
     }
@@ -221,14 +225,16 @@ int loss_blocks(long long n) {
 
 extern "C" {
 
-// `sums` must hold 1 + 3*8 doubles (fixed stride of 8 classes).
+// `sums` must hold b200unet_loss_sums_doubles() doubles: [CE, I[8], Z[8], Y[8]], one scalar per 128-byte line.
+int b200unet_loss_sums_doubles(void) { return SUM_SLOTS * SUM_STRIDE; }
+
 int b200unet_loss_ce_dice_fwd(const float* logits, const float* target, double* sums, float* loss_out, int* err_flag,
                               int N, int ncls, int64_t HW, int mode, b200_stream_t stream) {
   B2_REQUIRE(ncls >= 1 && ncls <= MAXC, "loss_ce_dice_fwd: n_classes=%d must be in [1,%d]", ncls, MAXC);
   B2_REQUIRE(mode == 0 || mode == 1, "loss_ce_dice_fwd: bad mode %d", mode);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long P = static_cast<long long>(N) * HW;
-  cudaMemsetAsync(sums, 0, sizeof(double) * (1 + 3 * MAXC), st);
+  cudaMemsetAsync(sums, 0, sizeof(double) * SUM_SLOTS * SUM_STRIDE, st);
   cudaMemsetAsync(err_flag, 0, sizeof(int), st);
   ce_dice_fwd_kernel<<<loss_blocks(P), LOSS_THREADS, 0, st>>>(logits, target, sums, err_flag, P, HW, ncls);
   if (int e = b2h::check_launch("loss_ce_dice_fwd")) return e;

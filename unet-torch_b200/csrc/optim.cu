@@ -27,27 +27,39 @@ __device__ __forceinline__ float sgd_update(float& w, float g, float& buf, const
   return w;
 }
 
-// Parameter tensor w[A][B][TAPS] (fp32). Tile = 16 a x 64 b x TAPS.
+// Parameter tensor w[A][B][TAPS] (fp32). Tile = 32 a x 64 b x TAPS, walked as float4's in the tensor's own order.
 //   op1[a][tap][b]                                   (conv3: fprop operand [K][rs][C]; convT: dgrad operand [ci][ij][d])
 //   ROT ? op2[b][TAPS-1-tap][a] : op2[tap][b][a]     (conv3: dgrad operand [C][8-rs][K]; convT: fprop operand [ij][d][ci])
 template <int TAPS, bool ROT>
 __global__ void __launch_bounds__(256) sgd_weight_kernel(float* __restrict__ w, const float* __restrict__ g,
                                                          float* __restrict__ buf, __nv_bfloat16* __restrict__ op1,
                                                          __nv_bfloat16* __restrict__ op2, int A, int B, SgdHyper h) {
-  constexpr int TA = 16, TB = 64;
+  constexpr int TA = 32, TB = 64;
+  constexpr int ROW4 = TB * TAPS / 4;  // float4's per a-row of the tile (contiguous in the parameter tensor)
   __shared__ __align__(16) __nv_bfloat16 sm[TA][TAPS][TB];
   const int b0 = blockIdx.x * TB, a0 = blockIdx.y * TA;
-  for (int idx = threadIdx.x; idx < TA * TB * TAPS; idx += 256) {
-    const int aa = idx / (TB * TAPS), r = idx - aa * (TB * TAPS);
-    const int bb = r / TAPS, tap = r - bb * TAPS;
-    const size_t gi = (static_cast<size_t>(a0 + aa) * B + b0) * TAPS + r;
-    float wv = w[gi], bv = (buf != nullptr && !h.first_step) ? buf[gi] : 0.f;
+  const bool have_buf = (buf != nullptr) && !h.first_step;
+  for (int v = threadIdx.x; v < TA * ROW4; v += 256) {
+    const int aa = v / ROW4, r4 = v - aa * ROW4;
+    const size_t gi = (static_cast<size_t>(a0 + aa) * B + b0) * TAPS + static_cast<size_t>(r4) * 4;
+    float4 w4 = *reinterpret_cast<const float4*>(w + gi);
     if (g != nullptr) {
-      sgd_update(wv, g[gi], bv, h);
-      w[gi] = wv;
-      if (buf != nullptr) buf[gi] = bv;
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + gi));
+      float4 b4 = have_buf ? *reinterpret_cast<const float4*>(buf + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sgd_update(w4.x, g4.x, b4.x, h);
+      sgd_update(w4.y, g4.y, b4.y, h);
+      sgd_update(w4.z, g4.z, b4.z, h);
+      sgd_update(w4.w, g4.w, b4.w, h);
+      *reinterpret_cast<float4*>(w + gi) = w4;
+      if (buf != nullptr) *reinterpret_cast<float4*>(buf + gi) = b4;
     }
-    sm[aa][tap][bb] = __float2bfloat16_rn(wv);
+    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = r4 * 4 + e;
+      const int bb = r / TAPS, tap = r - bb * TAPS;
+      sm[aa][tap][bb] = __float2bfloat16_rn(wv[e]);
+    }
   }
   __syncthreads();
   // operand 1: rows of 64 b (128 B), 8 threads per row
@@ -57,17 +69,17 @@ __global__ void __launch_bounds__(256) sgd_weight_kernel(float* __restrict__ w, 
     *reinterpret_cast<uint4*>(op1 + (static_cast<size_t>(a0 + aa) * TAPS + tap) * B + b0 + ch * 8) =
         *reinterpret_cast<const uint4*>(&sm[aa][tap][ch * 8]);
   }
-  // operand 2: runs of 16 a (32 B) per (b, tap)
+  // operand 2: runs of 32 a (64 B) per (b, tap), four 16-byte stores each
   if (op2 != nullptr) {
-    for (int idx = threadIdx.x; idx < TB * TAPS * 2; idx += 256) {
-      const int half = idx & 1, pr = idx >> 1;
+    for (int idx = threadIdx.x; idx < TB * TAPS * 4; idx += 256) {
+      const int q = idx & 3, pr = idx >> 2;
       const int bb = pr % TB, tap = pr / TB;
       __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = sm[half * 8 + i][tap][bb];
+      for (int i = 0; i < 8; ++i) v[i] = sm[q * 8 + i][tap][bb];
       const size_t row = ROT ? (static_cast<size_t>(b0 + bb) * TAPS + (TAPS - 1 - tap))
                              : (static_cast<size_t>(tap) * B + b0 + bb);
-      *reinterpret_cast<uint4*>(op2 + row * A + a0 + half * 8) = *reinterpret_cast<const uint4*>(v);
+      *reinterpret_cast<uint4*>(op2 + row * A + a0 + q * 8) = *reinterpret_cast<const uint4*>(v);
     }
   }
 }
@@ -102,10 +114,10 @@ extern "C" {
 int b200unet_sgd_conv3x3_weight(float* w_oihw, const float* grad, float* momentum_buf, void* w_fprop, void* w_dgrad,
                                 int K, int C, float lr, float momentum, float dampening, float weight_decay,
                                 int nesterov, int first_step, b200_stream_t stream) {
-  B2_REQUIRE(K % 16 == 0 && C % 64 == 0, "sgd_conv3x3_weight: K=%d must be a multiple of 16 and C=%d of 64", K, C);
+  B2_REQUIRE(K % 32 == 0 && C % 64 == 0, "sgd_conv3x3_weight: K=%d must be a multiple of 32 and C=%d of 64", K, C);
   B2_REQUIRE(w_oihw != nullptr && w_fprop != nullptr, "sgd_conv3x3_weight: null parameter / operand");
   SgdHyper h{lr, momentum, dampening, weight_decay, nesterov, first_step};
-  dim3 grid(C / 64, K / 16);
+  dim3 grid(C / 64, K / 32);
   sgd_weight_kernel<9, true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w_oihw, grad, momentum_buf, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), K, C, h);
   return b2h::check_launch("sgd_conv3x3_weight");
@@ -114,10 +126,10 @@ int b200unet_sgd_conv3x3_weight(float* w_oihw, const float* grad, float* momentu
 int b200unet_sgd_convt2x2_weight(float* w, const float* grad, float* momentum_buf, void* w_fprop, void* w_dgrad,
                                  int Cin, int Cup, float lr, float momentum, float dampening, float weight_decay,
                                  int nesterov, int first_step, b200_stream_t stream) {
-  B2_REQUIRE(Cin % 16 == 0 && Cup % 64 == 0, "sgd_convt2x2_weight: Cin=%d must be a multiple of 16 and Cup=%d of 64", Cin, Cup);
+  B2_REQUIRE(Cin % 32 == 0 && Cup % 64 == 0, "sgd_convt2x2_weight: Cin=%d must be a multiple of 32 and Cup=%d of 64", Cin, Cup);
   B2_REQUIRE(w != nullptr && w_dgrad != nullptr, "sgd_convt2x2_weight: null parameter / operand");
   SgdHyper h{lr, momentum, dampening, weight_decay, nesterov, first_step};
-  dim3 grid(Cup / 64, Cin / 16);
+  dim3 grid(Cup / 64, Cin / 32);
   // parameter [Cin][Cup][4]: operand 1 = dgrad operand [ci][ij][d], operand 2 = fprop operand [ij][d][ci]
   sgd_weight_kernel<4, false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, grad, momentum_buf, static_cast<__nv_bfloat16*>(w_dgrad), static_cast<__nv_bfloat16*>(w_fprop), Cin, Cup, h);

@@ -178,17 +178,25 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   if (warp == 1) tmem_dealloc(tmem_base, P::TMEM_COLS);
 }
 
-// partial [Z][K][9][C] -> dw OIHW [K][C][3][3]
-__global__ void reduce_conv3_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Z, int K, int C) {
+// partial [Z][K][9][C] -> dw OIHW [K][C][3][3]. Block = one k x 64 channels: the 9 x 64 sums are read as nine coalesced
+// 256-byte rows per split, transposed through smem and written as one contiguous 576-float run of the OIHW tensor.
+__global__ void __launch_bounds__(192) reduce_conv3_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Z,
+                                                           int K, int C) {
+  __shared__ float t[9][65];
+  const int c0 = blockIdx.x * 64, k = blockIdx.y;
   const size_t total = static_cast<size_t>(K) * 9 * C;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  for (int idx = threadIdx.x; idx < 576; idx += 192) {
+    const int rs = idx >> 6, cc = idx & 63;
+    const float* p = partial + (static_cast<size_t>(k) * 9 + rs) * C + c0 + cc;
     float acc = 0.f;
-    for (int z = 0; z < Z; ++z) acc += partial[z * total + i];
-    const int c = static_cast<int>(i % C);
-    const int rs = static_cast<int>((i / C) % 9);
-    const size_t k = i / (static_cast<size_t>(C) * 9);
-    dw[(k * C + c) * 9 + rs] = acc;
+    for (int z = 0; z < Z; ++z) acc += p[z * total];
+    t[rs][cc] = acc;
+  }
+  __syncthreads();
+  float* out = dw + (static_cast<size_t>(k) * C + c0) * 9;
+  for (int idx = threadIdx.x; idx < 576; idx += 192) {
+    const int cc = idx / 9, rs = idx - cc * 9;
+    out[idx] = t[rs][cc];
   }
 }
 // partial [Z][Cin][4][Cup] -> dw [Cin][Cup][2][2]
@@ -524,9 +532,7 @@ int b200unet_conv3x3_wgrad(const void* x, int x_cs, const void* dy, int dy_cs, f
   }
   int e = (bnc == 128) ? launch_wgrad<KIND_CONV3, 128>(a, st) : launch_wgrad<KIND_CONV3, 64>(a, st);
   if (e) return e;
-  const size_t total = static_cast<size_t>(Cout) * 9 * Cin;
-  const int blocks = static_cast<int>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  reduce_conv3_kernel<<<blocks, 256, 0, st>>>(partial, dw_oihw, a.splits, Cout, Cin);
+  reduce_conv3_kernel<<<dim3(Cin / 64, Cout), 192, 0, st>>>(partial, dw_oihw, a.splits, Cout, Cin);
   return b2h::check_launch("conv3x3_wgrad_reduce");
 }
 

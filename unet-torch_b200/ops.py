@@ -293,7 +293,7 @@ def channel_sum(x, out):
 # --------------------------------------------------------------------------------------------- losses / inference
 def loss_ce_dice_fwd(logits, target, mode):
     n, ncls, h, w = logits.shape
-    sums = torch.empty((25,), dtype=torch.float64, device=logits.device)
+    sums = torch.empty((_lib.query("b200unet_loss_sums_doubles"),), dtype=torch.float64, device=logits.device)
     out = torch.empty((3,), dtype=torch.float32, device=logits.device)
     err = torch.empty((1,), dtype=torch.int32, device=logits.device)
     _lib.call("b200unet_loss_ce_dice_fwd", _f32(logits), _f32(target), sums.data_ptr(), out.data_ptr(), err.data_ptr(),
