@@ -316,6 +316,21 @@ bool use_resident(int Cin, int Cout) {
   return !off && b2h::conv3_res_applicable(Cin, Cout);
 }
 
+// CTA pairs (conv3_res2.cu) for the resident-weight layers. Measured on B200 (profiles/): pairs win 25-35 % when a
+// tile carries two K blocks (Cin = 128: 128->128, 128->256 and 128->64 up to 256^2), and lose when the per-tile MMA
+// burst is short (Cin = 64) or for 128->64 at 512^2 and above, where the cluster-wide barrier round trip per tile is
+// exposed. B200UNET_RES2=0 / 1 forces the choice off / on for every resident-weight layer.
+bool use_pairs(int N, int H, int W, int Cin, int Cout) {
+  static int mode = -2;
+  if (mode == -2) {
+    const char* e = getenv("B200UNET_RES2");
+    mode = e ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }
+  if (mode >= 0) return mode == 1;
+  if (Cin != 128) return false;
+  return Cout >= 128 || static_cast<long long>(N) * H * W <= 16ll * 256 * 256;
+}
+
 int pick_bn(int ncols, int limit) {
   int want = env_bn();
   if (want != 64 && want != 128 && want != 256) want = 128;
@@ -333,8 +348,11 @@ int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int 
   B2_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv3x3_igemm: Cin (%d) and Cout (%d) must be multiples of 64", Cin, Cout);
   B2_REQUIRE(N > 0 && H > 0 && W > 0, "conv3x3_igemm: empty tensor");
   B2_REQUIRE(x_cs >= Cin && y_cs >= Cout && x_cs % 8 == 0 && y_cs % 8 == 0, "conv3x3_igemm: bad pitches %d %d", x_cs, y_cs);
-  if (use_resident(Cin, Cout))
+  if (use_resident(Cin, Cout)) {
+    if (use_pairs(N, H, W, Cin, Cout))
+      return b2h::conv3_res2_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream));
     return b2h::conv3_res_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream));
+  }
   IgemmArgs a;
   a.tiles_w = b2h::ceil_div(W, TW);
   a.tiles_h = b2h::ceil_div(H, TH);
@@ -357,7 +375,8 @@ int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int 
 }
 
 int b200unet_conv3x3_stat_rows(int N, int H, int W, int Cin, int Cout) {
-  if (use_resident(Cin, Cout)) return b2h::conv3_res_stat_rows(N, H, W, Cin, Cout);
+  if (use_resident(Cin, Cout))
+    return use_pairs(N, H, W, Cin, Cout) ? b2h::conv3_res2_stat_rows(N, H, W, Cin, Cout) : b2h::conv3_res_stat_rows(N, H, W, Cin, Cout);
   return N * b2h::ceil_div(H, TH) * b2h::ceil_div(W, TW);
 }
 

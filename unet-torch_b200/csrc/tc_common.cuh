@@ -178,3 +178,70 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 }  // namespace b2
+
+// ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a 2-CTA cluster (one TPC) drive ONE 256-row MMA: each provides its 128 rows of A and half of the B rows
+// from its own shared memory, and holds its 128 accumulator rows in its own TMEM. Only the leader (cluster rank 0)
+// issues MMAs; operand-arrival barriers live in the leader, release barriers are signalled in both CTAs by a
+// multicast commit. PTX forms follow CUTLASS (cute/arch/copy_sm100_tma.hpp, cutlass/arch/barrier.h).
+namespace b2 {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_dst, uint32_t ncols) {  // same warp id in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_lh_2cta(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{ .reg .pred p; .reg .b64 da, db; mov.b64 da, {%1, %2}; mov.b64 db, {%3, %4}; setp.ne.b32 p, %6, 0; "
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p; }" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once) on the barrier at this smem offset in BOTH CTAs when all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// TMA loads into THIS CTA's smem whose completion bytes are credited to a barrier given as a shared::cluster address
+// (the leader's). 0x1000000000000000 = the default (EVICT_NORMAL) L2 policy.
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+      "l"(m), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(0x1000000000000000ull)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(m), "r"(cluster_bar), "r"(c0), "r"(c1), "l"(0x1000000000000000ull)
+      : "memory");
+}
+
+}  // namespace b2
