@@ -32,6 +32,10 @@ CONV_SHAPES = [
     (2, 40, 72, 64, 128),     # BN = 128, ragged rows
     (3, 64, 64, 128, 64),     # two K blocks per tile
     (2, 48, 64, 128, 256),    # four channel slices share each pixel tile
+    # deep-layer shapes (streaming kernels; CTA pairs with B200UNET_PAIR=1): odd tile count, BN = 256 and 128
+    (3, 16, 24, 256, 256),
+    (1, 32, 40, 512, 128),
+    (2, 16, 16, 256, 512),
 ]
 
 

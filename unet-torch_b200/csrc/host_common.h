@@ -38,6 +38,11 @@ int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, 
 int conv3_res2_stat_rows(int N, int H, int W, int Cin, int Cout);
 int conv3_res2_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
                       int W, int Cin, int Cout, cudaStream_t st);
+// conv3_pair.cu: streaming CTA-pair kernel for Cin >= 256
+bool conv3_pair_applicable(int Cin, int Cout);
+int conv3_pair_stat_rows(int N, int H, int W, int Cin, int Cout);
+int conv3_pair_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
+                      int W, int Cin, int Cout, cudaStream_t st);
 // ... as ConvTranspose2d(k2,s2) forward (scatter epilogue) and backward-data (4-map gather) for the shallow levels
 bool convt_res_applicable(int Cin, int Cup);
 int convt_res_fprop_launch(const void* x, int x_cs, const void* w_fprop, const float* bias, void* out, int out_cs, int N,

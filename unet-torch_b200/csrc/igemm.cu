@@ -331,6 +331,16 @@ bool use_pairs(int N, int H, int W, int Cin, int Cout) {
   return Cout >= 128 || static_cast<long long>(N) * H * W <= 16ll * 256 * 256;
 }
 
+// streaming CTA-pair kernel (conv3_pair.cu) for the deep layers; B200UNET_PAIR=0 keeps the one-tile-per-CTA igemm
+bool use_stream_pairs(int Cin, int Cout) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("B200UNET_PAIR");
+    on = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  return on != 0 && b2h::conv3_pair_applicable(Cin, Cout);
+}
+
 int pick_bn(int ncols, int limit) {
   int want = env_bn();
   if (want != 64 && want != 128 && want != 256) want = 128;
@@ -353,6 +363,8 @@ int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int 
       return b2h::conv3_res2_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream));
     return b2h::conv3_res_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream));
   }
+  if (use_stream_pairs(Cin, Cout))
+    return b2h::conv3_pair_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream));
   IgemmArgs a;
   a.tiles_w = b2h::ceil_div(W, TW);
   a.tiles_h = b2h::ceil_div(H, TH);
@@ -377,6 +389,7 @@ int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int 
 int b200unet_conv3x3_stat_rows(int N, int H, int W, int Cin, int Cout) {
   if (use_resident(Cin, Cout))
     return use_pairs(N, H, W, Cin, Cout) ? b2h::conv3_res2_stat_rows(N, H, W, Cin, Cout) : b2h::conv3_res_stat_rows(N, H, W, Cin, Cout);
+  if (use_stream_pairs(Cin, Cout)) return b2h::conv3_pair_stat_rows(N, H, W, Cin, Cout);
   return N * b2h::ceil_div(H, TH) * b2h::ceil_div(W, TW);
 }
 
