@@ -16,6 +16,8 @@
 #include "host_common.h"
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 using namespace b2;
@@ -338,6 +340,9 @@ int max_pairs() {
     else
       n = 64;  // conservative
     cudaGetLastError();
+    const char* e = getenv("B200UNET_RESERVE_SMS");  // see conv3_res.cu num_sms()
+    const int r = e ? atoi(e) : 0;
+    if (r > 0 && r / 2 < n / 2) n -= (r + 1) / 2;
   }
   return n;
 }
