@@ -43,6 +43,16 @@ def peaks():
         return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def conv_traffic():
+    """DRAM bytes per conv3x3 fprop/dgrad launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the launches
+    of one step) from the committed ncu capture, or None if it has not been taken for this build."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons. The process is started before the warm-up (its start-up takes longer than
     a short timed region); only samples that ARRIVE between mark_begin() and mark_end() are reported."""
@@ -297,10 +307,12 @@ def run_ours(args):
     kms = sum(p[1].elapsed_time(p[2]) for p in prof)
     pk = peaks()
     achieved = flops / (kms / 1e3) / 1e12 if kms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "igemm_kernel<MODE_CONV3> (conv3x3 fprop+dgrad, tcgen05)",
+    roofline = {"bound": "tensor",
+                "kernel": "conv3x3 fprop+dgrad implicit GEMMs (conv3_pair / conv3_res2 / conv3_res kernels, tcgen05; "
+                          "34 launches per step, 12.3 of the 18.5 TFLOP of a step)",
                 "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
                 "peak_source": f"{pk['src']} bf16_tflops_sustained", "launches_timed": len(prof),
-                "share_of_step": (kms / 2) / ms_per_step, "traffic": None}
+                "share_of_step": (kms / 2) / ms_per_step, "traffic": conv_traffic()}
 
     if rank != 0:
         return 0

@@ -15,12 +15,18 @@ full() {  # name, kernel regex, skip (matching launches), count, extra flags
       > gpurun_out/${TAG}_ncu_$1.log 2>&1
   echo "full capture $1 rc=$?"
 }
-for what in ${FULL:-res igemm wgrad bn}; do
+# per-launch DRAM bytes of every conv3x3 fprop/dgrad launch of one step (34 launches; 4 steps precede: 1 eager + 3 warm-up)
+$CMD > gpurun_out/${TAG}_plain_convdram.log 2>&1 &&
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+    -k "regex:conv3_pair_kernel|conv3_res2_kernel|conv3_res_kernel<.*9, 0>" -s 136 -c 34 --csv \
+    --log-file gpurun_out/${TAG}_convdram.csv $CMD > gpurun_out/${TAG}_ncu_convdram.log 2>&1
+echo "conv dram rc=$?"
+for what in ${FULL:-pair res wgrad bn}; do
   case $what in
-    res)   full res   'conv3_res_kernel' 45 8 "" ;;
-    igemm) full igemm 'igemm_kernel' 84 6 "" ;;
-    wgrad) full wgrad 'wgrad_kernel' 66 5 "" ;;
-    bn)    full bn    'bn_bwd_apply_kernel|bn_bwd_reduce_kernel|bn_relu_fwd_kernel' 162 5 "" ;;
+    pair)  full pair  'conv3_pair_kernel' 80 7 "" ;;
+    res)   full res   'conv3_res2_kernel|conv3_res_kernel' 96 8 "" ;;
+    wgrad) full wgrad 'wgrad_kernel|wgrad_swap_kernel' 88 6 "" ;;
+    bn)    full bn    'bn_bwd_apply_kernel|bn_bwd_reduce_kernel|bn_relu_fwd_kernel' 216 5 "" ;;
   esac
 done
 # gpurun copies back at most 64 MiB: drop the largest reports until the directory fits
