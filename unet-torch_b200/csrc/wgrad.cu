@@ -298,20 +298,30 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------------
 // Cout = 64 layers (inc.conv2, up4.conv1, up4.conv2 at 512^2: 20 % of the wgrad FLOPs). With dy on the M side half of
 // every 128-row MMA would be idle, so the roles are swapped: M = x channels, N = the 64 dy channels.
-//   CB = 2 (Cin = 128): M = 128 x channels; one MMA per vertical tap r (A start = halo row k + r).
+// One CTA covers ALL NINE taps of its pixel tiles from ONE x tile with a full halo (10 rows x 18 pixels): a K step is
+// the 16 pixels of one tile row, i.e. 16 consecutive 128-byte rows of the halo tile starting at pixel row
+// (k + r) * 18 + s - any start works because the swizzle is a function of the absolute address (probe_shift.py).
+// One x + one dy tile per 8x16 pixels instead of three of each keeps the kernel off the L2->SM limit it hit with one
+// CTA per horizontal tap (ncu: 3.4x the tensor bytes, 58 % tensor-pipe active).
+//   CB = 2 (Cin = 128): M = 128 x channels; one MMA per tap, 9 accumulators of 64 columns would need 576 TMEM columns,
+//                       so the CTA runs the taps of ONE horizontal shift s (grid x3), 3 accumulators.
 //   CB = 1 (Cin = 64) : two vertical taps are STACKED in M: the second 64-row block of the MN-major A descriptor is
-//                       "the same 64 channels one image row further down" (LBO = one tile row = 2048 B), so taps
-//                       (0,1) are one M = 128 MMA and tap 2 rides in a second one (its upper half is discarded).
-// One CTA = one horizontal tap s and one split of the pixel tiles. Partials: [z][tap][Cin][64].
+//                       "the same 64 channels one halo row further down" (LBO = 18 pixels = 2304 B), so taps (0,s),(1,s)
+//                       are one M = 128 MMA and tap (2,s) rides in a second one (upper half discarded): 6 accumulators
+//                       of 64 columns, all 9 taps in one CTA.
+// Partials: [z][tap][Cin][64].
 template <int CB>
 struct WSPlan {
-  static constexpr int X_BOX = (TH + 2) * TW * 128;  // 20480
-  static constexpr int Y_BOX = BM * 128;             // 16384
-  static constexpr int STAGE = CB * X_BOX + Y_BOX;
+  static constexpr int HW_ = TW + 2;                       // halo tile width in pixels
+  static constexpr int X_BOX = (TH + 2) * HW_ * 128;       // 23040
+  static constexpr int X_BOX_PAD = (X_BOX + 2 * HW_ * 128 + 1023) / 1024 * 1024;  // + the junk rows tap "3" touches
+  static constexpr int Y_BOX = BM * 128;                   // 16384
+  static constexpr int STAGE = CB * X_BOX_PAD + Y_BOX;
   static constexpr int NS_MAX = (227 * 1024 - 2048) / STAGE;
-  static constexpr int NS = NS_MAX > 6 ? 6 : NS_MAX;
-  static constexpr int NACC = (CB == 1) ? 2 : 3;
-  static constexpr int TMEM_COLS = (CB == 1) ? 128 : 256;
+  static constexpr int NS = NS_MAX > 5 ? 5 : NS_MAX;
+  static constexpr int S_PER_CTA = (CB == 1) ? 3 : 1;      // horizontal taps handled by one CTA
+  static constexpr int NACC = (CB == 1) ? 6 : 3;
+  static constexpr int TMEM_COLS = (CB == 1) ? 512 : 256;
   static constexpr int BAR_OFF = NS * STAGE;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
@@ -319,7 +329,7 @@ struct WSPlan {
 template <int CB>
 __global__ void __launch_bounds__(192, 1) wgrad_swap_kernel(const __grid_constant__ WgradArgs args) {
   using P = WSPlan<CB>;
-  constexpr int NS = P::NS;
+  constexpr int NS = P::NS, HW_ = P::HW_;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -330,7 +340,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_swap_kernel(const __grid_constan
   const uint32_t tmem_slot = acc_full + 8;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + P::BAR_OFF + 8 * (2 * NS) + 8);
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
-  const int s = blockIdx.x % 3, z = blockIdx.x / 3;
+  const int s_cta = (P::S_PER_CTA == 1) ? static_cast<int>(blockIdx.x % 3) : 0;
+  const int z = (P::S_PER_CTA == 1) ? static_cast<int>(blockIdx.x / 3) : static_cast<int>(blockIdx.x);
   const int t_begin = static_cast<int>(static_cast<long long>(args.tiles_total) * z / args.splits);
   const int t_end = static_cast<int>(static_cast<long long>(args.tiles_total) * (z + 1) / args.splits);
 
@@ -359,12 +370,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_swap_kernel(const __grid_constan
         const int img = t / (args.tiles_w * args.tiles_h);
         const int h0 = thi * TH, w0 = twi * TW;
         mbar_wait(empty(st), ph ^ 1);
-        mbar_arrive_expect_tx(full(st), P::STAGE);
+        mbar_arrive_expect_tx(full(st), CB * P::X_BOX + P::Y_BOX);
         const uint32_t sX = smem_base + st * P::STAGE;
 #pragma unroll
         for (int cb = 0; cb < CB; ++cb)
-          tma_load_4d(sX + cb * P::X_BOX, &args.tmB[0], full(st), cb * 64, w0 + s - 1, h0 - 1, img);  // x, with halo
-        tma_load_4d(sX + CB * P::X_BOX, &args.tmA, full(st), 0, w0, h0, img);                          // dy
+          tma_load_4d(sX + cb * P::X_BOX_PAD, &args.tmB[0], full(st), cb * 64, w0 - 1, h0 - 1, img);  // x, full halo
+        tma_load_4d(sX + CB * P::X_BOX_PAD, &args.tmA, full(st), 0, w0, h0, img);                      // dy
         if (++st == NS) { st = 0; ph ^= 1; }
       }
     }
@@ -379,18 +390,22 @@ __global__ void __launch_bounds__(192, 1) wgrad_swap_kernel(const __grid_constan
         mbar_wait(full(st), ph);
         tc_fence_after();
         const uint32_t sX = smem_base + st * P::STAGE;
-        const uint32_t sY = sX + CB * P::X_BOX;
+        const uint32_t sY = sX + CB * P::X_BOX_PAD;
 #pragma unroll
         for (int k = 0; k < BM / 16; ++k) {  // 16 pixels (one tile row) per MMA
           const uint32_t b_lo = umma_desc_lo(sY + k * 2048, P::Y_BOX);
           if (CB == 2) {
 #pragma unroll
             for (int r = 0; r < 3; ++r)
-              umma_bf16_lh(tmem_base + r * 64, umma_desc_lo(sX + (k + r) * 2048, P::X_BOX), d_hi, b_lo, d_hi, idesc, acc);
+              umma_bf16_lh(tmem_base + r * 64, umma_desc_lo(sX + ((k + r) * HW_ + s_cta) * 128, P::X_BOX_PAD), d_hi, b_lo,
+                           d_hi, idesc, acc);
           } else {
 #pragma unroll
-            for (int pr = 0; pr < 2; ++pr)
-              umma_bf16_lh(tmem_base + pr * 64, umma_desc_lo(sX + (k + 2 * pr) * 2048, 2048), d_hi, b_lo, d_hi, idesc, acc);
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int pr = 0; pr < 2; ++pr)
+                umma_bf16_lh(tmem_base + (s * 2 + pr) * 64, umma_desc_lo(sX + ((k + 2 * pr) * HW_ + s) * 128, HW_ * 128),
+                             d_hi, b_lo, d_hi, idesc, acc);
           }
           acc = 1;
         }
@@ -408,9 +423,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_swap_kernel(const __grid_constan
     const int Cin = args.Cb;
 #pragma unroll 1
     for (int a = 0; a < P::NACC; ++a) {
-      int r, c;
-      if (CB == 2) { r = a; c = row; }
-      else { r = 2 * a + (row >> 6); c = row & 63; }
+      int r, s, c;
+      if (CB == 2) { r = a; s = s_cta; c = row; }
+      else { s = a >> 1; r = 2 * (a & 1) + (row >> 6); c = row & 63; }
       float* dst = args.partial + ((static_cast<size_t>(z) * 9 + (r * 3 + s)) * Cin + c) * 64;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
@@ -456,7 +471,7 @@ int launch_wgrad_swap(const WgradArgs& a, cudaStream_t st) {
     }
     configured = true;
   }
-  kern<<<3 * a.splits, 192, P::TOTAL, st>>>(a);
+  kern<<<P::S_PER_CTA == 1 ? 3 * a.splits : a.splits, 192, P::TOTAL, st>>>(a);
   return b2h::check_launch("wgrad_swap");
 }
 
@@ -498,6 +513,8 @@ static void conv3_wgrad_geometry(int N, int H, int W, int Cin, int Cout, int* bn
   if (use_swap(Cin, Cout)) {
     *mtiles = 1;
     *ntiles = 1;
+    *splits = pick_splits(Cin == 64 ? 1 : 3, *tiles);
+    return;
   }
   *splits = pick_splits(*mtiles * *ntiles * 3, *tiles);
 }
@@ -526,6 +543,7 @@ int b200unet_conv3x3_wgrad(const void* x, int x_cs, const void* dy, int dy_cs, f
   for (int i = 1; i < 4; ++i) a.tmB[i] = a.tmB[0];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_swap(Cin, Cout)) {
+    if (int e = b2h::make_tmap_4d(&a.tmB[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TW + 2, TH + 2)) return e;
     if (int e = (Cin == 64) ? launch_wgrad_swap<1>(a, st) : launch_wgrad_swap<2>(a, st)) return e;
     reduce_conv3_swapped_kernel<<<b2h::ceil_div(9 * Cin * 64, 256), 256, 0, st>>>(partial, dw_oihw, a.splits, Cin);
     return b2h::check_launch("conv3x3_wgrad_reduce");
