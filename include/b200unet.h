@@ -53,6 +53,11 @@ int b200unet_prep_convt2x2_weight(const float* w, void* w_fprop, void* w_dgrad, 
  * kernel used when Cin <= 128); feeds BatchNorm2d (Model.py:17,21) through b200unet_bn_reduce_partials.
  * Requires Cin % 64 == 0 and Cout % 64 == 0. */
 int b200unet_conv3x3_stat_rows(int N, int H, int W, int Cin, int Cout);
+/* Which of the 3x3 kernels b200unet_conv3x3_igemm picks: each argument -1 = automatic (measured rule), 0 = never,
+ * 1 = whenever applicable. resident: persistent resident-weight kernels (Cin <= 128); resident_pairs: their CTA-pair
+ * (cta_group::2) form; streaming_pairs: the CTA-pair streaming kernel (Cin >= 256). Test / tuning aid; call
+ * b200unet_conv3x3_stat_rows again afterwards (the statistics row count depends on the kernel). */
+int b200unet_set_kernel_choice(int resident, int resident_pairs, int streaming_pairs);
 int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial,
                            int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
 /* ConvTranspose2d(Cin, Cup, 2, 2) + bias (Model.py:56-57,66): out[n,2h+i,2w+j,d] = b[d] + sum_c x[n,h,w,c] W[c,d,i,j],

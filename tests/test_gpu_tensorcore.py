@@ -36,6 +36,8 @@ CONV_SHAPES = [
     (3, 16, 24, 256, 256),
     (1, 32, 40, 512, 128),
     (2, 16, 16, 256, 512),
+    (1, 16, 8, 256, 256),     # a single tile: the second CTA of the pair works on an out-of-range tile
+    (1, 16, 8, 128, 128),
 ]
 
 
@@ -82,6 +84,37 @@ def test_conv3x3_wgrad(ops, n, h, w, cin, cout):
     dw = torch.empty(cout, cin, 3, 3, device="cuda")
     ops.conv3x3_wgrad(to_nhwc_bf16(x), to_nhwc_bf16(dy), dw)
     assert rel_l2(dw, wv.grad) < 1e-4  # fp32 accumulation of exact bf16 products
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(64, 64, 512), (128, 64, 512), (128, 128, 256), (256, 256, 128), (512, 512, 64),
+                                         (1024, 512, 64), (1024, 1024, 32), (256, 128, 256)])
+def test_full_size_layers_all_kernel_choices_agree(ops, cin, cout, hw):
+    """BASELINE config-2 layer shapes (batch 16): the oracle is too slow here, so the property is that every kernel
+    able to run the layer (one-tile-per-CTA igemm, resident, resident pairs, streaming pairs) produces the same
+    tensor up to bf16 rounding of differently ordered fp32 sums, and identical BatchNorm statistics to 1e-4."""
+    from unet_torch_b200 import _lib
+
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = (torch.randn(16, hw, hw, cin, device="cuda", generator=g) * 0.5).to(BF16)
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5
+    wf, _ = ops.prep_conv3x3_weight(w)
+    outs = []
+    try:
+        for choice in ((0, 0, 0), (1, 0, 0), (1, 1, 1), (-1, -1, -1)):
+            _lib.call("b200unet_set_kernel_choice", *choice)
+            rows = ops.conv3x3_stat_rows(16, hw, hw, cin, cout)
+            st = torch.zeros(rows * 2 * cout, device="cuda")
+            y = torch.empty(16, hw, hw, cout, dtype=BF16, device="cuda")
+            ops.conv3x3(x, wf, y, st)
+            outs.append((y.float(), st.view(rows, 2, cout).double().sum(0)))
+    finally:
+        _lib.call("b200unet_set_kernel_choice", -1, -1, -1)
+    y0, s0 = outs[0]
+    assert torch.isfinite(y0).all() and float(y0.abs().max()) > 0
+    for y, st in outs[1:]:
+        assert rel_l2(y, y0) < 2e-3           # both are bf16 roundings of the same fp32 sums, differently ordered
+        assert rel_l2(st[1], s0[1]) < 1e-4    # sum of squares
+        assert float((st[0] - s0[0]).abs().max()) <= 1e-4 * float(s0[1].sqrt().max()) * (16 * hw * hw) ** 0.5
 
 
 def test_conv3x3_reads_and_writes_channel_slices(ops):

@@ -27,6 +27,7 @@ SIGNATURES = {
     "b200unet_tile_w": (c_int, []),
     "b200unet_prep_conv3x3_weight": (c_int, [_P, _P, _P, _I, _I, _P]),
     "b200unet_prep_convt2x2_weight": (c_int, [_P, _P, _P, _I, _I, _P]),
+    "b200unet_set_kernel_choice": (c_int, [_I, _I, _I]),
     "b200unet_conv3x3_stat_rows": (c_int, [_I, _I, _I, _I, _I]),
     "b200unet_conv3x3_igemm": (c_int, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "b200unet_convt2x2_fprop": (c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -307,13 +307,24 @@ int launch_mode(IgemmArgs& a, int bn, int mtiles, cudaStream_t st) {
   return 1;
 }
 
+// Kernel-selection overrides: -1 = automatic (measured rules below), 0 = off, 1 = forced on. Initialised from the
+// environment (B200UNET_NO_RES, B200UNET_RES2, B200UNET_PAIR), changeable at run time with b200unet_set_kernel_choice.
+int g_opt_res = -2, g_opt_res2 = -2, g_opt_pair = -2;
+int opt_from_env(const char* name, bool invert) {
+  const char* e = getenv(name);
+  if (!e) return -1;
+  const int v = atoi(e) != 0 ? 1 : 0;
+  return invert ? 1 - v : v;
+}
+void init_opts() {
+  if (g_opt_res == -2) g_opt_res = opt_from_env("B200UNET_NO_RES", true);
+  if (g_opt_res2 == -2) g_opt_res2 = opt_from_env("B200UNET_RES2", false);
+  if (g_opt_pair == -2) g_opt_pair = opt_from_env("B200UNET_PAIR", false);
+}
+
 bool use_resident(int Cin, int Cout) {
-  static int off = -1;
-  if (off < 0) {
-    const char* e = getenv("B200UNET_NO_RES");
-    off = (e && atoi(e) != 0) ? 1 : 0;
-  }
-  return !off && b2h::conv3_res_applicable(Cin, Cout);
+  init_opts();
+  return g_opt_res != 0 && b2h::conv3_res_applicable(Cin, Cout);
 }
 
 // CTA pairs (conv3_res2.cu) for the resident-weight layers. Measured on B200 (profiles/): pairs win 25-35 % when a
@@ -321,24 +332,16 @@ bool use_resident(int Cin, int Cout) {
 // burst is short (Cin = 64) or for 128->64 at 512^2 and above, where the cluster-wide barrier round trip per tile is
 // exposed. B200UNET_RES2=0 / 1 forces the choice off / on for every resident-weight layer.
 bool use_pairs(int N, int H, int W, int Cin, int Cout) {
-  static int mode = -2;
-  if (mode == -2) {
-    const char* e = getenv("B200UNET_RES2");
-    mode = e ? (atoi(e) != 0 ? 1 : 0) : -1;
-  }
-  if (mode >= 0) return mode == 1;
+  init_opts();
+  if (g_opt_res2 >= 0) return g_opt_res2 == 1;
   if (Cin != 128) return false;
   return Cout >= 128 || static_cast<long long>(N) * H * W <= 16ll * 256 * 256;
 }
 
 // streaming CTA-pair kernel (conv3_pair.cu) for the deep layers; B200UNET_PAIR=0 keeps the one-tile-per-CTA igemm
 bool use_stream_pairs(int Cin, int Cout) {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("B200UNET_PAIR");
-    on = e ? (atoi(e) != 0 ? 1 : 0) : 1;
-  }
-  return on != 0 && b2h::conv3_pair_applicable(Cin, Cout);
+  init_opts();
+  return g_opt_pair != 0 && b2h::conv3_pair_applicable(Cin, Cout);
 }
 
 int pick_bn(int ncols, int limit) {
@@ -384,6 +387,16 @@ int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int 
   if (int e = b2h::make_tmap_4d(&a.tmO[0], y, Cout, W, H, N, ys, ys * W, ys * W * H, TW, TH)) return e;
   for (int i = 1; i < 4; ++i) a.tmO[i] = a.tmO[0];
   return launch_mode<MODE_CONV3>(a, bn, N * a.tiles_w * a.tiles_h, static_cast<cudaStream_t>(stream));
+}
+
+int b200unet_set_kernel_choice(int resident, int resident_pairs, int streaming_pairs) {
+  B2_REQUIRE(resident >= -1 && resident <= 1 && resident_pairs >= -1 && resident_pairs <= 1 && streaming_pairs >= -1 &&
+                 streaming_pairs <= 1,
+             "set_kernel_choice: each argument is -1 (automatic), 0 (off) or 1 (on)");
+  g_opt_res = resident;
+  g_opt_res2 = resident_pairs;
+  g_opt_pair = streaming_pairs;
+  return 0;
 }
 
 int b200unet_conv3x3_stat_rows(int N, int H, int W, int Cin, int Cout) {
