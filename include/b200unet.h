@@ -182,6 +182,23 @@ int b200unet_mse_bwd(const float* pred, const float* target, const float* grad_o
 /* ---- inference head (test_mc3serousv5.py:880-881): fp32 softmax over classes, then first-maximum argmax --- */
 int b200unet_softmax_argmax(const float* logits, int64_t* mask, int N, int ncls, int64_t HW, b200_stream_t stream);
 
+/* ---- the steps either side of the network (edge.cu) ------------------------------------ */
+/* Input edge (DataLoader.py:661-671, test_mc3serousv5.py:115-125): uint8 images [N][H][W][C] (C <= 4, BGR order as
+ * cv2.imread returns) -> fp32 NCHW, each image/channel z-normalised with its own mean and (population) standard
+ * deviation over H*W computed exactly (integer sums, fp64 finalisation like numpy); reverse_channels = BGR -> RGB.
+ * workspace: b200unet_znorm_workspace_bytes(N, C) bytes. */
+int64_t b200unet_znorm_workspace_bytes(int N, int C);
+int b200unet_znorm_to_chw(const uint8_t* img_nhwc, void* workspace, float* out_nchw, int N, int H, int W, int C,
+                          int reverse_channels, b200_stream_t stream);
+/* Inference epilogue (test_mc3serousv5.py:879-887): OutConv + softmax(dim=1) + argmax(dim=1) + np.uint8 in one pass over the
+ * last activation (NHWC bf16); bit-identical to b200unet_head_fprop followed by b200unet_softmax_argmax. */
+int b200unet_head_mask(const void* a, int a_cs, const float* w, const float* bias, uint8_t* mask, int N, int H, int W,
+                       int Cin, int ncls, b200_stream_t stream);
+/* Density-map epilogue (test_mc3serousv5.py:961-974): OutConv + F.relu + fp32 division by `divisor` (200 in the
+ * reference; 1 = plain F.relu(model(x))) -> fp32 NCHW maps; counts (nullable): [N][ncls] fp64 sums of the stored maps. */
+int b200unet_head_density(const void* a, int a_cs, const float* w, const float* bias, float* out_nchw, double* counts,
+                          int N, int H, int W, int Cin, int ncls, float divisor, b200_stream_t stream);
+
 /* ---- SyncBN over NVLink peer memory (nvl_sync.cu): one-shot all-reduce of a small fp64 vector through
  * symmetric buffers mapped into every rank (peer_bufs = HOST array of `world` device pointers, index = rank; each
  * buffer b200unet_nvl_buffer_bytes() bytes, zeroed once before first use), optionally fused with the BatchNorm

@@ -194,3 +194,30 @@ def softmax_argmax(logits):
         best = torch.where(take, p[:, j], best)
         idx = torch.where(take, torch.full_like(idx, j), idx)
     return idx
+
+
+# ------------------------------------------------------------------------------------------------ edges of the path
+def preprocess(img_org):
+    """`preprocess` of test_mc3serousv5.py:100-127 (= DataLoader.py:661-671) without the resize branch: per-channel
+    z-normalisation in numpy float64 (np.mean / np.std over axes (0,1)), HWC -> CHW, BGR -> RGB, float32, batch dim."""
+    import numpy as np
+
+    img = np.asarray(img_org)
+    mean3d = np.mean(img, axis=(0, 1))
+    std3d = np.std(img, axis=(0, 1))
+    out = (img - mean3d) / std3d
+    if img.ndim == 2:
+        return torch.from_numpy(out.astype(np.float32)).unsqueeze(0).unsqueeze(0)
+    out = out.transpose((2, 0, 1))[::-1]
+    return torch.from_numpy(np.ascontiguousarray(out.astype(np.float32))).unsqueeze(0)
+
+
+def mask_uint8(logits):
+    """np.uint8(torch.argmax(F.softmax(outputs, dim=1), dim=1)) (test_mc3serousv5.py:880-887)."""
+    return softmax_argmax(logits).to(torch.uint8)
+
+
+def density_maps(logits, divisor=200.0):
+    """F.relu(model(x)) then the float32 maps / 200 (test_mc3serousv5.py:961-974); also their per-map sums (counts)."""
+    d = relu(logits) / torch.tensor(divisor, dtype=logits.dtype)
+    return d, d.double().sum(dim=(2, 3))

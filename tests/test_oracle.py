@@ -146,3 +146,25 @@ def test_cpu_baseline_port_matches_oracle():
     a = CB.unet_forward_torchops({k: v.clone() for k, v in sd.items()}, x, True)
     b, _ = O.unet_forward(sd, x, True)
     assert rel(a, b) < 1e-5
+
+
+def test_preprocess_restatement_matches_reference_golden(golden):
+    """oracle.preprocess against the outputs of the reference's own `preprocess` (oracle/make_golden_edge.py)."""
+    import numpy as np
+
+    g = golden("ref_edge.pt")
+    assert len(g) >= 5
+    with np.errstate(all="ignore"):
+        for name, c in g.items():
+            got = O.preprocess(c["img"].numpy())
+            assert got.shape == c["out"].shape and got.dtype == torch.float32, name
+            same = (got == c["out"]) | (got.isnan() & c["out"].isnan())
+            assert bool(same.all()), name
+    assert bool(g["bgr_constant_channel"]["out"].isnan().any())  # std = 0 channel: the reference yields nan
+
+
+def test_inference_epilogue_restatements():
+    z = torch.randn(2, 5, 8, 8, generator=torch.Generator().manual_seed(3))
+    assert torch.equal(O.mask_uint8(z).long(), torch.argmax(torch.softmax(z, 1), 1))
+    d, cnt = O.density_maps(z, 200.0)
+    assert torch.equal(d, torch.relu(z) / 200) and torch.allclose(cnt, d.double().sum((2, 3)))

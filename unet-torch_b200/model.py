@@ -209,7 +209,9 @@ class UNetEngine:
         return scale, shift, mean, rstd, count
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, training: bool, save: bool):
+    def forward(self, x: torch.Tensor, training: bool, save: bool, head: str = "logits", divisor: float = 200.0):
+        """head: "logits" (Model.py:152, fp32 NCHW), or one of the fused inference epilogues "mask" (uint8 class mask,
+        test_mc3serousv5.py:879-887) / "density" ((relu(z) / divisor, per-map sums), test_mc3serousv5.py:961-974)."""
         net = self.net
         if x.dim() != 4 or x.shape[1] != net.n_channels:
             raise ValueError(f"UNet expects [B,{net.n_channels},H,W] input, got {tuple(x.shape)}")
@@ -285,6 +287,10 @@ class UNetEngine:
             dec_rec.append((d_in, r1, r2, a2))
             d_in = a2
         # ---- head
+        if head == "mask":
+            return ops.head_mask(d_in, self.head.weight.detach(), self.head.bias.detach()), None
+        if head == "density":
+            return ops.head_density(d_in, self.head.weight.detach(), self.head.bias.detach(), divisor), None
         logits = torch.empty((n, net.n_classes, h, w), dtype=torch.float32, device=dev)
         ops.head_fprop(d_in, self.head.weight.detach(), self.head.bias.detach(), logits)
         if save:
@@ -549,8 +555,46 @@ class UNet(nn.Module):
         logits, _ = eng.forward(x, training=self.training, save=False)
         return logits
 
+    # ---- fused inference epilogues: the logits never reach HBM
+    def _fused_head(self, x, head, divisor=200.0):
+        eng = self._engine_for(x)
+        if not isinstance(eng, UNetEngine):
+            raise ValueError("fused inference heads run on the tensor-core engine (H, W multiples of 16, default widths); "
+                             "use predict_mask(net(x)) for other variants")
+        with torch.no_grad():
+            out, _ = eng.forward(x, training=self.training, save=False, head=head, divisor=divisor)
+        return out
+
+    def predict(self, x):
+        """np.uint8(argmax(softmax(self(x), 1), 1)) of test_mc3serousv5.py:879-887 as one fused epilogue -> uint8 [B,H,W]."""
+        return self._fused_head(x, "mask")
+
+    def predict_density(self, x, divisor=200.0):
+        """(F.relu(self(x)) / divisor, per-map sums) of test_mc3serousv5.py:961-974 -> (fp32 [B,C,H,W], fp64 [B,C])."""
+        return self._fused_head(x, "density", divisor)
+
     def use_checkpointing(self):
         raise NotImplementedError("activation checkpointing is not needed: bf16 activations fit in HBM3e")
+
+
+def preprocess(img_org, input_size=None, device=None) -> torch.Tensor:
+    """`preprocess(img_org, input_size)` of test_mc3serousv5.py:100-127 / the z-normalisation of DataLoader.py:661-671 on
+    the GPU: uint8 image(s) as cv2.imread returns them ([H,W,C] BGR, [H,W] grey, or a batch [N,H,W,C]) -> fp32 [N,C,H,W],
+    each image and channel z-normalised with its own mean / population std, channels reversed to RGB.
+    Resizing (scipy `zoom`, order 3) stays with the caller: a size mismatch with `input_size` raises."""
+    if not torch.is_tensor(img_org):
+        img_org = torch.from_numpy(img_org)
+    if img_org.dtype != torch.uint8:
+        raise TypeError(f"preprocess expects uint8 pixels (cv2.imread), got {img_org.dtype}")
+    if img_org.dim() not in (2, 3, 4):
+        raise ValueError(f"preprocess expects [H,W], [H,W,C] or [N,H,W,C], got {tuple(img_org.shape)}")
+    hw = tuple(img_org.shape[:2]) if img_org.dim() < 4 else tuple(img_org.shape[1:3])
+    if input_size is not None and tuple(input_size) != hw:
+        raise ValueError(f"image is {hw}, input_size {tuple(input_size)}: resize (scipy zoom) before preprocess")
+    if not img_org.is_cuda:
+        dev = torch.device(device if device is not None else "cuda")
+        img_org = (img_org.pin_memory() if torch.cuda.is_available() else img_org).to(dev, non_blocking=True)
+    return ops.znorm_to_chw(img_org, reverse_channels=True)
 
 
 def predict_mask(logits: torch.Tensor) -> torch.Tensor:

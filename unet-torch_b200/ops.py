@@ -329,3 +329,42 @@ def softmax_argmax(logits):
     mask = torch.empty((n, h, w), dtype=torch.int64, device=logits.device)
     _lib.call("b200unet_softmax_argmax", _f32(logits), mask.data_ptr(), n, ncls, h * w, _stream())
     return mask
+
+
+# --------------------------------------------------------------------------------------------- edges of the path
+def znorm_to_chw(img_u8: torch.Tensor, reverse_channels: bool = True) -> torch.Tensor:
+    """uint8 [N,H,W,C] (or [H,W,C] / [H,W]) -> z-normalised fp32 [N,C,H,W] (DataLoader.py:661-671)."""
+    if img_u8.dtype != torch.uint8 or not img_u8.is_cuda:
+        raise TypeError("znorm_to_chw expects a CUDA uint8 tensor (no CPU fallback)")
+    if img_u8.dim() == 2:
+        img_u8 = img_u8[None, :, :, None]
+    elif img_u8.dim() == 3:
+        img_u8 = img_u8[None]
+    img_u8 = img_u8.contiguous()
+    n, h, w, c = img_u8.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=img_u8.device)
+    ws = torch.empty(_lib.query("b200unet_znorm_workspace_bytes", n, c), dtype=torch.uint8, device=img_u8.device)
+    _lib.call("b200unet_znorm_to_chw", img_u8.data_ptr(), ws.data_ptr(), _f32(out), n, h, w, c,
+              int(bool(reverse_channels) and c > 1), _stream())
+    return out
+
+
+def head_mask(a, w, bias):
+    """OutConv + softmax + argmax + uint8 in one pass (test_mc3serousv5.py:879-887); a: NHWC bf16."""
+    ap, acs, n, h, wd, cin = _nhwc(a)
+    ncls = w.shape[0]
+    mask = torch.empty((n, h, wd), dtype=torch.uint8, device=a.device)
+    _lib.call("b200unet_head_mask", ap, acs, _f32(w.view(ncls, cin)), _f32(bias), mask.data_ptr(), n, h, wd, cin, ncls,
+              _stream())
+    return mask
+
+
+def head_density(a, w, bias, divisor=200.0, with_counts=True):
+    """OutConv + F.relu + /divisor -> fp32 NCHW maps (+ fp64 [N,ncls] sums) (test_mc3serousv5.py:961-974)."""
+    ap, acs, n, h, wd, cin = _nhwc(a)
+    ncls = w.shape[0]
+    out = torch.empty((n, ncls, h, wd), dtype=torch.float32, device=a.device)
+    counts = torch.empty((n, ncls), dtype=torch.float64, device=a.device) if with_counts else None
+    _lib.call("b200unet_head_density", ap, acs, _f32(w.view(ncls, cin)), _f32(bias), _f32(out),
+              counts.data_ptr() if counts is not None else None, n, h, wd, cin, ncls, float(divisor), _stream())
+    return out, counts
