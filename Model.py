@@ -1,9 +1,9 @@
 """Drop-in for the reference's Model.py: `from Model import UNet` now builds the B200-native network.
 
 Put this repository first on sys.path and the reference's train.py / Trainer.py / test.py run unchanged
-(train.py:6 imports UNet, UNet_multitask, UNet_attention; only UNet is on the hot path).
+(train.py:6 imports UNet, UNet_multitask, UNet_attention; UNet and UNet_multitask run on the B200 engine).
 """
-from unet_torch_b200 import UNet, DoubleConv, Down, Up, OutConv  # noqa: F401
+from unet_torch_b200 import UNet, UNet_multitask, DoubleConv, Down, Up, OutConv  # noqa: F401
 
 
 def _outside_hot_path(name):
@@ -15,5 +15,4 @@ def _outside_hot_path(name):
     return _Unavailable
 
 
-UNet_multitask = _outside_hot_path("UNet_multitask")
 UNet_attention = _outside_hot_path("UNet_attention")

@@ -156,6 +156,12 @@ int b200unet_bn_relu_bwd_apply(const void* g1, int g1_cs, const void* g_pool, co
 int b200unet_partial_colsum(const float* partial, int64_t rows, int row_pitch, int col_lo, int n, float* out,
                             b200_stream_t stream);
 /* per-channel sum over pixels of a bf16 NHWC tensor (ConvTranspose2d bias gradient). */
+/* Two decoders over one encoder (UNet_multitask, Model.py:172-250): copy a channel slice of an NHWC bf16 buffer into another
+ * (the skip half of the second decoder's concat buffer), and out = a + b over channel slices (sum of the two decoders'
+ * gradients; out may alias a). Pitches in elements, multiples of 8. */
+int b200unet_nhwc_copy(const void* src, int src_cs, void* dst, int dst_cs, int64_t pixels, int C, b200_stream_t stream);
+int b200unet_nhwc_add(const void* a, int a_cs, const void* b, int b_cs, void* out, int out_cs, int64_t pixels, int C,
+                      b200_stream_t stream);
 int64_t b200unet_channel_sum_workspace_floats(int C);
 int b200unet_channel_sum(const void* x, int x_cs, float* workspace, float* out, int64_t pixels, int C,
                          b200_stream_t stream);

@@ -135,6 +135,37 @@ def unet_forward(sd, x, training=True, dropout_masks=None):
     return conv1x1(cur, sd["outc.conv.weight"], sd["outc.conv.bias"]), nb
 
 
+def unet_multitask_forward(sd, x, training=True):
+    """UNet_multitask.forward (Model.py:232-250): one encoder, two decoders (`up{i}_decod{d}`, `outc_decod{d}`) over the
+    same skips; returns ((logits_decod1, logits_decod2), updated BatchNorm buffers)."""
+    nb = {}
+    x1 = _double_conv(sd, "inc.double_conv", x, training, nb)
+    skips = [x1]
+    cur = x1
+    for i in range(1, 5):
+        cur, _, _ = maxpool2x2(cur)
+        cur = _double_conv(sd, f"down{i}.maxpool_conv.1.double_conv", cur, training, nb)
+        skips.append(cur)
+    outs = []
+    for d in (1, 2):
+        cur = skips[4]
+        for i in range(1, 5):
+            up = conv_transpose2x2(cur, sd[f"up{i}_decod{d}.up.weight"], sd[f"up{i}_decod{d}.up.bias"])
+            cur = _double_conv(sd, f"up{i}_decod{d}.conv.double_conv", pad_and_cat(skips[4 - i], up), training, nb)
+        outs.append(conv1x1(cur, sd[f"outc_decod{d}.conv.weight"], sd[f"outc_decod{d}.conv.bias"]))
+    return tuple(outs), nb
+
+
+def multitask_uncertainty_loss(loss_values, log_var_tasks, regg_flag):
+    """MultitaskUncertaintyLoss.forward (loss.py:313-325): sum_i c_i * L_i + log(std_i), std_i = exp(log_var_i)^(1/2),
+    c_i = 1/(2 std_i^2) for regression tasks, 1/std_i^2 otherwise."""
+    total = 0
+    for l, lv, reg in zip(loss_values, log_var_tasks, regg_flag):
+        std = torch.exp(lv) ** 0.5
+        total = total + (1 / (2 * std ** 2) if reg else 1 / std ** 2) * l + torch.log(std)
+    return total
+
+
 def dropout_mask_shapes(n, h, w, width=64):
     """Shapes of the tensors nn.Dropout sees, in the order the reference draws its masks (down1-4, then up1-4)."""
     hs, ws = [h], [w]

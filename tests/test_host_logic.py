@@ -70,7 +70,29 @@ def test_root_shims_mirror_reference_imports():
     loss.CLASS_NUMBER = 5  # train.py:163
     assert U.loss.CLASS_NUMBER == 5
     assert callable(loss.calc_loss) and loss.DiceLoss is U.DiceLoss
+    assert Model.UNet_multitask is U.UNet_multitask and issubclass(Model.UNet_multitask, torch.nn.Module)
     with pytest.raises(NotImplementedError):
-        Model.UNet_multitask(3, 2)
+        Model.UNet_attention(3, 2)
     with pytest.raises(NotImplementedError):
         loss.calc_loss(torch.zeros(1, 1, 4, 4), torch.zeros(1, 4, 4), loss_type="HausdorffDTLoss")
+
+
+def test_multitask_module_mirrors_reference_layout():
+    """UNet_multitask (Model.py:172-250): key names and order, parameter count, RNG consumption of the constructor."""
+    import unet_torch_b200 as U
+
+    torch.manual_seed(0)
+    net = U.UNet_multitask(-2, 2, 8)
+    keys = list(net.state_dict().keys())
+    assert len(keys) == 176 and net.n_channels == 3
+    assert keys[0] == "inc.double_conv.0.weight"
+    order = [k.split(".")[0] for k in keys]
+    first = {name: order.index(name) for name in ("down4", "up1_decod1", "outc_decod1", "up1_decod2", "outc_decod2")}
+    assert first["down4"] < first["up1_decod1"] < first["outc_decod1"] < first["up1_decod2"] < first["outc_decod2"]
+    assert net.up1_decod2.up.weight.shape == (128, 64, 2, 2) and net.outc_decod2.conv.weight.shape == (2, 8, 1, 1)
+    # no Dropout layers are built whatever the flag says (Model.py:188-230 never pass it on)
+    assert not any(isinstance(m, torch.nn.Dropout) for m in U.UNet_multitask(3, 2, 8, dropout=True).modules())
+    # the two decoders draw different weights from the RNG stream
+    assert not torch.equal(net.up1_decod1.up.weight, net.up1_decod2.up.weight)
+    with pytest.raises(RuntimeError):
+        net.inc(torch.zeros(1, 3, 16, 16))  # containers are not the product path

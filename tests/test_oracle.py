@@ -168,3 +168,33 @@ def test_inference_epilogue_restatements():
     assert torch.equal(O.mask_uint8(z).long(), torch.argmax(torch.softmax(z, 1), 1))
     d, cnt = O.density_maps(z, 200.0)
     assert torch.equal(d, torch.relu(z) / 200) and torch.allclose(cnt, d.double().sum((2, 3)))
+
+
+@pytest.mark.parametrize("case", ["w4_sum", "w4_uncertainty"])
+def test_multitask_restatement_matches_reference_golden(golden, case):
+    """oracle.unet_multitask_forward (+ relu/mseMC, MultitaskUncertaintyLoss) against the reference's UNet_multitask."""
+    g = golden("ref_multitask.pt")[case]
+    ch, ncls, width, n, h, w, seed = g["cfg"]
+    sd = {k: (v.double() if v.is_floating_point() else v) for k, v in g["sd0"].items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    sd_req = dict(sd)
+    sd_req.update(params)
+    (o1, o2), new_buf = O.unet_multitask_forward(sd_req, g["x"].double(), training=True)
+    l1 = O.calc_loss(O.relu(o1), g["t1"].double(), "mseMC", ncls)
+    l2 = O.calc_loss(O.relu(o2), g["t2"].double(), "mseMC", ncls)
+    if g["combine"] == "sum":
+        loss = l1 + l2
+    else:
+        lv = [torch.tensor([0.3], dtype=torch.float64), torch.tensor([-0.2], dtype=torch.float64)]
+        loss = O.multitask_uncertainty_loss([l1, l2], lv, [True, True]).reshape(())
+    loss.backward()
+    assert rel(o1, g["o1_64"]) < 2e-6 and rel(o2, g["o2_64"]) < 2e-6
+    assert abs(float(loss) - float(g["loss64"])) < 1e-9 * max(1.0, abs(float(g["loss64"])))
+    assert rel(o1, g["o1"]) < 1e-4 and rel(o2, g["o2"]) < 1e-4
+    for k, p in params.items():
+        assert rel(p.grad, g["grads64"][k]) < 1e-5, k
+    for k, v in g["buffers1"].items():
+        if "num_batches" in k:
+            assert int(new_buf[k]) == int(v)
+        else:
+            assert rel(new_buf[k], v) < 1e-5, k

@@ -59,6 +59,8 @@ SIGNATURES = {
         [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _D, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     ),
     "b200unet_partial_colsum": (c_int, [_P, _L, _I, _I, _I, _P, _P]),
+    "b200unet_nhwc_copy": (c_int, [_P, _I, _P, _I, _L, _I, _P]),
+    "b200unet_nhwc_add": (c_int, [_P, _I, _P, _I, _P, _I, _L, _I, _P]),
     "b200unet_channel_sum_workspace_floats": (c_int64, [_I]),
     "b200unet_channel_sum": (c_int, [_P, _I, _P, _P, _L, _I, _P]),
     "b200unet_loss_sums_doubles": (c_int, []),

@@ -418,6 +418,34 @@ __global__ void partial_colsum_kernel(const float* __restrict__ partial, long lo
   }
 }
 
+// ------------------------------------------------------------------------------------------ channel-slice copy / sum
+// A network with two decoders over one encoder (UNet_multitask, Model.py:172-250) needs the skip activations in a second
+// concat buffer and the sum of the two decoders' gradients on the way back: out = a (+ b) over a channel slice of NHWC
+// buffers with independent pixel pitches. out may alias a. fp32 sum, one bf16 rounding.
+template <bool ADD>
+__global__ void __launch_bounds__(EW_THREADS) slice_copy_add_kernel(const __nv_bfloat16* __restrict__ a, int a_cs,
+                                                                    const __nv_bfloat16* __restrict__ b, int b_cs,
+                                                                    __nv_bfloat16* __restrict__ out, int out_cs,
+                                                                    long long pixels, int C) {
+  const int cgs = C >> 3;
+  const long long total = pixels * cgs;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long p = i / cgs;
+    const int c = static_cast<int>(i - p * cgs) * 8;
+    uint4 v = ldg128(a + p * a_cs + c);
+    if (ADD) {
+      float fa[8], fb[8];
+      unpack8(v, fa);
+      unpack8(ldg128(b + p * b_cs + c), fb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fa[j] += fb[j];
+      v = pack8(fa);
+    }
+    *reinterpret_cast<uint4*>(out + p * out_cs + c) = v;
+  }
+}
+
 __global__ void double_to_float_kernel(const double* in, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = static_cast<float>(in[i]);
@@ -538,6 +566,26 @@ int b200unet_channel_sum(const void* x, int x_cs, float* workspace, float* out, 
   if (int e = launch_reduce_partials(workspace, blocks, C, acc, st)) return e;
   double_to_float_kernel<<<(C + 127) / 128, 128, 0, st>>>(acc, out, C);
   return b2h::check_launch("channel_sum_cast");
+}
+
+int b200unet_nhwc_copy(const void* src, int src_cs, void* dst, int dst_cs, int64_t pixels, int C, b200_stream_t stream) {
+  B2_REQUIRE(C > 0 && C % 8 == 0 && src_cs % 8 == 0 && dst_cs % 8 == 0 && src_cs >= C && dst_cs >= C,
+             "nhwc_copy: C=%d and the pixel pitches (%d, %d) must be multiples of 8 with pitch >= C", C, src_cs, dst_cs);
+  B2_REQUIRE(pixels > 0, "nhwc_copy: empty tensor");
+  slice_copy_add_kernel<false><<<ew_blocks(pixels * (C / 8)), EW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), src_cs, nullptr, 0, static_cast<__nv_bfloat16*>(dst), dst_cs, pixels, C);
+  return b2h::check_launch("nhwc_copy");
+}
+
+int b200unet_nhwc_add(const void* a, int a_cs, const void* b, int b_cs, void* out, int out_cs, int64_t pixels, int C,
+                      b200_stream_t stream) {
+  B2_REQUIRE(C > 0 && C % 8 == 0 && a_cs % 8 == 0 && b_cs % 8 == 0 && out_cs % 8 == 0 && a_cs >= C && b_cs >= C && out_cs >= C,
+             "nhwc_add: C=%d and the pixel pitches (%d, %d, %d) must be multiples of 8 with pitch >= C", C, a_cs, b_cs, out_cs);
+  B2_REQUIRE(pixels > 0, "nhwc_add: empty tensor");
+  slice_copy_add_kernel<true><<<ew_blocks(pixels * (C / 8)), EW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), a_cs, static_cast<const __nv_bfloat16*>(b), b_cs,
+      static_cast<__nv_bfloat16*>(out), out_cs, pixels, C);
+  return b2h::check_launch("nhwc_add");
 }
 
 }  // extern "C"

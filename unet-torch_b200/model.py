@@ -128,14 +128,21 @@ class UNetEngine:
 
     def __init__(self, net: "UNet"):
         self.net = net
-        downs = [net.down1, net.down2, net.down3, net.down4]
-        ups = [net.up1, net.up2, net.up3, net.up4]
-        enc_dc = [_dc(net.inc)] + [_dc(d.maxpool_conv[-1]) for d in downs]
+        inc, downs, decoders = net._topology()
+        enc_dc = [_dc(inc)] + [_dc(d.maxpool_conv[-1]) for d in downs]
         self.enc = [(_ConvBN(s[0], s[1], first=(i == 0)), _ConvBN(s[3], s[4], first=False)) for i, s in enumerate(enc_dc)]
-        # decoder index j = 0..3 <-> up1..up4, operates at level 3-j
-        self.ups = [_UpOp(u.up) for u in ups]
-        self.dec = [(_ConvBN(_dc(u.conv)[0], _dc(u.conv)[1], False), _ConvBN(_dc(u.conv)[3], _dc(u.conv)[4], False)) for u in ups]
-        self.head = net.outc.conv
+        # one entry per decoder (UNet: one; UNet_multitask: two over the same encoder): (ups, dec, head) where
+        # decoder index j = 0..3 <-> up1..up4, operating at level 3-j
+        self.decoders = []
+        for ups, outc in decoders:
+            self.decoders.append((
+                [_UpOp(u.up) for u in ups],
+                [(_ConvBN(_dc(u.conv)[0], _dc(u.conv)[1], False), _ConvBN(_dc(u.conv)[3], _dc(u.conv)[4], False)) for u in ups],
+                outc.conv))
+        # flat views over all decoders (operand refresh, FusedSGD)
+        self.ups = [u for d in self.decoders for u in d[0]]
+        self.dec = [c for d in self.decoders for c in d[1]]
+        self.head = self.decoders[0][2]
         self._graphs = {}     # (shape, device, training, save) -> _GraphedStep
         self._seen = set()    # keys that already ran once eagerly (kernel attributes configured, allocator warm)
 
@@ -147,7 +154,7 @@ class UNetEngine:
             return None
         if training and DataParallelContext.current() is not None:
             return None
-        if torch.cuda.is_current_stream_capturing():
+        if torch.cuda.is_current_stream_capturing() or len(self.decoders) > 1:
             return None
         key = (tuple(x.shape), x.device.index, bool(training), bool(save))
         st = self._graphs.get(key)
@@ -168,11 +175,13 @@ class UNetEngine:
 
     # parameters in the order their gradients are produced by backward (used for DP bucketing)
     def params_in_backward_order(self):
-        out = [self.head.weight, self.head.bias]
-        for j in (3, 2, 1, 0):
-            c1, c2 = self.dec[j]
-            out += [c2.bn.weight, c2.bn.bias, c2.conv.weight, c1.bn.weight, c1.bn.bias, c1.conv.weight,
-                    self.ups[j].up.bias, self.ups[j].up.weight]
+        out = []
+        for ups, dec, head in reversed(self.decoders):
+            out += [head.weight, head.bias]
+            for j in (3, 2, 1, 0):
+                c1, c2 = dec[j]
+                out += [c2.bn.weight, c2.bn.bias, c2.conv.weight, c1.bn.weight, c1.bn.bias, c1.conv.weight,
+                        ups[j].up.bias, ups[j].up.weight]
         for l in (4, 3, 2, 1, 0):
             c1, c2 = self.enc[l]
             out += [c2.bn.weight, c2.bn.bias, c2.conv.weight, c1.bn.weight, c1.bn.bias, c1.conv.weight]
@@ -272,37 +281,56 @@ class UNetEngine:
                 idx = None
                 r2 = conv_bn_relu(c2, a1, ch[l], hs[l], wsz[l], a2)
             enc_rec.append((r1, r2, a2, idx))
-        # ---- decoder
-        d_in = enc_rec[4][2]
-        for j in range(4):
-            l = 3 - j
-            upo = self.ups[j]
-            wf, _ = upo.operands()
-            ops.convt2x2(d_in, wf, upo.up.bias.detach(), cat[l][..., ch[l]:])
-            c1, c2 = self.dec[j]
-            a1 = torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
-            r1 = conv_bn_relu(c1, cat[l], ch[l], hs[l], wsz[l], a1)
-            a2 = torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
-            r2 = conv_bn_relu(c2, a1, ch[l], hs[l], wsz[l], a2)
-            dec_rec.append((d_in, r1, r2, a2))
-            d_in = a2
-        # ---- head
-        if head == "mask":
-            return ops.head_mask(d_in, self.head.weight.detach(), self.head.bias.detach()), None
-        if head == "density":
-            return ops.head_density(d_in, self.head.weight.detach(), self.head.bias.detach(), divisor), None
-        logits = torch.empty((n, net.n_classes, h, w), dtype=torch.float32, device=dev)
-        ops.head_fprop(d_in, self.head.weight.detach(), self.head.bias.detach(), logits)
-        if save:
-            saved.x, saved.enc, saved.dec, saved.head_in = x, enc_rec, dec_rec, d_in
+        # ---- decoder(s)
+        outs, heads_in = [], []
+        for k, (ups, dec, head_conv) in enumerate(self.decoders):
+            if k == 0:
+                catk = cat
+            else:  # a further decoder over the same encoder: its own concat buffers, skip halves copied in
+                catk = [torch.empty_like(c) for c in cat]
+                for l in range(4):
+                    ops.nhwc_copy(cat[l][..., : ch[l]], catk[l][..., : ch[l]])
+            d_in = enc_rec[4][2]
+            rec = []
+            for j in range(4):
+                l = 3 - j
+                upo = ups[j]
+                wf, _ = upo.operands()
+                ops.convt2x2(d_in, wf, upo.up.bias.detach(), catk[l][..., ch[l]:])
+                c1, c2 = dec[j]
+                a1 = torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
+                r1 = conv_bn_relu(c1, catk[l], ch[l], hs[l], wsz[l], a1)
+                a2 = torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
+                r2 = conv_bn_relu(c2, a1, ch[l], hs[l], wsz[l], a2)
+                rec.append((d_in, r1, r2, a2))
+                d_in = a2
+            dec_rec.append(rec)
+            heads_in.append(d_in)
+            # ---- head
+            hw_, hb_ = head_conv.weight.detach(), head_conv.bias.detach()
+            if head == "mask":
+                outs.append(ops.head_mask(d_in, hw_, hb_))
+            elif head == "density":
+                outs.append(ops.head_density(d_in, hw_, hb_, divisor))
+            else:
+                logits = torch.empty((n, hw_.shape[0], h, w), dtype=torch.float32, device=dev)
+                outs.append(ops.head_fprop(d_in, hw_, hb_, logits))
+        out = outs[0] if len(outs) == 1 else tuple(outs)
+        if save and head == "logits":
+            saved.x, saved.enc, saved.dec, saved.head_in = x, enc_rec, dec_rec, heads_in
             saved.shapes = (n, ch, hs, wsz)
             saved.dp = dp
-        return logits, saved
+        return out, saved
 
     # ------------------------------------------------------------------ backward
-    def backward(self, saved: _Saved, dlogits: torch.Tensor):
+    def backward(self, saved: _Saved, dlogits):
+        """dlogits: one tensor, or one per decoder (None = that output did not take part in the loss)."""
         n, ch, hs, wsz = saved.shapes
-        dev = dlogits.device
+        dlogits_all = list(dlogits) if isinstance(dlogits, (tuple, list)) else [dlogits]
+        ref = next(d for d in dlogits_all if d is not None)
+        dev = ref.device
+        dlogits_all = [(torch.zeros((n, dc[2].weight.shape[0], hs[0], wsz[0]), dtype=torch.float32, device=dev)
+                        if d is None else d.contiguous().float()) for d, dc in zip(dlogits_all, self.decoders)]
         dp = saved.dp
         grads = {}
         flat = dp.make_flat_grads(self.params_in_backward_order()) if dp is not None else None
@@ -348,32 +376,39 @@ class UNetEngine:
                 ops.partial_colsum(part, rows, 2 * cdx, lo, cdx - lo, out)
             return dx
 
-        # ---- head
-        dlogits = dlogits.contiguous().float()
-        hw_, hb_ = self.head.weight, self.head.bias
-        g = torch.empty((n, hs[0], wsz[0], ch[0]), dtype=BF16, device=dev)
-        dwh, dbh = gbuf(hw_), gbuf(hb_)
-        ops.head_bwd(dlogits, saved.head_in, hw_.detach(), g, dwh, dbh)
-        grads[hw_], grads[hb_] = dwh, dbh
-        done(hw_, hb_)
-        # ---- decoder, up4 -> up1
+        # ---- decoder(s): head, then up4 -> up1; the skip and bottleneck gradients of several decoders are summed
         skip_grads = [None] * 4
-        for j in (3, 2, 1, 0):
-            l = 3 - j
-            d_in, r1, r2, _ = saved.dec[j]
-            c1, c2 = self.dec[j]
-            g = bn_conv_bwd(c2, r2, g, None, None, hs[l], wsz[l], True)
-            upo = self.ups[j]
-            db, dwu = gbuf(upo.up.bias), gbuf(upo.up.weight)
-            dcat = bn_conv_bwd(c1, r1, g, None, None, hs[l], wsz[l], True, dx_colsum=(ch[l], db))
-            skip_grads[l] = dcat[..., : ch[l]]
-            du = dcat[..., ch[l]:]
-            ops.convt2x2_wgrad(d_in, du, dwu)
-            grads[upo.up.bias], grads[upo.up.weight] = db, dwu
-            done(upo.up.bias, upo.up.weight)
-            _, wd = upo.operands()
-            g = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l + 1]), dtype=BF16, device=dev)
-            ops.convt2x2_dgrad(du, wd, g)
+        g5 = None
+        for k in reversed(range(len(self.decoders))):
+            ups, dec, head_conv = self.decoders[k]
+            dz = dlogits_all[k]
+            hw_, hb_ = head_conv.weight, head_conv.bias
+            g = torch.empty((n, hs[0], wsz[0], ch[0]), dtype=BF16, device=dev)
+            dwh, dbh = gbuf(hw_), gbuf(hb_)
+            ops.head_bwd(dz, saved.head_in[k], hw_.detach(), g, dwh, dbh)
+            grads[hw_], grads[hb_] = dwh, dbh
+            done(hw_, hb_)
+            for j in (3, 2, 1, 0):
+                l = 3 - j
+                d_in, r1, r2, _ = saved.dec[k][j]
+                c1, c2 = dec[j]
+                g = bn_conv_bwd(c2, r2, g, None, None, hs[l], wsz[l], True)
+                upo = ups[j]
+                db, dwu = gbuf(upo.up.bias), gbuf(upo.up.weight)
+                dcat = bn_conv_bwd(c1, r1, g, None, None, hs[l], wsz[l], True, dx_colsum=(ch[l], db))
+                if skip_grads[l] is None:
+                    skip_grads[l] = dcat[..., : ch[l]]
+                else:
+                    ops.nhwc_add(skip_grads[l], dcat[..., : ch[l]])
+                du = dcat[..., ch[l]:]
+                ops.convt2x2_wgrad(d_in, du, dwu)
+                grads[upo.up.bias], grads[upo.up.weight] = db, dwu
+                done(upo.up.bias, upo.up.weight)
+                _, wd = upo.operands()
+                g = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l + 1]), dtype=BF16, device=dev)
+                ops.convt2x2_dgrad(du, wd, g)
+            g5 = g if g5 is None else ops.nhwc_add(g5, g)
+        g = g5
         # ---- encoder, level 4 -> 0
         g_pool = None
         for l in (4, 3, 2, 1, 0):
@@ -452,16 +487,16 @@ class _UNetFn(torch.autograd.Function):
             logits, saved = engine.forward(x, training=training, save=True)
             ctx.step, ctx.saved = None, saved
         ctx.engine, ctx.params = engine, params
-        return logits
+        return logits  # one tensor, or one per decoder
 
     @staticmethod
-    def backward(ctx, dlogits):
+    def backward(ctx, *dlogits):
         if ctx.step is not None:
-            grads = ctx.step.backward(ctx.epoch, dlogits.contiguous().float())
+            grads = ctx.step.backward(ctx.epoch, dlogits[0].contiguous().float())
             return (None, None) + tuple(grads.get(p) for p in ctx.params)
         if ctx.saved is None:
             raise RuntimeError("UNet backward called twice: activations are consumed in place")
-        grads = ctx.engine.backward(ctx.saved, dlogits)
+        grads = ctx.engine.backward(ctx.saved, dlogits if len(dlogits) > 1 else dlogits[0])
         ctx.saved = None
         return (None, None) + tuple(grads.get(p) for p in ctx.params)
 
@@ -494,6 +529,11 @@ class UNet(nn.Module):
         self._generic = None
         self._check_fp32 = os.environ.get("B200UNET_CHECK_FP32", "0") not in ("", "0")
         self._cuda_graphs = os.environ.get("B200UNET_CUDA_GRAPHS", "0") not in ("", "0")
+
+    def _topology(self):
+        """(inc, [down1..4], [([up1..4], outc)]) - what the engines execute."""
+        return self.inc, [self.down1, self.down2, self.down3, self.down4], [
+            ([self.up1, self.up2, self.up3, self.up4], self.outc)]
 
     def enable_cuda_graphs(self, flag: bool = True):
         """Replay forward/backward as captured CUDA graphs (per input shape; first call of a shape runs eagerly).
@@ -575,6 +615,60 @@ class UNet(nn.Module):
 
     def use_checkpointing(self):
         raise NotImplementedError("activation checkpointing is not needed: bf16 activations fit in HBM3e")
+
+
+class UNet_multitask(UNet):
+    """Same constructor, state_dict keys (inc, down1-4, up{1-4}_decod{1,2}, outc_decod{1,2}), RNG consumption and
+    forward(x) -> (logits_decod1, logits_decod2) as the reference's two-decoder network (Model.py:172-250): one encoder
+    pass, two decoder passes over it with the same kernels; backward sums the two decoders' skip / bottleneck gradients.
+    As in the reference, `dropout` is stored but no Dropout layer is built (Model.py:188-230 pass no dropout flag)."""
+
+    def __init__(self, n_channels, n_classes, initial_feature_map=64, usa_cuda=True, dropout=False, dropout_p=0.5):
+        nn.Module.__init__(self)
+        self.usa_cuda = usa_cuda
+        self.n_channels = {-2: 3, -1: 1}.get(n_channels, n_channels)  # Model.py:176-181
+        self.n_classes = n_classes
+        self.initial_feature_map = initial_feature_map
+        self.dropout = dropout
+        self.dropout_p = dropout_p
+        f = initial_feature_map
+        blocks = [("inc", lambda: DoubleConv(self.n_channels, f))]
+        for i in range(4):
+            blocks.append((f"down{i + 1}", lambda i=i: Down(f << i, f << (i + 1))))
+        for d in (1, 2):
+            for i in range(4):
+                blocks.append((f"up{i + 1}_decod{d}", lambda i=i: Up(f << (4 - i), f << (3 - i))))
+            blocks.append((f"outc_decod{d}", lambda: OutConv(f, n_classes)))
+        for name, make in blocks:
+            mod = make()
+            setattr(self, name, mod)
+            mod.apply(self.weights_init)
+        self._engine = None
+        self._generic = None
+        self._check_fp32 = False
+        self._cuda_graphs = False
+
+    def _topology(self):
+        return self.inc, [self.down1, self.down2, self.down3, self.down4], [
+            ([getattr(self, f"up{i}_decod{d}") for i in (1, 2, 3, 4)], getattr(self, f"outc_decod{d}")) for d in (1, 2)]
+
+    def _fast_supported(self) -> bool:
+        return self.initial_feature_map % 64 == 0 and self.n_channels <= 7 and self.n_classes <= 8
+
+    def _engine_for(self, x):
+        if x.dim() != 4 or x.shape[2] % 16 or x.shape[3] % 16 or not self._fast_supported():
+            raise ValueError("UNet_multitask runs on the tensor-core engine only: H and W multiples of 16, "
+                             "initial_feature_map % 64 == 0, n_channels <= 7, n_classes <= 8")
+        return self._get_engine()
+
+    def set_check_mode(self, flag: bool = True):
+        raise NotImplementedError("the fp32 check engine covers UNet only")
+
+    def enable_cuda_graphs(self, flag: bool = True):
+        raise NotImplementedError("CUDA-graph replay covers UNet only")
+
+    def _fused_head(self, x, head, divisor=200.0):
+        raise NotImplementedError("fused inference heads cover UNet only; apply predict_mask / F.relu to the two outputs")
 
 
 def preprocess(img_org, input_size=None, device=None) -> torch.Tensor:

@@ -283,6 +283,28 @@ def partial_colsum(stats_partial, rows, row_pitch, col_lo, n, out):
     return out
 
 
+def nhwc_copy(src, dst):
+    """dst[..., :] = src over NHWC bf16 channel slices (skip half of a second decoder's concat buffer)."""
+    sp, scs, n, h, w, c = _nhwc(src)
+    dp, dcs, n2, h2, w2, c2 = _nhwc(dst)
+    if (n, h, w, c) != (n2, h2, w2, c2):
+        raise ValueError(f"nhwc_copy: shapes differ {tuple(src.shape)} vs {tuple(dst.shape)}")
+    _lib.call("b200unet_nhwc_copy", sp, scs, dp, dcs, n * h * w, c, _stream())
+    return dst
+
+
+def nhwc_add(a, b, out=None):
+    """out = a + b over NHWC bf16 channel slices (out defaults to a: in-place accumulation)."""
+    out = a if out is None else out
+    ap, acs, n, h, w, c = _nhwc(a)
+    bp, bcs, *sb = _nhwc(b)
+    op, ocs, *so = _nhwc(out)
+    if sb != [n, h, w, c] or so != [n, h, w, c]:
+        raise ValueError(f"nhwc_add: shapes differ {tuple(a.shape)} {tuple(b.shape)} {tuple(out.shape)}")
+    _lib.call("b200unet_nhwc_add", ap, acs, bp, bcs, op, ocs, n * h * w, c, _stream())
+    return out
+
+
 def channel_sum(x, out):
     xp, xcs, n, h, w, c = _nhwc(x)
     ws = _workspace(_lib.query("b200unet_channel_sum_workspace_floats", c), x.device)
