@@ -60,6 +60,11 @@ int b200unet_conv3x3_stat_rows(int N, int H, int W, int Cin, int Cout);
 int b200unet_set_kernel_choice(int resident, int resident_pairs, int streaming_pairs);
 int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial,
                            int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
+/* Eval-mode variant (running statistics, Model.py:17-18 with module.eval()): BatchNorm folded to a per-channel
+ * scale/shift ([Cout] fp32 each, 16-byte aligned; b200unet_bn_eval_affine produces them) and applied with the ReLU in the
+ * epilogue on the fp32 accumulators: a = bf16(relu(scale * conv(x) + shift)). The pre-BN tensor never reaches HBM. */
+int b200unet_conv3x3_bn_relu_igemm(const void* x, int x_cs, const void* w, const float* scale, const float* shift, void* a,
+                                   int a_cs, int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
 /* ConvTranspose2d(Cin, Cup, 2, 2) + bias (Model.py:56-57,66): out[n,2h+i,2w+j,d] = b[d] + sum_c x[n,h,w,c] W[c,d,i,j],
  * written with pitch out_cs into a (H2 x W2) canvas at row/col offset (pad_top, pad_left) (F.pad, Model.py:69-73). */
 int b200unet_convt2x2_fprop(const void* x, int x_cs, const void* w_fprop, const float* bias, void* out, int out_cs,
@@ -92,6 +97,8 @@ int b200unet_prep_first_weight(const float* w_oihw, void* w1, int Cout, int Cin,
 int b200unet_conv1x1_c64_stat_rows(int N, int H, int W, int Cout);
 int b200unet_conv1x1_c64_igemm(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial,
                                int N, int H, int W, int Cout, b200_stream_t stream);
+int b200unet_conv1x1_c64_bn_relu_igemm(const void* x, int x_cs, const void* w, const float* scale, const float* shift, void* a,
+                                       int a_cs, int N, int H, int W, int Cout, b200_stream_t stream);
 /* dw[k][j] = sum_{n,h,w} dy[n,h,w,k] col[n,h,w,j] for j < T (T = 9*Cin): inc.conv1's weight gradient, written as
  * fp32 OIHW [Cout][Cin][3][3] (= [Cout][T]). partial: b200unet_conv1x1_c64_wgrad_workspace_floats() floats. */
 int64_t b200unet_conv1x1_c64_wgrad_workspace_floats(int N, int H, int W, int Cout);

@@ -100,3 +100,33 @@ def test_config5_regression_mse_768():
         losses.append(float(loss))
     print("config5 losses:", losses)
     assert losses[-1] < losses[0]
+
+
+def test_eval_folded_bn_matches_unfolded_path(monkeypatch):
+    """Inference folds BatchNorm + ReLU into the conv epilogues (14 of 18 layers); B200UNET_FOLD_EVAL_BN=0 keeps the
+    separate BN-apply pass. Both must agree to bf16 noise, masks almost everywhere, and the folded path must launch
+    fewer kernels."""
+    import unet_torch_b200 as U
+    from unet_torch_b200 import _lib
+
+    torch.manual_seed(8)
+    net = U.UNet(3, 5)
+    with torch.no_grad():
+        _trained_buffers(net)
+    net = net.cuda().eval()
+    x = torch.randn(2, 3, 128, 160, device="cuda")
+    eng = net._get_engine()
+    with torch.no_grad():
+        net(x)  # first call prepares the bf16 weight operands (extra launches)
+        c0 = _lib.query("b200unet_launch_count")
+        folded = net(x)
+        c1 = _lib.query("b200unet_launch_count")
+        eng.fold_eval_bn = False
+        plain = net(x)
+        c2 = _lib.query("b200unet_launch_count")
+        eng.fold_eval_bn = True
+    e = rel_l2(folded, plain)
+    agree = float((U.predict_mask(folded) == U.predict_mask(plain)).float().mean())
+    print(f"folded vs unfolded eval logits rel-L2 {e:.3e}, mask agreement {agree:.4f}, launches {c1 - c0} vs {c2 - c1}")
+    assert e < 1e-2 and agree > 0.97
+    assert (c1 - c0) < (c2 - c1)

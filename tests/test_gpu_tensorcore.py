@@ -86,6 +86,40 @@ def test_conv3x3_wgrad(ops, n, h, w, cin, cout):
     assert rel_l2(dw, wv.grad) < 1e-4  # fp32 accumulation of exact bf16 products
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [CONV_SHAPES[i] for i in (1, 2, 7, 8, 9, 10, 11, 12)])
+@pytest.mark.parametrize("choice", [(-1, -1, -1), (0, 0, 0)])
+def test_conv3x3_eval_bn_relu_folded_epilogue(ops, n, h, w, cin, cout, choice):
+    """Eval mode: a = bf16(relu(scale * conv(x) + shift)) in the epilogue of every conv kernel (automatic dispatch =
+    resident / pair kernels, and the one-tile-per-CTA igemm), against the oracle's conv + eval BatchNorm + ReLU;
+    negative scales, a NaN-free zero plateau and a channel-slice destination included."""
+    from unet_torch_b200 import _lib
+
+    g = torch.Generator().manual_seed(5)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+    gamma, beta = torch.randn(cout, generator=g), torch.randn(cout, generator=g) * 0.3
+    rm, rv = torch.randn(cout, generator=g) * 0.2, torch.rand(cout, generator=g) + 0.5
+    wf, _ = ops.prep_conv3x3_weight(wt.cuda())
+    scale, shift = torch.empty(cout, device="cuda"), torch.empty(cout, device="cuda")
+    ops.bn_eval_affine(gamma.cuda(), beta.cuda(), rm.cuda(), rv.cuda(), 1e-5, scale, shift)
+    canvas = torch.full((n, h, w, 2 * cout), 7.0, dtype=BF16, device="cuda")
+    try:
+        _lib.call("b200unet_set_kernel_choice", *choice)
+        ops.conv3x3_bn_relu(to_nhwc_bf16(x), wf, scale, shift, canvas[..., cout:])
+    finally:
+        _lib.call("b200unet_set_kernel_choice", -1, -1, -1)
+    want = O.relu(O.batchnorm_eval(O.conv3x3(x, wt), gamma, beta, rm, rv))
+    got = from_nhwc(canvas[..., cout:].contiguous())
+    assert rel_l2(got, want) < TOL
+    assert float(got.min()) == 0.0 and bool((canvas[..., :cout] == 7.0).all())   # ReLU applied; the other slice untouched
+    # the unfused pair of launches rounds y to bf16 before the affine: the folded result is at least as close
+    y = torch.empty(n, h, w, cout, dtype=BF16, device="cuda")
+    ops.conv3x3(to_nhwc_bf16(x), wf, y)
+    a = torch.empty_like(y)
+    ops.bn_relu_fwd(y, scale, shift, a)
+    assert rel_l2(got, want) <= rel_l2(from_nhwc(a), want) * 1.05 + 1e-6
+
+
 @pytest.mark.parametrize("cin,cout,hw", [(64, 64, 512), (128, 64, 512), (128, 128, 256), (256, 256, 128), (512, 512, 64),
                                          (1024, 512, 64), (1024, 1024, 32), (256, 128, 256)])
 def test_full_size_layers_all_kernel_choices_agree(ops, cin, cout, hw):

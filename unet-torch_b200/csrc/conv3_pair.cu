@@ -31,6 +31,8 @@ struct PairArgs {
   int kblocks;   // Cin / 64
   int ktap;      // Cin (K extent of one tap in the weight operand)
   float* stats;  // [2 * workers][2][ncols] or null
+  const float* scale;  // eval-mode BatchNorm + ReLU folded into the epilogue: [ncols] each, or null
+  const float* shift;
 };
 
 template <int BN, int NA, int NB, int OB>
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(192, 1) conv3_pair_kernel(const __grid_constan
           uint32_t v[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN + q * 64 + half * 32, v);
           tmem_ld_wait();
+          if (args.scale != nullptr) affine_relu32(v, args.scale + n0 + q * 64 + half * 32, args.shift + n0 + q * 64 + half * 32);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * t + 0]), __uint_as_float(v[8 * t + 1]));
@@ -376,7 +379,8 @@ int conv3_pair_stat_rows(int N, int H, int W, int Cin, int Cout) {
 }
 
 int conv3_pair_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
-                      int W, int Cin, int Cout, cudaStream_t st) {
+                      int W, int Cin, int Cout, cudaStream_t st, const float* scale,
+                     const float* shift) {
   PairArgs a;
   int bn;
   pair_geometry(N, H, W, Cout, &bn, &a.ntiles_n, &a.workers, &a.tiles_total);
@@ -388,6 +392,8 @@ int conv3_pair_launch(const void* x, int x_cs, const void* w, void* y, int y_cs,
   a.kblocks = Cin / 64;
   a.ktap = Cin;
   a.stats = stats_partial;
+  a.scale = scale;
+  a.shift = shift;
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
   if (int e = make_tmap_4d(&a.tmA, x, Cin, W, H, N, xs, xs * W, xs * W * H, IN_W, IN_H)) return e;
   if (int e = make_tmap_2d(&a.tmW, w, static_cast<uint64_t>(9) * Cin, Cout, bn / 2)) return e;

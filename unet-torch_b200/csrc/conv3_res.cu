@@ -49,6 +49,8 @@ struct ResArgs {
   int cup;            // UP: output channels per (i,j) sub-position
   float* stats;       // [workers][2][ncols] or null
   const float* bias;  // UP: [cup] or null
+  const float* scale;  // CONV: eval-mode BatchNorm + ReLU folded into the epilogue: [ncols] each, or null
+  const float* shift;
 };
 
 // What the GEMM is:            A operand per K block                      epilogue
@@ -221,6 +223,8 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
           uint32_t v[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN + q * 64 + half * 32, v);
           tmem_ld_wait();
+          if (KIND == RES_CONV && args.scale != nullptr)
+            affine_relu32(v, args.scale + n0 + q * 64 + half * 32, args.shift + n0 + q * 64 + half * 32);
           if (KIND == RES_UP && args.bias != nullptr) {
             const float* bp = args.bias + (n0 + q * 64 + half * 32) % args.cup;
 #pragma unroll
@@ -371,7 +375,8 @@ int conv3_res_stat_rows(int N, int H, int W, int Cin, int Cout) {
 }
 
 int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
-                     int W, int Cin, int Cout, cudaStream_t st) {
+                     int W, int Cin, int Cout, cudaStream_t st, const float* scale,
+                     const float* shift) {
   ResArgs a;
   const int bn = res_bn(Cin, Cout);
   res_geometry(N, H, W, bn, Cout, &a.ntiles_n, &a.workers, &a.tiles_total);
@@ -381,6 +386,8 @@ int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, 
   a.W = W;
   a.ncols = Cout;
   a.stats = stats_partial;
+  a.scale = scale;
+  a.shift = shift;
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
   a.cup = Cout;
   a.bias = nullptr;
@@ -401,7 +408,8 @@ int conv1x1_c64_stat_rows(int N, int H, int W, int Cout) {
 }
 
 int conv1x1_c64_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
-                       int W, int Cout, cudaStream_t st) {
+                       int W, int Cout, cudaStream_t st, const float* scale,
+                     const float* shift) {
   ResArgs a;
   res_geometry(N, H, W, 64, Cout, &a.ntiles_n, &a.workers, &a.tiles_total);
   a.tiles_w = ceil_div(W, RTW);
@@ -410,6 +418,8 @@ int conv1x1_c64_launch(const void* x, int x_cs, const void* w, void* y, int y_cs
   a.W = W;
   a.ncols = Cout;
   a.stats = stats_partial;
+  a.scale = scale;
+  a.shift = shift;
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
   a.cup = Cout;
   a.bias = nullptr;
@@ -437,6 +447,8 @@ int convt_res_fprop_launch(const void* x, int x_cs, const void* w_fprop, const f
   a.ncols = 4 * Cup;
   a.cup = Cup;
   a.stats = nullptr;
+  a.scale = nullptr;
+  a.shift = nullptr;
   a.bias = bias;
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, os = static_cast<uint64_t>(out_cs) * 2;
   if (int e = make_tmap_4d(&a.tmA[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, RTW, RTH)) return e;
@@ -466,6 +478,8 @@ int convt_res_dgrad_launch(const void* du, int du_cs, const void* w_dgrad, void*
   a.ncols = Cin;
   a.cup = Cin;
   a.stats = nullptr;
+  a.scale = nullptr;
+  a.shift = nullptr;
   a.bias = nullptr;
   const uint64_t us = static_cast<uint64_t>(du_cs) * 2, xs = static_cast<uint64_t>(dx_cs) * 2;
   for (int ij = 0; ij < 4; ++ij) {

@@ -105,4 +105,15 @@ int b200unet_conv1x1_c64_igemm(const void* x, int x_cs, const void* w, void* y, 
   return b2h::conv1x1_c64_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cout, static_cast<cudaStream_t>(stream));
 }
 
+int b200unet_conv1x1_c64_bn_relu_igemm(const void* x, int x_cs, const void* w, const float* scale, const float* shift, void* a,
+                                       int a_cs, int N, int H, int W, int Cout, b200_stream_t stream) {
+  B2_REQUIRE(Cout % 64 == 0 && Cout > 0, "conv1x1_c64_bn_relu_igemm: Cout=%d must be a multiple of 64", Cout);
+  B2_REQUIRE(x_cs >= 64 && a_cs >= Cout && x_cs % 8 == 0 && a_cs % 8 == 0, "conv1x1_c64_bn_relu_igemm: bad pitches %d %d", x_cs, a_cs);
+  B2_REQUIRE(N > 0 && H > 0 && W > 0, "conv1x1_c64_bn_relu_igemm: empty tensor");
+  B2_REQUIRE(scale != nullptr && shift != nullptr && reinterpret_cast<uintptr_t>(scale) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(shift) % 16 == 0,
+             "conv1x1_c64_bn_relu_igemm: scale and shift are required, 16-byte aligned");
+  return b2h::conv1x1_c64_launch(x, x_cs, w, a, a_cs, nullptr, N, H, W, Cout, static_cast<cudaStream_t>(stream), scale, shift);
+}
+
 }  // extern "C"

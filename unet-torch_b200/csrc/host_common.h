@@ -29,20 +29,24 @@ int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t k, uint64_t rows, ui
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// scale/shift (optional, [Cout] each): eval-mode BatchNorm + ReLU folded into the epilogue (stats_partial must be null)
 // conv3_res.cu: persistent resident-weight 3x3 kernel for Cin in {64, 128}
 bool conv3_res_applicable(int Cin, int Cout);
 int conv3_res_stat_rows(int N, int H, int W, int Cin, int Cout);
 int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
-                     int W, int Cin, int Cout, cudaStream_t st);
+                     int W, int Cin, int Cout, cudaStream_t st, const float* scale = nullptr,
+                     const float* shift = nullptr);
 // conv3_res2.cu: the same as CTA pairs (tcgen05 cta_group::2, M = 256)
 int conv3_res2_stat_rows(int N, int H, int W, int Cin, int Cout);
 int conv3_res2_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
-                      int W, int Cin, int Cout, cudaStream_t st);
+                      int W, int Cin, int Cout, cudaStream_t st, const float* scale = nullptr,
+                     const float* shift = nullptr);
 // conv3_pair.cu: streaming CTA-pair kernel for Cin >= 256
 bool conv3_pair_applicable(int Cin, int Cout);
 int conv3_pair_stat_rows(int N, int H, int W, int Cin, int Cout);
 int conv3_pair_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
-                      int W, int Cin, int Cout, cudaStream_t st);
+                      int W, int Cin, int Cout, cudaStream_t st, const float* scale = nullptr,
+                     const float* shift = nullptr);
 // ... as ConvTranspose2d(k2,s2) forward (scatter epilogue) and backward-data (4-map gather) for the shallow levels
 bool convt_res_applicable(int Cin, int Cup);
 int convt_res_fprop_launch(const void* x, int x_cs, const void* w_fprop, const float* bias, void* out, int out_cs, int N,
@@ -53,6 +57,7 @@ int convt_res_dgrad_launch(const void* du, int du_cs, const void* w_dgrad, void*
 // the same kernel as a 1x1 convolution over a 64-channel input (inc.conv1 on its im2col'ed input, first_layer.cu)
 int conv1x1_c64_stat_rows(int N, int H, int W, int Cout);
 int conv1x1_c64_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,
-                       int W, int Cout, cudaStream_t st);
+                       int W, int Cout, cudaStream_t st, const float* scale = nullptr,
+                       const float* shift = nullptr);
 
 }  // namespace b2h

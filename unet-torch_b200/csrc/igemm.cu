@@ -38,6 +38,8 @@ struct IgemmArgs {
   int cup;               // MODE_UP: channels per (i,j) group of the N dimension
   float* stats;          // [mtiles][2][ncols] or null
   const float* bias;     // MODE_UP: [cup] or null
+  const float* scale;    // MODE_CONV3: eval-mode BatchNorm + ReLU folded into the epilogue: [ncols] each, or null
+  const float* shift;
 };
 
 template <int MODE>
@@ -197,6 +199,8 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ Igem
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + q * 64 + half * 32, v);
         tmem_ld_wait();
+        if (MODE == MODE_CONV3 && args.scale != nullptr)
+          affine_relu32(v, args.scale + n0 + q * 64 + half * 32, args.shift + n0 + q * 64 + half * 32);
         if (MODE == MODE_UP && args.bias != nullptr) {
           const int cbase = (n0 + q * 64 + half * 32) % args.cup;
 #pragma unroll
@@ -352,22 +356,23 @@ int pick_bn(int ncols, int limit) {
   return bn;
 }
 
-}  // namespace
-
-extern "C" {
-
-int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N,
-                           int H, int W, int Cin, int Cout, b200_stream_t stream) {
+// conv3x3 dispatch shared by the training entry point (BN statistics epilogue) and the eval entry point (BatchNorm + ReLU
+// folded into the epilogue: scale/shift per output channel)
+int conv3x3_dispatch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, const float* scale,
+                     const float* shift, int N, int H, int W, int Cin, int Cout, b200_stream_t stream) {
   B2_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv3x3_igemm: Cin (%d) and Cout (%d) must be multiples of 64", Cin, Cout);
   B2_REQUIRE(N > 0 && H > 0 && W > 0, "conv3x3_igemm: empty tensor");
   B2_REQUIRE(x_cs >= Cin && y_cs >= Cout && x_cs % 8 == 0 && y_cs % 8 == 0, "conv3x3_igemm: bad pitches %d %d", x_cs, y_cs);
   if (use_resident(Cin, Cout)) {
     if (use_pairs(N, H, W, Cin, Cout))
-      return b2h::conv3_res2_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream));
-    return b2h::conv3_res_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream));
+      return b2h::conv3_res2_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream),
+                                    scale, shift);
+    return b2h::conv3_res_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream),
+                                 scale, shift);
   }
   if (use_stream_pairs(Cin, Cout))
-    return b2h::conv3_pair_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream));
+    return b2h::conv3_pair_launch(x, x_cs, w, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream),
+                                  scale, shift);
   IgemmArgs a;
   a.tiles_w = b2h::ceil_div(W, TW);
   a.tiles_h = b2h::ceil_div(H, TH);
@@ -378,6 +383,8 @@ int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int 
   a.ncols = Cout;
   a.cup = Cout;
   a.stats = stats_partial;
+  a.scale = scale;
+  a.shift = shift;
   a.bias = nullptr;
   const int bn = pick_bn(Cout, 256);
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
@@ -387,6 +394,23 @@ int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int 
   if (int e = b2h::make_tmap_4d(&a.tmO[0], y, Cout, W, H, N, ys, ys * W, ys * W * H, TW, TH)) return e;
   for (int i = 1; i < 4; ++i) a.tmO[i] = a.tmO[0];
   return launch_mode<MODE_CONV3>(a, bn, N * a.tiles_w * a.tiles_h, static_cast<cudaStream_t>(stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N,
+                           int H, int W, int Cin, int Cout, b200_stream_t stream) {
+  return conv3x3_dispatch(x, x_cs, w, y, y_cs, stats_partial, nullptr, nullptr, N, H, W, Cin, Cout, stream);
+}
+
+int b200unet_conv3x3_bn_relu_igemm(const void* x, int x_cs, const void* w, const float* scale, const float* shift, void* a,
+                                   int a_cs, int N, int H, int W, int Cin, int Cout, b200_stream_t stream) {
+  B2_REQUIRE(scale != nullptr && shift != nullptr, "conv3x3_bn_relu_igemm: scale and shift are required");
+  B2_REQUIRE(reinterpret_cast<uintptr_t>(scale) % 16 == 0 && reinterpret_cast<uintptr_t>(shift) % 16 == 0,
+             "conv3x3_bn_relu_igemm: scale/shift must be 16-byte aligned");
+  return conv3x3_dispatch(x, x_cs, w, a, a_cs, nullptr, scale, shift, N, H, W, Cin, Cout, stream);
 }
 
 int b200unet_set_kernel_choice(int resident, int resident_pairs, int streaming_pairs) {
@@ -426,6 +450,8 @@ int b200unet_convt2x2_fprop(const void* x, int x_cs, const void* w_fprop, const 
   a.ncols = 4 * Cup;
   a.cup = Cup;
   a.stats = nullptr;
+  a.scale = nullptr;
+  a.shift = nullptr;
   a.bias = bias;
   const int bn = (env_bn() == 0) ? 256 : pick_bn(4 * Cup, 256);  // all four (i,j) sub-positions of 64 channels per CTA
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, os = static_cast<uint64_t>(out_cs) * 2;
@@ -458,6 +484,8 @@ int b200unet_convt2x2_dgrad(const void* du, int du_cs, const void* w_dgrad, void
   a.ncols = Cin;
   a.cup = Cin;
   a.stats = nullptr;
+  a.scale = nullptr;
+  a.shift = nullptr;
   a.bias = nullptr;
   const int bn = pick_bn(Cin, 256);
   const uint64_t us = static_cast<uint64_t>(du_cs) * 2, xs = static_cast<uint64_t>(dx_cs) * 2;

@@ -177,6 +177,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Eval-mode BatchNorm folded into the conv epilogue: v[j] = relu(scale[j] * v[j] + shift[j]) for the 32 consecutive
+// output channels a thread holds after one tcgen05.ld (sc/sh point at the first of them; 128-byte aligned). NaN is kept.
+__device__ __forceinline__ void affine_relu32(uint32_t (&v)[32], const float* __restrict__ sc, const float* __restrict__ sh) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(sc) + j), b = __ldg(reinterpret_cast<const float4*>(sh) + j);
+    const float x0 = fmaf(__uint_as_float(v[4 * j + 0]), a.x, b.x), x1 = fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y);
+    const float x2 = fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z), x3 = fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w);
+    v[4 * j + 0] = __float_as_uint(x0 < 0.f ? 0.f : x0);
+    v[4 * j + 1] = __float_as_uint(x1 < 0.f ? 0.f : x1);
+    v[4 * j + 2] = __float_as_uint(x2 < 0.f ? 0.f : x2);
+    v[4 * j + 3] = __float_as_uint(x3 < 0.f ? 0.f : x3);
+  }
+}
+
 }  // namespace b2
 
 // ----------------------------------------------------------------------------- CTA pairs (cta_group::2)

@@ -89,6 +89,7 @@ class DataParallelContext:
         self.sync_bn = sync_bn and self.world_size > 1
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self.extra_wait_streams = []  # streams (besides the current one) whose work a gradient bucket depends on
         # SyncBN statistics over NVLink peer memory (csrc/nvl_sync.cu): symmetric buffer + peer pointer table
         self._nvl = None
         self._seq = 0
@@ -179,6 +180,8 @@ class DataParallelContext:
             ev.record(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
+                for st in self.extra_wait_streams:
+                    self.comm_stream.wait_stream(st)
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
                 t.mul_(1.0 / self.world_size)
             works.append(None)

@@ -145,6 +145,14 @@ class UNetEngine:
         self.head = self.decoders[0][2]
         self._graphs = {}     # (shape, device, training, save) -> _GraphedStep
         self._seen = set()    # keys that already ran once eagerly (kernel attributes configured, allocator warm)
+        # B200UNET_WGRAD_STREAM=1: weight-gradient kernels on a second stream (nothing downstream in backward depends on
+        # them), overlapping the bandwidth-bound BN/ReLU backward of the next layer. Measured neutral on B200 (687-691
+        # img/s either way: the step runs at the 1000 W power cap, so co-scheduling does not add throughput) -> off.
+        # eval forward without saving for backward: layers that are not followed by a pooling fold BN + ReLU into the
+        # conv epilogue (14 of the 18 conv layers); B200UNET_FOLD_EVAL_BN=0 keeps the separate BN-apply pass
+        self.fold_eval_bn = os.environ.get("B200UNET_FOLD_EVAL_BN", "1") not in ("", "0")
+        self.wgrad_overlap = os.environ.get("B200UNET_WGRAD_STREAM", "0") not in ("", "0")
+        self._wgrad_stream = None
 
     def graphed_step(self, x, training, save):
         """The captured step for this input, or None when the call must run eagerly: graphs disabled, data parallel
@@ -243,6 +251,16 @@ class UNetEngine:
         enc_rec, dec_rec = [], []
 
         def conv_bn_relu(cb: _ConvBN, inp, c_out, hh, ww, a_out, pooled=None, pool_idx=None):
+            if not training and not save and pooled is None and self.fold_eval_bn:
+                # inference: BatchNorm (running statistics) + ReLU folded into the conv epilogue; y never reaches HBM
+                scale, shift, _, _, _ = self._bn_affine(cb, None, 0, n * hh * ww, False, None)
+                if cb.first:
+                    col = torch.empty((n, hh, ww, 64), dtype=BF16, device=dev)
+                    ops.first_im2col(inp, col)
+                    ops.conv1x1_c64_bn_relu(col, cb.operands()[0], scale, shift, a_out)
+                else:
+                    ops.conv3x3_bn_relu(inp, cb.operands()[0], scale, shift, a_out)
+                return None
             y = torch.empty((n, hh, ww, c_out), dtype=BF16, device=dev)
             stats = None
             if cb.first:
@@ -345,6 +363,25 @@ class UNetEngine:
                 flat.mark_ready(ps)
 
         sync = (lambda s: dp.all_reduce_sum(s)) if (dp is not None and dp.sync_bn) else None
+        side = None
+        if self.wgrad_overlap:
+            if self._wgrad_stream is None:
+                self._wgrad_stream = torch.cuda.Stream(device=dev)
+            side = self._wgrad_stream
+            side.wait_stream(torch.cuda.current_stream())  # fork (also puts the stream into an ongoing graph capture)
+            if dp is not None:
+                dp.extra_wait_streams = [side]
+
+        def on_wgrad_stream(launch):
+            """Run `launch()` (weight-gradient kernels reading tensors that stay alive until backward returns) on the
+            side stream, ordered after everything enqueued so far."""
+            if side is None:
+                return launch()
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                launch()
 
         def bn_conv_bwd(cb: _ConvBN, rec, g1, g_pool, pool_idx, hh, ww, need_dx, dx_colsum=None):
             inp, y, scale, shift, mean, rstd, count = rec
@@ -355,9 +392,9 @@ class UNetEngine:
             dy = y  # dy overwrote y in place
             dw = gbuf(cb.conv.weight)
             if cb.first:
-                ops.conv1x1_c64_wgrad(inp, dy, dw)
+                on_wgrad_stream(lambda: ops.conv1x1_c64_wgrad(inp, dy, dw))
             else:
-                ops.conv3x3_wgrad(inp, dy, dw)
+                on_wgrad_stream(lambda: ops.conv3x3_wgrad(inp, dy, dw))
             grads[bn.weight], grads[bn.bias], grads[cb.conv.weight] = dgamma, dbeta, dw
             done(bn.weight, bn.bias, cb.conv.weight)
             if not need_dx:
@@ -401,7 +438,7 @@ class UNetEngine:
                 else:
                     ops.nhwc_add(skip_grads[l], dcat[..., : ch[l]])
                 du = dcat[..., ch[l]:]
-                ops.convt2x2_wgrad(d_in, du, dwu)
+                on_wgrad_stream(lambda d_in=d_in, du=du, dwu=dwu: ops.convt2x2_wgrad(d_in, du, dwu))
                 grads[upo.up.bias], grads[upo.up.weight] = db, dwu
                 done(upo.up.bias, upo.up.weight)
                 _, wd = upo.operands()
@@ -419,6 +456,8 @@ class UNetEngine:
             else:
                 g1 = bn_conv_bwd(c2, r2, skip_grads[l], g_pool, idx, hs[l], wsz[l], True)
             g_pool = bn_conv_bwd(c1, r1, g1, None, None, hs[l], wsz[l], need_dx=(l > 0))
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)  # join
         if flat is not None:
             flat.finish()
         return grads

@@ -90,6 +90,20 @@ def conv3x3(x: torch.Tensor, w_op: torch.Tensor, out: torch.Tensor, stats_partia
     return out
 
 
+def conv3x3_bn_relu(x, w_op, scale, shift, out):
+    """Eval mode: out = bf16(relu(scale * conv3x3(x) + shift)), BatchNorm (running statistics) and ReLU folded into the
+    conv epilogue on the fp32 accumulators; `out` may be a channel slice of a concat buffer."""
+    xp, xcs, n, h, w, cin = _nhwc(x)
+    op, ocs, n2, h2, w2, cout = _nhwc(out)
+    if (n, h, w) != (n2, h2, w2) or tuple(w_op.shape) != (cout, 3, 3, cin) or w_op.dtype != BF16:
+        raise ValueError(f"conv3x3_bn_relu: shape mismatch x{tuple(x.shape)} w{tuple(w_op.shape)} out{tuple(out.shape)}")
+    if scale.numel() != cout or shift.numel() != cout:
+        raise ValueError("conv3x3_bn_relu: scale/shift must have Cout elements")
+    _lib.call("b200unet_conv3x3_bn_relu_igemm", xp, xcs, w_op.data_ptr(), _f32(scale), _f32(shift), op, ocs, n, h, w, cin,
+              cout, _stream())
+    return out
+
+
 def convt2x2(x, w_fprop, bias, out_canvas_slice, pad_top=0, pad_left=0):
     """ConvTranspose2d(k=2,s=2)+bias of x [N,H,W,Cin] written into out_canvas_slice [N,H2,W2,Cup] (a channel slice
     of the concat buffer) at offset (pad_top, pad_left)."""
@@ -171,6 +185,19 @@ def conv1x1_c64(x, w1, out, stats_partial=None):
     if stats_partial is not None and stats_partial.numel() < conv1x1_c64_stat_rows(n, h, w, cout) * 2 * cout:
         raise ValueError("conv1x1_c64: stats_partial too small")
     _lib.call("b200unet_conv1x1_c64_igemm", xp, xcs, w1.data_ptr(), op, ocs, _f32(stats_partial), n, h, w, cout, _stream())
+    return out
+
+
+def conv1x1_c64_bn_relu(x, w1, scale, shift, out):
+    """Eval mode of conv1x1_c64: BatchNorm + ReLU folded into the epilogue."""
+    xp, xcs, n, h, w, c = _nhwc(x)
+    op, ocs, n2, h2, w2, cout = _nhwc(out)
+    if (n, h, w) != (n2, h2, w2) or c != 64 or tuple(w1.shape) != (cout, 64) or w1.dtype != BF16:
+        raise ValueError("conv1x1_c64_bn_relu: shape mismatch")
+    if scale.numel() != cout or shift.numel() != cout:
+        raise ValueError("conv1x1_c64_bn_relu: scale/shift must have Cout elements")
+    _lib.call("b200unet_conv1x1_c64_bn_relu_igemm", xp, xcs, w1.data_ptr(), _f32(scale), _f32(shift), op, ocs, n, h, w, cout,
+              _stream())
     return out
 
 
