@@ -19,7 +19,18 @@ def main(path, out):
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6}.get(unit, 1.0)
         d = per.setdefault(r["ID"], {"name": r["Kernel Name"]})
         d[r["Metric Name"]] = v * scale
-    rows = [d for d in per.values() if "dram__bytes_read.sum" in d]
+    import re
+
+    # conv3x3 fprop/dgrad launches only: the pair kernels, and conv3_res_kernel with TAPS = 9, KIND = 0 (the same kernel
+    # also runs the 1x1 first-layer GEMM and the ConvTranspose2d GEMMs, which are not part of this figure)
+    def is_conv3(name):
+        return ("conv3_pair_kernel" in name or "conv3_res2_kernel" in name
+                or re.search(r"conv3_res_kernel<\d+, \d+, \d+, \d+, 9, 0>", name) is not None)
+
+    rows = [d for d in per.values() if "dram__bytes_read.sum" in d and is_conv3(d["name"])]
+    starts = [i for i, d in enumerate(rows)]
+    if len(rows) > 34:  # the capture window may cover more than one step: keep the first whole step's 34 launches
+        rows = rows[:34]
     n = len(rows)
     rd = sum(d["dram__bytes_read.sum"] for d in rows)
     wr = sum(d["dram__bytes_write.sum"] for d in rows)

@@ -5,7 +5,7 @@
 mkdir -p gpurun_out
 TAG=${TAG:-prof}
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
-$CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
+[ "${LAUNCHES:-1}" = 1 ] && $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-900} -c ${COUNT:-700} --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
@@ -15,13 +15,17 @@ full() {  # name, kernel regex, skip (matching launches), count, extra flags
       > gpurun_out/${TAG}_ncu_$1.log 2>&1
   echo "full capture $1 rc=$?"
 }
-# per-launch DRAM bytes of every conv3x3 fprop/dgrad launch of one step (34 launches; 4 steps precede: 1 eager + 3 warm-up)
+# per-launch DRAM bytes of every conv3x3 fprop/dgrad launch of one step. ncu matches -k against the function name without
+# template arguments, and conv3_res_kernel also runs the first-layer and ConvTranspose2d GEMMs: 40 matching launches per
+# step (34 conv3x3 + 6 others; scripts/conv_traffic.py keeps the 34); 4 steps precede (1 eager + 3 warm-up).
+if [ "${CONVDRAM:-1}" = 1 ]; then
 $CMD > gpurun_out/${TAG}_plain_convdram.log 2>&1 &&
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-    -k "regex:conv3_pair_kernel|conv3_res2_kernel|conv3_res_kernel<.*9, 0>" -s 136 -c 34 --csv \
+    -k "regex:conv3_pair_kernel|conv3_res2_kernel|conv3_res_kernel" -s 160 -c 40 --csv \
     --log-file gpurun_out/${TAG}_convdram.csv $CMD > gpurun_out/${TAG}_ncu_convdram.log 2>&1
+fi
 echo "conv dram rc=$?"
-for what in ${FULL:-pair res wgrad bn}; do
+for what in ${FULL-pair res wgrad bn}; do   # FULL="" skips the full captures
   case $what in
     pair)  full pair  'conv3_pair_kernel' 80 7 "" ;;
     res)   full res   'conv3_res2_kernel|conv3_res_kernel' 96 8 "" ;;
