@@ -6,6 +6,7 @@
 //                   test_mc3serousv5.py:961-974: OutConv + F.relu + /200 (density maps) and their per-map sums (counts).
 #include "../../include/b200unet.h"
 #include "host_common.h"
+#include "head_common.cuh"
 
 #include <cuda_bf16.h>
 
@@ -137,47 +138,25 @@ __global__ void __launch_bounds__(256) znorm_apply_kernel(const uint8_t* __restr
 }
 
 // ---------------------------------------------------------------------------------------------- fused inference heads
-constexpr int MAXC = 8;
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-  }
-}
+using b2head::MAXC;
 
-// logits of one pixel: same arithmetic, in the same order, as head_fprop_kernel (small.cu)
-__device__ __forceinline__ void head_px(const __nv_bfloat16* __restrict__ a, const float* __restrict__ wsm,
-                                        const float* __restrict__ bias, int Cin, int ncls, float (&acc)[MAXC]) {
-#pragma unroll
-  for (int j = 0; j < MAXC; ++j) acc[j] = (j < ncls) ? bias[j] : 0.f;
-  for (int c8 = 0; c8 < Cin / 8; ++c8) {
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(a + c8 * 8)), f);
-#pragma unroll
-    for (int j = 0; j < MAXC; ++j) {
-      if (j < ncls) {
-        const float* wr = wsm + j * Cin + c8 * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[j] = fmaf(f[i], wr[i], acc[j]);
-      }
-    }
-  }
-}
-
-// head_fprop_kernel followed by softmax_argmax_kernel (loss.cu), bit-identical to the two-kernel path: torch.softmax
-// in fp32, then the first maximum (probabilities that round to the same float tie), then np.uint8.
+// head_fprop_kernel (small.cu) followed by softmax_argmax_kernel (loss.cu), bit-identical to the two-kernel path (the
+// logits come from the same warp-cooperative routine): torch.softmax in fp32, then the first maximum (probabilities that
+// round to the same float tie), then np.uint8.
 __global__ void __launch_bounds__(256) head_mask_kernel(const __nv_bfloat16* __restrict__ a, int a_cs,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        uint8_t* __restrict__ mask, long long P, int Cin, int ncls) {
-  extern __shared__ float wsm[];  // [ncls][Cin]
-  for (int i = threadIdx.x; i < ncls * Cin; i += blockDim.x) wsm[i] = w[i];
+  extern __shared__ __align__(16) float wsm[];
+  b2head::load_weights(wsm, w, Cin, ncls);
+  uint32_t* stage = b2head::warp_stage(wsm, Cin, ncls);
   __syncthreads();
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < P;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long g = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); g * 32 < P; g += warps) {
     float acc[MAXC];
-    head_px(a + p * a_cs, wsm, bias, Cin, ncls, acc);
+    b2head::logits_warp32(a, a_cs, wsm, stage, bias, g * 32, P, Cin, ncls, acc);
+    const long long p = g * 32 + lane;
+    if (p >= P) continue;
     float m = -INFINITY;
 #pragma unroll
     for (int j = 0; j < MAXC; ++j)
@@ -210,18 +189,22 @@ __global__ void __launch_bounds__(256) head_density_kernel(const __nv_bfloat16* 
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           float* __restrict__ out, double* __restrict__ counts, long long HW,
                                                           int blocks_per_image, int Cin, int ncls, float divisor) {
-  extern __shared__ float wsm[];  // [ncls][Cin]
+  extern __shared__ __align__(16) float wsm[];
   __shared__ double red[8][MAXC];
-  for (int i = threadIdx.x; i < ncls * Cin; i += blockDim.x) wsm[i] = w[i];
+  b2head::load_weights(wsm, w, Cin, ncls);
+  uint32_t* stage = b2head::warp_stage(wsm, Cin, ncls);
   __syncthreads();
   const int n = blockIdx.x / blocks_per_image, b = blockIdx.x % blocks_per_image;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const __nv_bfloat16* src = a + static_cast<long long>(n) * HW * a_cs;
   double part[MAXC];
 #pragma unroll
   for (int j = 0; j < MAXC; ++j) part[j] = 0.0;
-  for (long long hw = static_cast<long long>(b) * blockDim.x + threadIdx.x; hw < HW;
-       hw += static_cast<long long>(blocks_per_image) * blockDim.x) {
+  for (long long g = static_cast<long long>(b) * 8 + warp; g * 32 < HW; g += static_cast<long long>(blocks_per_image) * 8) {
     float acc[MAXC];
-    head_px(a + (static_cast<long long>(n) * HW + hw) * a_cs, wsm, bias, Cin, ncls, acc);
+    b2head::logits_warp32(src, a_cs, wsm, stage, bias, g * 32, HW, Cin, ncls, acc);
+    const long long hw = g * 32 + lane;
+    if (hw >= HW) continue;
 #pragma unroll
     for (int j = 0; j < MAXC; ++j)
       if (j < ncls) {
@@ -233,7 +216,6 @@ __global__ void __launch_bounds__(256) head_density_kernel(const __nv_bfloat16* 
       }
   }
   if (counts == nullptr) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int j = 0; j < MAXC; ++j) {
     double v = part[j];
@@ -300,12 +282,13 @@ int b200unet_znorm_to_chw(const uint8_t* img_nhwc, void* workspace, float* out_n
 int b200unet_head_mask(const void* a, int a_cs, const float* w, const float* bias, uint8_t* mask, int N, int H, int W,
                        int Cin, int ncls, b200_stream_t stream) {
   B2_REQUIRE(ncls >= 1 && ncls <= MAXC, "head_mask: n_classes=%d must be in [1,%d]", ncls, MAXC);
-  B2_REQUIRE(Cin % 8 == 0 && a_cs % 8 == 0, "head_mask: Cin=%d must be a multiple of 8", Cin);
+  B2_REQUIRE(Cin > 0 && Cin % 64 == 0 && a_cs % 8 == 0 && a_cs >= Cin, "head_mask: Cin=%d must be a multiple of 64 (pitch %d)", Cin, a_cs);
+  B2_REQUIRE(b2head::smem_bytes(Cin, ncls, 8) <= 48 * 1024, "head_mask: Cin=%d x n_classes=%d weights do not fit shared memory", Cin, ncls);
   const long long P = static_cast<long long>(N) * H * W;
   long long blocks = (P + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  head_mask_kernel<<<static_cast<int>(blocks), 256, ncls * Cin * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  head_mask_kernel<<<static_cast<int>(blocks), 256, b2head::smem_bytes(Cin, ncls, 8), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(a), a_cs, w, bias, mask, P, Cin, ncls);
   return b2h::check_launch("head_mask");
 }
@@ -313,7 +296,8 @@ int b200unet_head_mask(const void* a, int a_cs, const float* w, const float* bia
 int b200unet_head_density(const void* a, int a_cs, const float* w, const float* bias, float* out_nchw, double* counts,
                           int N, int H, int W, int Cin, int ncls, float divisor, b200_stream_t stream) {
   B2_REQUIRE(ncls >= 1 && ncls <= MAXC, "head_density: n_classes=%d must be in [1,%d]", ncls, MAXC);
-  B2_REQUIRE(Cin % 8 == 0 && a_cs % 8 == 0, "head_density: Cin=%d must be a multiple of 8", Cin);
+  B2_REQUIRE(Cin > 0 && Cin % 64 == 0 && a_cs % 8 == 0 && a_cs >= Cin, "head_density: Cin=%d must be a multiple of 64 (pitch %d)", Cin, a_cs);
+  B2_REQUIRE(b2head::smem_bytes(Cin, ncls, 8) <= 48 * 1024, "head_density: Cin=%d x n_classes=%d weights do not fit shared memory", Cin, ncls);
   B2_REQUIRE(N > 0 && H > 0 && W > 0, "head_density: empty input");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long HW = static_cast<long long>(H) * W;
@@ -327,7 +311,7 @@ int b200unet_head_density(const void* a, int a_cs, const float* w, const float* 
   long long bpi = (148 * 8 + N - 1) / N;
   const long long cap = (HW + 255) / 256;
   if (bpi > cap) bpi = cap;
-  head_density_kernel<<<static_cast<int>(N * bpi), 256, ncls * Cin * sizeof(float), st>>>(
+  head_density_kernel<<<static_cast<int>(N * bpi), 256, b2head::smem_bytes(Cin, ncls, 8), st>>>(
       static_cast<const __nv_bfloat16*>(a), a_cs, w, bias, out_nchw, counts, HW, static_cast<int>(bpi), Cin, ncls, divisor);
   return b2h::check_launch("head_density");
 }

@@ -4,6 +4,7 @@
 // Both are bound by the 64-channel bf16 activation they write / read (128 B per pixel), not by arithmetic.
 #include "../../include/b200unet.h"
 #include "host_common.h"
+#include "head_common.cuh"
 
 #include <cuda_bf16.h>
 
@@ -214,34 +215,27 @@ __global__ void __launch_bounds__(256) first_wgrad_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------- head
+// OutConv forward -> fp32 NCHW logits; the dot products are warp-cooperative (head_common.cuh): coalesced 512-byte loads.
 __global__ void __launch_bounds__(256) head_fprop_kernel(const __nv_bfloat16* __restrict__ a, int a_cs,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          float* __restrict__ z, long long P, long long HW, int Cin,
                                                          int ncls) {
-  extern __shared__ float wsm[];  // [ncls][Cin]
-  for (int i = threadIdx.x; i < ncls * Cin; i += blockDim.x) wsm[i] = w[i];
+  extern __shared__ __align__(16) float wsm[];
+  b2head::load_weights(wsm, w, Cin, ncls);
+  uint32_t* stage = b2head::warp_stage(wsm, Cin, ncls);
   __syncthreads();
-  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < P;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float acc[8];
+  const int lane = threadIdx.x & 31;
+  const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long g = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); g * 32 < P; g += warps) {
+    float acc[b2head::MAXC];
+    b2head::logits_warp32(a, a_cs, wsm, stage, bias, g * 32, P, Cin, ncls, acc);
+    const long long p = g * 32 + lane;
+    if (p < P) {
+      const long long n = p / HW, hw = p % HW;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = (j < ncls) ? bias[j] : 0.f;
-    for (int c8 = 0; c8 < Cin / 8; ++c8) {
-      float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(a + p * a_cs + c8 * 8)), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < ncls) {
-          const float* wr = wsm + j * Cin + c8 * 8;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[j] = fmaf(f[i], wr[i], acc[j]);
-        }
-      }
+      for (int j = 0; j < b2head::MAXC; ++j)
+        if (j < ncls) z[(n * ncls + j) * HW + hw] = acc[j];
     }
-    const long long n = p / HW, hw = p % HW;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < ncls) z[(n * ncls + j) * HW + hw] = acc[j];
   }
 }
 
@@ -409,11 +403,12 @@ int b200unet_conv3x3_first_wgrad(const float* x_nchw, const void* dy, int dy_cs,
 int b200unet_head_fprop(const void* a, int a_cs, const float* w, const float* bias, float* logits_nchw, int N, int H,
                         int W, int Cin, int ncls, b200_stream_t stream) {
   B2_REQUIRE(ncls >= 1 && ncls <= 8, "head_fprop: n_classes=%d must be in [1,8]", ncls);
-  B2_REQUIRE(Cin % 8 == 0 && a_cs % 8 == 0, "head_fprop: Cin=%d must be a multiple of 8", Cin);
+  B2_REQUIRE(Cin > 0 && Cin % 64 == 0 && a_cs % 8 == 0 && a_cs >= Cin, "head_fprop: Cin=%d must be a multiple of 64 (pitch %d)", Cin, a_cs);
+  B2_REQUIRE(b2head::smem_bytes(Cin, ncls, 8) <= 48 * 1024, "head_fprop: Cin=%d x n_classes=%d weights do not fit shared memory", Cin, ncls);
   const long long P = static_cast<long long>(N) * H * W;
   long long blocks = (P + 255) / 256;
   if (blocks > MAX_BLOCKS) blocks = MAX_BLOCKS;
-  head_fprop_kernel<<<static_cast<int>(blocks), 256, ncls * Cin * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  head_fprop_kernel<<<static_cast<int>(blocks), 256, b2head::smem_bytes(Cin, ncls, 8), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(a), a_cs, w, bias, logits_nchw, P, static_cast<long long>(H) * W, Cin, ncls);
   return b2h::check_launch("head_fprop");
 }
