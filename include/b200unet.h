@@ -163,6 +163,11 @@ int b200unet_bn_relu_bwd_apply(const void* g1, int g1_cs, const void* g_pool, co
 int b200unet_partial_colsum(const float* partial, int64_t rows, int row_pitch, int col_lo, int n, float* out,
                             b200_stream_t stream);
 /* per-channel sum over pixels of a bf16 NHWC tensor (ConvTranspose2d bias gradient). */
+/* nn.MaxPool2d(2) alone (Model.py:36,42) on an NHWC bf16 tensor: first maximum in row-major window order, NaN wins;
+ * pool_idx (nullable): window position 0..3 per pooled element ([N][H/2][W/2][C] bytes). Inference path: BatchNorm + ReLU
+ * already ran in the conv epilogue (b200unet_conv3x3_bn_relu_igemm). */
+int b200unet_maxpool2x2_fwd(const void* a, int a_cs, void* pooled, int p_cs, uint8_t* pool_idx, int N, int H, int W, int C,
+                            b200_stream_t stream);
 /* Two decoders over one encoder (UNet_multitask, Model.py:172-250): copy a channel slice of an NHWC bf16 buffer into another
  * (the skip half of the second decoder's concat buffer), and out = a + b over channel slices (sum of the two decoders'
  * gradients; out may alias a). Pitches in elements, multiples of 8. */
@@ -207,6 +212,9 @@ int b200unet_znorm_to_chw(const uint8_t* img_nhwc, void* workspace, float* out_n
  * last activation (NHWC bf16); bit-identical to b200unet_head_fprop followed by b200unet_softmax_argmax. */
 int b200unet_head_mask(const void* a, int a_cs, const float* w, const float* bias, uint8_t* mask, int N, int H, int W,
                        int Cin, int ncls, b200_stream_t stream);
+/* Binary-mask epilogue (test.py:393-399): OutConv channel 0 + torch.sigmoid (fp32) + `>= threshold` (0.5) -> {0,1} uint8. */
+int b200unet_head_sigmoid_mask(const void* a, int a_cs, const float* w, const float* bias, uint8_t* mask, int N, int H, int W,
+                               int Cin, int ncls, float threshold, b200_stream_t stream);
 /* Density-map epilogue (test_mc3serousv5.py:961-974): OutConv + F.relu + fp32 division by `divisor` (200 in the
  * reference; 1 = plain F.relu(model(x))) -> fp32 NCHW maps; counts (nullable): [N][ncls] fp64 sums of the stored maps. */
 int b200unet_head_density(const void* a, int a_cs, const float* w, const float* bias, float* out_nchw, double* counts,

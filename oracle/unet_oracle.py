@@ -248,6 +248,13 @@ def mask_uint8(logits):
     return softmax_argmax(logits).to(torch.uint8)
 
 
+def sigmoid_mask(logits, threshold=0.5):
+    """torch.sigmoid(out) then out[0, 0] >= 0.5 -> 1 else 0 (test.py:393-399), for every image of the batch; the sigmoid is
+    evaluated in the logits' dtype as 1 / (1 + exp(-z)) like torch does."""
+    s = 1 / (1 + torch.exp(-logits[:, 0]))
+    return (s >= threshold).to(torch.uint8)
+
+
 def density_maps(logits, divisor=200.0):
     """F.relu(model(x)) then the float32 maps / 200 (test_mc3serousv5.py:961-974); also their per-map sums (counts)."""
     d = relu(logits) / torch.tensor(divisor, dtype=logits.dtype)

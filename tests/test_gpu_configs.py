@@ -130,3 +130,40 @@ def test_eval_folded_bn_matches_unfolded_path(monkeypatch):
     print(f"folded vs unfolded eval logits rel-L2 {e:.3e}, mask agreement {agree:.4f}, launches {c1 - c0} vs {c2 - c1}")
     assert e < 1e-2 and agree > 0.97
     assert (c1 - c0) < (c2 - c1)
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 400, 400), (3, 48, 80)])
+def test_training_step_at_config_yml_size_against_oracle(n, h, w):
+    """config.yml trains at 400x400 (25x25 at the bottleneck: every level has ragged 16x8 tiles), and an odd batch of
+    non-square images: logits, loss and parameter gradients of one training step against the fp32 CPU oracle."""
+    import unet_torch_b200 as U
+
+    torch.manual_seed(1063)
+    net = U.UNet(3, 2)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(n, 3, h, w, generator=g)
+    y = (torch.rand(n, h, w, generator=g) > 0.6).float()
+    net = net.cuda().train()
+    U.loss.CLASS_NUMBER = 2
+    out = net(x.cuda())
+    loss = U.calc_loss(out, y.cuda(), loss_type="dice_bce_mc")
+    loss.backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    sd_req = dict(sd)
+    sd_req.update(params)
+    want, _ = O.unet_forward(sd_req, x, training=True)
+    want_loss = O.calc_loss(want, y, "dice_bce_mc", 2)
+    want_loss.backward()
+    e = rel_l2(out.detach(), want.detach())
+    e_loss = abs(float(loss.detach()) - float(want_loss.detach())) / abs(float(want_loss.detach()))
+    print(f"{n}x{h}x{w}: logits rel {e:.3e}, loss rel {e_loss:.3e}")
+    assert e < 3e-2 and e_loss < 1e-2
+    grads = dict(net.named_parameters())
+    worst = max(rel_l2(grads[k].grad, p.grad) for k, p in params.items())
+    # the deepest layers see 25x25 (or 3x5) maps: per-parameter error of a bf16 BatchNorm network vs fp32 (SURVEY 7.4-1)
+    print(f"{n}x{h}x{w}: worst param-grad rel error vs the fp32 oracle {worst:.3e}")
+    assert worst < 0.75
+    gn = torch.sqrt(sum(grads[k].grad.double().norm() ** 2 for k in params))
+    wn = torch.sqrt(sum(p.grad.double().norm() ** 2 for p in params.values()))
+    assert abs(float(gn / wn) - 1) < 0.1

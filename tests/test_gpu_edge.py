@@ -91,6 +91,10 @@ def test_fused_heads_bit_exact(ncls, n, h, w):
     want, want_counts = O.density_maps(logits.cpu(), 200.0)
     assert torch.equal(dens.cpu(), want)
     assert torch.allclose(counts.cpu(), want_counts, rtol=1e-12, atol=1e-12)
+    sm = ops.head_sigmoid_mask(a, wt, b, 0.5)
+    assert torch.equal(sm, (torch.sigmoid(logits)[:, 0] >= 0.5).to(torch.uint8))   # torch's own CUDA sigmoid on the same logits
+    assert torch.equal(sm.cpu(), O.sigmoid_mask(logits.cpu()))
+    assert 0.2 < float(sm.float().mean()) < 0.8
     relu_only, none = ops.head_density(a, wt, b, 1.0, with_counts=False)
     assert none is None and torch.equal(relu_only.cpu(), torch.relu(logits.cpu()))
 
@@ -107,6 +111,7 @@ def test_model_predict_equals_unfused_path():
         mask = net.predict(x)
         dens, counts = net.predict_density(x)
     assert torch.equal(mask.long(), U.predict_mask(logits))
+    assert torch.equal(net.predict_binary(x), (torch.sigmoid(logits)[:, 0] >= 0.5).to(torch.uint8))
     # the reference divides on the CPU in numpy (true fp32 division; torch's CUDA div-by-scalar multiplies by 1/200)
     assert np.array_equal(dens.cpu().numpy(), torch.relu(logits).cpu().numpy() / 200)
     assert torch.allclose(counts, dens.double().sum(dim=(2, 3)), rtol=1e-12)

@@ -218,3 +218,32 @@ def test_softmax_argmax_bit_exact(golden):
     # larger random case against the oracle restatement
     z = torch.randn(2, 5, 64, 64, generator=torch.Generator().manual_seed(9)) * 0.01
     assert torch.equal(U.predict_mask(z.cuda()).cpu(), O.softmax_argmax(z))
+
+
+def test_maxpool_alone_matches_reference_semantics(ops, golden):
+    """b200unet_maxpool2x2_fwd (inference path): values and window positions against torch's max_pool2d goldens (ties ->
+    first, NaN wins, -0.0/+0.0 tie) and against the oracle on a random channel-slice input."""
+    g = golden("ref_ops.pt")["pool"]
+    x = g["x"]                                      # [2,3,6,8] fp32 with ties / NaN / signed zeros
+    n, c, h, w = x.shape
+    xp = torch.zeros(n, 8, h, w)
+    xp[:, :c] = x
+    a = to_nhwc_bf16(bf16_round(xp))
+    pooled = torch.empty(n, h // 2, w // 2, 8, dtype=BF16, device="cuda")
+    idx = torch.empty(n, h // 2, w // 2, 8, dtype=torch.uint8, device="cuda")
+    ops.maxpool2x2(a, pooled, idx)
+    want_v, want_i = torch.nn.functional.max_pool2d(bf16_round(xp), 2, return_indices=True)
+    got_v = from_nhwc(pooled)
+    assert bool(((got_v == want_v) | (got_v.isnan() & want_v.isnan())).all())
+    k = idx.permute(0, 3, 1, 2).cpu().long()
+    hp = torch.arange(h // 2).view(1, 1, -1, 1)
+    wp = torch.arange(w // 2).view(1, 1, 1, -1)
+    flat = (2 * hp + k // 2) * w + (2 * wp + k % 2)  # window position -> torch's flat index h * W_in + w
+    assert torch.equal(flat, want_i)
+    gen = torch.Generator().manual_seed(3)
+    big = bf16_round(torch.randn(2, 128, 16, 24, generator=gen))
+    canvas = to_nhwc_bf16(big)
+    out = torch.empty(2, 8, 12, 64, dtype=BF16, device="cuda")
+    ops.maxpool2x2(canvas[..., 64:], out)            # strided channel slice in, contiguous out
+    wv, _, _ = O.maxpool2x2(big[:, 64:])
+    assert torch.equal(from_nhwc(out), wv)

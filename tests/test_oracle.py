@@ -166,6 +166,9 @@ def test_preprocess_restatement_matches_reference_golden(golden):
 def test_inference_epilogue_restatements():
     z = torch.randn(2, 5, 8, 8, generator=torch.Generator().manual_seed(3))
     assert torch.equal(O.mask_uint8(z).long(), torch.argmax(torch.softmax(z, 1), 1))
+    assert torch.equal(O.sigmoid_mask(z), (torch.sigmoid(z)[:, 0] >= 0.5).to(torch.uint8))
+    tiny = torch.tensor([-1e-9, -3e-8, -2e-7, -4e-7, 0.0, 1e-9]).reshape(1, 1, 1, 6)  # fp32 rounding decides around z = 0-
+    assert torch.equal(O.sigmoid_mask(tiny), (torch.sigmoid(tiny)[:, 0] >= 0.5).to(torch.uint8))
     d, cnt = O.density_maps(z, 200.0)
     assert torch.equal(d, torch.relu(z) / 200) and torch.allclose(cnt, d.double().sum((2, 3)))
 

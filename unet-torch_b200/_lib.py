@@ -61,6 +61,7 @@ SIGNATURES = {
         [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _D, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     ),
     "b200unet_partial_colsum": (c_int, [_P, _L, _I, _I, _I, _P, _P]),
+    "b200unet_maxpool2x2_fwd": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "b200unet_nhwc_copy": (c_int, [_P, _I, _P, _I, _L, _I, _P]),
     "b200unet_nhwc_add": (c_int, [_P, _I, _P, _I, _P, _I, _L, _I, _P]),
     "b200unet_channel_sum_workspace_floats": (c_int64, [_I]),
@@ -88,6 +89,7 @@ SIGNATURES = {
     "b200unet_znorm_workspace_bytes": (c_int64, [_I, _I]),
     "b200unet_znorm_to_chw": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200unet_head_mask": (c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200unet_head_sigmoid_mask": (c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
     "b200unet_head_density": (c_int, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
     "b200unet_nvl_buffer_bytes": (c_int64, []),
     "b200unet_nvl_allreduce_f64": (c_int, [_P, _P, _I, _P, _I, _I, _L, _P]),

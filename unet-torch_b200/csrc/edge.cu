@@ -143,9 +143,12 @@ using b2head::MAXC;
 // head_fprop_kernel (small.cu) followed by softmax_argmax_kernel (loss.cu), bit-identical to the two-kernel path (the
 // logits come from the same warp-cooperative routine): torch.softmax in fp32, then the first maximum (probabilities that
 // round to the same float tie), then np.uint8.
+// SIGMOID: test.py:393-399 instead - torch.sigmoid (fp32: 1 / (1 + exp(-z))) of channel 0, then >= threshold -> {0, 1}.
+template <bool SIGMOID>
 __global__ void __launch_bounds__(256) head_mask_kernel(const __nv_bfloat16* __restrict__ a, int a_cs,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                       uint8_t* __restrict__ mask, long long P, int Cin, int ncls) {
+                                                       uint8_t* __restrict__ mask, long long P, int Cin, int ncls,
+                                                       float threshold) {
   extern __shared__ __align__(16) float wsm[];
   b2head::load_weights(wsm, w, Cin, ncls);
   uint32_t* stage = b2head::warp_stage(wsm, Cin, ncls);
@@ -157,6 +160,11 @@ __global__ void __launch_bounds__(256) head_mask_kernel(const __nv_bfloat16* __r
     b2head::logits_warp32(a, a_cs, wsm, stage, bias, g * 32, P, Cin, ncls, acc);
     const long long p = g * 32 + lane;
     if (p >= P) continue;
+    if (SIGMOID) {
+      const float sg = 1.f / (1.f + expf(-acc[0]));
+      mask[p] = sg >= threshold ? 1 : 0;
+      continue;
+    }
     float m = -INFINITY;
 #pragma unroll
     for (int j = 0; j < MAXC; ++j)
@@ -288,9 +296,24 @@ int b200unet_head_mask(const void* a, int a_cs, const float* w, const float* bia
   long long blocks = (P + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  head_mask_kernel<<<static_cast<int>(blocks), 256, b2head::smem_bytes(Cin, ncls, 8), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(a), a_cs, w, bias, mask, P, Cin, ncls);
+  head_mask_kernel<false><<<static_cast<int>(blocks), 256, b2head::smem_bytes(Cin, ncls, 8), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), a_cs, w, bias, mask, P, Cin, ncls, 0.f);
   return b2h::check_launch("head_mask");
+}
+
+int b200unet_head_sigmoid_mask(const void* a, int a_cs, const float* w, const float* bias, uint8_t* mask, int N, int H, int W,
+                               int Cin, int ncls, float threshold, b200_stream_t stream) {
+  B2_REQUIRE(ncls >= 1 && ncls <= MAXC, "head_sigmoid_mask: n_classes=%d must be in [1,%d]", ncls, MAXC);
+  B2_REQUIRE(Cin > 0 && Cin % 64 == 0 && a_cs % 8 == 0 && a_cs >= Cin, "head_sigmoid_mask: Cin=%d must be a multiple of 64 (pitch %d)", Cin, a_cs);
+  B2_REQUIRE(b2head::smem_bytes(Cin, 1, 8) <= 48 * 1024, "head_sigmoid_mask: Cin=%d weights do not fit shared memory", Cin);
+  const long long P = static_cast<long long>(N) * H * W;
+  long long blocks = (P + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  // only channel 0 is thresholded (out[0, 0] in the reference): its weight row and bias come first, so ncls = 1 suffices
+  head_mask_kernel<true><<<static_cast<int>(blocks), 256, b2head::smem_bytes(Cin, 1, 8), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), a_cs, w, bias, mask, P, Cin, 1, threshold);
+  return b2h::check_launch("head_sigmoid_mask");
 }
 
 int b200unet_head_density(const void* a, int a_cs, const float* w, const float* bias, float* out_nchw, double* counts,

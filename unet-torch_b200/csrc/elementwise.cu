@@ -185,6 +185,50 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_fwd_kernel(const __nv_bflo
   }
 }
 
+// nn.MaxPool2d(2) alone (Model.py:36,42) over an NHWC bf16 tensor (possibly a channel slice): used by the inference path,
+// where BatchNorm + ReLU already ran in the conv epilogue. Same window semantics as the fused kernel above (first maximum
+// in row-major window order; NaN wins); position bytes optional.
+__global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ a, int a_cs,
+                                                                 __nv_bfloat16* __restrict__ pooled, int p_cs,
+                                                                 uint8_t* __restrict__ pool_idx, int N, int H, int W, int C) {
+  const int cgs = C >> 3;
+  const int Hp = H >> 1, Wp = W >> 1;
+  const long long total = static_cast<long long>(N) * Hp * Wp * cgs;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long pp = i / cgs;
+    const int cg = static_cast<int>(i - pp * cgs);
+    const int wp = static_cast<int>(pp % Wp);
+    const int hp = static_cast<int>((pp / Wp) % Hp);
+    const long long n = pp / (static_cast<long long>(Wp) * Hp);
+    const long long p00 = (n * H + 2 * hp) * W + 2 * wp;
+    uint4 raw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) raw[k] = ldg128(a + (p00 + (k >> 1) * W + (k & 1)) * a_cs + cg * 8);
+    float best[8];
+    uint32_t bidx[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8(raw[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (k == 0 || f[j] > best[j] || f[j] != f[j]) {
+          best[j] = f[j];
+          bidx[j] = k;
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(pooled + pp * p_cs + cg * 8) = pack8(best);
+    if (pool_idx != nullptr) {
+      uint2 pk;
+      pk.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+      pk.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+      *reinterpret_cast<uint2*>(pool_idx + pp * C + cg * 8) = pk;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ backward
 // da for one pixel / channel group: (g1 + unpool(g_pool)) * [bn(y) > 0]
 struct BwdSrc {
@@ -566,6 +610,17 @@ int b200unet_channel_sum(const void* x, int x_cs, float* workspace, float* out, 
   if (int e = launch_reduce_partials(workspace, blocks, C, acc, st)) return e;
   double_to_float_kernel<<<(C + 127) / 128, 128, 0, st>>>(acc, out, C);
   return b2h::check_launch("channel_sum_cast");
+}
+
+int b200unet_maxpool2x2_fwd(const void* a, int a_cs, void* pooled, int p_cs, uint8_t* pool_idx, int N, int H, int W, int C,
+                            b200_stream_t stream) {
+  B2_REQUIRE(C > 0 && C % 8 == 0 && a_cs % 8 == 0 && p_cs % 8 == 0 && a_cs >= C && p_cs >= C,
+             "maxpool2x2_fwd: C=%d and the pitches (%d, %d) must be multiples of 8 with pitch >= C", C, a_cs, p_cs);
+  B2_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "maxpool2x2_fwd: H=%d W=%d must be even and >= 2", H, W);
+  const int blocks = ew_blocks(static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8));
+  maxpool_fwd_kernel<<<blocks, EW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), a_cs, static_cast<__nv_bfloat16*>(pooled), p_cs, pool_idx, N, H, W, C);
+  return b2h::check_launch("maxpool2x2_fwd");
 }
 
 int b200unet_nhwc_copy(const void* src, int src_cs, void* dst, int dst_cs, int64_t pixels, int C, b200_stream_t stream) {

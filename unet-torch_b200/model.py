@@ -148,8 +148,8 @@ class UNetEngine:
         # B200UNET_WGRAD_STREAM=1: weight-gradient kernels on a second stream (nothing downstream in backward depends on
         # them), overlapping the bandwidth-bound BN/ReLU backward of the next layer. Measured neutral on B200 (687-691
         # img/s either way: the step runs at the 1000 W power cap, so co-scheduling does not add throughput) -> off.
-        # eval forward without saving for backward: layers that are not followed by a pooling fold BN + ReLU into the
-        # conv epilogue (14 of the 18 conv layers); B200UNET_FOLD_EVAL_BN=0 keeps the separate BN-apply pass
+        # eval forward without saving for backward: BN + ReLU are folded into the conv epilogues (the four pooled layers
+        # are followed by a plain max-pool pass); B200UNET_FOLD_EVAL_BN=0 keeps the separate BN-apply pass
         self.fold_eval_bn = os.environ.get("B200UNET_FOLD_EVAL_BN", "1") not in ("", "0")
         self.wgrad_overlap = os.environ.get("B200UNET_WGRAD_STREAM", "0") not in ("", "0")
         self._wgrad_stream = None
@@ -228,7 +228,8 @@ class UNetEngine:
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, training: bool, save: bool, head: str = "logits", divisor: float = 200.0):
         """head: "logits" (Model.py:152, fp32 NCHW), or one of the fused inference epilogues "mask" (uint8 class mask,
-        test_mc3serousv5.py:879-887) / "density" ((relu(z) / divisor, per-map sums), test_mc3serousv5.py:961-974)."""
+        test_mc3serousv5.py:879-887) / "sigmoid" (channel 0 thresholded at `divisor`, test.py:393-399) / "density"
+        ((relu(z) / divisor, per-map sums), test_mc3serousv5.py:961-974)."""
         net = self.net
         if x.dim() != 4 or x.shape[1] != net.n_channels:
             raise ValueError(f"UNet expects [B,{net.n_channels},H,W] input, got {tuple(x.shape)}")
@@ -251,7 +252,7 @@ class UNetEngine:
         enc_rec, dec_rec = [], []
 
         def conv_bn_relu(cb: _ConvBN, inp, c_out, hh, ww, a_out, pooled=None, pool_idx=None):
-            if not training and not save and pooled is None and self.fold_eval_bn:
+            if not training and not save and self.fold_eval_bn:
                 # inference: BatchNorm (running statistics) + ReLU folded into the conv epilogue; y never reaches HBM
                 scale, shift, _, _, _ = self._bn_affine(cb, None, 0, n * hh * ww, False, None)
                 if cb.first:
@@ -260,6 +261,8 @@ class UNetEngine:
                     ops.conv1x1_c64_bn_relu(col, cb.operands()[0], scale, shift, a_out)
                 else:
                     ops.conv3x3_bn_relu(inp, cb.operands()[0], scale, shift, a_out)
+                if pooled is not None:
+                    ops.maxpool2x2(a_out, pooled)
                 return None
             y = torch.empty((n, hh, ww, c_out), dtype=BF16, device=dev)
             stats = None
@@ -328,6 +331,8 @@ class UNetEngine:
             hw_, hb_ = head_conv.weight.detach(), head_conv.bias.detach()
             if head == "mask":
                 outs.append(ops.head_mask(d_in, hw_, hb_))
+            elif head == "sigmoid":
+                outs.append(ops.head_sigmoid_mask(d_in, hw_, hb_, divisor))
             elif head == "density":
                 outs.append(ops.head_density(d_in, hw_, hb_, divisor))
             else:
@@ -647,6 +652,10 @@ class UNet(nn.Module):
     def predict(self, x):
         """np.uint8(argmax(softmax(self(x), 1), 1)) of test_mc3serousv5.py:879-887 as one fused epilogue -> uint8 [B,H,W]."""
         return self._fused_head(x, "mask")
+
+    def predict_binary(self, x, threshold=0.5):
+        """(torch.sigmoid(self(x))[:, 0] >= threshold) of test.py:393-399 as one fused epilogue -> {0,1} uint8 [B,H,W]."""
+        return self._fused_head(x, "sigmoid", threshold)
 
     def predict_density(self, x, divisor=200.0):
         """(F.relu(self(x)) / divisor, per-map sums) of test_mc3serousv5.py:961-974 -> (fp32 [B,C,H,W], fp64 [B,C])."""

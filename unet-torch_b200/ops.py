@@ -310,6 +310,16 @@ def partial_colsum(stats_partial, rows, row_pitch, col_lo, n, out):
     return out
 
 
+def maxpool2x2(a, pooled, pool_idx=None):
+    """pooled = MaxPool2d(2)(a) over NHWC bf16 (a may be a channel slice); optional 1-byte window positions."""
+    ap, acs, n, h, w, c = _nhwc(a)
+    pp, pcs, n2, h2, w2, c2 = _nhwc(pooled)
+    if (n2, h2, w2, c2) != (n, h // 2, w // 2, c):
+        raise ValueError(f"maxpool2x2: shapes {tuple(a.shape)} -> {tuple(pooled.shape)}")
+    _lib.call("b200unet_maxpool2x2_fwd", ap, acs, pp, pcs, _ptr(pool_idx), n, h, w, c, _stream())
+    return pooled
+
+
 def nhwc_copy(src, dst):
     """dst[..., :] = src over NHWC bf16 channel slices (skip half of a second decoder's concat buffer)."""
     sp, scs, n, h, w, c = _nhwc(src)
@@ -405,6 +415,16 @@ def head_mask(a, w, bias):
     mask = torch.empty((n, h, wd), dtype=torch.uint8, device=a.device)
     _lib.call("b200unet_head_mask", ap, acs, _f32(w.view(ncls, cin)), _f32(bias), mask.data_ptr(), n, h, wd, cin, ncls,
               _stream())
+    return mask
+
+
+def head_sigmoid_mask(a, w, bias, threshold=0.5):
+    """OutConv channel 0 + sigmoid + `>= threshold` -> {0,1} uint8 [N,H,W] (test.py:393-399); a: NHWC bf16."""
+    ap, acs, n, h, wd, cin = _nhwc(a)
+    ncls = w.shape[0]
+    mask = torch.empty((n, h, wd), dtype=torch.uint8, device=a.device)
+    _lib.call("b200unet_head_sigmoid_mask", ap, acs, _f32(w.view(ncls, cin)), _f32(bias), mask.data_ptr(), n, h, wd, cin,
+              ncls, float(threshold), _stream())
     return mask
 
 
