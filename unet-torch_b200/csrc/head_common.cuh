@@ -66,9 +66,20 @@ __device__ __forceinline__ void logits_warp32(const __nv_bfloat16* __restrict__ 
 #pragma unroll
       for (int j = 0; j < MAXC; ++j) {
         if (j < ncls) {
-          const float* wr = wsm + j * Cin + c0 + c8 * 8;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) z[j] = fmaf(f[i], wr[i], z[j]);
+          // 128-bit broadcast reads (Cin % 64 == 0 keeps every row 16-byte aligned): the scalar form issues 64 x ncls
+          // shared-memory loads per pixel and is bound by the load/store pipe, not by HBM
+          const float4 w0 = *reinterpret_cast<const float4*>(wsm + j * Cin + c0 + c8 * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wsm + j * Cin + c0 + c8 * 8 + 4);
+          float t = z[j];
+          t = fmaf(f[0], w0.x, t);
+          t = fmaf(f[1], w0.y, t);
+          t = fmaf(f[2], w0.z, t);
+          t = fmaf(f[3], w0.w, t);
+          t = fmaf(f[4], w1.x, t);
+          t = fmaf(f[5], w1.y, t);
+          t = fmaf(f[6], w1.z, t);
+          t = fmaf(f[7], w1.w, t);
+          z[j] = t;
         }
       }
     }

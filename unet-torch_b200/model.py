@@ -226,10 +226,10 @@ class UNetEngine:
         return scale, shift, mean, rstd, count
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, training: bool, save: bool, head: str = "logits", divisor: float = 200.0):
+    def forward(self, x: torch.Tensor, training: bool, save: bool, head: str = "logits", head_arg: float = 0.0):
         """head: "logits" (Model.py:152, fp32 NCHW), or one of the fused inference epilogues "mask" (uint8 class mask,
-        test_mc3serousv5.py:879-887) / "sigmoid" (channel 0 thresholded at `divisor`, test.py:393-399) / "density"
-        ((relu(z) / divisor, per-map sums), test_mc3serousv5.py:961-974)."""
+        test_mc3serousv5.py:879-887) / "sigmoid" (channel 0 thresholded at `head_arg`, test.py:393-399) / "density"
+        ((relu(z) / head_arg, per-map sums), test_mc3serousv5.py:961-974)."""
         net = self.net
         if x.dim() != 4 or x.shape[1] != net.n_channels:
             raise ValueError(f"UNet expects [B,{net.n_channels},H,W] input, got {tuple(x.shape)}")
@@ -332,9 +332,9 @@ class UNetEngine:
             if head == "mask":
                 outs.append(ops.head_mask(d_in, hw_, hb_))
             elif head == "sigmoid":
-                outs.append(ops.head_sigmoid_mask(d_in, hw_, hb_, divisor))
+                outs.append(ops.head_sigmoid_mask(d_in, hw_, hb_, head_arg))
             elif head == "density":
-                outs.append(ops.head_density(d_in, hw_, hb_, divisor))
+                outs.append(ops.head_density(d_in, hw_, hb_, head_arg))
             else:
                 logits = torch.empty((n, hw_.shape[0], h, w), dtype=torch.float32, device=dev)
                 outs.append(ops.head_fprop(d_in, hw_, hb_, logits))
@@ -640,13 +640,13 @@ class UNet(nn.Module):
         return logits
 
     # ---- fused inference epilogues: the logits never reach HBM
-    def _fused_head(self, x, head, divisor=200.0):
+    def _fused_head(self, x, head, head_arg=0.0):
         eng = self._engine_for(x)
         if not isinstance(eng, UNetEngine):
             raise ValueError("fused inference heads run on the tensor-core engine (H, W multiples of 16, default widths); "
                              "use predict_mask(net(x)) for other variants")
         with torch.no_grad():
-            out, _ = eng.forward(x, training=self.training, save=False, head=head, divisor=divisor)
+            out, _ = eng.forward(x, training=self.training, save=False, head=head, head_arg=head_arg)
         return out
 
     def predict(self, x):
@@ -715,7 +715,7 @@ class UNet_multitask(UNet):
     def enable_cuda_graphs(self, flag: bool = True):
         raise NotImplementedError("CUDA-graph replay covers UNet only")
 
-    def _fused_head(self, x, head, divisor=200.0):
+    def _fused_head(self, x, head, head_arg=0.0):
         raise NotImplementedError("fused inference heads cover UNet only; apply predict_mask / F.relu to the two outputs")
 
 
