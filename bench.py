@@ -157,8 +157,9 @@ def workload_config(n_gpus, batch_override=None, graphs=False, torch_optim=False
         "optimizer": "SGD(lr=0.01, momentum=0.9, weight_decay=1e-4)" + ("" if torch_optim else
                      " as unet_torch_b200.FusedSGD (torch.optim.SGD arithmetic fused with the bf16 operand re-cast)"),
         "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
-        "cuda_graphs": "forward and backward of the network replayed as captured CUDA graphs (single GPU); loss and "
-                       "optimizer eager" if (n_gpus == 1 and graphs) else "off",
+        "cuda_graphs": ("forward and backward of the network replayed as captured CUDA graphs"
+                        + (" (SyncBN NVLink kernels and NCCL gradient all-reduces captured with them)" if n_gpus > 1 else "")
+                        + "; loss and optimizer eager") if graphs else "off",
         "l2": "per-step working set (~10 GB of bf16 activations) is far larger than the 126 MB L2; no explicit flush",
     }
 
@@ -349,6 +350,12 @@ def _shutdown_dist():
         import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized():
+            try:
+                import unet_torch_b200 as U
+
+                U.DataParallelContext.disable()  # drops CUDA graphs that captured NCCL kernels (they block the teardown)
+            except Exception:
+                pass
             dist.destroy_process_group()
     except Exception:
         pass

@@ -223,8 +223,10 @@ int b200unet_head_density(const void* a, int a_cs, const float* w, const float* 
 /* ---- SyncBN over NVLink peer memory (nvl_sync.cu): one-shot all-reduce of a small fp64 vector through
  * symmetric buffers mapped into every rank (peer_bufs = HOST array of `world` device pointers, index = rank; each
  * buffer b200unet_nvl_buffer_bytes() bytes, zeroed once before first use), optionally fused with the BatchNorm
- * finalisation of b200unet_bn_finalize. `seq` = 1, 2, 3, ... must advance identically on all ranks. One kernel per
- * rank; it spins (bounded) until every peer has published, so each rank must run on its own GPU. */
+ * finalisation of b200unet_bn_finalize. `seq` = 1, 2, 3, ... must advance identically on all ranks; `seq` = 0 takes the
+ * next number from a counter inside the rank's own buffer (a launch captured in a CUDA graph then stays valid on replay);
+ * do not mix the two numberings on one buffer. One kernel per rank; it spins (bounded) until every peer has published,
+ * so each rank must run on its own GPU. */
 int64_t b200unet_nvl_buffer_bytes(void);
 int b200unet_nvl_allreduce_f64(const double* local, double* out, int n, void* const* peer_bufs, int world, int rank,
                                int64_t seq, b200_stream_t stream);

@@ -11,6 +11,9 @@
 //   3. sum the `world` vectors in rank order (bit-identical on all ranks), optionally finalise BatchNorm.
 // Two slots suffice: a rank can only reach reduction seq+2 after every peer has published seq+1, i.e. after every peer
 // has finished reading seq. Sequence numbers never repeat, so flags are never reset.
+// seq = 0 in the call means "next": the kernel takes the number from a counter in its own buffer and advances it, so a
+// launch captured in a CUDA graph stays valid on every replay (all ranks issue the same reductions in the same order, hence
+// their counters agree). Explicit (host-side) and counter-based numbering must not be mixed on one buffer.
 #include "../../include/b200unet.h"
 #include "host_common.h"
 
@@ -19,7 +22,8 @@ namespace {
 constexpr int MAX_WORLD = 8;
 constexpr int SLOT_DOUBLES = 2048;                                   // 2 * Cmax
 constexpr size_t FLAG_OFFSET = size_t(2) * MAX_WORLD * SLOT_DOUBLES * 8;  // bytes: data region first, then flags
-constexpr size_t BUFFER_BYTES = FLAG_OFFSET + 2 * MAX_WORLD * 8;
+constexpr size_t COUNTER_OFFSET = FLAG_OFFSET + 2 * MAX_WORLD * 8;  // this rank's own reduction counter (device-side seq)
+constexpr size_t BUFFER_BYTES = COUNTER_OFFSET + 64;
 
 struct PeerTable {
   unsigned char* buf[MAX_WORLD];
@@ -56,6 +60,16 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
 __global__ void __launch_bounds__(256) nvl_allreduce_kernel(const double* __restrict__ local, double* __restrict__ out, int n,
                                                            PeerTable peers, int world, int rank,
                                                            unsigned long long seq, FinalizeArgs fin) {
+  unsigned long long* counter = reinterpret_cast<unsigned long long*>(peers.buf[rank] + COUNTER_OFFSET);
+  if (seq == 0) {  // device-side numbering (graph-replayable)
+    __shared__ unsigned long long seq_sh;
+    if (threadIdx.x == 0) {
+      seq_sh = *counter + 1;
+      *counter = seq_sh;  // only this kernel (stream-ordered, one block) touches the counter
+    }
+    __syncthreads();
+    seq = seq_sh;
+  }
   const int slot = static_cast<int>(seq & 1ull);
   const size_t my_off = (static_cast<size_t>(slot) * MAX_WORLD + rank) * SLOT_DOUBLES;
   // 1. publish
@@ -141,7 +155,7 @@ int b200unet_nvl_allreduce_f64(const double* local, double* out, int n, void* co
                                int64_t seq, b200_stream_t stream) {
   PeerTable t;
   if (int e = fill_table(&t, peer_bufs, world, rank, n)) return e;
-  B2_REQUIRE(seq > 0, "nvl_allreduce_f64: sequence numbers start at 1");
+  B2_REQUIRE(seq >= 0, "nvl_allreduce_f64: sequence numbers start at 1 (0 = device-side counter)");
   FinalizeArgs fin{};
   fin.C = 0;
   nvl_allreduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(local, out, n, t, world, rank,
@@ -155,7 +169,7 @@ int b200unet_nvl_bn_sync_finalize(const double* local_sums, double* global_sums,
                                   float* rstd, float* scale, float* shift, int C, b200_stream_t stream) {
   PeerTable t;
   if (int e = fill_table(&t, peer_bufs, world, rank, 2 * C)) return e;
-  B2_REQUIRE(seq > 0 && C > 0, "nvl_bn_sync_finalize: bad arguments");
+  B2_REQUIRE(seq >= 0 && C > 0, "nvl_bn_sync_finalize: bad arguments");
   FinalizeArgs fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, global_count, eps, momentum, C};
   nvl_allreduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(local_sums, global_sums, 2 * C, t, world, rank,
                                                                         static_cast<unsigned long long>(seq), fin);

@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes
 import os
 import warnings
+import weakref
 
 import torch
 import torch.distributed as dist
@@ -89,6 +90,12 @@ class DataParallelContext:
         self.sync_bn = sync_bn and self.world_size > 1
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+        # CUDA-graph replay of the data-parallel step (NCCL collectives and the NVLink SyncBN kernels are captured with
+        # the compute kernels): removes the host launch path, whose jitter every one of the 36 SyncBN synchronisations
+        # per step would otherwise wait for on the slowest rank. B200UNET_DP_GRAPHS=0 keeps the eager launches.
+        self.graph_capturable = (torch.cuda.is_available() and dist.get_backend() == "nccl"
+                                 and os.environ.get("B200UNET_DP_GRAPHS", "1") not in ("", "0"))
+        self._graph_owners = weakref.WeakSet()  # engines holding graphs captured under this context
         self.extra_wait_streams = []  # streams (besides the current one) whose work a gradient bucket depends on
         # SyncBN statistics over NVLink peer memory (csrc/nvl_sync.cu): symmetric buffer + peer pointer table
         self._nvl = None
@@ -133,10 +140,10 @@ class DataParallelContext:
         """All-reduce the fp64 [sum, sum^2] vector over NVLink and finalise BatchNorm in the same kernel."""
         from . import _lib
 
-        self._seq += 1
         c = bn.num_features
+        # seq = 0: device-side reduction counter, so the launch can be captured in a CUDA graph and replayed
         _lib.call("b200unet_nvl_bn_sync_finalize", sums.data_ptr(), sums.data_ptr(), self._nvl[2], self.world_size,
-                  self.rank, self._seq, float(global_count), bn.weight.data_ptr(), bn.bias.data_ptr(), float(eps),
+                  self.rank, 0, float(global_count), bn.weight.data_ptr(), bn.bias.data_ptr(), float(eps),
                   float(momentum), bn.running_mean.data_ptr() if track else None,
                   bn.running_var.data_ptr() if track else None, mean.data_ptr(), rstd.data_ptr(), scale.data_ptr(),
                   shift.data_ptr(), c, torch.cuda.current_stream().cuda_stream)
@@ -149,6 +156,15 @@ class DataParallelContext:
 
     @classmethod
     def disable(cls):
+        """Leave data-parallel mode. CUDA graphs that captured collectives are destroyed first: a live graph holding
+        NCCL kernels makes `destroy_process_group()` wait forever (observed with torch 2.11 / NCCL 2.28), so call this
+        before tearing the process group down."""
+        cur = cls._current
+        if cur is not None:
+            for eng in list(cur._graph_owners):
+                eng._graphs.clear()
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
         cls._current = None
 
     @classmethod
@@ -164,9 +180,8 @@ class DataParallelContext:
                 and 0 < t.numel() <= 2048):
             from . import _lib
 
-            self._seq += 1
             _lib.call("b200unet_nvl_allreduce_f64", t.data_ptr(), t.data_ptr(), t.numel(), self._nvl[2], self.world_size,
-                      self.rank, self._seq, torch.cuda.current_stream().cuda_stream)
+                      self.rank, 0, torch.cuda.current_stream().cuda_stream)
             return
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 

@@ -156,15 +156,17 @@ class UNetEngine:
 
     def graphed_step(self, x, training, save):
         """The captured step for this input, or None when the call must run eagerly: graphs disabled, data parallel
-        active (NCCL collectives are issued eagerly), or first call for this shape (eager warm-up)."""
+        over a backend whose collectives cannot be captured, or first call for this shape (eager warm-up: kernel
+        attributes, allocator, NCCL communicators)."""
         net = self.net
         if not net._cuda_graphs or not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
             return None
-        if training and DataParallelContext.current() is not None:
+        dp = DataParallelContext.current() if training else None
+        if dp is not None and not dp.graph_capturable:
             return None
         if torch.cuda.is_current_stream_capturing() or len(self.decoders) > 1:
             return None
-        key = (tuple(x.shape), x.device.index, bool(training), bool(save))
+        key = (tuple(x.shape), x.device.index, bool(training), bool(save), dp is not None)
         st = self._graphs.get(key)
         if st is None:
             if key not in self._seen:
@@ -481,6 +483,12 @@ class _GraphedStep:
         self.engine, self.training, self.save = engine, training, save
         self.x = torch.empty_like(x)
         self.pool = torch.cuda.graph_pool_handle()
+        # data parallel: the NCCL watchdog thread queries CUDA events while this thread captures, which the default
+        # "global" capture mode would reject
+        dp = DataParallelContext.current() if training else None
+        self.capture_mode = "thread_local" if dp is not None else "global"
+        if dp is not None:
+            dp._graph_owners.add(engine)  # DataParallelContext.disable() drops these graphs before NCCL teardown
         self.fwd = self.bwd = None
         self.logits = self.saved = self.dlogits = self.grads = None
         self.epoch = 0
@@ -491,7 +499,7 @@ class _GraphedStep:
         self.x.copy_(x)
         if self.fwd is None:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self.pool):
+            with torch.cuda.graph(g, pool=self.pool, capture_error_mode=self.capture_mode):
                 self.logits, self.saved = self.engine.forward(self.x, self.training, self.save)
             self.fwd = g
         self.fwd.replay()
@@ -510,7 +518,7 @@ class _GraphedStep:
         self.dlogits.copy_(dlogits)
         if self.bwd is None:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self.pool):
+            with torch.cuda.graph(g, pool=self.pool, capture_error_mode=self.capture_mode):
                 self.grads = self.engine.backward(self.saved, self.dlogits)
             self.bwd = g
         self.bwd.replay()
