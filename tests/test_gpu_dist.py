@@ -26,7 +26,9 @@ def test_data_parallel_matches_single_gpu_global_batch(nvl):
     """nvl=1: SyncBN statistics through the NVLink peer-memory kernel; nvl=0: through NCCL."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dp_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, B200UNET_NVL_SYNCBN=nvl))
+    # nvl=1 also replays the data-parallel step as CUDA graphs (opt-in, B200UNET_DP_GRAPHS=1) against the eager launches
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, B200UNET_NVL_SYNCBN=nvl, B200UNET_DP_GRAPHS="1"))
     sys.stdout.write(r.stdout[-4000:])
     sys.stderr.write(r.stderr[-4000:])
     assert r.returncode == 0 and "DP_OK" in r.stdout

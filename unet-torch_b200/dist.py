@@ -90,11 +90,13 @@ class DataParallelContext:
         self.sync_bn = sync_bn and self.world_size > 1
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
-        # CUDA-graph replay of the data-parallel step (NCCL collectives and the NVLink SyncBN kernels are captured with
-        # the compute kernels): removes the host launch path, whose jitter every one of the 36 SyncBN synchronisations
-        # per step would otherwise wait for on the slowest rank. B200UNET_DP_GRAPHS=0 keeps the eager launches.
-        self.graph_capturable = (torch.cuda.is_available() and dist.get_backend() == "nccl"
-                                 and os.environ.get("B200UNET_DP_GRAPHS", "1") not in ("", "0"))
+        # B200UNET_DP_GRAPHS=1: CUDA-graph replay of the data-parallel step (the NVLink SyncBN kernels and the NCCL gradient
+        # all-reduces are captured with the compute kernels). Opt-in: validated on 2 B200 (replay == eager launches bit
+        # for bit, tests/dp_worker.py; 23.65 vs 23.75 ms/step), not yet at 8 ranks. Needs the NVLink SyncBN path (the
+        # NCCL fallback would put 36 tiny collectives per step into the graph) - decided after _setup_nvl below.
+        self._want_graphs = (torch.cuda.is_available() and dist.get_backend() == "nccl"
+                             and os.environ.get("B200UNET_DP_GRAPHS", "0") not in ("", "0"))
+        self.graph_capturable = False
         self._graph_owners = weakref.WeakSet()  # engines holding graphs captured under this context
         self.extra_wait_streams = []  # streams (besides the current one) whose work a gradient bucket depends on
         # SyncBN statistics over NVLink peer memory (csrc/nvl_sync.cu): symmetric buffer + peer pointer table
@@ -103,6 +105,7 @@ class DataParallelContext:
         if (self.sync_bn and torch.cuda.is_available() and group is None and self.world_size <= 8
                 and dist.get_backend() == "nccl" and os.environ.get("B200UNET_NVL_SYNCBN", "1") not in ("", "0")):
             self._setup_nvl()
+        self.graph_capturable = self._want_graphs and (self._nvl is not None or not self.sync_bn)
 
     def _setup_nvl(self):
         """Allocate the symmetric buffer and exchange peer pointers. Any failure (no P2P, older torch) leaves the NCCL
