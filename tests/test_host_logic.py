@@ -96,3 +96,21 @@ def test_multitask_module_mirrors_reference_layout():
     assert not torch.equal(net.up1_decod1.up.weight, net.up1_decod2.up.weight)
     with pytest.raises(RuntimeError):
         net.inc(torch.zeros(1, 3, 16, 16))  # containers are not the product path
+
+
+@pytest.mark.parametrize("cls_name,n_dec", [("UNet", 1), ("UNet_multitask", 2)])
+def test_backward_order_covers_every_parameter_once(cls_name, n_dec):
+    """The flat data-parallel gradient buffer is laid out in params_in_backward_order(): it must be a permutation of
+    the module's parameters (both decoders of UNet_multitask included), heads first, encoder last."""
+    import unet_torch_b200 as U
+
+    net = getattr(U, cls_name)(3, 2)
+    eng = net._get_engine()          # host-side bookkeeping only: no CUDA call until forward
+    order = eng.params_in_backward_order()
+    assert len(order) == len(list(net.parameters())) == len({id(p) for p in order})
+    assert {id(p) for p in order} == {id(p) for p in net.parameters()}
+    assert len(eng.decoders) == n_dec and len(eng.ups) == 4 * n_dec and len(eng.dec) == 4 * n_dec
+    names = {id(p): n for n, p in net.named_parameters()}
+    assert names[id(order[0])].startswith("outc") and names[id(order[-1])] == "inc.double_conv.0.weight"
+    if n_dec == 2:  # the decoder that ran last in forward is differentiated first
+        assert names[id(order[0])] == "outc_decod2.conv.weight"
