@@ -28,6 +28,15 @@ def reference_preprocess():
     return ns["preprocess"]
 
 
+def reference_preprocess_crop():
+    """`preprocessCrop` of test.py:91-126 (pad to a multiple of crop_size with 255, z-normalise the padded image)."""
+    src = open(os.path.join(REF, "test.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "preprocessCrop")
+    ns = {"np": np, "torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "test.py", "exec"), ns)
+    return ns["preprocessCrop"]
+
+
 def main():
     torch.Tensor.cuda = lambda self, *a, **k: self  # no GPU here; the function ends in .cuda()
     pre = reference_preprocess()
@@ -51,6 +60,13 @@ def main():
     with np.errstate(all="ignore"):
         for k, img in cases.items():
             out[k] = dict(img=torch.from_numpy(img.copy()), out=pre(img, img.shape[:2]).clone())
+    # tiled inference front end (test.py:91-126): image, crop size -> padded z-normalised tensor (+ padded label)
+    crop = reference_preprocess_crop()
+    for k, (img, cs) in {"crop_bgr_50x70_c32": (cases["bgr_50x70_ragged"], 32), "crop_bgr_64x96_c32": (cases["bgr_64x96"], 32),
+                         "crop_bgr_50x70_c48": (cases["bgr_50x70_ragged"], 48)}.items():
+        lab = (rng.random(img.shape[:2]) > 0.5).astype(np.uint8)
+        x, lab_p, _ = crop(img, lab, lab.copy(), cs)
+        out[k] = dict(img=torch.from_numpy(img.copy()), crop=cs, out=x.clone(), label_shape=tuple(lab_p.shape))
     torch.save(out, OUT)
     print(OUT, os.path.getsize(OUT))
 

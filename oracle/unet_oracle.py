@@ -243,6 +243,27 @@ def preprocess(img_org):
     return torch.from_numpy(np.ascontiguousarray(out.astype(np.float32))).unsqueeze(0)
 
 
+def preprocess_crop(img_org, crop_size):
+    """`preprocessCrop` of test.py:91-126 (image part): pad H and W up to multiples of crop_size, split (p//2, p - p//2),
+    constant 255, then the same z-normalisation / CHW / RGB as `preprocess` on the PADDED image."""
+    import numpy as np
+
+    img = np.asarray(img_org)
+    ph, pw = (-img.shape[0]) % crop_size, (-img.shape[1]) % crop_size
+    pads = ((ph // 2, ph - ph // 2), (pw // 2, pw - pw // 2)) + (((0, 0),) if img.ndim == 3 else ())
+    return preprocess(np.pad(img, pads, mode="constant", constant_values=255))
+
+
+def tiled_masks(forward, x, crop_size, decide):
+    """The crop loop of test_single_crop (test.py:432-441): `decide(forward(crop))` for every crop_size x crop_size crop
+    of the padded input, stitched back; forward(crop) -> logits, decide(logits) -> [1,h,w] mask."""
+    pred = torch.zeros(x.shape[2], x.shape[3], dtype=torch.uint8)
+    for i in range(0, x.shape[2], crop_size):
+        for j in range(0, x.shape[3], crop_size):
+            pred[i:i + crop_size, j:j + crop_size] = decide(forward(x[:, :, i:i + crop_size, j:j + crop_size]))[0]
+    return pred
+
+
 def mask_uint8(logits):
     """np.uint8(torch.argmax(F.softmax(outputs, dim=1), dim=1)) (test_mc3serousv5.py:880-887)."""
     return softmax_argmax(logits).to(torch.uint8)

@@ -26,6 +26,10 @@ def test_preprocess_matches_reference_golden(golden):
 
     g = golden("ref_edge.pt")
     for name, c in g.items():
+        if name.startswith("crop_"):   # preprocessCrop (test.py:91-126): padded with 255 to a multiple of the crop size
+            got = U.preprocess_crop(c["img"].numpy(), c["crop"]).cpu()
+            assert got.shape == c["out"].shape and _same_bits(got, c["out"]), name
+            continue
         got = U.preprocess(c["img"].numpy(), c["img"].shape[:2]).cpu()
         assert got.shape == c["out"].shape and got.dtype == torch.float32, name
         assert _same_bits(got, c["out"]), f"{name}: max diff {float((got - c['out']).abs().nan_to_num().max()):.3e}"
@@ -121,3 +125,30 @@ def test_model_predict_equals_unfused_path():
     with torch.no_grad():
         ref = O.mask_uint8(net(O.preprocess(img.numpy()).cuda()).cpu())
     assert torch.equal(m2.cpu(), ref)
+
+
+def test_predict_tiled_equals_the_reference_crop_loop():
+    """test_single_crop (test.py:420-447): every crop through the network one at a time, sigmoid >= 0.5, stitched - against
+    the batched, fused-head `predict_tiled`; the per-crop logits do not depend on which batch a crop is in."""
+    import unet_torch_b200 as U
+
+    torch.manual_seed(9)
+    net = U.UNet(3, 1).cuda().eval()
+    img = torch.randint(0, 256, (100, 150, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(2))
+    crop = 64
+    got = U.predict_tiled(net, img.numpy(), crop, head="sigmoid", max_batch=4)
+    assert got.shape == (128, 192) and got.dtype == torch.uint8
+    x = O.preprocess_crop(img.numpy(), crop)
+    with torch.no_grad():
+        want = O.tiled_masks(lambda t: net(t.cuda()).cpu(), x, crop, O.sigmoid_mask)
+    agree = float((got.cpu() == want).float().mean())
+    print(f"predict_tiled vs crop-by-crop loop: agreement {agree:.6f}")
+    assert agree > 0.9999
+    assert 0.05 < float(got.float().mean()) < 0.95
+    multi = U.UNet(3, 3).cuda().eval()
+    m = U.predict_tiled(multi, img.numpy(), crop, head="mask")
+    with torch.no_grad():
+        want_m = O.tiled_masks(lambda t: multi(t.cuda()).cpu(), x, crop, O.mask_uint8)
+    assert float((m.cpu() == want_m).float().mean()) > 0.9999
+    with pytest.raises(ValueError):
+        U.predict_tiled(net, img.numpy(), 50)

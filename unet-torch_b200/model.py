@@ -747,6 +747,48 @@ def preprocess(img_org, input_size=None, device=None) -> torch.Tensor:
     return ops.znorm_to_chw(img_org, reverse_channels=True)
 
 
+def preprocess_crop(img_org, crop_size, device=None) -> torch.Tensor:
+    """`preprocessCrop` of test.py:91-126 (image part) on the GPU: pad H and W up to multiples of `crop_size` with 255
+    (split p//2 before, the rest after), then z-normalise the padded image like `preprocess` -> fp32 [1,C,Hp,Wp]."""
+    if not torch.is_tensor(img_org):
+        img_org = torch.from_numpy(img_org)
+    if img_org.dtype != torch.uint8 or img_org.dim() not in (2, 3):
+        raise TypeError("preprocess_crop expects one uint8 image [H,W] or [H,W,C]")
+    if not img_org.is_cuda:
+        img_org = img_org.to(torch.device(device if device is not None else "cuda"))
+    if img_org.dim() == 2:
+        img_org = img_org[:, :, None]
+    ph, pw = (-img_org.shape[0]) % crop_size, (-img_org.shape[1]) % crop_size
+    if ph or pw:
+        padded = torch.full((img_org.shape[0] + ph, img_org.shape[1] + pw, img_org.shape[2]), 255, dtype=torch.uint8,
+                            device=img_org.device)
+        padded[ph // 2: ph // 2 + img_org.shape[0], pw // 2: pw // 2 + img_org.shape[1]] = img_org
+        img_org = padded
+    return ops.znorm_to_chw(img_org, reverse_channels=True)
+
+
+def predict_tiled(net, img_org, crop_size, head="sigmoid", threshold=0.5, max_batch=64) -> torch.Tensor:
+    """`test_single_crop` (test.py:420-447): pad + z-normalise the image (preprocess_crop), run every crop_size x crop_size
+    crop through the network in eval mode and stitch the per-crop masks -> uint8 [Hp,Wp]. The reference loops over the
+    crops one forward at a time; here they form batches (eval-mode BatchNorm makes crops independent of each other) and the
+    mask comes from the fused head: head="sigmoid" (channel 0 >= threshold, test.py:436-440) or "mask" (softmax/argmax)."""
+    if crop_size % 16:
+        raise ValueError("predict_tiled: crop_size must be a multiple of 16")
+    if net.training:
+        raise RuntimeError("predict_tiled is an inference path: call net.eval() first (test.py:430)")
+    x = preprocess_crop(img_org, crop_size, device=next(net.parameters()).device)
+    _, c, hp, wp = x.shape
+    nh, nw = hp // crop_size, wp // crop_size
+    tiles = (x.view(c, nh, crop_size, nw, crop_size).permute(1, 3, 0, 2, 4).reshape(nh * nw, c, crop_size, crop_size)
+             .contiguous())
+    outs = []
+    for i in range(0, nh * nw, max_batch):
+        t = tiles[i:i + max_batch]
+        outs.append(net.predict_binary(t, threshold) if head == "sigmoid" else net.predict(t))
+    m = torch.cat(outs, 0)
+    return m.view(nh, nw, crop_size, crop_size).permute(0, 2, 1, 3).reshape(hp, wp).contiguous()
+
+
 def predict_mask(logits: torch.Tensor) -> torch.Tensor:
     """softmax(dim=1) -> argmax(dim=1) of test_mc3serousv5.py:880-881, fused."""
     return ops.softmax_argmax(logits.contiguous().float())
