@@ -167,3 +167,52 @@ def test_training_step_at_config_yml_size_against_oracle(n, h, w):
     gn = torch.sqrt(sum(grads[k].grad.double().norm() ** 2 for k in params))
     wn = torch.sqrt(sum(p.grad.double().norm() ** 2 for p in params.values()))
     assert abs(float(gn / wn) - 1) < 0.1
+
+
+def test_config2_full_size_training_invariants():
+    """BASELINE configs[1] at full size (16 x 3 x 512 x 512, too large for the CPU oracle) through properties of the exact
+    gradient that hold for any weights:
+      * every 3x3 conv is followed by a train-mode BatchNorm, so the loss does not change when its weight tensor is
+        scaled: <dL/dW, W> = 0 - a whole-backward check (dgrad, wgrad, BN backward) of all 18 conv layers;
+      * softmax-CE + Dice depend on the logits only through softmax, so the logit gradient sums to zero over the classes at
+        every pixel: sum(dL/d outc.bias) = 0;
+      * the step is reproducible: same weights and inputs -> same loss and gradients (fp64 statistics are order-dependent
+        only below fp32 resolution)."""
+    import unet_torch_b200 as U
+
+    torch.manual_seed(35)
+    net = U.UNet(3, 2).cuda().train()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    U.loss.CLASS_NUMBER = 2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(16, 3, 512, 512, device="cuda", generator=g)
+    f = torch.nn.functional.interpolate(torch.randn(16, 1, 32, 32, device="cuda", generator=g), size=(512, 512), mode="bilinear")
+    y = (f[:, 0] > 0.2).float()
+
+    def step():
+        net.load_state_dict(sd)
+        net.zero_grad(set_to_none=True)
+        out = net(x)
+        loss = U.calc_loss(out, y, loss_type="dice_bce_mc")
+        loss.backward()
+        return float(loss.detach()), {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+
+    l1, g1 = step()
+    l2, g2 = step()
+    assert l1 == l1 and abs(l1 - l2) <= 1e-6 * abs(l1)
+    worst_rep = max(rel_l2(g2[k], g1[k]) for k in g1)
+    params = dict(net.named_parameters())
+    cos = {}
+    for k, gr in g1.items():
+        assert torch.isfinite(gr).all(), k
+        if gr.dim() == 4 and gr.shape[-1] == 3:      # 3x3 conv weight (all of them feed a BatchNorm)
+            w = params[k].detach().double()
+            cos[k] = float((gr.double() * w).sum() / (gr.double().norm() * w.norm() + 1e-300))
+    assert len(cos) == 18
+    worst_k = max(cos, key=lambda k: abs(cos[k]))
+    db = g1["outc.conv.bias"].double()
+    print(f"config2 full size: loss {l1:.5f}, repeat rel diff {worst_rep:.2e}, worst |cos(dW, W)| {abs(cos[worst_k]):.2e} ({worst_k}), "
+          f"sum(d bias) / |d bias| = {float(db.sum() / db.norm()):.2e}")
+    assert worst_rep < 1e-4
+    assert abs(cos[worst_k]) < 1e-2      # measured 6e-4
+    assert abs(float(db.sum())) < 1e-3 * float(db.norm())
