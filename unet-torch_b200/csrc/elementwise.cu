@@ -6,6 +6,7 @@
 #include "host_common.h"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -497,9 +498,20 @@ __global__ void double_to_float_kernel(const double* in, float* out, int n) {
 
 bool ok_channels(int C) { return C >= 64 && C <= 2048 && (C & (C - 1)) == 0; }
 
+// The backward kernels keep 100-128 registers per thread, i.e. two resident blocks per SM: a grid of 148 x 8 blocks runs
+// as four waves, each paying its own ramp-up, block reduction and tail (ncu: bn_bwd_reduce at 4.9 TB/s, 24 % warps
+// active). One wave of exactly-resident blocks that loop longer removes that. B200UNET_BWD_BLOCKS_PER_SM overrides (8 =
+// the former grid).
 int bwd_blocks(int N, int H, int W, int C, bool pool) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* e = getenv("B200UNET_BWD_BLOCKS_PER_SM");
+    per_sm = e != nullptr ? atoi(e) : 2;
+    if (per_sm < 1 || per_sm > 8) per_sm = 2;
+  }
   const long long items = pool ? static_cast<long long>(N) * (H / 2) * (W / 2) : static_cast<long long>(N) * H * W;
-  return ew_blocks(items * (C / 8));
+  const int b = ew_blocks(items * (C / 8));
+  return b < 148 * per_sm ? b : 148 * per_sm;
 }
 
 }  // namespace
