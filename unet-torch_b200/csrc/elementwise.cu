@@ -544,12 +544,20 @@ int b200unet_bn_relu_fwd(const void* y, int y_cs, const float* scale, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const auto* yy = static_cast<const __nv_bfloat16*>(y);
   auto* aa = static_cast<__nv_bfloat16*>(a);
+  static int fwd_per_sm = 0;  // B200UNET_FWD_BLOCKS_PER_SM: grid cap of the BN-apply pass in resident blocks per SM (default 8)
+  if (fwd_per_sm == 0) {
+    const char* e = getenv("B200UNET_FWD_BLOCKS_PER_SM");
+    fwd_per_sm = e != nullptr ? atoi(e) : 8;
+    if (fwd_per_sm < 1 || fwd_per_sm > 8) fwd_per_sm = 8;
+  }
   if (pooled == nullptr) {
-    const int blocks = ew_blocks(static_cast<long long>(N) * H * W * (C / 8));
+    int blocks = ew_blocks(static_cast<long long>(N) * H * W * (C / 8));
+    if (blocks > 148 * fwd_per_sm) blocks = 148 * fwd_per_sm;
     bn_relu_fwd_kernel<false><<<blocks, EW_THREADS, 0, st>>>(yy, y_cs, scale, shift, aa, a_cs, nullptr, nullptr, N, H, W, C);
   } else {
     B2_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_fwd(pool): H=%d W=%d must be even", H, W);
-    const int blocks = ew_blocks(static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8));
+    int blocks = ew_blocks(static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8));
+    if (blocks > 148 * fwd_per_sm) blocks = 148 * fwd_per_sm;
     bn_relu_fwd_kernel<true><<<blocks, EW_THREADS, 0, st>>>(yy, y_cs, scale, shift, aa, a_cs,
                                                             static_cast<__nv_bfloat16*>(pooled), pool_idx, N, H, W, C);
   }
