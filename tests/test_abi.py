@@ -64,3 +64,39 @@ def test_bad_shapes_are_errors_not_fallbacks(lib):
     with pytest.raises(RuntimeError, match="n_classes"):
         lib.call("b200unet_head_fprop", None, 64, None, None, None, 1, 8, 8, 64, 9, None)
     assert "n_classes" in lib.last_error()
+
+
+def test_header_is_plain_c_and_a_c_host_links_the_library(lib, tmp_path):
+    """The boundary is a C ABI: include/b200unet.h must compile as C99 (no C++ in the signatures), and a C host program
+    must link libb200unet.so and reach the host-only entry points (what a cgo / JNI / FFI binding does)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "b200unet.h")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = tmp_path / "host.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "b200unet.h"\n'
+        "int main(void) {\n"
+        '  printf("%d %d %d %lld\\n", b200unet_version(), b200unet_tile_h(), b200unet_tile_w(),\n'
+        "         (long long)b200unet_conv3x3_wgrad_workspace_floats(16, 32, 32, 1024, 1024));\n"
+        "  /* a bad shape is an error code + message, never a fallback */\n"
+        "  int rc = b200unet_head_fprop(0, 64, 0, 0, 0, 1, 8, 8, 64, 9, 0);\n"
+        '  printf("%d %s\\n", rc, b200unet_last_error());\n'
+        "  return rc == 0;\n}\n")
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(lib.LIB_PATH)
+    r = subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                        "-l:libb200unet.so", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    first, second = r.stdout.strip().splitlines()
+    v, th, tw, ws = first.split()
+    assert int(v) >= 100 and (int(th), int(tw)) == (8, 16) and int(ws) == 3 * 1024 * 9 * 1024
+    assert second.split()[0] != "0" and "n_classes" in second
