@@ -114,3 +114,34 @@ def test_backward_order_covers_every_parameter_once(cls_name, n_dec):
     assert names[id(order[0])].startswith("outc") and names[id(order[-1])] == "inc.double_conv.0.weight"
     if n_dec == 2:  # the decoder that ran last in forward is differentiated first
         assert names[id(order[0])] == "outc_decod2.conv.weight"
+
+
+def test_product_path_never_touches_the_oracle_or_a_cpu_fallback():
+    """The oracle is test infrastructure: nothing under the package (or the root shims) may import or execute it, and
+    importing the package must not pull it in as a side effect. bench.py may use it only in its CPU legs."""
+    import ast
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "unet-torch_b200", f) for f in os.listdir(os.path.join(root, "unet-torch_b200")) if f.endswith(".py")]
+    files += [os.path.join(root, f) for f in ("Model.py", "loss.py", "unet_torch_b200.py")]
+    for path in files:
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), f"{path} imports the oracle"
+    code = "import sys; sys.path.insert(0, %r); import unet_torch_b200, Model, loss; print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))" % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "False", (r.stdout, r.stderr[-500:])
+    # bench.py: oracle use is confined to the CPU legs (cpu_baseline_leg / reference arm)
+    bench = ast.parse(open(os.path.join(root, "bench.py")).read())
+    for fn in [n for n in ast.walk(bench) if isinstance(n, ast.FunctionDef)]:
+        uses = any(isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n) for n in ast.walk(fn))
+        if uses:
+            assert fn.name in ("cpu_baseline_leg", "reference_arm", "run_reference", "cpu_port_step") or "cpu" in fn.name or "reference" in fn.name, fn.name
