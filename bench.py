@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the U-Net hot path (BASELINE.json metric: UNet train img/s @512^2 bf16).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
 
-ours      : one step = forward + 'dice_bce_mc' loss + backward + SGD step of UNet(3, 2) on a synthetic
-            16 x 3 x 512 x 512 batch per GPU (BASELINE.json configs[1]); N > 1 = data parallel under torchrun
-            (batch 16 per GPU, SyncBN, bucketed gradient all-reduce), weak scaling.
-            `value`  : images/s with the batch already resident in HBM, CUDA-event timed, max over ranks.
-            `e2e`    : the same through the public API with HOST buffers: pinned-host -> device copy of inputs and
-                       labels and a device -> host read of the loss inside the timed region, every step.
-            `roofline`: tcgen05 conv3x3 implicit-GEMM launches (fprop + dgrad), algorithmic FLOPs / CUDA-event time.
-            `cpu_baseline`: the oracle port of the reference's CPU path timed on this box's host cores (rank 0, N=1).
-reference : the reference's own CPU implementation of the path (oracle port: the exact torch CPU ops Model.py /
-            loss.py call), all host threads, bounded sample of the same workload.
+--config (default train512 = the headline, BASELINE.json configs[1]; the others give the remaining named shapes a line):
+  train512       UNet(3,2) training step, 16 x 3x512x512 per GPU, dice_bce_mc + SGD; N > 1 = data parallel + SyncBN (weak)
+  train512_g128  the same with configs[2]'s FIXED global batch 128 (128/N images per GPU; strong scaling)
+  infer1024      configs[3]: UNet(3,5).eval(), 32 x 3x1024x1024 tiles -> uint8 class mask (replicas only at N > 1)
+  reg768         configs[4]: regression head, F.relu + 'mseMC' + SGD, 8 x 3x768x768 per GPU
+
+ours      : `value`   images/s with the batch already resident in HBM, CUDA-event timed, max over ranks.
+            `e2e`     the same through the public API with HOST buffers: pinned-host -> device copy of inputs (and labels)
+                      and a device -> host read of the result (loss / mask) inside the timed region, every step.
+            `roofline` tcgen05 conv3x3 implicit-GEMM launches, algorithmic FLOPs / CUDA-event time of those launches.
+            `cpu_baseline` the reference's CPU path timed on this box's host cores (rank 0, N = 1, bounded sample).
+reference : the UNMODIFIED reference modules (oracle/_ref/Model.py + loss.py, staged by oracle/build_ref.py) running the
+            same step on the host CPU with all host threads; each step is a bounded sample (fewer images) of the same
+            workload. Falls back to the oracle port (kind "port") only if the staged copy is missing.
 """
 from __future__ import annotations
 
@@ -29,9 +33,23 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-CFG = dict(n_channels=3, n_classes=2, H=512, W=512, batch_per_gpu=16, loss="dice_bce_mc",
-           lr=0.01, momentum=0.9, weight_decay=1e-4)
-TRAIN_GFLOP_PER_IMG = 1155.21  # fwd + dgrad + wgrad of config 2
+SGD = dict(lr=0.01, momentum=0.9, weight_decay=1e-4)  # config.yml:15-18
+# gflop_per_img: SURVEY.md section 8(d) (train = fwd + dgrad + wgrad; infer = fwd); conv_share = the part of it in the
+# 3x3 conv fprop+dgrad launches the roofline object covers (train: 2 x 5889 - 14.5 of 18483 GFLOP per 16-image batch)
+WORKLOADS = {
+    "train512": dict(kind="train", ch=3, cls=2, H=512, W=512, batch=16, loss="dice_bce_mc", relu=False,
+                     metric="unet_train_img_per_s_512", gflop_per_img=1155.21, scaling="weak", cpu_sample=4,
+                     what="BASELINE configs[1]: UNet(3,2) training step (fwd + dice_bce_mc loss + bwd + SGD), 3x512x512"),
+    "train512_g128": dict(kind="train", ch=3, cls=2, H=512, W=512, global_batch=128, loss="dice_bce_mc", relu=False,
+                          metric="unet_train_img_per_s_512_global128", gflop_per_img=1155.21, scaling="strong", cpu_sample=4,
+                          what="BASELINE configs[2]: UNet(3,2) data-parallel training step, FIXED global batch 128, 3x512x512"),
+    "infer1024": dict(kind="infer", ch=3, cls=5, H=1024, W=1024, batch=32, loss=None, relu=False,
+                      metric="unet_infer_img_per_s_1024", gflop_per_img=1541.89, scaling="weak", cpu_sample=2,
+                      what="BASELINE configs[3]: UNet(3,5).eval() forward + softmax/argmax -> uint8 mask, 3x1024x1024 tiles"),
+    "reg768": dict(kind="train", ch=3, cls=2, H=768, W=768, batch=8, loss="mseMC", relu=True,
+                   metric="unet_train_img_per_s_768_regression", gflop_per_img=2599.23, scaling="weak", cpu_sample=2,
+                   what="BASELINE configs[4]: UNet(3,2) regression training step (fwd + F.relu + mseMC loss + bwd + SGD), 3x768x768"),
+}
 
 
 def peaks():
@@ -45,12 +63,37 @@ def peaks():
 
 def conv_traffic():
     """DRAM bytes per conv3x3 fprop/dgrad launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the launches
-    of one step) from the committed ncu capture, or None if it has not been taken for this build."""
+    of one train512 step) from the committed ncu capture of the current kernels, or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as f:
             return json.load(f)["dram_bytes_per_launch"]
     except Exception:
         return None
+
+
+def batch_per_gpu(wl, n_gpus):
+    if "global_batch" in wl:
+        if wl["global_batch"] % n_gpus:
+            raise SystemExit(f"global batch {wl['global_batch']} does not divide over {n_gpus} GPUs")
+        return wl["global_batch"] // n_gpus
+    return wl["batch"]
+
+
+def workload_config(name, n_gpus):
+    """Identical for both arms: it names the workload, not how an arm executes it."""
+    wl = WORKLOADS[name]
+    b = batch_per_gpu(wl, n_gpus)
+    par = "single" if n_gpus == 1 else (f"replicas{n_gpus}" if wl["kind"] == "infer" else f"dp{n_gpus}")
+    cfg = {
+        "workload": f"{wl['what']}, batch {b} per GPU"
+                    + (", data parallel + SyncBN" if n_gpus > 1 and wl["kind"] == "train" else ""),
+        "name": name, "global_batch": b * n_gpus, "image": [wl["ch"], wl["H"], wl["W"]], "n_classes": wl["cls"],
+        "loss": ("relu+" if wl["relu"] else "") + wl["loss"] if wl["loss"] else None,
+        "optimizer": "SGD(lr=0.01, momentum=0.9, weight_decay=1e-4)" if wl["kind"] == "train" else None,
+        "parallelism": par,
+        "l2": "per-step working set (GBs of bf16 activations) is far larger than the 126 MB L2; no explicit flush",
+    }
+    return cfg
 
 
 class ClockSampler:
@@ -111,22 +154,66 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------- reference arm
-def cpu_reference_step_factory(batch, h, w, seed=0):
-    """The reference's CPU path (Model.UNet + calc_loss('dice_bce_mc') forward+backward, fp32, all host threads),
-    restated by the oracle port with the exact torch ops the reference modules dispatch to."""
+def synthetic_batch(wl, batch, seed):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, wl["ch"], wl["H"], wl["W"], generator=gen)
+    if wl["kind"] == "infer":
+        return x, None
+    if wl["loss"] == "mseMC":  # density x 200, sparse (DataLoader.py:369-370)
+        y = torch.rand(batch, wl["cls"], wl["H"], wl["W"], generator=gen) * 200.0 * (
+            torch.rand(batch, wl["cls"], wl["H"], wl["W"], generator=gen) > 0.9)
+    else:
+        y = torch.randint(0, wl["cls"], (batch, wl["H"], wl["W"]), generator=gen).float()
+    return x, y
+
+
+def reference_cpu_step(wl, batch, seed=0):
+    """step() = the workload's step on the host CPU in fp32 through the reference's own modules (kind "reference":
+    oracle/_ref/Model.py + loss.py, unmodified), or through the oracle port when the staged copy is missing."""
+    from oracle import ref_loader
+
+    x, y = synthetic_batch(wl, batch, 1234 + seed)
+    if ref_loader.available():
+        RefModel, ref_loss = ref_loader.load()
+        torch.manual_seed(seed)
+        net = RefModel.UNet(wl["ch"], wl["cls"])
+        ref_loss.CLASS_NUMBER = wl["cls"]
+        if wl["kind"] == "infer":
+            net.eval()
+
+            def step():  # test_mc3serousv5.py:878-887
+                with torch.no_grad():
+                    out = net(x)
+                    return torch.argmax(torch.nn.functional.softmax(out, dim=1), dim=1).to(torch.uint8)
+        else:
+            net.train()
+            opt = torch.optim.SGD(net.parameters(), **SGD)
+
+            def step():  # Trainer.py:706-722
+                out = net(x)
+                if wl["relu"]:
+                    out = torch.nn.functional.relu(out)
+                loss = ref_loss.calc_loss(out, y, loss_type=wl["loss"])
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                return float(loss)
+        return step, "reference"
     from oracle import cpu_baseline
 
-    return cpu_baseline.make_step(CFG["n_channels"], CFG["n_classes"], batch, h, w, seed)
+    return cpu_baseline.make_step(wl["ch"], wl["cls"], batch, wl["H"], wl["W"], seed, loss_type=wl["loss"],
+                                  relu=wl["relu"], train=wl["kind"] == "train", sgd=SGD), "port"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    wl = WORKLOADS[args.config]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    batch = 2
-    step = cpu_reference_step_factory(batch, CFG["H"], CFG["W"])
+    batch = min(wl["cpu_sample"], batch_per_gpu(wl, args.gpus))
+    step, kind = reference_cpu_step(wl, batch)
     for _ in range(max(args.warmup, 0)):
         step()
     t0 = time.perf_counter()
@@ -134,13 +221,16 @@ def run_reference(args):
         step()
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     v = batch / dt
-    sample = f"{args.steps} fwd+bwd steps of batch {batch} x 3x512x512 fp32 on {cores} host threads (oracle port, torch CPU ops)"
+    what = "fwd + loss + bwd + SGD" if wl["kind"] == "train" else "eval fwd + softmax/argmax"
+    sample = (f"each step = {what} on a {batch}-image sample of the workload's batch, fp32, {torch.get_num_threads()} host "
+              f"threads, " + ("unmodified reference Model.py + loss.py (oracle/_ref)" if kind == "reference"
+                              else "oracle port (torch CPU ops the reference dispatches to)"))
     line = {
-        "impl": "reference", "metric": "unet_train_img_per_s_512", "value": v, "unit": "img/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": wl["metric"], "value": v, "unit": "img/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": v, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.config, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "img/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -148,20 +238,21 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n_gpus, batch_override=None, graphs=False, torch_optim=False):
-    b = batch_override or CFG["batch_per_gpu"]
-    return {
-        "workload": "BASELINE configs[1]: UNet(3,2) training step (fwd + dice_bce_mc loss + bwd + SGD), 3x512x512, "
-                    f"batch {b} per GPU" + (", data parallel + SyncBN (configs[2] per-GPU batch)" if n_gpus > 1 else ""),
-        "global_batch": b * n_gpus, "image": [CFG["n_channels"], CFG["H"], CFG["W"]], "loss": CFG["loss"],
-        "optimizer": "SGD(lr=0.01, momentum=0.9, weight_decay=1e-4)" + ("" if torch_optim else
-                     " as unet_torch_b200.FusedSGD (torch.optim.SGD arithmetic fused with the bf16 operand re-cast)"),
-        "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
-        "cuda_graphs": ("forward and backward of the network replayed as captured CUDA graphs"
-                        + (" (SyncBN NVLink kernels and NCCL gradient all-reduces captured with them)" if n_gpus > 1 else "")
-                        + "; loss and optimizer eager") if graphs else "off",
-        "l2": "per-step working set (~10 GB of bf16 activations) is far larger than the 126 MB L2; no explicit flush",
-    }
+def cpu_baseline_leg(wl):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = 1 if wl["H"] * wl["W"] > 512 * 512 else 2
+    step, kind = reference_cpu_step(wl, batch)
+    step()  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while n < 4 and time.perf_counter() - t0 < 20.0:
+        step()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    what = "fwd + loss + bwd + SGD" if wl["kind"] == "train" else "eval fwd + softmax/argmax"
+    return {"value": batch / dt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{n} steps ({what}) of a {batch}-image sample, {wl['ch']}x{wl['H']}x{wl['W']} fp32, "
+                      + ("unmodified reference Model.py + loss.py (oracle/_ref)" if kind == "reference" else "oracle port")}
 
 
 # --------------------------------------------------------------------------------------------------- our arm
@@ -169,48 +260,66 @@ def run_ours(args):
     import unet_torch_b200 as U
     from unet_torch_b200 import _lib, ops
 
+    wl = WORKLOADS[args.config]
+    train = wl["kind"] == "train"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
-    dp = U.init_from_env(sync_bn=True) if world > 1 else None
+    dist_on = world > 1
+    dp = U.init_from_env(sync_bn=True) if dist_on else None
+    if dist_on and not train:
+        U.DataParallelContext.disable()  # inference: replicas only, no data-path collective (process group kept for timing)
+        dp = None
     dev = torch.device("cuda", local)
 
     torch.manual_seed(0)
-    net = U.UNet(CFG["n_channels"], CFG["n_classes"]).to(dev).train()
-    U.loss.CLASS_NUMBER = CFG["n_classes"]
-    if world > 1:
+    net = U.UNet(wl["ch"], wl["cls"]).to(dev)
+    net = net.train() if train else net.eval()
+    U.loss.CLASS_NUMBER = wl["cls"]
+    if dist_on:
         import torch.distributed as dist
 
         for p in list(net.parameters()) + list(net.buffers()):
             dist.broadcast(p.data, 0)
-    okw = dict(lr=CFG["lr"], momentum=CFG["momentum"], weight_decay=CFG["weight_decay"])
-    opt = torch.optim.SGD(net.parameters(), **okw) if args.torch_optim else U.FusedSGD(net, **okw)
-    B, H, W = CFG["batch_per_gpu"], CFG["H"], CFG["W"]
-    gen = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(B, CFG["n_channels"], H, W, generator=gen).pin_memory()
-    y_host = torch.randint(0, CFG["n_classes"], (B, H, W), generator=gen).float().pin_memory()
-    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    opt = None
+    if train:
+        opt = torch.optim.SGD(net.parameters(), **SGD) if args.torch_optim else U.FusedSGD(net, **SGD)
+    B, H, W = batch_per_gpu(wl, world), wl["H"], wl["W"]
+    x_host, y_host = synthetic_batch(wl, B, 1234 + rank)
+    x_host = x_host.pin_memory()
+    x_dev = x_host.to(dev)
+    y_dev = None
+    if y_host is not None:
+        y_host = y_host.pin_memory()
+        y_dev = y_host.to(dev)
 
-    def step(x, y):
-        out = net(x)
-        loss = U.calc_loss(out, y, loss_type=CFG["loss"])
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        return loss
+    if train:
+        def step(x, y):
+            out = net(x)
+            if wl["relu"]:
+                out = torch.nn.functional.relu(out)  # Trainer.py:709-710
+            loss = U.calc_loss(out, y, loss_type=wl["loss"])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss
+    else:
+        def step(x, y):
+            with torch.no_grad():
+                return net.predict(x)  # OutConv + softmax + argmax + uint8 fused (test_mc3serousv5.py:878-887)
 
     def barrier():
-        if world > 1:
+        if dist_on:
             import torch.distributed as dist
 
             dist.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if world > 1:
+        if dist_on:
             import torch.distributed as dist
 
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -225,10 +334,12 @@ def run_ours(args):
     l0 = _lib.query("b200unet_launch_count")
     step(x_dev, y_dev)
     launches_per_step = _lib.query("b200unet_launch_count") - l0
-    use_graphs = not args.no_graphs
+    use_graphs = train and not args.no_graphs
     net.enable_cuda_graphs(use_graphs)
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
+    # what actually replays as a graph (data parallel: only with B200UNET_DP_GRAPHS=1 and the NVLink SyncBN path)
+    graphs_live = bool(getattr(net, "_engine", None) is not None and net._engine._graphs)
     # ---- device-resident timing
     barrier()
     sampler.mark_begin()
@@ -245,7 +356,7 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = B * world * args.steps / (ms / 1e3)
 
-    # ---- end to end: host buffers in, loss out, every step
+    # ---- end to end: host buffers in, result out, every step
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # Double-buffered input pipeline (what a pin_memory DataLoader + non_blocking copies amount to): the pinned host batch
@@ -253,7 +364,7 @@ def run_ours(args):
     copy_stream = torch.cuda.Stream()
     cur = torch.cuda.current_stream()
     xbuf = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
-    ybuf = [torch.empty_like(y_dev), torch.empty_like(y_dev)]
+    ybuf = [torch.empty_like(y_dev), torch.empty_like(y_dev)] if y_dev is not None else [None, None]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     done = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -263,13 +374,16 @@ def run_ours(args):
             if i >= 2:
                 copy_stream.wait_event(done[b])  # the step that last read this buffer has finished
             xbuf[b].copy_(x_host, non_blocking=True)
-            ybuf[b].copy_(y_host, non_blocking=True)
+            if y_host is not None:
+                ybuf[b].copy_(y_host, non_blocking=True)
             ready[b].record(copy_stream)
 
-    # The loss of every step is read on the host (pinned 4-byte copy + event wait), one step behind its launch, so the
-    # host keeps enqueueing step i+1 while step i runs (asynchronous logging); all reads complete inside the timed region.
-    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    # The result of every step (loss scalar / uint8 mask) is copied to pinned host memory and read one step behind its
+    # launch, so the host keeps enqueueing step i+1 while step i runs; all reads complete inside the timed region.
+    res_shape = () if train else (B, H, W)
+    res_dtype = torch.float32 if train else torch.uint8
+    res_host = [torch.empty(res_shape, dtype=res_dtype).pin_memory() for _ in range(2)]
+    res_ready = [torch.cuda.Event(), torch.cuda.Event()]
     torch.cuda.synchronize()
     e0.record()
     last = None
@@ -279,15 +393,15 @@ def run_ours(args):
         if i + 1 < args.steps:
             fetch(i + 1)  # issued BEFORE this step's kernels, so it overlaps them; every step's inputs cross PCIe in the region
         cur.wait_event(ready[b])
-        loss = step(xbuf[b], ybuf[b])
+        res = step(xbuf[b], ybuf[b])
         done[b].record(cur)
-        loss_host[b].copy_(loss.detach(), non_blocking=True)  # device -> host read of the step's result, every step
-        loss_ready[b].record(cur)
+        res_host[b].copy_(res.detach(), non_blocking=True)  # device -> host read of the step's result, every step
+        res_ready[b].record(cur)
         if i >= 1:
-            loss_ready[1 - b].synchronize()
-            last = float(loss_host[1 - b])
-    loss_ready[(args.steps - 1) & 1].synchronize()
-    last = float(loss_host[(args.steps - 1) & 1])
+            res_ready[1 - b].synchronize()
+            last = float(res_host[1 - b].float().mean())
+    res_ready[(args.steps - 1) & 1].synchronize()
+    last = float(res_host[(args.steps - 1) & 1].float().mean())
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -296,51 +410,73 @@ def run_ours(args):
     # ---- roofline of the dominant kernel class (tcgen05 conv3x3 implicit GEMM), CUDA events around each launch
     net.enable_cuda_graphs(False)  # per-launch CUDA events need the eager launch path
     prof = []
-    orig = ops.conv3x3
+    orig, orig_eval = ops.conv3x3, ops.conv3x3_bn_relu
 
-    def timed_conv3x3(x, w_op, out, stats_partial=None):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        r = orig(x, w_op, out, stats_partial)
-        b.record()
-        n, h, w, cin = x.shape
-        prof.append((2.0 * n * h * w * out.shape[3] * 9 * cin, a, b))
-        return r
+    def timed(fn, out_index):
+        def wrapper(*a, **k):
+            t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0_.record()
+            r = fn(*a, **k)
+            t1_.record()
+            x, out = a[0], a[out_index]
+            n, h, w, cin = x.shape
+            prof.append((2.0 * n * h * w * out.shape[3] * 9 * cin, t0_, t1_))
+            return r
+        return wrapper
 
-    ops.conv3x3 = timed_conv3x3
+    ops.conv3x3, ops.conv3x3_bn_relu = timed(orig, 2), timed(orig_eval, 4)
     try:
         for _ in range(2):
             step(x_dev, y_dev)
         torch.cuda.synchronize()
     finally:
-        ops.conv3x3 = orig
+        ops.conv3x3, ops.conv3x3_bn_relu = orig, orig_eval
     flops = sum(p[0] for p in prof)
     kms = sum(p[1].elapsed_time(p[2]) for p in prof)
     pk = peaks()
     achieved = flops / (kms / 1e3) / 1e12 if kms > 0 else 0.0
+    step_tflop = B * wl["gflop_per_img"] / 1e3
     roofline = {"bound": "tensor",
-                "kernel": "conv3x3 fprop+dgrad implicit GEMMs (conv3_pair / conv3_res2 / conv3_res kernels, tcgen05; "
-                          "34 launches per step, 12.3 of the 18.5 TFLOP of a step)",
+                "kernel": "conv3x3 " + ("fprop+dgrad" if train else "fprop (BatchNorm+ReLU folded)")
+                          + " implicit GEMMs (conv3_pair / conv3_res2 / conv3_res kernels, tcgen05); "
+                          f"{len(prof) // 2} launches and {flops / 2 / 1e12:.2f} of the {step_tflop:.2f} TFLOP of a step",
                 "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
-                "peak_source": f"{pk['src']} bf16_tflops_sustained", "launches_timed": len(prof),
-                "share_of_step": (kms / 2) / ms_per_step, "traffic": conv_traffic()}
+                "peak_source": f"{pk['src']} bf16_tflops_sustained (kernels timed inside a long step)",
+                "peak_burst": pk["tf_burst"], "frac_of_burst": achieved / pk["tf_burst"],
+                "launches_timed": len(prof), "share_of_step": (kms / 2) / ms_per_step,
+                "traffic": conv_traffic() if args.config == "train512" else None}
 
     if rank != 0:
         return 0
+    if train:
+        how = ("pinned host batch + labels -> one of two device buffers on a copy stream, one step ahead; the loss of every "
+               "step is copied to pinned host memory and read one step behind its launch")
+        h2d, d2h = int(x_host.numel() * 4 + y_host.numel() * 4), 4
+    else:
+        how = ("pinned host tiles -> one of two device buffers on a copy stream, one step ahead; the uint8 mask of every step "
+               "is copied to pinned host memory and read one step behind its launch")
+        h2d, d2h = int(x_host.numel() * 4), int(B * H * W)
     line = {
-        "metric": "unet_train_img_per_s_512", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world, graphs=use_graphs, torch_optim=args.torch_optim),
+        "metric": wl["metric"], "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl["scaling"],
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args.config, world),
+        "execution": {
+            "optimizer_impl": None if not train else ("torch.optim.SGD" if args.torch_optim else
+                                                      "unet_torch_b200.FusedSGD (torch.optim.SGD arithmetic fused with the bf16 operand re-cast)"),
+            "cuda_graphs": ("forward and backward of the network replayed as captured CUDA graphs; loss and optimizer eager"
+                            if graphs_live else "off (every kernel launched eagerly)"),
+            "sync_bn": bool(dp is not None and dp.sync_bn),
+            "sync_bn_path": None if dp is None else ("nvlink peer-memory kernel" if dp.has_nvl else "nccl"),
+        },
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4),
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last,
-                "how": "pinned host batch -> one of two device buffers on a copy stream, one step ahead; the loss of every step is copied to pinned host memory and read one step behind its launch"},
+        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps, "last_result_mean": last, "how": how},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "model_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3 / world,
+        "model_tflops": value * wl["gflop_per_img"] / 1e3 / world,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_leg()
+        line["cpu_baseline"] = cpu_baseline_leg(wl)
     print(json.dumps(line), flush=True)
     return 0
 
@@ -361,27 +497,13 @@ def _shutdown_dist():
         pass
 
 
-def cpu_baseline_leg():
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    batch = 1
-    step = cpu_reference_step_factory(batch, CFG["H"], CFG["W"])
-    step()  # warm-up
-    n, t0 = 0, time.perf_counter()
-    while n < 3 and time.perf_counter() - t0 < 25.0:
-        step()
-        n += 1
-    dt = (time.perf_counter() - t0) / n
-    return {"value": batch / dt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} fwd+bwd steps of batch {batch} x 3x512x512 fp32 (oracle port of Model.UNet + calc_loss, torch CPU ops)"}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="train512", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-optim", action="store_true", help="step with stock torch.optim.SGD instead of FusedSGD")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay)")

@@ -64,20 +64,37 @@ def init_state(n_channels, n_classes, width=64, seed=0):
     return sd
 
 
-def make_step(n_channels, n_classes, batch, h, w, seed=0):
-    """Returns step() = one forward + dice_bce_mc loss + backward of the reference path on the host CPU."""
+def make_step(n_channels, n_classes, batch, h, w, seed=0, loss_type="dice_bce_mc", relu=False, train=True, sgd=None):
+    """Returns step() = one step of the reference path on the host CPU: forward + loss (`dice_bce_mc`, loss.py:488-500, or
+    relu + `mseMC`, Trainer.py:709-712 / loss.py:476) + backward (+ the torch.optim.SGD update when `sgd` is given), or,
+    with train=False, the eval forward + softmax/argmax mask (test_mc3serousv5.py:878-881)."""
     sd = init_state(n_channels, n_classes, 64, seed)
     params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
     g = torch.Generator().manual_seed(seed + 1)
     x = torch.randn(batch, n_channels, h, w, generator=g)
-    y = torch.randint(0, n_classes, (batch, h, w), generator=g).float()
+    if loss_type == "mseMC":
+        y = torch.rand(batch, n_classes, h, w, generator=g) * 200.0 * (torch.rand(batch, n_classes, h, w, generator=g) > 0.9)
+    else:
+        y = torch.randint(0, n_classes, (batch, h, w), generator=g).float()
+    opt = torch.optim.SGD(list(params.values()), **sgd) if (sgd and train) else None
 
     def step():
+        if not train:
+            with torch.no_grad():
+                out = unet_forward_torchops(sd, x, False)
+                return torch.argmax(F.softmax(out, dim=1), dim=1).to(torch.uint8)
         for p in params.values():
             p.grad = None
         out = unet_forward_torchops(sd, x, True)
-        loss = 0.5 * F.cross_entropy(out, y.long()) + 0.5 * O.dice_softmax(out, y, n_classes)
+        if relu:
+            out = F.relu(out)
+        if loss_type == "mseMC":
+            loss = F.mse_loss(out, y)
+        else:
+            loss = 0.5 * F.cross_entropy(out, y.long()) + 0.5 * O.dice_softmax(out, y, n_classes)
         loss.backward()
+        if opt is not None:
+            opt.step()
         return float(loss)
 
     return step
