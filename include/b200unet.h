@@ -287,11 +287,6 @@ int b200unet_sgd_small(float* const* w, const float* const* grad, float* const* 
                        int count, float lr, float momentum, float dampening, float weight_decay, int nesterov,
                        int first_step, b200_stream_t stream);
 
-/* ---- bring-up probe (test aid): UMMA operand whose start is offset by `shift` 128-byte rows inside a
- * 128B-swizzled tile. out[128][64] = A[shift:shift+128][:] * B^T; A is 160x64 bf16, B is 64x64 bf16. */
-int b200unet_probe_shift(const void* a_256x64, const void* b_64x64, float* out_128x64, int shift,
-                         int use_base_offset, int sbo_bytes, b200_stream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

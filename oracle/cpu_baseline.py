@@ -15,25 +15,71 @@ import torch.nn.functional as F
 from . import unet_oracle as O
 
 
-def _double_conv(p, prefix, x, training=True):
+class _RoundBF16(torch.autograd.Function):
+    """bf16 storage point: the value is rounded to bf16 on the way forward AND its gradient on the way back (the B200
+    engine stores activations, pre-BatchNorm conv outputs and their gradients as bf16 tensors)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _st(t, emulate):
+    return _RoundBF16.apply(t) if emulate else t
+
+
+def _w(t, emulate):
+    """GEMM weight operand: bf16 copy of the fp32 master parameter (gradient flows to the master unrounded, fp32)."""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach() if emulate else t
+
+
+def _double_conv(p, prefix, x, training=True, emulate=False, fold=False):
     for ci, bi in ((0, 1), (3, 4)):
-        x = F.conv2d(x, p[f"{prefix}.{ci}.weight"], None, padding=1)
+        x = F.conv2d(_st(x, emulate), _w(p[f"{prefix}.{ci}.weight"], emulate), None, padding=1)
+        if not fold:
+            x = _st(x, emulate)  # y is stored (bf16) before BatchNorm; eval folds BN + ReLU into the conv epilogue instead
         x = F.batch_norm(x, p[f"{prefix}.{bi}.running_mean"], p[f"{prefix}.{bi}.running_var"], p[f"{prefix}.{bi}.weight"],
                          p[f"{prefix}.{bi}.bias"], training, O.MOMENTUM, O.EPS_BN)
-        x = F.relu(x)
+        x = _st(F.relu(x), emulate)
     return x
 
 
-def unet_forward_torchops(p, x, training=True):
-    x1 = _double_conv(p, "inc.double_conv", x, training)
+def unet_forward_torchops(p, x, training=True, emulate_bf16=False):
+    """Model.UNet.forward (Model.py:142-153) through the torch CPU ops the reference dispatches to.
+
+    emulate_bf16=True inserts the B200 engine's bf16 STORAGE points (and nothing else) into the same fp32 computation:
+    conv / convT inputs and weight operands, the pre-BatchNorm conv output, every activation, and - through
+    `_RoundBF16.backward` - the gradients stored at the same places. Arithmetic stays fp32 (the tensor cores accumulate
+    bf16 products in fp32), so what is left between this and the CUDA path is summation order: a composition check that is
+    two orders of magnitude tighter than comparing a bf16 network with an fp32 one."""
+    return _forward(p, x, training, emulate_bf16, [("up{i}.up", "up{i}.conv.double_conv", "outc.conv")])[0]
+
+
+def unet_multitask_forward_torchops(p, x, training=True, emulate_bf16=False):
+    """Model.UNet_multitask.forward (Model.py:232-250): one encoder, two decoders over the same skips -> (logits1, logits2)."""
+    return tuple(_forward(p, x, training, emulate_bf16,
+                          [(f"up{{i}}_decod{d}.up", f"up{{i}}_decod{d}.conv.double_conv", f"outc_decod{d}.conv") for d in (1, 2)]))
+
+
+def _forward(p, x, training, e, decoders):
+    fold = e and not training
+    x1 = _double_conv(p, "inc.double_conv", x, training, e, fold)
     skips, cur = [x1], x1
     for i in range(1, 5):
-        cur = _double_conv(p, f"down{i}.maxpool_conv.1.double_conv", F.max_pool2d(cur, 2), training)
+        cur = _double_conv(p, f"down{i}.maxpool_conv.1.double_conv", F.max_pool2d(cur, 2), training, e, fold)
         skips.append(cur)
-    for i in range(1, 5):
-        up = F.conv_transpose2d(cur, p[f"up{i}.up.weight"], p[f"up{i}.up.bias"], stride=2)
-        cur = _double_conv(p, f"up{i}.conv.double_conv", O.pad_and_cat(skips[4 - i], up), training)
-    return F.conv2d(cur, p["outc.conv.weight"], p["outc.conv.bias"])
+    outs = []
+    for up_name, dc_name, head_name in decoders:
+        cur = skips[4]
+        for i in range(1, 5):
+            up = F.conv_transpose2d(_st(cur, e), _w(p[up_name.format(i=i) + ".weight"], e), p[up_name.format(i=i) + ".bias"], stride=2)
+            cur = _double_conv(p, dc_name.format(i=i), O.pad_and_cat(skips[4 - i], _st(up, e)), training, e, fold)
+        outs.append(F.conv2d(_st(cur, e), p[head_name + ".weight"], p[head_name + ".bias"]))
+    return outs
 
 
 def init_state(n_channels, n_classes, width=64, seed=0):

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 run() { name=$1; shift; timeout ${TMO:-600} "$@" > gpurun_out/$name.log 2>&1; echo "$name rc=$?" | tee -a gpurun_out/iter_summary.txt; }
 for st in ${STAGES:-probe tc model layers bench}; do
   case $st in
-    probe) run probe_shift python scripts/probe_shift.py ;;
+    probe) run probe_shift python -m pytest tests/test_gpu_probe.py -m gpu -q ;;
     ew) run t_elementwise python -m pytest tests/test_gpu_elementwise.py -m gpu -q -x --timeout 120 ;;
     tc) run t_tensorcore python -m pytest tests/test_gpu_tensorcore.py -m gpu -q --timeout 120 ;;
     model) run t_model python -m pytest tests/test_gpu_model.py -m gpu -q -s --timeout 300 ;;

@@ -1,11 +1,11 @@
+// TEST-ONLY object (tests/probe/libb200probe.so; NOT part of libb200unet.so or include/b200unet.h).
 // Hardware probe (bring-up / test aid, not on the product path): does a 128B-swizzled K-major UMMA operand work
 // when its start address is offset by a whole number of 128-byte rows that is NOT a multiple of the 8-row
 // swizzle atom, and when its 8-row groups are `sbo` bytes apart with sbo NOT a multiple of 1024 (the 16x8-pixel
 // tile inside an 18x10 halo tile of conv3_res.cu uses sbo = 1280)?
 // D[m = 8g + i][0:64] = A[shift + g * sbo/128 + i][0:64] * B[64 x 64]^T, A tile = 256 rows loaded by TMA.
-#include "../../include/b200unet.h"
-#include "host_common.h"
-#include "tc_common.cuh"
+#include "../../unet-torch_b200/csrc/host_common.h"
+#include "../../unet-torch_b200/csrc/tc_common.cuh"
 
 namespace {
 using namespace b2;
@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(128) probe_shift_kernel(const __grid_constant_
 }
 }  // namespace
 
-extern "C" int b200unet_probe_shift(const void* a_256x64, const void* b_64x64, float* out_128x64, int shift,
-                                    int use_base_offset, int sbo_bytes, b200_stream_t stream) {
+extern "C" int b200probe_shift(const void* a_256x64, const void* b_64x64, float* out_128x64, int shift,
+                                    int use_base_offset, int sbo_bytes, void* stream) {
   CUtensorMap ta, tb;
   if (int e = b2h::make_tmap_2d(&ta, a_256x64, 64, 256, 256)) return e;
   if (int e = b2h::make_tmap_2d(&tb, b_64x64, 64, 64, 64)) return e;

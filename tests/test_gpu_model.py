@@ -3,10 +3,12 @@ ref_full_nets.pt, produced by oracle/make_golden.py): same seed -> same initial 
 buffers and parameter gradients. Tolerances follow north_star: 1e-2 relative (bf16) for logits and loss; gradients
 of a BatchNorm network are judged against the fp64 reference with the reference's own fp32-vs-fp64 and
 bf16-autocast error as the yardstick."""
+import statistics
+
 import pytest
 import torch
 
-from gpu_util import rel_l2
+from gpu_util import cos, host_step, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -36,6 +38,8 @@ def test_forward_backward_against_reference_golden(golden, case):
     net = build(g["cfg"])
     for k, v in net.state_dict().items():  # identical initial weights as the reference under this seed
         assert torch.allclose(checksum(v), g["sd0_checksum"][k], rtol=1e-12, atol=0), k
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    yard = golden("ref_bf16_yardstick.pt")[case]["bf16_autocast"]  # the reference's OWN bf16-autocast error vs its fp64 run
     net = net.cuda().train()
     U.loss.CLASS_NUMBER = ncls
     x, y = g["x"].cuda(), g["y"].cuda()
@@ -47,8 +51,9 @@ def test_forward_backward_against_reference_golden(golden, case):
     torch.cuda.synchronize()
     e_logits = rel_l2(out.detach(), g["logits64"])
     e_loss = abs(float(loss) - float(g["loss64"])) / abs(float(g["loss64"]))
-    print(f"{case}: logits rel {e_logits:.3e} loss rel {e_loss:.3e}")
-    assert e_logits < 3e-2     # reference bf16-autocast itself: 1.8e-2
+    print(f"{case}: logits rel {e_logits:.3e} (reference bf16-autocast {yard['logits']:.3e}) loss rel {e_loss:.3e} "
+          f"(reference bf16-autocast {yard['loss']:.3e})")
+    assert e_logits <= 1.5 * yard["logits"]
     assert e_loss < 1e-2
     # BatchNorm buffers after one training step
     sd1 = net.state_dict()
@@ -61,15 +66,28 @@ def test_forward_backward_against_reference_golden(golden, case):
     # gradients: norm and direction vs the fp64 reference
     grads = {k: p.grad for k, p in net.named_parameters()}
     assert all(gr is not None for gr in grads.values())
-    worst = 0.0
-    for k, gs in g["grad_small64"].items():
-        e = rel_l2(grads[k], gs)
-        worst = max(worst, e)
-    for k, gs in g["grad_sample64"].items():
-        e = rel_l2(grads[k].flatten()[::997], gs)
-        worst = max(worst, e)
-    print(f"{case}: worst param-grad rel error vs fp64 reference {worst:.3e}")
-    assert worst < 0.75  # reference bf16-autocast vs fp32: 31% median / 48% worst on this kind of run
+    errs = {k: rel_l2(grads[k], gs) for k, gs in g["grad_small64"].items()}
+    errs.update({k: rel_l2(grads[k].flatten()[::997], gs) for k, gs in g["grad_sample64"].items()})
+    assert set(errs) == set(yard["grads"])
+    med, med_yard = statistics.median(errs.values()), statistics.median(yard["grads"].values())
+    kw = max(errs, key=lambda k: errs[k] / (yard["grads"][k] + 1e-12))
+    print(f"{case}: param-grad rel error vs the fp64 reference: median {med:.3e} (reference bf16-autocast {med_yard:.3e}), worst "
+          f"{max(errs.values()):.3e} (reference {max(yard['grads'].values()):.3e}), worst ratio to the reference's own error "
+          f"{errs[kw] / (yard['grads'][kw] + 1e-12):.2f} ({kw})")
+    assert med <= 1.5 * med_yard
+    for k, e in errs.items():  # no parameter is worse than 1.5 x what the reference's own bf16 run shows for it
+        assert e <= 1.5 * yard["grads"][k] + 0.02, (k, e, yard["grads"][k])
+    # composition check: the same torch CPU ops with ONLY the engine's bf16 storage points inserted (oracle/cpu_baseline.py)
+    el, eloss, eg, _ = host_step(sd0, g["x"], g["y"], ncls, g["loss_type"], relu=g["loss_type"].startswith("mse"), emulate=True)
+    rows = {k: (rel_l2(grads[k], eg[k]), cos(grads[k], eg[k])) for k in eg}
+    kw = max(rows, key=lambda k: rows[k][0])
+    print(f"{case}: vs the bf16-storage emulation on the host: logits {rel_l2(out.detach(), el):.3e}, loss "
+          f"{abs(float(loss) - eloss) / abs(eloss):.2e}, grads median rel {statistics.median(r[0] for r in rows.values()):.3e} "
+          f"worst {rows[kw][0]:.3e} ({kw}), min cos {min(r[1] for r in rows.values()):.4f}")
+    # two correct bf16-storage runs decorrelate within a few layers (tests/test_gpu_fullsize.py): they must be no further
+    # apart than either is from the fp64 truth; the tight composition check is tests/test_gpu_replay.py
+    assert rel_l2(out.detach(), el) <= yard["logits"]
+    assert statistics.median(r[0] for r in rows.values()) <= med_yard and min(r[1] for r in rows.values()) > 0.9
     # eval mode (running statistics)
     net.eval()
     with torch.no_grad():
@@ -79,7 +97,7 @@ def test_forward_backward_against_reference_golden(golden, case):
     # and well conditioned: compare values, not only shapes (reference: eval forward right after its own first step)
     e_eval = rel_l2(oe, g["logits_eval"])
     print(f"{case}: eval logits rel {e_eval:.3e}")
-    assert e_eval < 3e-2
+    assert e_eval <= 1.5 * yard["logits"]
 
 
 def test_module_interface_matches_reference():

@@ -2,10 +2,14 @@
 against the UNMODIFIED reference's outputs (tests/golden/ref_multitask.pt, oracle/make_golden_multitask.py): same seed ->
 same weights -> both logits, the summed relu+MSE loss of Trainer.py:877-900, BatchNorm buffers and parameter gradients.
 Tolerances as in test_gpu_model.py (north_star: 1e-2 relative in bf16)."""
+import statistics
+
 import pytest
 import torch
+import torch.nn.functional as F
 
-from gpu_util import rel_l2, to_nhwc_bf16, from_nhwc
+from gpu_util import cos, rel_l2, to_nhwc_bf16, from_nhwc
+from oracle import cpu_baseline
 from test_gpu_model import checksum
 
 pytestmark = pytest.mark.gpu
@@ -37,7 +41,7 @@ def test_multitask_forward_backward_against_reference_golden(golden):
     ch, ncls, width, n, h, w, seed = g["cfg"]
     torch.manual_seed(seed)
     net = U.UNet_multitask(ch, ncls, width)
-    sd0 = net.state_dict()
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
     assert list(sd0.keys()) == list(g["sd0_checksum"].keys()) and len(sd0) == 176
     for k, v in sd0.items():  # identical initial weights as the reference under this seed
         assert torch.allclose(checksum(v), g["sd0_checksum"][k], rtol=1e-12, atol=0), k
@@ -49,8 +53,16 @@ def test_multitask_forward_backward_against_reference_golden(golden):
     torch.cuda.synchronize()
     e1, e2 = rel_l2(o1.detach(), g["o1_64"]), rel_l2(o2.detach(), g["o2_64"])
     e_loss = abs(float(loss) - float(g["loss64"])) / abs(float(g["loss64"]))
-    print(f"multitask: logits rel {e1:.3e} / {e2:.3e}, loss rel {e_loss:.3e}")
-    assert e1 < 3e-2 and e2 < 3e-2 and e_loss < 1e-2
+    # yardstick + composition check: the same torch CPU ops with ONLY the engine's bf16 storage points inserted
+    # (oracle/cpu_baseline.py; reproduces the reference's own bf16-autocast error to a few percent, tests/test_oracle.py)
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd0.items()}
+    m1, m2 = cpu_baseline.unet_multitask_forward_torchops(p, g["x"], True, emulate_bf16=True)
+    (F.mse_loss(F.relu(m1), g["t1"]) + F.mse_loss(F.relu(m2), g["t2"])).backward()
+    y1, y2 = rel_l2(m1.detach(), g["o1_64"]), rel_l2(m2.detach(), g["o2_64"])
+    print(f"multitask: logits rel {e1:.3e} / {e2:.3e} (bf16-storage emulation {y1:.3e} / {y2:.3e}), loss rel {e_loss:.3e}; "
+          f"vs the emulation {rel_l2(o1.detach(), m1.detach()):.3e} / {rel_l2(o2.detach(), m2.detach()):.3e}")
+    assert e1 <= 1.5 * y1 and e2 <= 1.5 * y2 and e_loss < 1e-2
+    assert rel_l2(o1.detach(), m1.detach()) <= y1 and rel_l2(o2.detach(), m2.detach()) <= y2
     sd1 = net.state_dict()
     for k, v in g["buffers1_checksum"].items():
         got = checksum(sd1[k])
@@ -60,15 +72,21 @@ def test_multitask_forward_backward_against_reference_golden(golden):
             assert abs(float(got[1]) - float(v[1])) <= 2e-2 * abs(float(v[1])) + 1e-6, k
     grads = {k: p.grad for k, p in net.named_parameters()}
     assert all(gr is not None for gr in grads.values())
-    worst, worst_enc = 0.0, 0.0
+    errs, yard = {}, {}
     for k, gs in list(g["grad_small64"].items()) + list(g["grad_sample64"].items()):
-        got = grads[k] if k in g["grad_small64"] else grads[k].flatten()[::997]
-        e = rel_l2(got, gs)
-        worst = max(worst, e)
-        if k.startswith(("inc", "down")):   # encoder gradients are the SUM of both decoders' contributions
-            worst_enc = max(worst_enc, e)
-    print(f"multitask: worst param-grad rel error vs fp64 reference {worst:.3e} (encoder {worst_enc:.3e})")
-    assert worst < 0.75
+        small = k in g["grad_small64"]
+        errs[k] = rel_l2(grads[k] if small else grads[k].flatten()[::997], gs)
+        yard[k] = rel_l2(p[k].grad if small else p[k].grad.flatten()[::997], gs)
+    med, med_yard = statistics.median(errs.values()), statistics.median(yard.values())
+    enc = [k for k in errs if k.startswith(("inc", "down"))]   # encoder gradients are the SUM of both decoders' contributions
+    vs_emu = {k: (rel_l2(grads[k], p[k].grad), cos(grads[k], p[k].grad)) for k in errs}
+    print(f"multitask: param-grad rel error vs fp64 reference: median {med:.3e} (emulation {med_yard:.3e}), worst "
+          f"{max(errs.values()):.3e} (emulation {max(yard.values()):.3e}), encoder worst {max(errs[k] for k in enc):.3e}; vs the "
+          f"emulation: median {statistics.median(v[0] for v in vs_emu.values()):.3e}, min cos {min(v[1] for v in vs_emu.values()):.4f}")
+    assert med <= 1.5 * med_yard
+    for k, e in errs.items():
+        assert e <= 1.5 * yard[k] + 0.02, (k, e, yard[k])
+    assert statistics.median(v[0] for v in vs_emu.values()) <= med_yard and min(v[1] for v in vs_emu.values()) > 0.9
     # gradient norms: the encoder's must reflect both decoders (a dropped contribution would roughly halve them)
     for k in ("down4.maxpool_conv.1.double_conv.3.weight", "inc.double_conv.3.weight", "down2.maxpool_conv.1.double_conv.0.weight"):
         ratio = float(grads[k].double().norm() / g["grad_norm64"][k])
@@ -76,7 +94,7 @@ def test_multitask_forward_backward_against_reference_golden(golden):
     net.eval()
     with torch.no_grad():
         v1, v2 = net(x)
-    assert rel_l2(v1, g["e1"]) < 3e-2 and rel_l2(v2, g["e2"]) < 3e-2
+    assert rel_l2(v1, g["e1"]) <= 1.5 * y1 and rel_l2(v2, g["e2"]) <= 1.5 * y2
 
 
 def test_multitask_one_output_unused_and_optimizer_step():

@@ -8,6 +8,7 @@ import torch
 
 from oracle import unet_oracle as O
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def rel(a, b):
     a, b = a.double(), b.double()
@@ -205,3 +206,56 @@ def test_multitask_restatement_matches_reference_golden(golden, case):
             assert int(new_buf[k]) == int(v)
         else:
             assert rel(new_buf[k], v) < 1e-5, k
+
+
+def test_bf16_storage_emulation_reproduces_the_references_own_bf16_error(golden):
+    """`cpu_baseline.unet_forward_torchops(emulate_bf16=True)` is the yardstick AND the composition checker of the -m gpu
+    end-to-end tests. It is pinned two ways: with the flag off it equals the oracle (test_cpu_baseline_port_matches_oracle);
+    with the flag on, its error against the reference's fp64 run must look like the reference's OWN error under
+    torch.autocast(bfloat16) (tests/golden/ref_bf16_yardstick.pt, oracle/make_golden_yardstick.py): logits within 10 %,
+    median parameter-gradient error within 10 %, no parameter above 2 x (measured 0.99-1.02 median, <= 1.74 worst)."""
+    import statistics
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gpu_util import host_step, rel_l2
+
+    import unet_torch_b200 as U
+
+    full = golden("ref_full_nets.pt")
+    yard_all = golden("ref_bf16_yardstick.pt")
+    for case in ("w64_c3_k2_dicebce", "w64_c3_k2_msemc"):
+        g, yard = full[case], yard_all[case]["bf16_autocast"]
+        ch, ncls, width, n, h, w, seed = g["cfg"]
+        torch.manual_seed(seed)
+        sd0 = {k: v.clone() for k, v in U.UNet(ch, ncls, width).state_dict().items()}
+        el, eloss, eg, _ = host_step(sd0, g["x"], g["y"], ncls, g["loss_type"], relu=g["loss_type"].startswith("mse"), emulate=True)
+        e_logits = rel_l2(el, g["logits64"])
+        errs = {k: rel_l2(eg[k], gs) for k, gs in g["grad_small64"].items()}
+        errs.update({k: rel_l2(eg[k].flatten()[::997], gs) for k, gs in g["grad_sample64"].items()})
+        med, med_yard = statistics.median(errs.values()), statistics.median(yard["grads"].values())
+        assert abs(e_logits / yard["logits"] - 1) < 0.1, (case, e_logits, yard["logits"])
+        assert abs(med / med_yard - 1) < 0.1, (case, med, med_yard)
+        assert all(errs[k] <= 2.0 * yard["grads"][k] + 0.02 for k in errs)
+        assert abs(eloss - float(g["loss64"])) / abs(float(g["loss64"])) < 1e-2
+
+
+def test_staged_reference_copy_is_the_reference_byte_for_byte():
+    """oracle/_ref (git-ignored, travels to the GPU box) must be the unmodified reference files: the manifest hashes match the
+    staged files, and - where /root/reference is mounted - the mounted files too."""
+    import hashlib
+    import json
+
+    from oracle import ref_loader
+
+    d = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(d, "MANIFEST.json")):
+        pytest.skip("oracle/_ref not staged (run python oracle/build_ref.py where /root/reference exists)")
+    man = json.load(open(os.path.join(d, "MANIFEST.json")))["files"]
+    for name, digest in man.items():
+        assert hashlib.sha256(open(os.path.join(d, name), "rb").read()).hexdigest() == digest, name
+        src = os.path.join("/root/reference", name)
+        if os.path.exists(src):
+            assert hashlib.sha256(open(src, "rb").read()).hexdigest() == digest, name
+    RefModel, ref_loss = ref_loader.load()
+    assert RefModel.UNet(1, 2, 4).state_dict().keys() and callable(ref_loss.calc_loss)

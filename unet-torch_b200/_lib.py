@@ -97,7 +97,6 @@ SIGNATURES = {
     "b200unet_sgd_conv3x3_weight": (c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_sgd_convt2x2_weight": (c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_sgd_small": (c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _P]),
-    "b200unet_probe_shift": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200unet.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "igemm.cu", "conv3_res.cu", "conv3_res2.cu", "conv3_pair.cu", "first_layer.cu", "wgrad.cu", "elementwise.cu", "small.cu", "loss.cu", "optim.cu", "generic_f32.cu", "nvl_sync.cu", "edge.cu", "probe.cu"]
+SOURCES = ["api.cu", "igemm.cu", "conv3_res.cu", "conv3_res2.cu", "conv3_pair.cu", "first_layer.cu", "wgrad.cu", "elementwise.cu", "small.cu", "loss.cu", "optim.cu", "generic_f32.cu", "nvl_sync.cu", "edge.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -73,6 +73,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with open(stamp_file, "w") as f:
         f.write(stamp)
     return OUT
+
+
+def build_probe(force: bool = False) -> str:
+    """tests/probe/libb200probe.so: the UMMA-descriptor hardware probe of tests/test_gpu_probe.py. A TEST-ONLY object (its
+    entry point is not in include/b200unet.h and not in libb200unet.so); it reuses api.cu's host helpers."""
+    root = os.path.join(HERE, "..", "tests", "probe")
+    src, out = os.path.join(root, "probe_shift.cu"), os.path.join(root, "libb200probe.so")
+    deps = [src, os.path.join(CSRC, "api.cu"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "host_common.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", src, os.path.join(CSRC, "api.cu"), "-o", out, "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for the probe:\n{r.stdout}\n{r.stderr}")
+    return out
 
 
 if __name__ == "__main__":

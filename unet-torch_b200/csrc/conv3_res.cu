@@ -9,7 +9,7 @@
 //     (128 B per pixel, 128B-swizzled by TMA, out-of-bounds = conv zero padding) is loaded; the 9 taps are UMMA
 //     shared-memory descriptors into that tile: start = (r*10 + s) pixel rows, 8-row groups 10 pixels (1280 B) apart.
 //     The tensor core applies the swizzle on absolute smem address bits, so neither the start nor the group stride
-//     has to be a multiple of the 1024-byte swizzle atom (scripts/probe_shift.py checks this on the device).
+//     has to be a multiple of the 1024-byte swizzle atom (tests/test_gpu_probe.py checks this on the device).
 //     => 1.4 activation tile loads per K block instead of 9 (im2col) or 3.75 (igemm.cu).
 //   * Two accumulator buffers in TMEM: the MMA warp runs tile i+1 while the epilogue warps drain tile i
 //     (tcgen05.ld -> bf16 -> swizzled smem staging -> TMA store) and accumulate the BatchNorm statistics

@@ -300,7 +300,7 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
 // every 128-row MMA would be idle, so the roles are swapped: M = x channels, N = the 64 dy channels.
 // One CTA covers ALL NINE taps of its pixel tiles from ONE x tile with a full halo (10 rows x 18 pixels): a K step is
 // the 16 pixels of one tile row, i.e. 16 consecutive 128-byte rows of the halo tile starting at pixel row
-// (k + r) * 18 + s - any start works because the swizzle is a function of the absolute address (probe_shift.py).
+// (k + r) * 18 + s - any start works because the swizzle is a function of the absolute address (tests/test_gpu_probe.py).
 // One x + one dy tile per 8x16 pixels instead of three of each keeps the kernel off the L2->SM limit it hit with one
 // CTA per horizontal tap (ncu: 3.4x the tensor bytes, 58 % tensor-pipe active).
 //   CB = 2 (Cin = 128): M = 128 x channels; one MMA per tap, 9 accumulators of 64 columns would need 576 TMEM columns,

@@ -3,7 +3,8 @@
 Hot branches ('dice_bce_mc', 'CE', 'mse', 'mseMC') run as fused sm_100a kernels (csrc/loss.cu) behind
 torch.autograd.Functions: one read of logits + labels per pass, no per-class `.item()` host syncs
 (reference loss.py:249). The remaining live branches of the reference's string dispatch are outside the hot path
- and are composed from stock torch ops purely so that callers keep working.
+ and are composed from stock torch ops purely so that callers keep working; each of them is
+checked against the reference's own outputs (tests/golden/ref_loss_branches.pt).
 """
 from __future__ import annotations
 
@@ -118,12 +119,12 @@ def calc_loss(pred, target, bce_weight=0.5, loss_type='mse'):
         return F.l1_loss(pred, target)
     if loss_type == 'BCE':
         return F.binary_cross_entropy_with_logits(pred.squeeze(1), target)
-    if loss_type == 'dice_bce':
+    if loss_type == 'dice_bce':  # loss.py:483-486 with BinaryDiceLoss (loss.py:254-306: per-sample, smooth 1, mean)
         p = pred.squeeze(1)
         bce = F.binary_cross_entropy_with_logits(p, target)
-        s = torch.sigmoid(p).reshape(p.shape[0], -1)
-        t = target.reshape(target.shape[0], -1)
-        dice = 1 - (2 * (s * t).sum(1) + 1) / (s.sum(1) + t.sum(1) + 1)
+        s = torch.sigmoid(p).contiguous().view(p.shape[0], -1)
+        t = target.contiguous().view(target.shape[0], -1).float()
+        dice = 1 - (2 * (s * t).sum(1) + 1) / ((s.abs() + t.abs()).sum(1) + 1)
         return 0.5 * bce + 0.5 * dice.mean()
     raise NotImplementedError(
         f"calc_loss(loss_type={loss_type!r}) is outside the B200 hot path (SURVEY.md section 8); "
@@ -131,12 +132,44 @@ def calc_loss(pred, target, bce_weight=0.5, loss_type='mse'):
 
 
 class MultitaskUncertaintyLoss(nn.Module):
-    """Name kept importable for Trainer.py:6; the multi-task path is outside the hot path."""
+    """Homoscedastic-uncertainty weighting of per-task losses, the reference's loss.py:309-325 (constructed at
+    Trainer.py:1007, called at :1065 on the two fused relu+MSE task losses of `UNet_multitask`):
+        total = sum_i coeff_i * loss_i + log(std_i),  std_i = exp(log_var_i) ** 0.5,
+        coeff_i = 1 / (2 std_i^2) for a regression task (regg_flag[i]) else 1 / std_i^2.
+    `log_var_tasks` are the caller's own leaf tensors (CPU `torch.zeros((1,), requires_grad=True)` in the Trainer, stepped
+    by its Adam next to the model parameters); they are moved to the loss' device / dtype here exactly as the reference does,
+    so autograd carries their gradients back across the device boundary. A handful of one-element tensor ops between the
+    fused loss kernels and backward: scalar glue, not a kernel of the path. Returns a tensor of log_var's shape ([1])."""
 
-    def __init__(self, *a, **k):
+    def __init__(self):
         super().__init__()
-        raise NotImplementedError("MultitaskUncertaintyLoss is outside the B200 hot path (SURVEY.md section 8f)")
+
+    def forward(self, loss_values, log_var_tasks, regg_flag):
+        total_loss = 0
+        for i in range(len(loss_values)):
+            dtype, device = loss_values[i].dtype, loss_values[i].device
+            stds = (torch.exp(log_var_tasks[i]) ** (1 / 2)).to(device).to(dtype)
+            coeff = 1 / (2 * (stds ** 2)) if regg_flag[i] else 1 / (stds ** 2)
+            total_loss = total_loss + coeff * loss_values[i] + torch.log(stds)
+        return total_loss
 
 
-def MRAccuracy(*a, **k):
-    raise NotImplementedError("MRAccuracy (CPU connected-components metric) is outside the B200 hot path")
+def MRAccuracy(pred, target):
+    """Mean relative counting error of the reference's loss.py:421-440 (validation metric, Trainer.py:382): sigmoid >= 0.5
+    mask per image, 8-connected components counted with OpenCV on the HOST, compared with the number of annotated dots.
+    CPU post-processing exactly like the reference; the mask itself comes from the device."""
+    import cv2
+    import numpy as np
+
+    batch_size = target.shape[0]
+    target = target.detach().cpu().numpy()
+    pred_bin = (torch.sigmoid(pred.detach().squeeze(1)) >= 0.5).to(torch.uint8).cpu().numpy()
+    mre = 0
+    for b in range(batch_size):
+        count_gt = int(np.sum(target[b]))
+        count_pred, _ = cv2.connectedComponents(pred_bin[b], connectivity=8)
+        if count_gt != 0:
+            mre += abs(count_gt - (count_pred - 1)) / count_gt   # minus the background component
+        elif count_pred != 1:
+            mre += 1
+    return mre / batch_size

@@ -153,6 +153,14 @@ class UNetEngine:
         self.fold_eval_bn = os.environ.get("B200UNET_FOLD_EVAL_BN", "1") not in ("", "0")
         self.wgrad_overlap = os.environ.get("B200UNET_WGRAD_STREAM", "0") not in ("", "0")
         self._wgrad_stream = None
+        # Test hook (tests/test_gpu_replay.py): set to a list and every operator of forward / backward appends a record of
+        # the tensors it read and wrote (tensors that are later overwritten in place are cloned), so the dataflow can be
+        # replayed operator by operator on the host. None = off (no cost).
+        self.trace = None
+
+    def _tr(self, kind, **kw):
+        if self.trace is not None:
+            self.trace.append((kind, kw))
 
     def graphed_step(self, x, training, save):
         """The captured step for this input, or None when the call must run eagerly: graphs disabled, data parallel
@@ -285,6 +293,9 @@ class UNetEngine:
                 ops.conv3x3(inp, wf, y, stats)
             scale, shift, mean, rstd, count = self._bn_affine(cb, stats, rows, n * hh * ww, training, dp)
             ops.bn_relu_fwd(y, scale, shift, a_out, pooled, pool_idx)
+            if self.trace is not None:
+                self._tr("conv_bn_relu", cb=cb, x=(x if cb.first else inp), y=y.clone(), scale=scale, shift=shift, mean=mean,
+                         rstd=rstd, count=count, a=a_out, pooled=pooled, pool_idx=pool_idx, training=training)
             return (inp, y, scale, shift, mean, rstd, count)
 
         # ---- encoder
@@ -320,6 +331,7 @@ class UNetEngine:
                 upo = ups[j]
                 wf, _ = upo.operands()
                 ops.convt2x2(d_in, wf, upo.up.bias.detach(), catk[l][..., ch[l]:])
+                self._tr("convt", up=upo, x=d_in, out=catk[l][..., ch[l]:], cat=catk[l], skip=enc_rec[l][2])
                 c1, c2 = dec[j]
                 a1 = torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
                 r1 = conv_bn_relu(c1, catk[l], ch[l], hs[l], wsz[l], a1)
@@ -340,6 +352,7 @@ class UNetEngine:
             else:
                 logits = torch.empty((n, hw_.shape[0], h, w), dtype=torch.float32, device=dev)
                 outs.append(ops.head_fprop(d_in, hw_, hb_, logits))
+                self._tr("head", conv=head_conv, x=d_in, logits=logits)
         out = outs[0] if len(outs) == 1 else tuple(outs)
         if save and head == "logits":
             saved.x, saved.enc, saved.dec, saved.head_in = x, enc_rec, dec_rec, heads_in
@@ -397,6 +410,8 @@ class UNetEngine:
             ops.bn_relu_bwd(g1, g_pool, pool_idx, y, bn.weight.detach(), scale, shift, mean, rstd, y, dgamma, dbeta,
                             count=count, allreduce=sync)
             dy = y  # dy overwrote y in place
+            rec_t = dict(cb=cb, g1=g1, g_pool=g_pool, pool_idx=pool_idx, dy=dy, dgamma=dgamma, dbeta=dbeta, inp=inp) \
+                if self.trace is not None else None
             dw = gbuf(cb.conv.weight)
             if cb.first:
                 on_wgrad_stream(lambda: ops.conv1x1_c64_wgrad(inp, dy, dw))
@@ -404,6 +419,9 @@ class UNetEngine:
                 on_wgrad_stream(lambda: ops.conv3x3_wgrad(inp, dy, dw))
             grads[bn.weight], grads[bn.bias], grads[cb.conv.weight] = dgamma, dbeta, dw
             done(bn.weight, bn.bias, cb.conv.weight)
+            if rec_t is not None:
+                rec_t["dw"] = dw
+                self.trace.append(("conv_bn_relu_bwd", rec_t))
             if not need_dx:
                 return None
             _, wd = cb.operands()
@@ -418,6 +436,8 @@ class UNetEngine:
                 part = torch.empty(rows * 2 * cdx, dtype=torch.float32, device=dev)
                 ops.conv3x3(dy, wd, dx, part)
                 ops.partial_colsum(part, rows, 2 * cdx, lo, cdx - lo, out)
+            if rec_t is not None:  # two decoders accumulate the skip gradients in place later on: keep this operator's own output
+                rec_t["dx"] = dx.clone() if len(self.decoders) > 1 else dx
             return dx
 
         # ---- decoder(s): head, then up4 -> up1; the skip and bottleneck gradients of several decoders are summed
@@ -430,6 +450,7 @@ class UNetEngine:
             g = torch.empty((n, hs[0], wsz[0], ch[0]), dtype=BF16, device=dev)
             dwh, dbh = gbuf(hw_), gbuf(hb_)
             ops.head_bwd(dz, saved.head_in[k], hw_.detach(), g, dwh, dbh)
+            self._tr("head_bwd", conv=head_conv, dz=dz, x=saved.head_in[k], g=g, dw=dwh, db=dbh)
             grads[hw_], grads[hb_] = dwh, dbh
             done(hw_, hb_)
             for j in (3, 2, 1, 0):
@@ -451,6 +472,10 @@ class UNetEngine:
                 _, wd = upo.operands()
                 g = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l + 1]), dtype=BF16, device=dev)
                 ops.convt2x2_dgrad(du, wd, g)
+                if self.trace is not None:
+                    multi = len(self.decoders) > 1
+                    self._tr("convt_bwd", up=upo, x=d_in, dcat=dcat, du=du.clone() if multi else du, dw=dwu, db=db,
+                             dx=g.clone() if multi else g)
             g5 = g if g5 is None else ops.nhwc_add(g5, g)
         g = g5
         # ---- encoder, level 4 -> 0
