@@ -136,6 +136,11 @@ int b200unet_bn_finalize(const double* sums, double count, const float* gamma, c
 int b200unet_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
                             const float* running_var, float eps, float* scale, float* shift, int C,
                             b200_stream_t stream);
+/* eval mode WITH autograd (frozen-BatchNorm fine-tuning, saliency maps): mean = running_mean, rstd = rsqrt(running_var +
+ * eps) in the form the backward kernels take. With these and an all-zero `sums` vector, b200unet_bn_relu_bwd_apply
+ * computes the running-statistics backward dy = gamma * rstd * da; dgamma / dbeta come from `sums_local`. */
+int b200unet_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd, int C,
+                           b200_stream_t stream);
 /* a = relu(scale*y + shift) written with pitch a_cs (possibly into the concat buffer). If pooled != NULL also
  * writes the 2x2/2 max-pooled tensor [N][H/2][W/2][C] (pitch C) and, if pool_idx != NULL, the window position
  * 0..3 (= 2*dh + dw, first maximum in row-major order, NaN wins: nn.MaxPool2d semantics) as uint8. */
@@ -234,6 +239,12 @@ int b200unet_nvl_bn_sync_finalize(const double* local_sums, double* global_sums,
                                   int rank, int64_t seq, double global_count, const float* gamma, const float* beta,
                                   float eps, float momentum, float* running_mean, float* running_var, float* mean,
                                   float* rstd, float* scale, float* shift, int C, b200_stream_t stream);
+/* Bound on the wait for a peer inside the two kernels above (default 600 000 ms, like NCCL's watchdog; 0 = wait forever).
+ * On expiry the kernel records the failure in its own buffer, writes NaN to its outputs and returns - it does not trap. */
+int b200unet_nvl_set_timeout_ms(int64_t ms);
+/* Host read (synchronises `stream`) of this rank's buffer: out3 = {reductions issued through the device-side counter,
+ * sequence number of the first reduction that timed out (0 = none), bit mask of the ranks that never arrived}. */
+int b200unet_nvl_status(const void* my_buffer, b200_stream_t stream, int64_t* out3);
 
 /* ---- generic fp32 path (generic_f32.cu): check mode and the slow-but-correct route for shapes outside the
  * tensor-core path (H, W not divisible by 16 -> F.pad branch Model.py:69-73 and floor-mode pooling; widths that are not
@@ -286,6 +297,21 @@ int b200unet_sgd_convt2x2_weight(float* w, const float* grad, float* momentum_bu
 int b200unet_sgd_small(float* const* w, const float* const* grad, float* const* momentum_buf, const int* numel,
                        int count, float lr, float momentum, float dampening, float weight_decay, int nesterov,
                        int first_step, b200_stream_t stream);
+
+/* ---- the same fused pass for Adam (train.py:341-343 `optim.Adam(params, lr, weight_decay)`; configseros.yml:15;
+ * Trainer.py:1009): torch.optim.Adam arithmetic - g += weight_decay*w; exp_avg = lerp(exp_avg, g, 1-beta1);
+ * exp_avg_sq = beta2*exp_avg_sq + (1-beta2)*g*g; w -= step_size * exp_avg / (sqrt(exp_avg_sq)*inv_sqrt_bc2 + eps) with
+ * step_size = lr/(1-beta1^t), inv_sqrt_bc2 = 1/sqrt(1-beta2^t) computed by the host - plus the bf16 GEMM operands.
+ * first_step != 0: the moment buffers are uninitialised (treated as zero). */
+int b200unet_adam_conv3x3_weight(float* w_oihw, const float* grad, float* exp_avg, float* exp_avg_sq, void* w_fprop,
+                                 void* w_dgrad, int K, int C, double beta1, double beta2, float eps, float weight_decay,
+                                 float step_size, float inv_sqrt_bc2, int first_step, b200_stream_t stream);
+int b200unet_adam_convt2x2_weight(float* w, const float* grad, float* exp_avg, float* exp_avg_sq, void* w_fprop,
+                                  void* w_dgrad, int Cin, int Cup, double beta1, double beta2, float eps, float weight_decay,
+                                  float step_size, float inv_sqrt_bc2, int first_step, b200_stream_t stream);
+int b200unet_adam_small(float* const* w, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq,
+                        const int* numel, int count, double beta1, double beta2, float eps, float weight_decay,
+                        float step_size, float inv_sqrt_bc2, int first_step, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,8 @@ def cos(a, b):
     return float((a * b).sum() / (a.norm() * b.norm() + 1e-300))
 
 
-def host_step(sd, x, y, ncls, loss_type, relu=False, emulate=False, use_ref_modules=False, dtype=torch.float32):
+def host_step(sd, x, y, ncls, loss_type, relu=False, emulate=False, use_ref_modules=False, dtype=torch.float32,
+              training=True, input_grad=False):
     """One training forward + loss + backward of the reference path on the HOST CPU, from a reference-format state_dict.
 
     use_ref_modules: the unmodified reference (oracle/_ref: Model.UNet + loss.calc_loss); otherwise the oracle port
@@ -52,18 +53,24 @@ def host_step(sd, x, y, ncls, loss_type, relu=False, emulate=False, use_ref_modu
         width = sd["inc.double_conv.0.weight"].shape[0]
         net = RefModel.UNet(x.shape[1], ncls, width)
         net.load_state_dict(sd)
-        net = net.to(dtype).train()
+        net = net.to(dtype).train(training)
         ref_loss.CLASS_NUMBER = ncls
+        if input_grad:
+            x = x.clone().requires_grad_(True)
         out = net(x)
         pred = F.relu(out) if relu else out
         loss = ref_loss.calc_loss(pred, y, loss_type=loss_type)
         loss.backward()
         grads = {k: p.grad for k, p in net.named_parameters()}
+        if input_grad:
+            grads["__input__"] = x.grad
         bufs = {k: v.clone() for k, v in net.state_dict().items() if "running" in k}
         return out.detach(), float(loss.detach()), grads, bufs
     p = {k: (v.to(dtype).clone().requires_grad_(True) if v.is_floating_point() and "running" not in k
              else (v.to(dtype).clone() if v.is_floating_point() else v.clone())) for k, v in sd.items()}
-    out = cpu_baseline.unet_forward_torchops(p, x, True, emulate_bf16=emulate)
+    if input_grad:
+        x = x.clone().requires_grad_(True)
+    out = cpu_baseline.unet_forward_torchops(p, x, training, emulate_bf16=emulate)
     pred = F.relu(out) if relu else out
     if loss_type == "mseMC":
         loss = F.mse_loss(pred, y)
@@ -75,5 +82,7 @@ def host_step(sd, x, y, ncls, loss_type, relu=False, emulate=False, use_ref_modu
         loss = 0.5 * F.cross_entropy(pred, y.long()) + 0.5 * O.dice_softmax(pred, y, ncls)
     loss.backward()
     grads = {k: v.grad for k, v in p.items() if v.requires_grad}
+    if input_grad:
+        grads["__input__"] = x.grad
     bufs = {k: v for k, v in p.items() if "running" in k}  # F.batch_norm updated them in place
     return out.detach(), float(loss.detach()), grads, bufs

@@ -233,3 +233,35 @@ def test_config2_full_size_training_invariants():
     assert worst_rep < 1e-4
     assert abs(cos[worst_k]) < 1e-2      # measured 6e-4
     assert abs(float(db.sum())) < 1e-3 * float(db.norm())
+
+
+def test_width_128_on_the_tensor_core_engine():
+    """initial_feature_map=128 (channel counts 128 ... 2048: the top of the BN / head kernels' range) runs on the tensor-core
+    engine; logits, loss and gradients against the fp32 oracle with the bf16-storage emulation as yardstick."""
+    import unet_torch_b200 as U
+
+    torch.manual_seed(2)
+    net = U.UNet(3, 2, 128)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 32, 48, generator=g)
+    y = (torch.rand(2, 32, 48, generator=g) > 0.5).float()
+    net = net.cuda().train()
+    assert isinstance(net._engine_for(x.cuda()), type(net._get_engine()))
+    U.loss.CLASS_NUMBER = 2
+    out = net(x.cuda())
+    loss = U.calc_loss(out, y.cuda(), loss_type="dice_bce_mc")
+    loss.backward()
+    rl, rloss, rg, _ = host_step(sd, x, y, 2, "dice_bce_mc")
+    el, eloss, eg, _ = host_step(sd, x, y, 2, "dice_bce_mc", emulate=True)
+    e, yard = rel_l2(out.detach(), rl), rel_l2(el, rl)
+    grads = dict(net.named_parameters())
+    errs = {k: rel_l2(grads[k].grad, rg[k]) for k in rg}
+    yards = {k: rel_l2(eg[k], rg[k]) for k in rg}
+    print(f"width 128: logits {e:.3e} (emulation {yard:.3e}), loss {abs(float(loss) - rloss) / abs(rloss):.2e}, grads median "
+          f"{statistics.median(errs.values()):.3e} (emulation {statistics.median(yards.values()):.3e})")
+    assert e <= 1.5 * yard and abs(float(loss) - rloss) / abs(rloss) < 1e-2
+    assert statistics.median(errs.values()) <= 1.5 * statistics.median(yards.values())
+    assert all(errs[k] <= 1.5 * yards[k] + 0.02 for k in errs)
+    with pytest.raises(ValueError):
+        U.UNet(3, 2, 192)._get_engine()                   # not a power-of-two width: generic fp32 engine only

@@ -227,3 +227,107 @@ def test_fused_sgd_matches_torch_sgd(nesterov, damp, wd):
     for u in eng.ups:
         wf, wd_ = ops.prep_convt2x2_weight(u.up.weight.detach())
         assert torch.equal(wf, u.wf) and torch.equal(wd_, u.wd)
+
+
+@pytest.mark.parametrize("check_mode", [False, True])
+def test_eval_mode_backward_uses_running_statistics(check_mode):
+    """model.eval() WITH autograd (frozen-BatchNorm fine-tuning, saliency maps): BatchNorm normalises with the running
+    statistics, so its backward is dy = gamma * rstd * da and dgamma / dbeta use the running mean / rstd (torch's
+    batch_norm backward with training=False; Model.py:17,21 under module.eval()). Against the reference modules / oracle
+    port on the host in fp32; buffers must stay untouched. check_mode: the fp32 generic engine, tight tolerance."""
+    import unet_torch_b200 as U
+    from oracle import ref_loader
+
+    torch.manual_seed(3)
+    net = U.UNet(3, 2)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.randn(2, 3, 48, 64, generator=g)
+    y = torch.randint(0, 2, (2, 48, 64), generator=g).float()
+    net = net.cuda().eval().set_check_mode(check_mode)
+    U.loss.CLASS_NUMBER = 2
+    out = net(x.cuda())
+    assert out.requires_grad
+    loss = U.calc_loss(out, y.cuda(), loss_type="dice_bce_mc")
+    loss.backward()
+    torch.cuda.synchronize()
+    for k, v in net.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k          # eval: parameters and buffers untouched by forward / backward
+    rl, rloss, rg, _ = host_step(sd, x, y, 2, "dice_bce_mc", use_ref_modules=ref_loader.available(), training=False)
+    e_logits, e_loss = rel_l2(out.detach(), rl), abs(float(loss) - rloss) / abs(rloss)
+    errs = {k: rel_l2(p.grad, rg[k]) for k, p in net.named_parameters()}
+    kw = max(errs, key=errs.get)
+    print(f"eval backward (check_mode={check_mode}): logits {e_logits:.3e} loss {e_loss:.3e} grads median "
+          f"{statistics.median(errs.values()):.3e} worst {errs[kw]:.3e} ({kw})")
+    if check_mode:
+        assert e_logits < 1e-4 and e_loss < 1e-4 and errs[kw] < 2e-3
+    else:
+        # no batch statistics in the loop -> no chaotic amplification: plain accumulated bf16 rounding
+        el, eloss, eg, _ = host_step(sd, x, y, 2, "dice_bce_mc", emulate=True, training=False)
+        yard = {k: rel_l2(eg[k], rg[k]) for k in rg}
+        print(f"   bf16-storage emulation vs fp32: logits {rel_l2(el, rl):.3e} grads median {statistics.median(yard.values()):.3e} "
+              f"worst {max(yard.values()):.3e}")
+        assert e_logits <= 1.5 * rel_l2(el, rl) + 1e-4 and e_loss < 1e-2
+        assert statistics.median(errs.values()) <= 1.5 * statistics.median(yard.values())
+        assert all(errs[k] <= 1.5 * yard[k] + 0.02 for k in errs)
+
+
+@pytest.mark.parametrize("wd,betas", [(1e-4, (0.9, 0.999)), (0.0, (0.8, 0.99))])
+def test_fused_adam_matches_torch_adam(wd, betas):
+    """FusedAdam (update + bf16 operand re-cast in one pass) against torch.optim.Adam (train.py:341-343) on identical
+    gradients over three steps: parameters, both moment buffers and the step count; operands == lazy re-cast."""
+    import unet_torch_b200 as U
+    from unet_torch_b200 import ops
+
+    U.loss.CLASS_NUMBER = 2
+    x = torch.randn(2, 3, 32, 32, device="cuda", generator=torch.Generator("cuda").manual_seed(7))
+    y = torch.randint(0, 2, (2, 32, 32), device="cuda", generator=torch.Generator("cuda").manual_seed(8)).float()
+    torch.manual_seed(5)
+    net_a = U.UNet(3, 2).cuda().train()
+    torch.manual_seed(5)
+    net_b = U.UNet(3, 2).cuda().train()
+    kw = dict(lr=2e-3, betas=betas, eps=1e-8, weight_decay=wd)
+    opt_a = torch.optim.Adam(net_a.parameters(), **kw)
+    opt_b = U.FusedAdam(net_b, **kw)
+    for it in range(3):
+        for net, opt in ((net_a, opt_a), (net_b, opt_b)):
+            loss = U.calc_loss(net(x), y, loss_type="dice_bce_mc")
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+        for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+            pb.grad.copy_(pa.grad)
+        opt_a.step()
+        opt_b.step()
+        for (k, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+            sa, sb = opt_a.state[pa], opt_b.state[pb]
+            assert float(sa["step"]) == float(sb["step"]) == it + 1
+            assert torch.allclose(sa["exp_avg"], sb["exp_avg"], rtol=1e-5, atol=1e-10), (it, k)
+            assert torch.allclose(sa["exp_avg_sq"], sb["exp_avg_sq"], rtol=1e-5, atol=1e-14), (it, k)
+            # the update is lr * m / (sqrt(v) + eps) ~ lr in magnitude: compare at that scale
+            assert float((pa - pb).abs().max()) <= 2e-3 * 1e-3 + 2e-6 * float(pa.abs().max()), (it, k, float((pa - pb).abs().max()))
+            pb.data.copy_(pa.data)
+        net_b.refresh_operands(force=True)   # .data writes bypass the version counter
+    eng = net_b._get_engine()
+    loss = U.calc_loss(net_b(x), y, loss_type="dice_bce_mc")
+    opt_b.zero_grad(set_to_none=True)
+    loss.backward()
+    opt_b.step()
+    for c1, c2 in eng.enc + eng.dec:
+        for cb in (c1, c2):
+            if cb.first:
+                continue
+            wf, wd_ = ops.prep_conv3x3_weight(cb.conv.weight.detach())
+            assert cb._ver == (cb.conv.weight._version, cb.conv.weight.data_ptr())
+            assert torch.equal(wf, cb.wf) and torch.equal(wd_, cb.wd)
+    for u in eng.ups:
+        wf, wd_ = ops.prep_convt2x2_weight(u.up.weight.detach())
+        assert torch.equal(wf, u.wf) and torch.equal(wd_, u.wd)
+    sd = opt_b.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and sd["param_groups"][0]["betas"] == betas

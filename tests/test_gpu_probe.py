@@ -34,4 +34,4 @@ def test_umma_descriptor_start_and_group_stride_need_no_atom_alignment():
             want = a[rows.cuda()].float() @ b.float().t()
             assert float((out - want).abs().max()) < 1e-3, (sbo, shift)
             checked += 1
-    assert checked >= 30
+    assert checked >= 20

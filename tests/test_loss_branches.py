@@ -74,3 +74,27 @@ def test_rmse_and_uncertainty_on_device(golden):
     assert tot.is_cuda and abs(float(tot) - float(want)) < 1e-5 * abs(float(want))
     assert lv[0].grad is not None and not lv[0].grad.is_cuda and abs(float(lv[0].grad) - float(-w1 / 2 + 0.5)) < 1e-5
     assert o1.grad is not None and float(o1.grad.abs().sum()) > 0
+
+
+@pytest.mark.gpu
+def test_out_of_range_labels_surface_like_the_reference():
+    """nn.CrossEntropyLoss raises for a label outside [0, C) (loss.py:469, 498). The fused kernel flags it on the device: an
+    immediate IndexError with check_labels=True, otherwise at the next loss call / check_pending_label_errors()."""
+    import unet_torch_b200 as U
+    from unet_torch_b200 import loss as L
+
+    L.check_pending_label_errors(wait=True)
+    z = torch.randn(2, 3, 16, 16, device="cuda")
+    t = torch.randint(0, 3, (2, 16, 16), device="cuda").float()
+    bad = t.clone()
+    bad[0, 3, 3] = 7
+    U.loss.CLASS_NUMBER = 3
+    with pytest.raises(IndexError):
+        L.ce_dice_loss(z, bad, check_labels=True)
+    L._pending.clear()
+    U.calc_loss(z, bad, loss_type="dice_bce_mc")          # no sync: flagged, not raised yet
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        U.calc_loss(z, t, loss_type="dice_bce_mc")        # the next call reports it
+    U.calc_loss(z, t, loss_type="CE")                     # and the state is clean again
+    L.check_pending_label_errors(wait=True)

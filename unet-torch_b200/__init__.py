@@ -8,7 +8,7 @@ from . import _lib  # noqa: F401
 from .model import UNet, UNet_multitask, DoubleConv, Down, Up, OutConv, predict_mask, preprocess, preprocess_crop, predict_tiled  # noqa: F401
 from .loss import calc_loss, DiceLoss, ce_dice_loss, relu_mse_loss, MultitaskUncertaintyLoss, MRAccuracy  # noqa: F401
 from .dist import DataParallelContext, init_from_env  # noqa: F401
-from .optim import FusedSGD  # noqa: F401
+from .optim import FusedAdam, FusedSGD  # noqa: F401
 
 __all__ = ["UNet", "UNet_multitask", "DoubleConv", "Down", "Up", "OutConv", "calc_loss", "DiceLoss", "ce_dice_loss", "relu_mse_loss", "MultitaskUncertaintyLoss", "MRAccuracy",
-           "predict_mask", "preprocess", "preprocess_crop", "predict_tiled", "DataParallelContext", "init_from_env", "FusedSGD"]
+           "predict_mask", "preprocess", "preprocess_crop", "predict_tiled", "DataParallelContext", "init_from_env", "FusedSGD", "FusedAdam"]

@@ -290,15 +290,14 @@ __global__ void __launch_bounds__(192, 1) conv3_pair_kernel(const __grid_constan
 template <int BN, int NA, int NB, int OB>
 int launch_pair(const PairArgs& a, cudaStream_t st) {
   using P = PairPlan<BN, NA, NB, OB>;
-  static bool configured = false;
+  static unsigned long long configured = 0;  // one bit per CUDA device
   auto kern = conv3_pair_kernel<BN, NA, NB, OB>;
-  if (!configured) {
+  if (b2h::first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) {
       b2h::set_error("conv3_pair: cudaFuncSetAttribute(smem=%d): %s", P::TOTAL, cudaGetErrorString(e));
       return 2;
     }
-    configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * a.workers * a.ntiles_n);

@@ -318,15 +318,14 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
 template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV>
 int launch_res(const ResArgs& a, cudaStream_t st) {
   using P = ResPlan<BN, KB, NA, OB, TAPS, KIND>;
-  static bool configured = false;
+  static unsigned long long configured = 0;  // one bit per CUDA device
   auto kern = conv3_res_kernel<BN, KB, NA, OB, TAPS, KIND>;
-  if (!configured) {
+  if (b2h::first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) {
       b2h::set_error("conv3_res: cudaFuncSetAttribute(smem=%d): %s", P::TOTAL, cudaGetErrorString(e));
       return 2;
     }
-    configured = true;
   }
   kern<<<a.workers * a.ntiles_n, 192, P::TOTAL, st>>>(a);
   return b2h::check_launch("conv3_res");

@@ -288,15 +288,14 @@ __global__ void __launch_bounds__(192, 1) conv3_res2_kernel(const __grid_constan
 template <int BN, int KB, int NA, int OB>
 int launch_res2(const Res2Args& a, cudaStream_t st) {
   using P = Res2Plan<BN, KB, NA, OB>;
-  static bool configured = false;
+  static unsigned long long configured = 0;  // one bit per CUDA device
   auto kern = conv3_res2_kernel<BN, KB, NA, OB>;
-  if (!configured) {
+  if (b2h::first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) {
       b2h::set_error("conv3_res2: cudaFuncSetAttribute(smem=%d): %s", P::TOTAL, cudaGetErrorString(e));
       return 2;
     }
-    configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * a.workers * a.ntiles_n);

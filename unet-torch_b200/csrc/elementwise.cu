@@ -105,6 +105,13 @@ __global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, con
   shift[c] = beta[c] - rm[c] * sc;
 }
 
+__global__ void bn_eval_stats_kernel(const float* rm, const float* rv, float eps, float* mean, float* rstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = rm[c];
+  rstd[c] = 1.0f / sqrtf(rv[c] + eps);
+}
+
 // ------------------------------------------------------------------------------------------ forward
 template <bool POOL>
 __global__ void __launch_bounds__(EW_THREADS) bn_relu_fwd_kernel(const __nv_bfloat16* __restrict__ y, int y_cs,
@@ -537,6 +544,14 @@ int b200unet_bn_eval_affine(const float* gamma, const float* beta, const float* 
   return b2h::check_launch("bn_eval_affine");
 }
 
+int b200unet_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd, int C,
+                           b200_stream_t stream) {
+  B2_REQUIRE(running_mean && running_var && mean && rstd && C > 0, "bn_eval_stats: null argument");
+  bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(running_mean, running_var, eps, mean,
+                                                                                     rstd, C);
+  return b2h::check_launch("bn_eval_stats");
+}
+
 int b200unet_bn_relu_fwd(const void* y, int y_cs, const float* scale, const float* shift, void* a, int a_cs, void* pooled,
                          uint8_t* pool_idx, int N, int H, int W, int C, b200_stream_t stream) {
   B2_REQUIRE(ok_channels(C), "bn_relu_fwd: C=%d must be a power of two in [64, 2048]", C);
@@ -574,6 +589,8 @@ int b200unet_bn_relu_bwd_reduce(const void* g1, int g1_cs, const void* g_pool, c
                                 float* partial, double* sums, int N, int H, int W, int C, b200_stream_t stream) {
   B2_REQUIRE(ok_channels(C), "bn_relu_bwd_reduce: C=%d must be a power of two in [64, 2048]", C);
   B2_REQUIRE(g1 != nullptr || g_pool != nullptr, "bn_relu_bwd_reduce: no gradient source");
+  B2_REQUIRE(y && scale && shift && mean && rstd && partial && sums,
+             "bn_relu_bwd_reduce: null argument (eval-mode forwards must save mean/rstd: b200unet_bn_eval_stats)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BwdSrc s{static_cast<const __nv_bfloat16*>(g1), g1_cs, static_cast<const __nv_bfloat16*>(g_pool), pool_idx,
            static_cast<const __nv_bfloat16*>(y), y_cs};
@@ -593,6 +610,8 @@ int b200unet_bn_relu_bwd_apply(const void* g1, int g1_cs, const void* g_pool, co
                                const float* rstd, const double* sums, double count, const double* sums_local, void* dy,
                                int dy_cs, float* dgamma, float* dbeta, int N, int H, int W, int C, b200_stream_t stream) {
   B2_REQUIRE(ok_channels(C), "bn_relu_bwd_apply: C=%d must be a power of two in [64, 2048]", C);
+  B2_REQUIRE(y && gamma && scale && shift && mean && rstd && sums && dy,
+             "bn_relu_bwd_apply: null argument (eval-mode forwards must save mean/rstd: b200unet_bn_eval_stats)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BwdSrc s{static_cast<const __nv_bfloat16*>(g1), g1_cs, static_cast<const __nv_bfloat16*>(g_pool), pool_idx,
            static_cast<const __nv_bfloat16*>(y), y_cs};

@@ -29,6 +29,17 @@ int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t k, uint64_t rows, ui
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Kernel attributes (opt-in dynamic shared memory) are per device: each kernel instantiation keeps one bit per CUDA device
+// and configures itself on its first launch there (a process may drive several GPUs).
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 // scale/shift (optional, [Cout] each): eval-mode BatchNorm + ReLU folded into the epilogue (stats_partial must be null)
 // conv3_res.cu: persistent resident-weight 3x3 kernel for Cin in {64, 128}
 bool conv3_res_applicable(int Cin, int Cout);

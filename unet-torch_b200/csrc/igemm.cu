@@ -275,15 +275,14 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ Igem
 template <int MODE, int BN, int NA, int NB>
 int launch_t(const IgemmArgs& a, int mtiles, cudaStream_t st) {
   using Plan = SmemPlan<MODE, BN, NA, NB>;
-  static bool configured = false;
+  static unsigned long long configured = 0;  // one bit per CUDA device
   auto kern = igemm_kernel<MODE, BN, NA, NB>;
-  if (!configured) {
+  if (b2h::first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::TOTAL);
     if (e != cudaSuccess) {
       b2h::set_error("igemm: cudaFuncSetAttribute(smem=%d): %s", Plan::TOTAL, cudaGetErrorString(e));
       return 2;
     }
-    configured = true;
   }
   const long long grid = static_cast<long long>(mtiles) * a.ntiles_n;
   kern<<<static_cast<unsigned>(grid), 192, Plan::TOTAL, st>>>(a);

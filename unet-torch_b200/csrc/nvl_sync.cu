@@ -14,6 +14,11 @@
 // seq = 0 in the call means "next": the kernel takes the number from a counter in its own buffer and advances it, so a
 // launch captured in a CUDA graph stays valid on every replay (all ranks issue the same reductions in the same order, hence
 // their counters agree). Explicit (host-side) and counter-based numbering must not be mixed on one buffer.
+// A peer that never arrives (crashed rank; a rank stuck in a data loader for longer than the timeout): the wait is bounded
+// by a configurable timeout (b200unet_nvl_set_timeout_ms, default 10 minutes like NCCL's watchdog, 0 = wait forever). On
+// expiry the kernel does NOT trap (that would poison the CUDA context of every waiting rank): it records {sequence number,
+// mask of missing ranks} in its own buffer, fills its outputs with NaN so that the failure is loud in the very next loss
+// value, and returns. The host reads the record with b200unet_nvl_status (DataParallelContext.check_health()).
 #include "../../include/b200unet.h"
 #include "host_common.h"
 
@@ -23,7 +28,9 @@ constexpr int MAX_WORLD = 8;
 constexpr int SLOT_DOUBLES = 2048;                                   // 2 * Cmax
 constexpr size_t FLAG_OFFSET = size_t(2) * MAX_WORLD * SLOT_DOUBLES * 8;  // bytes: data region first, then flags
 constexpr size_t COUNTER_OFFSET = FLAG_OFFSET + 2 * MAX_WORLD * 8;  // this rank's own reduction counter (device-side seq)
+constexpr size_t ERROR_OFFSET = COUNTER_OFFSET + 8;  // {failed sequence number, bit mask of ranks that never arrived}
 constexpr size_t BUFFER_BYTES = COUNTER_OFFSET + 64;
+unsigned long long g_timeout_ns = 600ull * 1000000000ull;
 
 struct PeerTable {
   unsigned char* buf[MAX_WORLD];
@@ -59,7 +66,8 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
 
 __global__ void __launch_bounds__(256) nvl_allreduce_kernel(const double* __restrict__ local, double* __restrict__ out, int n,
                                                            PeerTable peers, int world, int rank,
-                                                           unsigned long long seq, FinalizeArgs fin) {
+                                                           unsigned long long seq, FinalizeArgs fin,
+                                                           unsigned long long timeout_ns) {
   unsigned long long* counter = reinterpret_cast<unsigned long long*>(peers.buf[rank] + COUNTER_OFFSET);
   if (seq == 0) {  // device-side numbering (graph-replayable)
     __shared__ unsigned long long seq_sh;
@@ -72,7 +80,12 @@ __global__ void __launch_bounds__(256) nvl_allreduce_kernel(const double* __rest
   }
   const int slot = static_cast<int>(seq & 1ull);
   const size_t my_off = (static_cast<size_t>(slot) * MAX_WORLD + rank) * SLOT_DOUBLES;
-  // 1. publish
+  __shared__ unsigned int missing_sh;
+  if (threadIdx.x == 0)  // an earlier reduction already failed on this rank: do not wait another timeout per launch
+    missing_sh = reinterpret_cast<const unsigned long long*>(peers.buf[rank] + ERROR_OFFSET)[0] != 0ull ? 0x80000000u : 0u;
+  __syncthreads();
+  const bool already_failed = missing_sh != 0u;
+  // 1. publish (also after a failure: peers that are still healthy must not stall on THIS rank's account)
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double v = local[i];
     for (int p = 0; p < world; ++p) reinterpret_cast<double*>(peers.buf[p])[my_off + i] = v;
@@ -81,22 +94,39 @@ __global__ void __launch_bounds__(256) nvl_allreduce_kernel(const double* __rest
   __syncthreads();
   if (threadIdx.x < world)
     st_release_sys(reinterpret_cast<unsigned long long*>(peers.buf[threadIdx.x] + FLAG_OFFSET) + slot * MAX_WORLD + rank, seq);
-  // 2. wait for every rank's vector of this sequence number
-  if (threadIdx.x < world) {
+  // 2. wait for every rank's vector of this sequence number (bounded, see the header comment)
+  if (threadIdx.x < world && !already_failed) {
     const unsigned long long* f =
         reinterpret_cast<const unsigned long long*>(peers.buf[rank] + FLAG_OFFSET) + slot * MAX_WORLD + threadIdx.x;
     unsigned long long t0 = 0;
     unsigned int it = 0;
     while (ld_acquire_sys(f) != seq) {
-      if ((++it & 0xfffu) == 0) {
+      if ((++it & 0xfffu) == 0 && timeout_ns != 0) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
         if (t0 == 0) t0 = now;
-        else if (now - t0 > 20000000000ull) __trap();  // 20 s: a peer died; surface an error instead of hanging
+        else if (now - t0 > timeout_ns) {
+          atomicOr(&missing_sh, 1u << threadIdx.x);
+          break;
+        }
       }
     }
   }
   __syncthreads();
+  if (missing_sh != 0u) {  // uniform: a peer never arrived. Record it, poison the outputs, keep the context alive.
+    if (threadIdx.x == 0) {
+      unsigned long long* err = reinterpret_cast<unsigned long long*>(peers.buf[rank] + ERROR_OFFSET);
+      if (err[0] == 0ull) {
+        err[0] = seq;
+        err[1] = missing_sh;
+      }
+    }
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = qnan;
+    const float fnan = __int_as_float(0x7fc00000);
+    for (int c = threadIdx.x; c < fin.C; c += blockDim.x) fin.mean[c] = fin.rstd[c] = fin.scale[c] = fin.shift[c] = fnan;
+    return;
+  }
   // 3. reduce in rank order
   const double* mine = reinterpret_cast<const double*>(peers.buf[rank]) + static_cast<size_t>(slot) * MAX_WORLD * SLOT_DOUBLES;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -159,7 +189,7 @@ int b200unet_nvl_allreduce_f64(const double* local, double* out, int n, void* co
   FinalizeArgs fin{};
   fin.C = 0;
   nvl_allreduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(local, out, n, t, world, rank,
-                                                                        static_cast<unsigned long long>(seq), fin);
+                                                                        static_cast<unsigned long long>(seq), fin, g_timeout_ns);
   return b2h::check_launch("nvl_allreduce_f64");
 }
 
@@ -172,8 +202,30 @@ int b200unet_nvl_bn_sync_finalize(const double* local_sums, double* global_sums,
   B2_REQUIRE(seq >= 0 && C > 0, "nvl_bn_sync_finalize: bad arguments");
   FinalizeArgs fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, global_count, eps, momentum, C};
   nvl_allreduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(local_sums, global_sums, 2 * C, t, world, rank,
-                                                                        static_cast<unsigned long long>(seq), fin);
+                                                                        static_cast<unsigned long long>(seq), fin, g_timeout_ns);
   return b2h::check_launch("nvl_bn_sync_finalize");
+}
+
+int b200unet_nvl_set_timeout_ms(int64_t ms) {
+  B2_REQUIRE(ms >= 0, "nvl_set_timeout_ms: negative timeout (0 = wait forever)");
+  g_timeout_ns = static_cast<unsigned long long>(ms) * 1000000ull;
+  return 0;
+}
+
+int b200unet_nvl_status(const void* my_buffer, b200_stream_t stream, int64_t* out3) {
+  // {reductions issued with the device-side counter, failed sequence number (0 = none), mask of ranks that never arrived}
+  B2_REQUIRE(my_buffer != nullptr && out3 != nullptr, "nvl_status: null argument");
+  unsigned long long h[3] = {0, 0, 0};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(h, static_cast<const unsigned char*>(my_buffer) + COUNTER_OFFSET, sizeof(h),
+                                  cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    b2h::set_error("nvl_status: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  for (int i = 0; i < 3; ++i) out3[i] = static_cast<int64_t>(h[i]);
+  return 0;
 }
 
 }  // extern "C"

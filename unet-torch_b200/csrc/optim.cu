@@ -3,6 +3,9 @@
 //   g' = g + wd*w ;  buf = mom*buf + (1-damp)*g'  (buf = g' on the first step) ;  w -= lr * (nesterov ? g' + mom*buf : buf)
 // in fp32 on the master parameter AND writes the two bf16 GEMM operands the tensor-core kernels consume (fprop and
 // dgrad layouts), so the separate re-cast pass (prep_conv3_kernel) and torch's foreach kernels disappear.
+// The same pass exists for Adam (train.py:341-343 `optim.Adam(model.parameters(), lr, weight_decay)`, the optimizer of
+// configseros.yml:15 and of Trainer.multi_task_uc_train): torch.optim.Adam arithmetic (L2 weight decay added to the gradient,
+// bias-corrected first / second moments, no amsgrad) with the bias corrections folded into two host-computed scalars.
 // All global accesses are coalesced: the fp32 tensors are walked in their own order, the bf16 tile is transposed
 // through shared memory and written as 128-byte rows (operand 1) and 32-byte runs (operand 2).
 #include "../../include/b200unet.h"
@@ -15,7 +18,24 @@ namespace {
 struct SgdHyper {
   float lr, momentum, dampening, weight_decay;
   int nesterov, first_step;
+  // Adam (adam != 0): exp_avg lives in `buf`, exp_avg_sq in `buf2`
+  int adam;
+  float beta1, beta2, eps;
+  float omb1, omb2;     // 1 - beta1, 1 - beta2 rounded from the host's doubles (1.f - 0.999f is off by 5e-5 relative)
+  float step_size;      // lr / (1 - beta1^t)
+  float inv_sqrt_bc2;   // 1 / sqrt(1 - beta2^t)
 };
+
+// torch.optim.Adam (single-tensor path): g += wd*w; m = lerp(m, g, 1-b1); v = b2*v + (1-b2)*g*g;
+// w -= step_size * m / (sqrt(v) / sqrt(bc2) + eps)
+__device__ __forceinline__ float adam_update(float& w, float g, float& m, float& v, const SgdHyper& h) {
+  g = fmaf(h.weight_decay, w, g);
+  m = fmaf(g - m, h.omb1, m);
+  v = fmaf(h.beta2, v, h.omb2 * g * g);
+  const float denom = fmaf(sqrtf(v), h.inv_sqrt_bc2, h.eps);
+  w = fmaf(-h.step_size, m / denom, w);
+  return w;
+}
 
 __device__ __forceinline__ float sgd_update(float& w, float g, float& buf, const SgdHyper& h) {
   g = fmaf(h.weight_decay, w, g);
@@ -32,8 +52,9 @@ __device__ __forceinline__ float sgd_update(float& w, float g, float& buf, const
 //   ROT ? op2[b][TAPS-1-tap][a] : op2[tap][b][a]     (conv3: dgrad operand [C][8-rs][K]; convT: fprop operand [ij][d][ci])
 template <int TAPS, bool ROT>
 __global__ void __launch_bounds__(256) sgd_weight_kernel(float* __restrict__ w, const float* __restrict__ g,
-                                                         float* __restrict__ buf, __nv_bfloat16* __restrict__ op1,
-                                                         __nv_bfloat16* __restrict__ op2, int A, int B, SgdHyper h) {
+                                                         float* __restrict__ buf, float* __restrict__ buf2,
+                                                         __nv_bfloat16* __restrict__ op1, __nv_bfloat16* __restrict__ op2,
+                                                         int A, int B, SgdHyper h) {
   constexpr int TA = 32, TB = 64;
   constexpr int ROW4 = TB * TAPS / 4;  // float4's per a-row of the tile (contiguous in the parameter tensor)
   __shared__ __align__(16) __nv_bfloat16 sm[TA][TAPS][TB];
@@ -46,10 +67,19 @@ __global__ void __launch_bounds__(256) sgd_weight_kernel(float* __restrict__ w, 
     if (g != nullptr) {
       const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + gi));
       float4 b4 = have_buf ? *reinterpret_cast<const float4*>(buf + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
-      sgd_update(w4.x, g4.x, b4.x, h);
-      sgd_update(w4.y, g4.y, b4.y, h);
-      sgd_update(w4.z, g4.z, b4.z, h);
-      sgd_update(w4.w, g4.w, b4.w, h);
+      if (h.adam) {
+        float4 v4 = h.first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(buf2 + gi);
+        adam_update(w4.x, g4.x, b4.x, v4.x, h);
+        adam_update(w4.y, g4.y, b4.y, v4.y, h);
+        adam_update(w4.z, g4.z, b4.z, v4.z, h);
+        adam_update(w4.w, g4.w, b4.w, v4.w, h);
+        *reinterpret_cast<float4*>(buf2 + gi) = v4;
+      } else {
+        sgd_update(w4.x, g4.x, b4.x, h);
+        sgd_update(w4.y, g4.y, b4.y, h);
+        sgd_update(w4.z, g4.z, b4.z, h);
+        sgd_update(w4.w, g4.w, b4.w, h);
+      }
       *reinterpret_cast<float4*>(w + gi) = w4;
       if (buf != nullptr) *reinterpret_cast<float4*>(buf + gi) = b4;
     }
@@ -89,6 +119,7 @@ struct SmallTable {
   float* w[48];
   const float* g[48];
   float* buf[48];
+  float* buf2[48];
   int n[48];
   int count;
 };
@@ -101,10 +132,65 @@ __global__ void __launch_bounds__(256) sgd_small_kernel(SmallTable t, SgdHyper h
   float* buf = t.buf[ti];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t.n[ti]; i += gridDim.x * blockDim.x) {
     float wv = w[i], bv = (buf != nullptr && !h.first_step) ? buf[i] : 0.f;
-    sgd_update(wv, g[i], bv, h);
+    if (h.adam) {
+      float vv = h.first_step ? 0.f : t.buf2[ti][i];
+      adam_update(wv, g[i], bv, vv, h);
+      t.buf2[ti][i] = vv;
+    } else {
+      sgd_update(wv, g[i], bv, h);
+    }
     w[i] = wv;
     if (buf != nullptr) buf[i] = bv;
   }
+}
+
+SgdHyper sgd_hyper(float lr, float momentum, float dampening, float weight_decay, int nesterov, int first_step) {
+  SgdHyper h{};
+  h.lr = lr;
+  h.momentum = momentum;
+  h.dampening = dampening;
+  h.weight_decay = weight_decay;
+  h.nesterov = nesterov;
+  h.first_step = first_step;
+  return h;
+}
+
+SgdHyper adam_hyper(double beta1, double beta2, float eps, float weight_decay, float step_size, float inv_sqrt_bc2, int first_step) {
+  SgdHyper h{};
+  h.adam = 1;
+  h.beta1 = static_cast<float>(beta1);
+  h.beta2 = static_cast<float>(beta2);
+  h.omb1 = static_cast<float>(1.0 - beta1);
+  h.omb2 = static_cast<float>(1.0 - beta2);
+  h.eps = eps;
+  h.weight_decay = weight_decay;
+  h.step_size = step_size;
+  h.inv_sqrt_bc2 = inv_sqrt_bc2;
+  h.first_step = first_step;
+  h.momentum = 1.f;  // "has a first-moment buffer"
+  return h;
+}
+
+int launch_small(float* const* w, const float* const* grad, float* const* buf, float* const* buf2, const int* numel, int count,
+                 const SgdHyper& h, cudaStream_t st, const char* what) {
+  for (int base = 0; base < count; base += 48) {
+    SmallTable t;
+    t.count = count - base < 48 ? count - base : 48;
+    int maxn = 1;
+    for (int i = 0; i < t.count; ++i) {
+      t.w[i] = w[base + i];
+      t.g[i] = grad[base + i];
+      t.buf[i] = buf ? buf[base + i] : nullptr;
+      t.buf2[i] = buf2 ? buf2[base + i] : nullptr;
+      t.n[i] = numel[base + i];
+      if (t.n[i] > maxn) maxn = t.n[i];
+    }
+    int bx = (maxn + 255) / 256;
+    if (bx > 64) bx = 64;
+    sgd_small_kernel<<<dim3(bx, t.count), 256, 0, st>>>(t, h);
+    if (int e = b2h::check_launch(what)) return e;
+  }
+  return 0;
 }
 
 }  // namespace
@@ -116,10 +202,10 @@ int b200unet_sgd_conv3x3_weight(float* w_oihw, const float* grad, float* momentu
                                 int nesterov, int first_step, b200_stream_t stream) {
   B2_REQUIRE(K % 32 == 0 && C % 64 == 0, "sgd_conv3x3_weight: K=%d must be a multiple of 32 and C=%d of 64", K, C);
   B2_REQUIRE(w_oihw != nullptr && w_fprop != nullptr, "sgd_conv3x3_weight: null parameter / operand");
-  SgdHyper h{lr, momentum, dampening, weight_decay, nesterov, first_step};
+  const SgdHyper h = sgd_hyper(lr, momentum, dampening, weight_decay, nesterov, first_step);
   dim3 grid(C / 64, K / 32);
   sgd_weight_kernel<9, true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w_oihw, grad, momentum_buf, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), K, C, h);
+      w_oihw, grad, momentum_buf, nullptr, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), K, C, h);
   return b2h::check_launch("sgd_conv3x3_weight");
 }
 
@@ -128,11 +214,11 @@ int b200unet_sgd_convt2x2_weight(float* w, const float* grad, float* momentum_bu
                                  int nesterov, int first_step, b200_stream_t stream) {
   B2_REQUIRE(Cin % 32 == 0 && Cup % 64 == 0, "sgd_convt2x2_weight: Cin=%d must be a multiple of 32 and Cup=%d of 64", Cin, Cup);
   B2_REQUIRE(w != nullptr && w_dgrad != nullptr, "sgd_convt2x2_weight: null parameter / operand");
-  SgdHyper h{lr, momentum, dampening, weight_decay, nesterov, first_step};
+  const SgdHyper h = sgd_hyper(lr, momentum, dampening, weight_decay, nesterov, first_step);
   dim3 grid(Cup / 64, Cin / 32);
   // parameter [Cin][Cup][4]: operand 1 = dgrad operand [ci][ij][d], operand 2 = fprop operand [ij][d][ci]
   sgd_weight_kernel<4, false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, grad, momentum_buf, static_cast<__nv_bfloat16*>(w_dgrad), static_cast<__nv_bfloat16*>(w_fprop), Cin, Cup, h);
+      w, grad, momentum_buf, nullptr, static_cast<__nv_bfloat16*>(w_dgrad), static_cast<__nv_bfloat16*>(w_fprop), Cin, Cup, h);
   return b2h::check_launch("sgd_convt2x2_weight");
 }
 
@@ -140,24 +226,40 @@ int b200unet_sgd_small(float* const* w, const float* const* grad, float* const* 
                        int count, float lr, float momentum, float dampening, float weight_decay, int nesterov,
                        int first_step, b200_stream_t stream) {
   B2_REQUIRE(count >= 0, "sgd_small: negative count");
-  SgdHyper h{lr, momentum, dampening, weight_decay, nesterov, first_step};
-  for (int base = 0; base < count; base += 48) {
-    SmallTable t;
-    t.count = count - base < 48 ? count - base : 48;
-    int maxn = 1;
-    for (int i = 0; i < t.count; ++i) {
-      t.w[i] = w[base + i];
-      t.g[i] = grad[base + i];
-      t.buf[i] = momentum_buf ? momentum_buf[base + i] : nullptr;
-      t.n[i] = numel[base + i];
-      if (t.n[i] > maxn) maxn = t.n[i];
-    }
-    int bx = (maxn + 255) / 256;
-    if (bx > 64) bx = 64;
-    sgd_small_kernel<<<dim3(bx, t.count), 256, 0, static_cast<cudaStream_t>(stream)>>>(t, h);
-    if (int e = b2h::check_launch("sgd_small")) return e;
-  }
-  return 0;
+  return launch_small(w, grad, momentum_buf, nullptr, numel, count,
+                      sgd_hyper(lr, momentum, dampening, weight_decay, nesterov, first_step), static_cast<cudaStream_t>(stream),
+                      "sgd_small");
+}
+
+int b200unet_adam_conv3x3_weight(float* w_oihw, const float* grad, float* exp_avg, float* exp_avg_sq, void* w_fprop,
+                                 void* w_dgrad, int K, int C, double beta1, double beta2, float eps, float weight_decay,
+                                 float step_size, float inv_sqrt_bc2, int first_step, b200_stream_t stream) {
+  B2_REQUIRE(K % 32 == 0 && C % 64 == 0, "adam_conv3x3_weight: K=%d must be a multiple of 32 and C=%d of 64", K, C);
+  B2_REQUIRE(w_oihw && grad && exp_avg && exp_avg_sq && w_fprop, "adam_conv3x3_weight: null argument");
+  const SgdHyper h = adam_hyper(beta1, beta2, eps, weight_decay, step_size, inv_sqrt_bc2, first_step);
+  sgd_weight_kernel<9, true><<<dim3(C / 64, K / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oihw, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), K, C, h);
+  return b2h::check_launch("adam_conv3x3_weight");
+}
+
+int b200unet_adam_convt2x2_weight(float* w, const float* grad, float* exp_avg, float* exp_avg_sq, void* w_fprop, void* w_dgrad,
+                                  int Cin, int Cup, double beta1, double beta2, float eps, float weight_decay, float step_size,
+                                  float inv_sqrt_bc2, int first_step, b200_stream_t stream) {
+  B2_REQUIRE(Cin % 32 == 0 && Cup % 64 == 0, "adam_convt2x2_weight: Cin=%d must be a multiple of 32 and Cup=%d of 64", Cin, Cup);
+  B2_REQUIRE(w && grad && exp_avg && exp_avg_sq && w_dgrad, "adam_convt2x2_weight: null argument");
+  const SgdHyper h = adam_hyper(beta1, beta2, eps, weight_decay, step_size, inv_sqrt_bc2, first_step);
+  sgd_weight_kernel<4, false><<<dim3(Cup / 64, Cin / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(w_dgrad), static_cast<__nv_bfloat16*>(w_fprop), Cin, Cup, h);
+  return b2h::check_launch("adam_convt2x2_weight");
+}
+
+int b200unet_adam_small(float* const* w, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq,
+                        const int* numel, int count, double beta1, double beta2, float eps, float weight_decay, float step_size,
+                        float inv_sqrt_bc2, int first_step, b200_stream_t stream) {
+  B2_REQUIRE(count >= 0 && exp_avg && exp_avg_sq, "adam_small: bad arguments");
+  return launch_small(w, grad, exp_avg, exp_avg_sq, numel, count,
+                      adam_hyper(beta1, beta2, eps, weight_decay, step_size, inv_sqrt_bc2, first_step),
+                      static_cast<cudaStream_t>(stream), "adam_small");
 }
 
 }  // extern "C"

@@ -279,15 +279,14 @@ int pick_splits(int base_ctas, int tiles_total) {
 template <int KIND, int BNC>
 int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   using P = WPlan<KIND, BNC>;
-  static bool configured = false;
+  static unsigned long long configured = 0;  // one bit per CUDA device
   auto kern = wgrad_kernel<KIND, BNC>;
-  if (!configured) {
+  if (b2h::first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) {
       b2h::set_error("wgrad: cudaFuncSetAttribute(smem=%d): %s", P::TOTAL, cudaGetErrorString(e));
       return 2;
     }
-    configured = true;
   }
   const int grid = a.mtiles * a.ntiles * (KIND == KIND_CONV3 ? 3 : 1) * a.splits;
   kern<<<grid, 192, P::TOTAL, st>>>(a);
@@ -461,15 +460,14 @@ __global__ void reduce_conv3_swapped_kernel(const float* __restrict__ partial, f
 template <int CB>
 int launch_wgrad_swap(const WgradArgs& a, cudaStream_t st) {
   using P = WSPlan<CB>;
-  static bool configured = false;
+  static unsigned long long configured = 0;  // one bit per CUDA device
   auto kern = wgrad_swap_kernel<CB>;
-  if (!configured) {
+  if (b2h::first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) {
       b2h::set_error("wgrad_swap: cudaFuncSetAttribute(smem=%d): %s", P::TOTAL, cudaGetErrorString(e));
       return 2;
     }
-    configured = true;
   }
   kern<<<P::S_PER_CTA == 1 ? 3 * a.splits : a.splits, 192, P::TOTAL, st>>>(a);
   return b2h::check_launch("wgrad_swap");

@@ -134,10 +134,43 @@ class DataParallelContext:
         dist.barrier()
         if int(flag.item()) == 1:
             self._nvl = state
+            from . import _lib
+
+            # bound on the wait for a peer inside the SyncBN kernel: NCCL-like 10 minutes by default (rank-0-only
+            # validation / checkpointing or a stalled data loader must not kill the job); 0 = wait forever
+            tmo = float(os.environ.get("B200UNET_NVL_TIMEOUT_S", "600"))
+            _lib.call("b200unet_nvl_set_timeout_ms", int(tmo * 1000))
+
+    def check_health(self):
+        """Host-side health check of the NVLink SyncBN path (one device->host read + one small all-gather; call it once
+        per epoch or when a loss turns NaN). All ranks must issue the same sequence of training forwards/backwards
+        (lockstep, as under torch DDP + SyncBatchNorm): raises if a reduction timed out on this rank (naming the ranks that
+        never arrived) or if the ranks' reduction counters have diverged."""
+        if self._nvl is None:
+            return
+        from . import _lib
+
+        out = (ctypes.c_int64 * 3)()
+        _lib.call("b200unet_nvl_status", ctypes.c_void_p(self._nvl[0].data_ptr()), torch.cuda.current_stream().cuda_stream, out)
+        count, failed_seq, mask = int(out[0]), int(out[1]), int(out[2])
+        t = torch.tensor([count, failed_seq], dtype=torch.int64, device="cuda")
+        all_t = [torch.empty_like(t) for _ in range(self.world_size)]
+        dist.all_gather(all_t, t, group=self.group)
+        counts = [int(a[0]) for a in all_t]
+        fails = [int(a[1]) for a in all_t]
+        if failed_seq:
+            missing = [r for r in range(self.world_size) if mask >> r & 1]
+            raise RuntimeError(f"NVLink SyncBN reduction #{failed_seq} timed out on rank {self.rank}: ranks {missing} never "
+                               "arrived (outputs were set to NaN); re-create the DataParallelContext to continue")
+        if any(fails) or len(set(counts)) != 1:
+            raise RuntimeError(f"NVLink SyncBN state diverged across ranks: reduction counters {counts}, failed reductions "
+                               f"{fails} (every rank must run the same training forwards/backwards)")
 
     @property
     def has_nvl(self):
         return self._nvl is not None
+
+    nvl_max_doubles = 2048  # slot size of the symmetric buffer (csrc/nvl_sync.cu SLOT_DOUBLES); longer vectors go through NCCL
 
     def bn_sync_finalize(self, sums, global_count, bn, eps, momentum, track, mean, rstd, scale, shift):
         """All-reduce the fp64 [sum, sum^2] vector over NVLink and finalise BatchNorm in the same kernel."""

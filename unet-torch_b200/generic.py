@@ -65,7 +65,7 @@ class GenericEngine:
         pass
 
     # ------------------------------------------------------------------ pieces
-    def _conv_bn_relu(self, conv, bn, inp, a_out, training, dp):
+    def _conv_bn_relu(self, conv, bn, inp, a_out, training, dp, save=False):
         n, cin, h, w = inp.shape
         k = conv.weight.shape[0]
         dev = inp.device
@@ -79,6 +79,10 @@ class GenericEngine:
         count = n * h * w
         if not training:
             ops.bn_eval_affine(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, scale, shift)
+            if save:  # eval forward under autograd: the backward kernels need mean / rstd
+                mean = torch.empty(k, dtype=torch.float32, device=dev)
+                rstd = torch.empty(k, dtype=torch.float32, device=dev)
+                ops.bn_eval_stats(bn.running_mean, bn.running_var, bn.eps, mean, rstd)
         else:
             sums = torch.empty(2 * k, dtype=torch.float64, device=dev)
             _lib.call("b200unet_gen_channel_stats", y.data_ptr(), y.stride(0), sums.data_ptr(), n, k, h * w, _stream())
@@ -96,7 +100,7 @@ class GenericEngine:
         ap, ans = _v(a_out)
         _lib.call("b200unet_gen_bn_relu_fwd", y.data_ptr(), y.stride(0), scale.data_ptr(), shift.data_ptr(), ap, ans, n, k,
                   h * w, _stream())
-        return (inp, y, scale, shift, mean, rstd, count)
+        return (inp, y, scale, shift, mean, rstd, count, not training)
 
     def _dropout(self, t, training):
         """nn.Dropout on `t` (an NCHW view), mask drawn like the reference does; returns the mask or None."""
@@ -137,10 +141,10 @@ class GenericEngine:
         for l in range(5):
             (c1, b1), (c2, b2) = self.enc[l]
             a1 = torch.empty((n, ch[l], hs[l], wsz[l]), dtype=torch.float32, device=dev)
-            r1 = self._conv_bn_relu(c1, b1, inp, a1, training, dp)
+            r1 = self._conv_bn_relu(c1, b1, inp, a1, training, dp, save)
             if l < 4:
                 a2 = cat[l][:, : ch[l]]
-                r2 = self._conv_bn_relu(c2, b2, a1, a2, training, dp)
+                r2 = self._conv_bn_relu(c2, b2, a1, a2, training, dp, save)
                 pooled = torch.empty((n, ch[l], hs[l + 1], wsz[l + 1]), dtype=torch.float32, device=dev)
                 idx = torch.empty((n, ch[l], hs[l + 1], wsz[l + 1]), dtype=torch.uint8, device=dev) if save else None
                 ap, ans = _v(a2)
@@ -151,7 +155,7 @@ class GenericEngine:
                 inp = pooled
             else:
                 a2 = torch.empty((n, ch[l], hs[l], wsz[l]), dtype=torch.float32, device=dev)
-                r2 = self._conv_bn_relu(c2, b2, a1, a2, training, dp)
+                r2 = self._conv_bn_relu(c2, b2, a1, a2, training, dp, save)
                 enc_rec.append((r1, r2, a2, None, None))
         d_in = enc_rec[4][2]
         for j in range(4):
@@ -165,9 +169,9 @@ class GenericEngine:
             cmask = self._dropout(cat[l], training)  # Up: cat -> Dropout -> DoubleConv (Model.py:79-83)
             (c1, b1), (c2, b2) = self.dec[j]
             a1 = torch.empty((n, ch[l], hs[l], wsz[l]), dtype=torch.float32, device=dev)
-            r1 = self._conv_bn_relu(c1, b1, cat[l], a1, training, dp)
+            r1 = self._conv_bn_relu(c1, b1, cat[l], a1, training, dp, save)
             a2 = torch.empty((n, ch[l], hs[l], wsz[l]), dtype=torch.float32, device=dev)
-            r2 = self._conv_bn_relu(c2, b2, a1, a2, training, dp)
+            r2 = self._conv_bn_relu(c2, b2, a1, a2, training, dp, save)
             dec_rec.append((d_in, r1, r2, a2, cmask, (pt, pl)))
             d_in = a2
         logits = torch.empty((n, net.n_classes, h, w), dtype=torch.float32, device=dev)
@@ -197,14 +201,18 @@ class GenericEngine:
                 flat.mark_ready(ps)
 
         def bn_conv_bwd(conv, bn, rec, g, need_dx):
-            inp, y, scale, shift, mean, rstd, count = rec
+            inp, y, scale, shift, mean, rstd, count, frozen = rec
+            if mean is None:
+                raise RuntimeError("backward of a forward that ran without autograd (no BatchNorm statistics saved)")
             nn_, k, hh, ww = y.shape
             gp, gns = _v(g)
             sums = torch.empty(2 * k, dtype=torch.float64, device=dev)
             _lib.call("b200unet_gen_bn_relu_bwd_reduce", gp, gns, y.data_ptr(), y.stride(0), scale.data_ptr(),
                       shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), sums.data_ptr(), nn_, k, hh * ww, _stream())
             sums_local = None
-            if dp is not None and dp.sync_bn:
+            if frozen:  # running-statistics BatchNorm: dy = gamma * rstd * da, dgamma / dbeta from the local sums
+                sums_local, sums = sums, torch.zeros_like(sums)
+            elif dp is not None and dp.sync_bn:
                 sums_local = sums.clone()
                 dp.all_reduce_sum(sums)
             dgamma, dbeta = gbuf(bn.weight), gbuf(bn.bias)

@@ -21,6 +21,40 @@ def _as_f32(t):
     return t.detach().contiguous().float()
 
 
+# Out-of-range labels: nn.CrossEntropyLoss raises inside the reference's calc_loss (loss.py:469, 498). The fused kernel
+# records them in a device flag; reading it at once would cost a host sync per step, so the flag of every call is copied to
+# pinned host memory asynchronously and examined at the NEXT loss call (or by check_pending_label_errors()): the error
+# surfaces one step late instead of never. ce_dice_loss(check_labels=True) checks immediately.
+_pending = []
+
+
+def check_pending_label_errors(wait: bool = False):
+    """Raise IndexError if an earlier fused CE/Dice call saw a label outside [0, n_classes)."""
+    keep = []
+    for host, ev in _pending:
+        if wait:
+            ev.synchronize()
+        if ev.query():
+            if int(host.item()) != 0:
+                _pending.clear()
+                raise IndexError("Target out of bounds for the number of classes (seen in an earlier calc_loss call)")
+        else:
+            keep.append((host, ev))
+    _pending[:] = keep
+
+
+def _watch(err):
+    check_pending_label_errors()
+    if torch.cuda.is_current_stream_capturing():
+        return
+    host = torch.empty((1,), dtype=torch.int32).pin_memory()
+    host.copy_(err, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _pending.append((host, ev))
+    del _pending[:-8]
+
+
 class _CEDiceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target, mode):
@@ -30,7 +64,9 @@ class _CEDiceFn(torch.autograd.Function):
         tgt = _as_f32(target)
         if logits.dim() != 4 or tgt.shape != (logits.shape[0],) + tuple(logits.shape[2:]):
             raise ValueError(f"predict {tuple(pred.shape)} & target {tuple(target.shape)} shape do not match")
-        out, sums, err = ops.loss_ce_dice_fwd(logits, tgt, mode)
+        with torch.cuda.device(logits.device):
+            out, sums, err = ops.loss_ce_dice_fwd(logits, tgt, mode)
+            _watch(err)
         ctx.save_for_backward(logits, tgt, sums)
         ctx.mode = mode
         ctx.err = err
@@ -39,7 +75,8 @@ class _CEDiceFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, _g_parts, _g_err):
         logits, tgt, sums = ctx.saved_tensors
-        dz = ops.loss_ce_dice_bwd(logits, tgt, sums, g.contiguous().float().reshape(1), ctx.mode)
+        with torch.cuda.device(logits.device):
+            dz = ops.loss_ce_dice_bwd(logits, tgt, sums, g.contiguous().float().reshape(1), ctx.mode)
         return dz, None, None
 
 
@@ -54,12 +91,14 @@ class _MSEFn(torch.autograd.Function):
         ctx.save_for_backward(p, t)
         ctx.relu_input = relu_input
         ctx.shape = pred.shape
-        return ops.mse_fwd(p, t, relu_input)[0].clone()
+        with torch.cuda.device(p.device):
+            return ops.mse_fwd(p, t, relu_input)[0].clone()
 
     @staticmethod
     def backward(ctx, g):
         p, t = ctx.saved_tensors
-        d = ops.mse_bwd(p, t, g.contiguous().float().reshape(1), ctx.relu_input)
+        with torch.cuda.device(p.device):
+            d = ops.mse_bwd(p, t, g.contiguous().float().reshape(1), ctx.relu_input)
         return d.view(ctx.shape), None, None
 
 

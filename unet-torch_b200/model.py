@@ -19,6 +19,13 @@ from .dist import DataParallelContext
 BF16 = torch.bfloat16
 
 
+def _device_guard(x):
+    """Kernels launch on the current device's stream: make the tensor's device current (CPU tensors are rejected later)."""
+    import contextlib
+
+    return torch.cuda.device(x.device) if x.is_cuda else contextlib.nullcontext()
+
+
 # ------------------------------------------------------------------------------------------------ containers
 def _double_conv(cin, cout):
     # keys: double_conv.{0,1,3,4}.*  (Model.py:14-23)
@@ -206,15 +213,22 @@ class UNetEngine:
         return out
 
     # ------------------------------------------------------------------ BN helpers
-    def _bn_affine(self, cb: _ConvBN, stats_partial, rows, count, training, dp):
+    def _bn_affine(self, cb: _ConvBN, stats_partial, rows, count, training, dp, need_stats=False):
         bn = cb.bn
         c = bn.num_features
         dev = bn.weight.device
         scale = torch.empty(c, dtype=torch.float32, device=dev)
         shift = torch.empty(c, dtype=torch.float32, device=dev)
         if not training:
+            if bn.running_mean is None:
+                raise RuntimeError("eval-mode BatchNorm2d without running statistics (track_running_stats=False) is not supported")
             ops.bn_eval_affine(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, scale, shift)
-            return scale, shift, None, None, count
+            mean = rstd = None
+            if need_stats:  # eval forward under autograd (frozen-BN fine-tuning, saliency): backward needs mean / rstd
+                mean = torch.empty(c, dtype=torch.float32, device=dev)
+                rstd = torch.empty(c, dtype=torch.float32, device=dev)
+                ops.bn_eval_stats(bn.running_mean, bn.running_var, bn.eps, mean, rstd)
+            return scale, shift, mean, rstd, count
         sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
         ops.bn_reduce_partials(stats_partial, rows, c, sums)
         mean = torch.empty(c, dtype=torch.float32, device=dev)
@@ -223,7 +237,7 @@ class UNetEngine:
         track = bn.track_running_stats and bn.running_mean is not None
         if dp is not None and dp.sync_bn:
             count = count * dp.world_size
-            if dp.has_nvl:  # one kernel: NVLink one-shot all-reduce of [sum, sum^2] + finalisation
+            if dp.has_nvl and 2 * c <= dp.nvl_max_doubles:  # one kernel: NVLink one-shot all-reduce of [sum, sum^2] + finalisation
                 dp.bn_sync_finalize(sums, count, bn, bn.eps, mom, track, mean, rstd, scale, shift)
                 if track:
                     bn.num_batches_tracked += 1
@@ -291,12 +305,12 @@ class UNetEngine:
                     stats = torch.empty(rows * 2 * c_out, dtype=torch.float32, device=dev)
                 wf, _ = cb.operands()
                 ops.conv3x3(inp, wf, y, stats)
-            scale, shift, mean, rstd, count = self._bn_affine(cb, stats, rows, n * hh * ww, training, dp)
+            scale, shift, mean, rstd, count = self._bn_affine(cb, stats, rows, n * hh * ww, training, dp, need_stats=save)
             ops.bn_relu_fwd(y, scale, shift, a_out, pooled, pool_idx)
             if self.trace is not None:
                 self._tr("conv_bn_relu", cb=cb, x=(x if cb.first else inp), y=y.clone(), scale=scale, shift=shift, mean=mean,
                          rstd=rstd, count=count, a=a_out, pooled=pooled, pool_idx=pool_idx, training=training)
-            return (inp, y, scale, shift, mean, rstd, count)
+            return (inp, y, scale, shift, mean, rstd, count, not training)
 
         # ---- encoder
         inp = x
@@ -404,11 +418,11 @@ class UNetEngine:
                 launch()
 
         def bn_conv_bwd(cb: _ConvBN, rec, g1, g_pool, pool_idx, hh, ww, need_dx, dx_colsum=None):
-            inp, y, scale, shift, mean, rstd, count = rec
+            inp, y, scale, shift, mean, rstd, count, frozen = rec
             bn = cb.bn
             dgamma, dbeta = gbuf(bn.weight), gbuf(bn.bias)
             ops.bn_relu_bwd(g1, g_pool, pool_idx, y, bn.weight.detach(), scale, shift, mean, rstd, y, dgamma, dbeta,
-                            count=count, allreduce=sync)
+                            count=count, allreduce=None if frozen else sync, frozen=frozen)
             dy = y  # dy overwrote y in place
             rec_t = dict(cb=cb, g1=g1, g_pool=g_pool, pool_idx=pool_idx, dy=dy, dgamma=dgamma, dbeta=dbeta, inp=inp) \
                 if self.trace is not None else None
@@ -556,26 +570,29 @@ class _UNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, x, *params):
         training = engine.net.training
-        step = engine.graphed_step(x, training, save=True)
-        if step is not None:
-            logits = step.forward(x)
-            ctx.step, ctx.epoch, ctx.saved = step, step.epoch, None
-        else:
-            logits, saved = engine.forward(x, training=training, save=True)
-            ctx.step, ctx.saved = None, saved
+        ctx.device = x.device
+        with _device_guard(x):  # launches go to the current device's stream: make the input's device current
+            step = engine.graphed_step(x, training, save=True)
+            if step is not None:
+                logits = step.forward(x)
+                ctx.step, ctx.epoch, ctx.saved = step, step.epoch, None
+            else:
+                logits, saved = engine.forward(x, training=training, save=True)
+                ctx.step, ctx.saved = None, saved
         ctx.engine, ctx.params = engine, params
         return logits  # one tensor, or one per decoder
 
     @staticmethod
     def backward(ctx, *dlogits):
-        if ctx.step is not None:
-            grads = ctx.step.backward(ctx.epoch, dlogits[0].contiguous().float())
+        with torch.cuda.device(ctx.device):  # a CPU input was rejected in forward
+            if ctx.step is not None:
+                grads = ctx.step.backward(ctx.epoch, dlogits[0].contiguous().float())
+                return (None, None) + tuple(grads.get(p) for p in ctx.params)
+            if ctx.saved is None:
+                raise RuntimeError("UNet backward called twice: activations are consumed in place")
+            grads = ctx.engine.backward(ctx.saved, dlogits if len(dlogits) > 1 else dlogits[0])
+            ctx.saved = None
             return (None, None) + tuple(grads.get(p) for p in ctx.params)
-        if ctx.saved is None:
-            raise RuntimeError("UNet backward called twice: activations are consumed in place")
-        grads = ctx.engine.backward(ctx.saved, dlogits if len(dlogits) > 1 else dlogits[0])
-        ctx.saved = None
-        return (None, None) + tuple(grads.get(p) for p in ctx.params)
 
 
 # ------------------------------------------------------------------------------------------------ public module
@@ -624,6 +641,19 @@ class UNet(nn.Module):
         if isinstance(m, nn.Conv2d):  # Model.py:167-169: ConvTranspose2d keeps torch's default init
             nn.init.kaiming_normal_(m.weight)
 
+    def refresh_operands(self, force: bool = True):
+        """Re-derive the bf16 GEMM operands from the fp32 parameters. Done automatically when a parameter's autograd version
+        changes (optimizer steps, load_state_dict, in-place ops); writes that bypass the version counter - `p.data.copy_()`,
+        `dist.broadcast(p.data)` after the first forward - need this call (force=True re-derives all of them)."""
+        if self._engine is not None:
+            if force:
+                for c1, c2 in self._engine.enc + self._engine.dec:
+                    c1._ver = c2._ver = None
+                for u in self._engine.ups:
+                    u._ver = None
+            self._engine.refresh_operands()
+        return self
+
     def set_check_mode(self, flag: bool = True):
         """fp32 check mode: run every operator with the generic fp32 CUDA-core kernels (reference precision)."""
         self._check_fp32 = bool(flag)
@@ -631,13 +661,14 @@ class UNet(nn.Module):
 
     def _fast_supported(self) -> bool:
         """Can the tensor-core engine run this architecture at all (input size is checked per call)?"""
-        return (self.initial_feature_map % 64 == 0 and self.n_channels <= 7 and self.n_classes <= 8 and not self.dropout)
+        # widths: the BN / head kernels take power-of-two channel counts in [64, 2048] -> base width 64 or 128
+        return (self.initial_feature_map in (64, 128) and self.n_channels <= 7 and self.n_classes <= 8 and not self.dropout)
 
     def _get_engine(self) -> UNetEngine:
         """The tensor-core engine; raises if the architecture is outside its envelope."""
         if self._engine is None:
             if not self._fast_supported():
-                raise ValueError("tensor-core engine needs initial_feature_map % 64 == 0, n_channels <= 7, "
+                raise ValueError("tensor-core engine needs initial_feature_map in (64, 128), n_channels <= 7, "
                                  "n_classes <= 8 and dropout=False; other variants run on the generic fp32 engine")
             object.__setattr__(self, "_engine", UNetEngine(self))
         return self._engine
@@ -664,12 +695,15 @@ class UNet(nn.Module):
     def forward(self, x):
         eng = self._engine_for(x)
         params = eng.params_in_backward_order()
+        if x.is_cuda and params[0].device != x.device:
+            raise RuntimeError(f"UNet parameters live on {params[0].device} but the input is on {x.device}")
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _UNetFn.apply(eng, x, *params)
-        step = eng.graphed_step(x, self.training, save=False)
-        if step is not None:
-            return step.forward(x)
-        logits, _ = eng.forward(x, training=self.training, save=False)
+        with _device_guard(x):
+            step = eng.graphed_step(x, self.training, save=False)
+            if step is not None:
+                return step.forward(x)
+            logits, _ = eng.forward(x, training=self.training, save=False)
         return logits
 
     # ---- fused inference epilogues: the logits never reach HBM
@@ -678,7 +712,7 @@ class UNet(nn.Module):
         if not isinstance(eng, UNetEngine):
             raise ValueError("fused inference heads run on the tensor-core engine (H, W multiples of 16, default widths); "
                              "use predict_mask(net(x)) for other variants")
-        with torch.no_grad():
+        with torch.no_grad(), _device_guard(x):
             out, _ = eng.forward(x, training=self.training, save=False, head=head, head_arg=head_arg)
         return out
 
@@ -734,12 +768,12 @@ class UNet_multitask(UNet):
             ([getattr(self, f"up{i}_decod{d}") for i in (1, 2, 3, 4)], getattr(self, f"outc_decod{d}")) for d in (1, 2)]
 
     def _fast_supported(self) -> bool:
-        return self.initial_feature_map % 64 == 0 and self.n_channels <= 7 and self.n_classes <= 8
+        return self.initial_feature_map in (64, 128) and self.n_channels <= 7 and self.n_classes <= 8
 
     def _engine_for(self, x):
         if x.dim() != 4 or x.shape[2] % 16 or x.shape[3] % 16 or not self._fast_supported():
             raise ValueError("UNet_multitask runs on the tensor-core engine only: H and W multiples of 16, "
-                             "initial_feature_map % 64 == 0, n_channels <= 7, n_classes <= 8")
+                             "initial_feature_map in (64, 128), n_channels <= 7, n_classes <= 8")
         return self._get_engine()
 
     def set_check_mode(self, flag: bool = True):

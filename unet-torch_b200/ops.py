@@ -272,6 +272,12 @@ def bn_eval_affine(gamma, beta, running_mean, running_var, eps, scale, shift):
               _f32(scale), _f32(shift), gamma.numel(), _stream())
 
 
+def bn_eval_stats(running_mean, running_var, eps, mean, rstd):
+    """mean = running_mean, rstd = rsqrt(running_var + eps): what the backward kernels need after an eval-mode forward."""
+    _lib.call("b200unet_bn_eval_stats", _f32(running_mean), _f32(running_var), eps, _f32(mean), _f32(rstd), mean.numel(),
+              _stream())
+
+
 def bn_relu_fwd(y, scale, shift, a, pooled=None, pool_idx=None):
     yp, ycs, n, h, w, c = _nhwc(y)
     ap, acs, *_ = _nhwc(a)
@@ -280,10 +286,15 @@ def bn_relu_fwd(y, scale, shift, a, pooled=None, pool_idx=None):
 
 
 def bn_relu_bwd(g1, g_pool, pool_idx, y, gamma, scale, shift, mean, rstd, dy, dgamma, dbeta, count=None,
-                allreduce=None):
+                allreduce=None, frozen=False):
     """Backward of BN->ReLU(->skip+pool). g1: gradient w.r.t. the activation (may be a channel slice, or None);
     g_pool/pool_idx: gradient through the 2x2 max pool (or None). Writes dy (may alias y), dgamma, dbeta.
-    allreduce: optional callable(sums_f64) applied between the two passes (SyncBN)."""
+    allreduce: optional callable(sums_f64) applied between the two passes (SyncBN).
+    frozen: the forward normalised with RUNNING statistics (module.eval() under autograd): mean/rstd are the running ones,
+    statistics do not depend on y, so dy = gamma * rstd * da (the batch-statistics correction terms vanish: the apply pass
+    gets an all-zero sums vector) while dgamma / dbeta keep the reduced sums."""
+    if mean is None or rstd is None:
+        raise RuntimeError("bn_relu_bwd: this forward did not save BatchNorm statistics (mean/rstd)")
     yp, ycs, n, h, w, c = _nhwc(y)
     g1p, g1cs = (None, 0)
     if g1 is not None:
@@ -296,7 +307,10 @@ def bn_relu_bwd(g1, g_pool, pool_idx, y, gamma, scale, shift, mean, rstd, dy, dg
     sums_local = None
     if count is None:
         count = n * h * w
-    if allreduce is not None:
+    if frozen:
+        sums_local = sums
+        sums = torch.zeros_like(sums)
+    elif allreduce is not None:
         sums_local = sums.clone()
         allreduce(sums)
     _lib.call("b200unet_bn_relu_bwd_apply", g1p, g1cs, _ptr(g_pool), _ptr(pool_idx), yp, ycs, _f32(gamma), _f32(scale),

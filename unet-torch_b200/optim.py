@@ -5,6 +5,8 @@ it once per iteration (Trainer.py:719-725). `FusedSGD` is a drop-in for that obj
 `param_groups` / `state_dict()` layout with `momentum_buffer`, so Trainer's poly-LR writes to
 `param_group['lr']` keep working) whose `step()` runs the identical arithmetic in ONE pass per conv / convT weight
 and writes the bf16 GEMM operands of the tensor-core kernels in the same pass; all small tensors share one launch.
+`FusedAdam` is the same for `torch.optim.Adam(model.parameters(), lr, weight_decay)` (train.py:341-343; the optimizer of
+configseros.yml:15): identical arithmetic and `state_dict()` layout (`step`, `exp_avg`, `exp_avg_sq`).
 Stock `torch.optim` optimizers keep working with the UNet (operands are then re-cast lazily on the next forward).
 """
 from __future__ import annotations
@@ -96,5 +98,75 @@ class FusedSGD(torch.optim.Optimizer):
                 n_arr = IntArr(*[p.numel() for p, _, _ in items])
                 _lib.call("b200unet_sgd_small", w_arr, g_arr, b_arr, n_arr, n, lr, mom, damp, wd, nest, int(first), stream)
                 for p, _, _ in items:
+                    torch.autograd.graph.increment_version(p)
+        return loss
+
+
+class FusedAdam(FusedSGD):
+    """Drop-in for `torch.optim.Adam(net.parameters(), lr, betas, eps, weight_decay)` (no amsgrad / maximize): one fused pass
+    per conv / convT weight that also writes the bf16 GEMM operands, one launch for all small tensors."""
+
+    def __init__(self, net, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False):
+        from .model import UNet
+
+        if not isinstance(net, UNet):
+            raise TypeError("FusedAdam takes the B200 UNet module itself (it updates the kernels' bf16 operands in place)")
+        if amsgrad:
+            raise NotImplementedError("FusedAdam: amsgrad is not implemented (the reference never sets it, train.py:341-343)")
+        if not (0.0 <= betas[0] < 1.0 and 0.0 <= betas[1] < 1.0) or lr < 0 or eps < 0 or weight_decay < 0:
+            raise ValueError("FusedAdam: invalid hyper-parameter")
+        self.net = net
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False)
+        torch.optim.Optimizer.__init__(self, list(net.parameters()), defaults)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        big = self._plan()
+        stream = torch.cuda.current_stream().cuda_stream
+        for group in self.param_groups:
+            lr, (b1, b2), eps, wd = float(group["lr"]), group["betas"], float(group["eps"]), float(group["weight_decay"])
+            small = {}  # (step_size, inv_sqrt_bc2, first) -> items: parameters of one group normally share their step count
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("FusedAdam: parameters must be contiguous CUDA fp32 tensors")
+                g = p.grad
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    g = g.float().contiguous()
+                st = self.state[p]
+                first = 0
+                if "exp_avg" not in st:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)  # host scalar, like torch's default (non-capturable) Adam
+                    st["exp_avg"] = torch.empty_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.empty_like(p, memory_format=torch.contiguous_format)
+                    first = 1
+                st["step"] += 1
+                t = float(st["step"])
+                step_size = lr / (1.0 - b1 ** t)
+                inv_sqrt_bc2 = 1.0 / (1.0 - b2 ** t) ** 0.5
+                m_ptr, v_ptr = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                if p in big:
+                    holder, kind = big[p]
+                    wf, wd_op = holder.operands()
+                    name = "b200unet_adam_conv3x3_weight" if kind == "conv3" else "b200unet_adam_convt2x2_weight"
+                    _lib.call(name, p.data_ptr(), g.data_ptr(), m_ptr, v_ptr, wf.data_ptr(), wd_op.data_ptr(), p.shape[0],
+                              p.shape[1], b1, b2, eps, wd, step_size, inv_sqrt_bc2, first, stream)
+                    torch.autograd.graph.increment_version(p)
+                    holder._ver = (p._version, p.data_ptr())
+                else:
+                    small.setdefault((step_size, inv_sqrt_bc2, first), []).append((p, g, m_ptr, v_ptr))
+            for (step_size, inv_sqrt_bc2, first), items in small.items():
+                n = len(items)
+                PtrArr, IntArr = ctypes.c_void_p * n, ctypes.c_int * n
+                _lib.call("b200unet_adam_small", PtrArr(*[p.data_ptr() for p, _, _, _ in items]),
+                          PtrArr(*[g.data_ptr() for _, g, _, _ in items]), PtrArr(*[m for _, _, m, _ in items]),
+                          PtrArr(*[v for _, _, _, v in items]), IntArr(*[p.numel() for p, _, _, _ in items]), n, b1, b2, eps, wd,
+                          step_size, inv_sqrt_bc2, int(first), stream)
+                for p, _, _, _ in items:
                     torch.autograd.graph.increment_version(p)
         return loss
