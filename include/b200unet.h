@@ -281,6 +281,30 @@ int b200unet_gen_conv1x1_fwd(const float* a, int64_t a_ns, const float* w, const
 int b200unet_gen_conv1x1_bwd(const float* dz, const float* a, int64_t a_ns, const float* w, float* da, int64_t
     da_ns, float* dw, float* db, int N, int C, int J, int64_t HW, b200_stream_t stream);
 int b200unet_gen_mul(float* x, int64_t x_ns, const float* mask, int N, int64_t CHW, b200_stream_t stream);
+/* ---- attention gates of UNet_attention (Attention_block, Model.py:257-296) on the generic fp32 engine:
+ * a = act(scale*y + shift), act: 0 identity (BatchNorm of W_q / W_x), 1 relu, 2 sigmoid (psi) */
+int b200unet_gen_bn_act_fwd(const float* y, int64_t y_ns, const float* scale, const float* shift, float* a, int64_t a_ns,
+    int N, int C, int HW, int act, b200_stream_t stream);
+/* BatchNorm backward with (relu = 1) or without (relu = 0) the ReLU mask; otherwise as b200unet_gen_bn_relu_bwd_*. */
+int b200unet_gen_bn_bwd_reduce(const float* g, int64_t g_ns, const float* y, int64_t y_ns, const float* scale,
+    const float* shift, const float* mean, const float* rstd, double* sums, int N, int C, int HW, int relu,
+    b200_stream_t stream);
+int b200unet_gen_bn_bwd_apply(const float* g, int64_t g_ns, const float* y, int64_t y_ns, const float* gamma,
+    const float* scale, const float* shift, const float* mean, const float* rstd, const double* sums, double count,
+    const double* sums_local, float* dy, int64_t dy_ns, float* dgamma, float* dbeta, int N, int C, int HW, int relu,
+    b200_stream_t stream);
+/* e = relu(a + b) (Model.py:293) and d = de * [e > 0], dense tensors of `total` elements */
+int b200unet_gen_add_relu(const float* a, const float* b, float* e, int64_t total, b200_stream_t stream);
+int b200unet_gen_relu_bwd(const float* de, const float* e, float* d, int64_t total, b200_stream_t stream);
+/* out[n,c,q] = x[n,c,q] * gate[n,q] (Model.py:295); backward: dx = dout * gate and
+ * dpre[n,q] = (sum_c dout*x) * gate*(1-gate) = gradient w.r.t. the input of the sigmoid that produced `gate`. */
+int b200unet_gen_gate_fwd(const float* x, int64_t x_ns, const float* gate, float* out, int64_t out_ns, int N, int C,
+    int64_t HW, b200_stream_t stream);
+int b200unet_gen_gate_bwd(const float* dout, int64_t dout_ns, const float* x, int64_t x_ns, const float* gate, float* dx,
+    int64_t dx_ns, float* dpre, int N, int C, int64_t HW, b200_stream_t stream);
+/* dst[n,:] += src[n,:] over NCHW views (gradient accumulation where a tensor has two consumers) */
+int b200unet_gen_add_inplace(float* dst, int64_t dst_ns, const float* src, int64_t src_ns, int N, int64_t CHW,
+    b200_stream_t stream);
 
 /* ---- fused optimizer step (reference: torch.optim.SGD built in train.py:341-347, stepped in
  * Trainer.py:719-725). torch.optim.SGD arithmetic on the fp32 master parameter (weight decay, momentum, dampening,

@@ -156,6 +156,45 @@ def unet_multitask_forward(sd, x, training=True):
     return tuple(outs), nb
 
 
+def attention_block(sd, prefix, q, x, training, new_buffers):
+    """Attention_block.forward(q, x) (Model.py:286-296): q = up(q) (ConvTranspose2d C_q -> C_q), Q1 = BN(W_q q),
+    X1 = BN(W_x x) (1x1 convolutions WITH bias, BatchNorm without ReLU), E = relu(Q1 + X1), A = sigmoid(BN(psi E)) with one
+    channel, returns x * A (A broadcast over the channels)."""
+    def conv_bn(name, t):
+        y = conv1x1(t, sd[f"{prefix}.{name}.0.weight"], sd[f"{prefix}.{name}.0.bias"])
+        g, b = sd[f"{prefix}.{name}.1.weight"], sd[f"{prefix}.{name}.1.bias"]
+        rm, rv = sd[f"{prefix}.{name}.1.running_mean"], sd[f"{prefix}.{name}.1.running_var"]
+        if training:
+            y, nrm, nrv = batchnorm_train(y, g, b, rm, rv)
+            new_buffers[f"{prefix}.{name}.1.running_mean"] = nrm.detach()
+            new_buffers[f"{prefix}.{name}.1.running_var"] = nrv.detach()
+            new_buffers[f"{prefix}.{name}.1.num_batches_tracked"] = sd[f"{prefix}.{name}.1.num_batches_tracked"] + 1
+            return y
+        return batchnorm_eval(y, g, b, rm, rv)
+
+    q = conv_transpose2x2(q, sd[f"{prefix}.up.weight"], sd[f"{prefix}.up.bias"])
+    e = relu(conv_bn("W_q", q) + conv_bn("W_x", x))
+    a = torch.sigmoid(conv_bn("psi", e))
+    return x * a
+
+
+def unet_attention_forward(sd, x, training=True):
+    """UNet_attention.forward (Model.py:346-367): the UNet with every skip gated, `x_l_att = attenion_l(q=decoder input,
+    x=skip)`; BatchNorm modules run in the reference's order (gate of a level before that level's Up block)."""
+    nb = {}
+    x1 = _double_conv(sd, "inc.double_conv", x, training, nb)
+    skips, cur = [x1], x1
+    for i in range(1, 5):
+        cur, _, _ = maxpool2x2(cur)
+        cur = _double_conv(sd, f"down{i}.maxpool_conv.1.double_conv", cur, training, nb)
+        skips.append(cur)
+    for i in range(1, 5):
+        gated = attention_block(sd, f"attenion{5 - i}", cur, skips[4 - i], training, nb)
+        up = conv_transpose2x2(cur, sd[f"up{i}.up.weight"], sd[f"up{i}.up.bias"])
+        cur = _double_conv(sd, f"up{i}.conv.double_conv", pad_and_cat(gated, up), training, nb)
+    return conv1x1(cur, sd["outc.conv.weight"], sd["outc.conv.bias"]), nb
+
+
 def multitask_uncertainty_loss(loss_values, log_var_tasks, regg_flag):
     """MultitaskUncertaintyLoss.forward (loss.py:313-325): sum_i c_i * L_i + log(std_i), std_i = exp(log_var_i)^(1/2),
     c_i = 1/(2 std_i^2) for regression tasks, 1/std_i^2 otherwise."""

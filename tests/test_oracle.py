@@ -259,3 +259,54 @@ def test_staged_reference_copy_is_the_reference_byte_for_byte():
             assert hashlib.sha256(open(src, "rb").read()).hexdigest() == digest, name
     RefModel, ref_loss = ref_loader.load()
     assert RefModel.UNet(1, 2, 4).state_dict().keys() and callable(ref_loss.calc_loss)
+
+
+@pytest.mark.parametrize("case", ["w4_c3_k2_dicebce", "w4_c1_k3_msemc"])
+def test_attention_restatement_matches_reference_golden(golden, case):
+    """unet_oracle.unet_attention_forward / attention_block against the unmodified reference's UNet_attention
+    (Model.py:257-391): logits, loss, every parameter gradient, BatchNorm buffers (incl. the gates' three BatchNorms per
+    level), eval logits."""
+    g = golden("ref_attention.pt")[case]
+    ch, ncls, width, n, h, w, seed = g["cfg"]
+    sd = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else
+              (v.double() if v.is_floating_point() else v)) for k, v in g["sd0"].items()}
+    out, nb = O.unet_attention_forward(sd, g["x"].double(), training=True)
+    pred = torch.relu(out) if g["loss_type"].startswith("mse") else out
+    loss = O.calc_loss(pred, g["y"].double(), g["loss_type"], ncls)
+    loss.backward()
+    # fp64 oracle vs fp64 reference: tight; vs the fp32 reference: fp32 round-off
+    assert rel(out.detach(), g["logits64"]) < 2e-6 and rel(out.detach(), g["logits"]) < 1e-4
+    assert abs(float(loss) - float(g["loss64"])) < 1e-9 * max(1.0, abs(float(g["loss64"])))
+    # biases in front of a BatchNorm (W_q / W_x / psi conv, the gate's ConvTranspose2d) have an exactly-zero gradient:
+    # errors are measured against max(|reference gradient|, 1e-6 x the largest gradient norm of the net)
+    floor = 1e-6 * max(float(gr.double().norm()) for gr in g["grads64"].values())
+    for k, gr in g["grads64"].items():
+        assert float((sd[k].grad - gr.double()).norm()) / max(float(gr.double().norm()), floor) < 1e-4, k
+    for k, v in g["buffers1"].items():
+        if "num_batches" in k:
+            assert int(nb[k]) == int(v), k
+        else:
+            assert rel(nb[k], v) < 1e-5, k
+    sd_eval = {k: (v.double() if v.is_floating_point() else v) for k, v in g["sd0"].items()}
+    sd_eval.update({k: v.double() if v.is_floating_point() else v for k, v in g["buffers1"].items()})
+    oe, _ = O.unet_attention_forward(sd_eval, g["x"].double(), training=False)
+    assert rel(oe, g["logits_eval"]) < 1e-4
+
+
+def test_attention_module_matches_reference_interface():
+    """UNet_attention container: same 210 state_dict keys and - under the same seed - bit-identical initial weights as the
+    reference constructor (Model.py:299-345: gates keep torch's default init), with and without dropout."""
+    import unet_torch_b200 as U
+
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "ref_attention.pt"), weights_only=False)["w4_c3_k2_dicebce"]
+    ch, ncls, width, n, h, w, seed = g["cfg"]
+    torch.manual_seed(seed)
+    net = U.UNet_attention(ch, ncls, width)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(g["sd0"].keys()) and len(sd) == 210
+    assert all(torch.equal(sd[k], g["sd0"][k]) for k in sd)
+    import Model  # the root drop-in shim re-exports it (train.py:6)
+
+    assert Model.UNet_attention is U.UNet_attention
+    with pytest.raises(RuntimeError):
+        net.attenion4(torch.zeros(1), torch.zeros(1))   # containers are not the product path

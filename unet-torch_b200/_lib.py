@@ -87,6 +87,14 @@ SIGNATURES = {
     "b200unet_gen_conv1x1_fwd": (c_int, [_P, _L, _P, _P, _P, _I, _I, _I, _L, _P]),
     "b200unet_gen_conv1x1_bwd": (c_int, [_P, _P, _L, _P, _P, _L, _P, _P, _I, _I, _I, _L, _P]),
     "b200unet_gen_mul": (c_int, [_P, _L, _P, _I, _L, _P]),
+    "b200unet_gen_bn_act_fwd": (c_int, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "b200unet_gen_bn_bwd_reduce": (c_int, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200unet_gen_bn_bwd_apply": (c_int, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _D, _P, _P, _L, _P, _P, _I, _I, _I, _I, _P]),
+    "b200unet_gen_add_relu": (c_int, [_P, _P, _P, _L, _P]),
+    "b200unet_gen_relu_bwd": (c_int, [_P, _P, _P, _L, _P]),
+    "b200unet_gen_gate_fwd": (c_int, [_P, _L, _P, _P, _L, _I, _I, _L, _P]),
+    "b200unet_gen_gate_bwd": (c_int, [_P, _L, _P, _L, _P, _P, _L, _P, _I, _I, _L, _P]),
+    "b200unet_gen_add_inplace": (c_int, [_P, _L, _P, _L, _I, _L, _P]),
     "b200unet_znorm_workspace_bytes": (c_int64, [_I, _I]),
     "b200unet_znorm_to_chw": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200unet_head_mask": (c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -179,7 +179,7 @@ __global__ void gen_unpool_add_kernel(const float* __restrict__ gp, const uint8_
 __global__ void gen_bn_bwd_reduce_kernel(const float* __restrict__ g, long long g_ns, const float* __restrict__ y,
                                          long long y_ns, const float* __restrict__ scale, const float* __restrict__ shift,
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
-                                         double* __restrict__ sums, int N, int C, int HW) {
+                                         double* __restrict__ sums, int N, int C, int HW, int relu) {
   __shared__ double sh[8];
   const int c = blockIdx.x;
   const float sc = scale[c], sf = shift[c];
@@ -189,7 +189,7 @@ __global__ void gen_bn_bwd_reduce_kernel(const float* __restrict__ g, long long 
   for (long long p = threadIdx.x; p < P; p += blockDim.x) {
     const long long n = p / HW, q = p - n * HW;
     const float yv = y[n * y_ns + static_cast<long long>(c) * HW + q];
-    if (fmaf(sc, yv, sf) > 0.f) {
+    if (!relu || fmaf(sc, yv, sf) > 0.f) {
       const double da = g[n * g_ns + static_cast<long long>(c) * HW + q];
       s1 += da;
       s2 += da * ((static_cast<double>(yv) - m) * r);
@@ -209,7 +209,7 @@ __global__ void gen_bn_bwd_apply_kernel(const float* __restrict__ g, long long g
                                         const float* __restrict__ shift, const float* __restrict__ mean,
                                         const float* __restrict__ rstd, const double* __restrict__ sums, double count,
                                         const double* __restrict__ sums_local, float* __restrict__ dy, long long dy_ns,
-                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int C, int HW) {
+                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int C, int HW, int relu) {
   const long long total = static_cast<long long>(N) * C * HW;
   if (blockIdx.x == 0 && dgamma != nullptr) {
     const double* sl = sums_local != nullptr ? sums_local : sums;
@@ -223,7 +223,7 @@ __global__ void gen_bn_bwd_apply_kernel(const float* __restrict__ g, long long g
     const int c = static_cast<int>((idx / HW) % C);
     const long long n = idx / (static_cast<long long>(HW) * C);
     const float yv = y[n * y_ns + static_cast<long long>(c) * HW + q];
-    const double da = fmaf(scale[c], yv, shift[c]) > 0.f ? static_cast<double>(g[n * g_ns + static_cast<long long>(c) * HW + q]) : 0.0;
+    const double da = (!relu || fmaf(scale[c], yv, shift[c]) > 0.f) ? static_cast<double>(g[n * g_ns + static_cast<long long>(c) * HW + q]) : 0.0;
     const double r = rstd[c];
     const double xh = (static_cast<double>(yv) - static_cast<double>(mean[c])) * r;
     const double v = static_cast<double>(gamma[c]) * r * (da - sums[c] / count - xh * sums[C + c] / count);
@@ -358,6 +358,78 @@ __global__ void gen_mul_kernel(float* __restrict__ x, long long x_ns, const floa
   }
 }
 
+// ---- attention gates of UNet_attention (Attention_block, Model.py:257-296): BatchNorm without ReLU (W_q, W_x) or followed
+// by a sigmoid (psi), E = relu(Q1 + X1), out = x * A with A broadcast over the channels, and their backward.
+// act: 0 = identity, 1 = relu, 2 = sigmoid
+__global__ void gen_bn_act_fwd_kernel(const float* __restrict__ y, long long y_ns, const float* __restrict__ scale,
+                                      const float* __restrict__ shift, float* __restrict__ a, long long a_ns, int N, int C,
+                                      int HW, int act) {
+  const long long total = static_cast<long long>(N) * C * HW;
+  GEN_LOOP(idx, total) {
+    const long long q = idx % HW;
+    const int c = static_cast<int>((idx / HW) % C);
+    const long long n = idx / (static_cast<long long>(HW) * C);
+    float v = fmaf(scale[c], y[n * y_ns + static_cast<long long>(c) * HW + q], shift[c]);
+    if (act == 1) v = fmaxf(v, 0.f);
+    if (act == 2) v = 1.f / (1.f + expf(-v));
+    a[n * a_ns + static_cast<long long>(c) * HW + q] = v;
+  }
+}
+
+// e = relu(a + b) over dense tensors
+__global__ void gen_add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ e, long long total) {
+  GEN_LOOP(idx, total) e[idx] = fmaxf(a[idx] + b[idx], 0.f);
+}
+// d = de * [e > 0]
+__global__ void gen_relu_bwd_kernel(const float* __restrict__ de, const float* __restrict__ e, float* __restrict__ d, long long total) {
+  GEN_LOOP(idx, total) d[idx] = e[idx] > 0.f ? de[idx] : 0.f;
+}
+// out[n,c,q] = x[n,c,q] * gate[n,q]
+__global__ void gen_gate_fwd_kernel(const float* __restrict__ x, long long x_ns, const float* __restrict__ gate,
+                                    float* __restrict__ out, long long out_ns, int N, int C, long long HW) {
+  const long long total = static_cast<long long>(N) * C * HW;
+  GEN_LOOP(idx, total) {
+    const long long q = idx % HW;
+    const long long c = (idx / HW) % C;
+    const long long n = idx / (HW * C);
+    out[n * out_ns + c * HW + q] = x[n * x_ns + c * HW + q] * gate[n * HW + q];
+  }
+}
+// dx[n,c,q] = dout[n,c,q] * gate[n,q]
+__global__ void gen_gate_bwd_x_kernel(const float* __restrict__ dout, long long dout_ns, const float* __restrict__ gate,
+                                      float* __restrict__ dx, long long dx_ns, int N, int C, long long HW) {
+  const long long total = static_cast<long long>(N) * C * HW;
+  GEN_LOOP(idx, total) {
+    const long long q = idx % HW;
+    const long long c = (idx / HW) % C;
+    const long long n = idx / (HW * C);
+    dx[n * dx_ns + c * HW + q] = dout[n * dout_ns + c * HW + q] * gate[n * HW + q];
+  }
+}
+// dpre[n,q] = (sum_c dout[n,c,q] * x[n,c,q]) * A (1 - A): gradient w.r.t. the sigmoid's input (A = gate)
+__global__ void gen_gate_bwd_gate_kernel(const float* __restrict__ dout, long long dout_ns, const float* __restrict__ x,
+                                         long long x_ns, const float* __restrict__ gate, float* __restrict__ dpre, int N, int C,
+                                         long long HW) {
+  const long long total = static_cast<long long>(N) * HW;
+  GEN_LOOP(idx, total) {
+    const long long q = idx % HW, n = idx / HW;
+    double s = 0.0;
+    for (int c = 0; c < C; ++c)
+      s += static_cast<double>(dout[n * dout_ns + c * HW + q]) * static_cast<double>(x[n * x_ns + c * HW + q]);
+    const double a = gate[idx];
+    dpre[idx] = static_cast<float>(s * a * (1.0 - a));
+  }
+}
+// dst[n, :] += src[n, :] over views with their own batch strides
+__global__ void gen_add_inplace_kernel(float* __restrict__ dst, long long dst_ns, const float* __restrict__ src, long long src_ns,
+                                       int N, long long CHW) {
+  const long long total = static_cast<long long>(N) * CHW;
+  GEN_LOOP(idx, total) {
+    const long long n = idx / CHW, q = idx - n * CHW;
+    dst[n * dst_ns + q] += src[n * src_ns + q];
+  }
+}
+
 }  // namespace
 
 #define GEN_STREAM static_cast<cudaStream_t>(stream)
@@ -405,7 +477,7 @@ int b200unet_gen_unpool_add(const float* g_pooled, const uint8_t* idx, float* g,
 int b200unet_gen_bn_relu_bwd_reduce(const float* g, int64_t g_ns, const float* y, int64_t y_ns, const float* scale,
                                     const float* shift, const float* mean, const float* rstd, double* sums, int N, int C,
                                     int HW, b200_stream_t stream) {
-  gen_bn_bwd_reduce_kernel<<<C, GT, 0, GEN_STREAM>>>(g, g_ns, y, y_ns, scale, shift, mean, rstd, sums, N, C, HW);
+  gen_bn_bwd_reduce_kernel<<<C, GT, 0, GEN_STREAM>>>(g, g_ns, y, y_ns, scale, shift, mean, rstd, sums, N, C, HW, 1);
   return b2h::check_launch("gen_bn_relu_bwd_reduce");
 }
 
@@ -414,7 +486,7 @@ int b200unet_gen_bn_relu_bwd_apply(const float* g, int64_t g_ns, const float* y,
                                    const double* sums, double count, const double* sums_local, float* dy, int64_t dy_ns,
                                    float* dgamma, float* dbeta, int N, int C, int HW, b200_stream_t stream) {
   gen_bn_bwd_apply_kernel<<<gblocks(static_cast<long long>(N) * C * HW), GT, 0, GEN_STREAM>>>(
-      g, g_ns, y, y_ns, gamma, scale, shift, mean, rstd, sums, count, sums_local, dy, dy_ns, dgamma, dbeta, N, C, HW);
+      g, g_ns, y, y_ns, gamma, scale, shift, mean, rstd, sums, count, sums_local, dy, dy_ns, dgamma, dbeta, N, C, HW, 1);
   return b2h::check_launch("gen_bn_relu_bwd_apply");
 }
 
@@ -455,6 +527,59 @@ int b200unet_gen_conv1x1_bwd(const float* dz, const float* a, int64_t a_ns, cons
   if (int e = b2h::check_launch("gen_conv1x1_dgrad")) return e;
   gen_conv1x1_wgrad_kernel<<<dim3(C, J), GT, 0, GEN_STREAM>>>(dz, a, a_ns, dw, db, N, C, J, HW);
   return b2h::check_launch("gen_conv1x1_wgrad");
+}
+
+int b200unet_gen_bn_act_fwd(const float* y, int64_t y_ns, const float* scale, const float* shift, float* a, int64_t a_ns, int N,
+                            int C, int HW, int act, b200_stream_t stream) {
+  B2_REQUIRE(act >= 0 && act <= 2, "gen_bn_act_fwd: act=%d (0 identity, 1 relu, 2 sigmoid)", act);
+  gen_bn_act_fwd_kernel<<<gblocks(static_cast<long long>(N) * C * HW), GT, 0, GEN_STREAM>>>(y, y_ns, scale, shift, a, a_ns, N, C, HW, act);
+  return b2h::check_launch("gen_bn_act_fwd");
+}
+
+int b200unet_gen_bn_bwd_reduce(const float* g, int64_t g_ns, const float* y, int64_t y_ns, const float* scale, const float* shift,
+                               const float* mean, const float* rstd, double* sums, int N, int C, int HW, int relu,
+                               b200_stream_t stream) {
+  gen_bn_bwd_reduce_kernel<<<C, GT, 0, GEN_STREAM>>>(g, g_ns, y, y_ns, scale, shift, mean, rstd, sums, N, C, HW, relu);
+  return b2h::check_launch("gen_bn_bwd_reduce");
+}
+
+int b200unet_gen_bn_bwd_apply(const float* g, int64_t g_ns, const float* y, int64_t y_ns, const float* gamma, const float* scale,
+                              const float* shift, const float* mean, const float* rstd, const double* sums, double count,
+                              const double* sums_local, float* dy, int64_t dy_ns, float* dgamma, float* dbeta, int N, int C,
+                              int HW, int relu, b200_stream_t stream) {
+  gen_bn_bwd_apply_kernel<<<gblocks(static_cast<long long>(N) * C * HW), GT, 0, GEN_STREAM>>>(
+      g, g_ns, y, y_ns, gamma, scale, shift, mean, rstd, sums, count, sums_local, dy, dy_ns, dgamma, dbeta, N, C, HW, relu);
+  return b2h::check_launch("gen_bn_bwd_apply");
+}
+
+int b200unet_gen_add_relu(const float* a, const float* b, float* e, int64_t total, b200_stream_t stream) {
+  gen_add_relu_kernel<<<gblocks(total), GT, 0, GEN_STREAM>>>(a, b, e, total);
+  return b2h::check_launch("gen_add_relu");
+}
+
+int b200unet_gen_relu_bwd(const float* de, const float* e, float* d, int64_t total, b200_stream_t stream) {
+  gen_relu_bwd_kernel<<<gblocks(total), GT, 0, GEN_STREAM>>>(de, e, d, total);
+  return b2h::check_launch("gen_relu_bwd");
+}
+
+int b200unet_gen_gate_fwd(const float* x, int64_t x_ns, const float* gate, float* out, int64_t out_ns, int N, int C, int64_t HW,
+                          b200_stream_t stream) {
+  gen_gate_fwd_kernel<<<gblocks(static_cast<long long>(N) * C * HW), GT, 0, GEN_STREAM>>>(x, x_ns, gate, out, out_ns, N, C, HW);
+  return b2h::check_launch("gen_gate_fwd");
+}
+
+int b200unet_gen_gate_bwd(const float* dout, int64_t dout_ns, const float* x, int64_t x_ns, const float* gate, float* dx,
+                          int64_t dx_ns, float* dpre, int N, int C, int64_t HW, b200_stream_t stream) {
+  gen_gate_bwd_x_kernel<<<gblocks(static_cast<long long>(N) * C * HW), GT, 0, GEN_STREAM>>>(dout, dout_ns, gate, dx, dx_ns, N, C, HW);
+  if (int e = b2h::check_launch("gen_gate_bwd_x")) return e;
+  gen_gate_bwd_gate_kernel<<<gblocks(static_cast<long long>(N) * HW), GT, 0, GEN_STREAM>>>(dout, dout_ns, x, x_ns, gate, dpre, N, C, HW);
+  return b2h::check_launch("gen_gate_bwd_gate");
+}
+
+int b200unet_gen_add_inplace(float* dst, int64_t dst_ns, const float* src, int64_t src_ns, int N, int64_t CHW,
+                             b200_stream_t stream) {
+  gen_add_inplace_kernel<<<gblocks(static_cast<long long>(N) * CHW), GT, 0, GEN_STREAM>>>(dst, dst_ns, src, src_ns, N, CHW);
+  return b2h::check_launch("gen_add_inplace");
 }
 
 int b200unet_gen_mul(float* x, int64_t x_ns, const float* mask, int N, int64_t CHW, b200_stream_t stream) {

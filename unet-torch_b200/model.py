@@ -786,6 +786,84 @@ class UNet_multitask(UNet):
         raise NotImplementedError("fused inference heads cover UNet only; apply predict_mask / F.relu to the two outputs")
 
 
+class Attention_block(_Holder):
+    """Parameter container of the reference's attention gate (Model.py:257-296): W_q / W_x = 1x1 conv + bias + BatchNorm,
+    up = ConvTranspose2d(C_q, C_q, 2, 2), psi = 1x1 conv to one channel + BatchNorm + Sigmoid. Same construction order (RNG
+    consumption) and state_dict keys as the reference; executed by the engine (generic.py `_gate_fwd` / `_gate_bwd`)."""
+
+    def __init__(self, C_q, C_x, C_hidden):
+        super().__init__()
+        self.W_q = nn.Sequential(nn.Conv2d(C_q, C_hidden, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(C_hidden))
+        self.up = nn.ConvTranspose2d(C_q, C_q, kernel_size=2, stride=2)
+        self.W_x = nn.Sequential(nn.Conv2d(C_x, C_hidden, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(C_hidden))
+        self.psi = nn.Sequential(nn.Conv2d(C_hidden, 1, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(1),
+                                 nn.Sigmoid())
+        self.relu = nn.ReLU(inplace=True)
+
+
+class UNet_attention(UNet):
+    """Attention U-Net of the reference (Model.py:299-391): UNet whose skip connections pass through attention gates,
+    `x_l_attention = attenion_l(q = decoder input, x = skip)` (the misspelt attribute names are the reference's and fix the
+    state_dict keys). Same constructor, RNG consumption (the gates keep torch's default init: no `.apply(weights_init)`,
+    Model.py:325-341), 200 state_dict keys and forward(x) -> logits.
+    Runs on the library's generic fp32 CUDA engine (csrc/generic_f32.cu): reference precision, not tensor-core tuned - the
+    gates' 1x1 convolutions and the C_q -> C_q transposed convolution have no tcgen05 kernels yet. H and W must be divisible
+    by 16 (the reference's gate adds maps whose sizes only match then)."""
+
+    def __init__(self, n_channels, n_classes, initial_feature_map=64, usa_cuda=True, dropout=False, dropout_p=0.5):
+        nn.Module.__init__(self)
+        self.usa_cuda = usa_cuda
+        self.n_channels = {-2: 3, -1: 1}.get(n_channels, n_channels)  # Model.py:303-308
+        self.n_classes = n_classes   # (the reference forgets this attribute; kept for the engine)
+        self.initial_feature_map = initial_feature_map
+        self.dropout = dropout
+        self.dropout_p = dropout_p
+        f = initial_feature_map
+
+        def add(name, mod, init):
+            setattr(self, name, mod)
+            if init:
+                mod.apply(self.weights_init)
+
+        add("inc", DoubleConv(n_channels, f), True)   # the reference passes the RAW n_channels here (Model.py:314)
+        for i in range(4):
+            add(f"down{i + 1}", Down(f << i, f << (i + 1), dropout, dropout_p), True)
+        for lvl in (4, 3, 2, 1):                      # attenion4 .. attenion1, default init (Model.py:325-341)
+            add(f"attenion{lvl}", Attention_block(C_q=f << lvl, C_x=f << (lvl - 1), C_hidden=(f << (lvl - 1)) // 2), False)
+        for i in range(4):
+            add(f"up{i + 1}", Up(f << (4 - i), f << (3 - i), dropout, dropout_p), True)
+        add("outc", OutConv(f, n_classes), True)
+        self._engine = None
+        self._generic = None
+        self._check_fp32 = True
+        self._cuda_graphs = False
+
+    def _attention_gates(self):
+        """Gate of decoder block j = 0..3 (up1..up4)."""
+        return [self.attenion4, self.attenion3, self.attenion2, self.attenion1]
+
+    def _fast_supported(self) -> bool:
+        return False
+
+    def _engine_for(self, x):
+        if x.dim() == 4 and (x.shape[2] % 16 or x.shape[3] % 16):
+            raise ValueError("UNet_attention needs H and W divisible by 16 (its gates add a 2x-upsampled map to the skip)")
+        return super()._engine_for(x)
+
+    def set_check_mode(self, flag: bool = True):
+        if not flag:
+            raise NotImplementedError("UNet_attention runs on the generic fp32 engine only")
+        return self
+
+    def enable_cuda_graphs(self, flag: bool = True):
+        if flag:
+            raise NotImplementedError("CUDA-graph replay covers UNet only")
+        return self
+
+    def _fused_head(self, x, head, head_arg=0.0):
+        raise NotImplementedError("fused inference heads cover UNet only; apply predict_mask / F.relu / sigmoid to net(x)")
+
+
 def preprocess(img_org, input_size=None, device=None) -> torch.Tensor:
     """`preprocess(img_org, input_size)` of test_mc3serousv5.py:100-127 / the z-normalisation of DataLoader.py:661-671 on
     the GPU: uint8 image(s) as cv2.imread returns them ([H,W,C] BGR, [H,W] grey, or a batch [N,H,W,C]) -> fp32 [N,C,H,W],
