@@ -335,7 +335,7 @@ def run_ours(args):
     step(x_dev, y_dev)
     launches_per_step = _lib.query("b200unet_launch_count") - l0
     use_graphs = train and not args.no_graphs
-    net.enable_cuda_graphs(use_graphs)
+    net.enable_cuda_graphs(use_graphs, share_grads=use_graphs)  # step() clears gradients with set_to_none=True every step
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
     # what actually replays as a graph (data parallel: only with B200UNET_DP_GRAPHS=1 and the NVLink SyncBN path)
@@ -463,7 +463,8 @@ def run_ours(args):
         "execution": {
             "optimizer_impl": None if not train else ("torch.optim.SGD" if args.torch_optim else
                                                       "unet_torch_b200.FusedSGD (torch.optim.SGD arithmetic fused with the bf16 operand re-cast)"),
-            "cuda_graphs": ("forward and backward of the network replayed as captured CUDA graphs; loss and optimizer eager"
+            "cuda_graphs": ("forward and backward of the network replayed as captured CUDA graphs (net.enable_cuda_graphs(True, "
+                            "share_grads=True): .grad aliases the graph's gradient buffers); loss and optimizer eager"
                             if graphs_live else "off (every kernel launched eagerly)"),
             "sync_bn": bool(dp is not None and dp.sync_bn),
             "sync_bn_path": None if dp is None else ("nvlink peer-memory kernel" if dp.has_nvl else "nccl"),

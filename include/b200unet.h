@@ -132,6 +132,12 @@ int b200unet_bn_reduce_partials(const float* stats_partial, int64_t mtiles, int 
 int b200unet_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps,
                          float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
                          float* scale, float* shift, int C, b200_stream_t stream);
+/* The two calls above in ONE launch for the single-GPU forward (no cross-rank step in between): reduces the partial rows in
+ * a fixed order (fp64) and finalises; num_batches_tracked (int64 scalar, may be NULL) is incremented on the device. */
+int b200unet_bn_reduce_finalize(const float* stats_partial, int64_t rows, int C, double count, const float* gamma,
+                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                int64_t* num_batches_tracked, float* mean, float* rstd, float* scale, float* shift,
+                                b200_stream_t stream);
 /* eval mode: scale/shift from running statistics. */
 int b200unet_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
                             const float* running_var, float eps, float* scale, float* shift, int C,
@@ -321,6 +327,13 @@ int b200unet_sgd_convt2x2_weight(float* w, const float* grad, float* momentum_bu
 int b200unet_sgd_small(float* const* w, const float* const* grad, float* const* momentum_buf, const int* numel,
                        int count, float lr, float momentum, float dampening, float weight_decay, int nesterov,
                        int first_step, b200_stream_t stream);
+/* All conv3x3 weights (kind 0; dim_a = K, dim_b = C) or all ConvTranspose2d weights (kind 1; dim_a = Cin, dim_b = Cup) of a
+ * network in ONE launch (HOST arrays of device pointers / dims): most weight tensors are a few tiles, so a launch per tensor
+ * is latency-bound. Same arithmetic and operand outputs as the single-tensor entry points above. */
+int b200unet_sgd_weights(int kind, float* const* w, const float* const* grad, float* const* momentum_buf,
+                         void* const* w_fprop, void* const* w_dgrad, const int* dim_a, const int* dim_b, int count, float lr,
+                         float momentum, float dampening, float weight_decay, int nesterov, int first_step,
+                         b200_stream_t stream);
 
 /* ---- the same fused pass for Adam (train.py:341-343 `optim.Adam(params, lr, weight_decay)`; configseros.yml:15;
  * Trainer.py:1009): torch.optim.Adam arithmetic - g += weight_decay*w; exp_avg = lerp(exp_avg, g, 1-beta1);
@@ -336,6 +349,10 @@ int b200unet_adam_convt2x2_weight(float* w, const float* grad, float* exp_avg, f
 int b200unet_adam_small(float* const* w, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq,
                         const int* numel, int count, double beta1, double beta2, float eps, float weight_decay,
                         float step_size, float inv_sqrt_bc2, int first_step, b200_stream_t stream);
+int b200unet_adam_weights(int kind, float* const* w, const float* const* grad, float* const* exp_avg,
+                          float* const* exp_avg_sq, void* const* w_fprop, void* const* w_dgrad, const int* dim_a,
+                          const int* dim_b, int count, double beta1, double beta2, float eps, float weight_decay,
+                          float step_size, float inv_sqrt_bc2, int first_step, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

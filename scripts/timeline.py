@@ -33,7 +33,7 @@ def step():
 
 
 step()
-net.enable_cuda_graphs(GRAPHS)
+net.enable_cuda_graphs(GRAPHS, share_grads=GRAPHS)
 for _ in range(4):
     step()
 torch.cuda.synchronize()

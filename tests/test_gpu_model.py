@@ -331,3 +331,44 @@ def test_fused_adam_matches_torch_adam(wd, betas):
         assert torch.equal(wf, u.wf) and torch.equal(wd_, u.wd)
     sd = opt_b.state_dict()
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and sd["param_groups"][0]["betas"] == betas
+
+
+def test_cuda_graph_share_grads_is_identical_and_copy_free():
+    """enable_cuda_graphs(True, share_grads=True): .grad is the graph's own static gradient tensor (no per-step copy), the
+    training trajectory is bit-identical to the copying mode, and a foreign gradient already in .grad is accumulated."""
+    import unet_torch_b200 as U
+
+    U.loss.CLASS_NUMBER = 2
+    x = torch.randn(2, 3, 32, 48, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    y = torch.randint(0, 2, (2, 32, 48), device="cuda", generator=torch.Generator("cuda").manual_seed(4)).float()
+
+    def run(share):
+        torch.manual_seed(11)
+        net = U.UNet(3, 2).cuda().train().enable_cuda_graphs(True, share_grads=share)
+        opt = U.FusedSGD(net, lr=0.05, momentum=0.9)
+        ptrs, losses = [], []
+        for _ in range(4):
+            loss = U.calc_loss(net(x), y, loss_type="dice_bce_mc")
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            ptrs.append(net.up1.up.weight.grad.data_ptr())
+            losses.append(float(loss))
+            opt.step()
+        return net, losses, ptrs
+
+    net_a, la, pa = run(False)
+    net_b, lb, pb = run(True)
+    assert la == lb
+    for (k, a), (_, b) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert len(set(pb[1:])) == 1            # graph replays: always the same static buffer, never a copy
+    # accumulation into an existing foreign gradient
+    loss = U.calc_loss(net_b(x), y, loss_type="dice_bce_mc")
+    net_b.zero_grad(set_to_none=True)
+    w = net_b.outc.conv.bias
+    w.grad = torch.ones_like(w)
+    loss.backward()
+    ref = U.calc_loss(net_a(x), y, loss_type="dice_bce_mc")
+    net_a.zero_grad(set_to_none=True)
+    ref.backward()
+    assert torch.allclose(w.grad, net_a.outc.conv.bias.grad + 1.0)

@@ -71,8 +71,8 @@ def test_root_shims_mirror_reference_imports():
     assert U.loss.CLASS_NUMBER == 5
     assert callable(loss.calc_loss) and loss.DiceLoss is U.DiceLoss
     assert Model.UNet_multitask is U.UNet_multitask and issubclass(Model.UNet_multitask, torch.nn.Module)
-    with pytest.raises(NotImplementedError):
-        Model.UNet_attention(3, 2)
+    assert Model.UNet_attention is U.UNet_attention and len(Model.UNet_attention(3, 2, 4).state_dict()) == 210
+    assert isinstance(loss.MultitaskUncertaintyLoss(), torch.nn.Module) and callable(loss.MRAccuracy)  # Trainer.py:6
     with pytest.raises(NotImplementedError):
         loss.calc_loss(torch.zeros(1, 1, 4, 4), torch.zeros(1, 4, 4), loss_type="HausdorffDTLoss")
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "b200unet_head_bwd": (c_int, [_P, _P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200unet_bn_reduce_partials": (c_int, [_P, _L, _I, _P, _P]),
     "b200unet_bn_finalize": (c_int, [_P, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "b200unet_bn_reduce_finalize": (c_int, [_P, _L, _I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200unet_bn_eval_affine": (c_int, [_P, _P, _P, _P, _F, _P, _P, _I, _P]),
     "b200unet_bn_eval_stats": (c_int, [_P, _P, _F, _P, _P, _I, _P]),
     "b200unet_bn_relu_fwd": (c_int, [_P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
@@ -108,6 +109,8 @@ SIGNATURES = {
     "b200unet_sgd_conv3x3_weight": (c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_sgd_convt2x2_weight": (c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_sgd_small": (c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _P]),
+    "b200unet_sgd_weights": (c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _P]),
+    "b200unet_adam_weights": (c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _D, _D, _F, _F, _F, _F, _I, _P]),
     "b200unet_adam_conv3x3_weight": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _D, _F, _F, _F, _F, _I, _P]),
     "b200unet_adam_convt2x2_weight": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _D, _F, _F, _F, _F, _I, _P]),
     "b200unet_adam_small": (c_int, [_P, _P, _P, _P, _P, _I, _D, _D, _F, _F, _F, _F, _I, _P]),

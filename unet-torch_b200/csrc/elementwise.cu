@@ -31,6 +31,20 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+// Traversal direction of the three big elementwise passes (0 BN-apply forward, 1 BN-backward reduce, 2 BN-backward apply):
+// alternating the direction between a producer and its consumer turns the tail the producer left in L2 into hits.
+// B200UNET_EW_REV = three digits, 1 = back to front (default "000"). Measured on B200: no effect (22.5-22.9 ms per step for all
+// eight combinations, inside run-to-run noise) - streaming kernels do not find the producer's tail in L2; kept as a knob.
+int ew_rev(int which) {
+  static int mask = -1;
+  if (mask < 0) {
+    const char* e = getenv("B200UNET_EW_REV");
+    const char* d = (e != nullptr && e[0] && e[1] && e[2]) ? e : "000";
+    mask = (d[0] == '1' ? 1 : 0) | (d[1] == '1' ? 2 : 0) | (d[2] == '1' ? 4 : 0);
+  }
+  return (mask >> which) & 1;
+}
+
 int ew_blocks(long long work_items) {
   long long b = (work_items + EW_THREADS - 1) / EW_THREADS;
   if (b > EW_MAX_BLOCKS) b = EW_MAX_BLOCKS;
@@ -39,39 +53,81 @@ int ew_blocks(long long work_items) {
 }
 
 // ------------------------------------------------------------------------------------------ statistics
-// partial [rows][ncols] fp32 -> sums[ncols] fp64 (+=). 32 columns x 8 row-lanes per block.
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, long long rows, int ncols,
+// partial [rows][ncols] fp32 -> sums[ncols] fp64. One block per 32 columns (32 row-lanes each, fixed summation order: no
+// atomics, no memset, bit-reproducible).
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partial, long long rows, int ncols,
                                        double* __restrict__ sums) {
-  __shared__ double sh[8][32];
+  __shared__ double sh[32][33];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
   double acc = 0.0;
   if (col < ncols) {
-    for (long long r = static_cast<long long>(blockIdx.y) * 8 + rl; r < rows; r += static_cast<long long>(gridDim.y) * 8)
-      acc += static_cast<double>(partial[r * ncols + col]);
+#pragma unroll 4
+    for (long long r = rl; r < rows; r += 32) acc += static_cast<double>(__ldg(partial + r * ncols + col));
   }
   sh[rl][threadIdx.x & 31] = acc;
   __syncthreads();
   if (rl == 0 && col < ncols) {
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
-    atomicAdd(sums + col, t);
+    for (int i = 0; i < 32; ++i) t += sh[i][threadIdx.x];
+    sums[col] = t;
   }
 }
 
 int launch_reduce_partials(const float* partial, long long rows, int ncols, double* sums, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * ncols, st);
-  if (e != cudaSuccess) {
-    b2h::set_error("reduce_partials memset: %s", cudaGetErrorString(e));
-    return 2;
-  }
-  long long gy = (rows + 63) / 64;
-  if (gy > 64) gy = 64;
-  if (gy < 1) gy = 1;
-  dim3 grid((ncols + 31) / 32, static_cast<unsigned>(gy));
-  reduce_partials_kernel<<<grid, 256, 0, st>>>(partial, rows, ncols, sums);
+  reduce_partials_kernel<<<(ncols + 31) / 32, 1024, 0, st>>>(partial, rows, ncols, sums);
   return b2h::check_launch("reduce_partials");
+}
+
+// The forward statistics path in ONE launch (single GPU): reduce the conv epilogue's partial rows [rows][2][C] (fp64, fixed
+// order) and finalise BatchNorm2d for the block's 32 channels - mean, rstd, scale = gamma*rstd, shift = beta - mean*scale,
+// running statistics (unbiased variance) and num_batches_tracked += 1 (Model.py:17,21). Replaces memset + reduce_partials +
+// bn_finalize + a torch kernel for the counter: 4 launches per BatchNorm layer -> 1.
+__global__ void __launch_bounds__(1024) bn_reduce_finalize_kernel(const float* __restrict__ partial, long long rows, int C,
+                                                                  double count, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float eps, float momentum,
+                                                                  float* running_mean, float* running_var,
+                                                                  long long* num_batches, float* mean, float* rstd,
+                                                                  float* scale, float* shift) {
+  // 32 channels x 32 row-lanes: the loads of a lane are independent (latency-bound kernel: keep many in flight)
+  __shared__ double sh[2][32][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  double a1 = 0.0, a2 = 0.0;
+  if (c < C) {
+#pragma unroll 4
+    for (long long r = rl; r < rows; r += 32) {
+      a1 += static_cast<double>(__ldg(partial + r * 2 * C + c));
+      a2 += static_cast<double>(__ldg(partial + r * 2 * C + C + c));
+    }
+  }
+  sh[0][rl][threadIdx.x & 31] = a1;
+  sh[1][rl][threadIdx.x & 31] = a2;
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches != nullptr) *num_batches += 1;
+  if (rl != 0 || c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    s1 += sh[0][i][threadIdx.x];
+    s2 += sh[1][i][threadIdx.x];
+  }
+  const double m = s1 / count;
+  double var = s2 / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const float mf = static_cast<float>(m);
+  const float rs = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  mean[c] = mf;
+  rstd[c] = rs;
+  const float sc = gamma[c] * rs;
+  scale[c] = sc;
+  shift[c] = beta[c] - mf * sc;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mf;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
@@ -120,9 +176,11 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_fwd_kernel(const __nv_bflo
                                                                  __nv_bfloat16* __restrict__ a, int a_cs,
                                                                  __nv_bfloat16* __restrict__ pooled,
                                                                  uint8_t* __restrict__ pool_idx, int N, int H, int W,
-                                                                 int C) {
+                                                                 int C, int rev) {
+  // rev: walk the tensor back to front. The producer (a conv kernel, front to back) leaves the TAIL of y in the 126 MB L2
+  // and the consumer (the next conv, front to back) wants the HEAD of `a` there: a back-to-front pass gets both.
   const int cgs = C >> 3;  // 8-channel groups; divides blockDim, so a thread keeps its group across the loop
-  const int cg = threadIdx.x % cgs;
+  const int cg = rev ? cgs - 1 - static_cast<int>(threadIdx.x % cgs) : static_cast<int>(threadIdx.x % cgs);
   float sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -140,7 +198,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_fwd_kernel(const __nv_bflo
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long i = i0 + u * stride;
-        pix[u] = i / cgs;
+        pix[u] = (rev ? total - 1 - i : i) / cgs;
         if (i < total) raw[u] = ldg128(y + pix[u] * y_cs + cg * 8);
       }
 #pragma unroll
@@ -158,7 +216,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_fwd_kernel(const __nv_bflo
     const int Hp = H >> 1, Wp = W >> 1;
     const long long total = static_cast<long long>(N) * Hp * Wp * cgs;
     for (long long i = tid; i < total; i += stride) {
-      const long long pp = i / cgs;  // pooled pixel
+      const long long pp = (rev ? total - 1 - i : i) / cgs;  // pooled pixel
       const int wp = static_cast<int>(pp % Wp);
       const int hp = static_cast<int>((pp / Wp) % Hp);
       const long long n = pp / (static_cast<long long>(Wp) * Hp);
@@ -306,11 +364,11 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(BwdSrc s, 
                                                                       const float* __restrict__ mean,
                                                                       const float* __restrict__ rstd,
                                                                       float* __restrict__ partial, int N, int H, int W,
-                                                                      int C) {
+                                                                      int C, int rev) {
   constexpr int NP = POOL ? 4 : 1;
   constexpr int U = POOL ? 1 : 4;
   const int cgs = C >> 3;
-  const int cg = threadIdx.x % cgs;
+  const int cg = rev ? cgs - 1 - static_cast<int>(threadIdx.x % cgs) : static_cast<int>(threadIdx.x % cgs);
   float sc[8], sh[8], s1[8], s2[8];  // s1 = sum da, s2 = sum da*y (turned into sum da*xhat at the end)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -326,7 +384,8 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(BwdSrc s, 
     BwdRaw<POOL> raw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (i0 + u * stride < total) bwd_load<POOL>(s, (i0 + u * stride) / cgs, cg, C, H, W, raw[u]);
+      if (i0 + u * stride < total)
+        bwd_load<POOL>(s, (rev ? total - 1 - (i0 + u * stride) : (i0 + u * stride)) / cgs, cg, C, H, W, raw[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (i0 + u * stride < total) {
@@ -376,11 +435,11 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(BwdSrc s, c
                                                                      __nv_bfloat16* __restrict__ dy, int dy_cs,
                                                                      float* __restrict__ dgamma,
                                                                      float* __restrict__ dbeta, int N, int H, int W,
-                                                                     int C) {
+                                                                     int C, int rev) {
   constexpr int NP = POOL ? 4 : 1;
   constexpr int U = POOL ? 1 : 4;
   const int cgs = C >> 3;
-  const int cg = threadIdx.x % cgs;
+  const int cg = rev ? cgs - 1 - static_cast<int>(threadIdx.x % cgs) : static_cast<int>(threadIdx.x % cgs);
   float sc[8], sh[8], k1[8], k2[8], k3[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -408,7 +467,8 @@ __global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(BwdSrc s, c
     BwdRaw<POOL> raw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (i0 + u * stride < total) bwd_load<POOL>(s, (i0 + u * stride) / cgs, cg, C, H, W, raw[u]);
+      if (i0 + u * stride < total)
+        bwd_load<POOL>(s, (rev ? total - 1 - (i0 + u * stride) : (i0 + u * stride)) / cgs, cg, C, H, W, raw[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (i0 + u * stride < total) {
@@ -537,6 +597,19 @@ int b200unet_bn_finalize(const double* sums, double count, const float* gamma, c
   return b2h::check_launch("bn_finalize");
 }
 
+int b200unet_bn_reduce_finalize(const float* stats_partial, int64_t rows, int C, double count, const float* gamma,
+                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                int64_t* num_batches_tracked, float* mean, float* rstd, float* scale, float* shift,
+                                b200_stream_t stream) {
+  B2_REQUIRE(stats_partial && gamma && beta && mean && rstd && scale && shift && rows > 0 && C > 0 && count > 0,
+             "bn_reduce_finalize: bad arguments");
+  B2_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_reduce_finalize: running_mean / running_var go together");
+  bn_reduce_finalize_kernel<<<(C + 31) / 32, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats_partial, rows, C, count, gamma, beta, eps, momentum, running_mean, running_var,
+      reinterpret_cast<long long*>(num_batches_tracked), mean, rstd, scale, shift);
+  return b2h::check_launch("bn_reduce_finalize");
+}
+
 int b200unet_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                             float eps, float* scale, float* shift, int C, b200_stream_t stream) {
   bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma, beta, running_mean,
@@ -568,13 +641,15 @@ int b200unet_bn_relu_fwd(const void* y, int y_cs, const float* scale, const floa
   if (pooled == nullptr) {
     int blocks = ew_blocks(static_cast<long long>(N) * H * W * (C / 8));
     if (blocks > 148 * fwd_per_sm) blocks = 148 * fwd_per_sm;
-    bn_relu_fwd_kernel<false><<<blocks, EW_THREADS, 0, st>>>(yy, y_cs, scale, shift, aa, a_cs, nullptr, nullptr, N, H, W, C);
+    bn_relu_fwd_kernel<false><<<blocks, EW_THREADS, 0, st>>>(yy, y_cs, scale, shift, aa, a_cs, nullptr, nullptr, N, H, W, C,
+                                                             ew_rev(0));
   } else {
     B2_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_fwd(pool): H=%d W=%d must be even", H, W);
     int blocks = ew_blocks(static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8));
     if (blocks > 148 * fwd_per_sm) blocks = 148 * fwd_per_sm;
     bn_relu_fwd_kernel<true><<<blocks, EW_THREADS, 0, st>>>(yy, y_cs, scale, shift, aa, a_cs,
-                                                            static_cast<__nv_bfloat16*>(pooled), pool_idx, N, H, W, C);
+                                                            static_cast<__nv_bfloat16*>(pooled), pool_idx, N, H, W, C,
+                                                            ew_rev(0));
   }
   return b2h::check_launch("bn_relu_fwd");
 }
@@ -598,9 +673,9 @@ int b200unet_bn_relu_bwd_reduce(const void* g1, int g1_cs, const void* g_pool, c
   if (pool) B2_REQUIRE(H % 2 == 0 && W % 2 == 0 && pool_idx != nullptr, "bn_relu_bwd_reduce(pool): bad arguments");
   const int blocks = bwd_blocks(N, H, W, C, pool);
   if (pool)
-    bn_bwd_reduce_kernel<true><<<blocks, EW_THREADS, 0, st>>>(s, scale, shift, mean, rstd, partial, N, H, W, C);
+    bn_bwd_reduce_kernel<true><<<blocks, EW_THREADS, 0, st>>>(s, scale, shift, mean, rstd, partial, N, H, W, C, ew_rev(1));
   else
-    bn_bwd_reduce_kernel<false><<<blocks, EW_THREADS, 0, st>>>(s, scale, shift, mean, rstd, partial, N, H, W, C);
+    bn_bwd_reduce_kernel<false><<<blocks, EW_THREADS, 0, st>>>(s, scale, shift, mean, rstd, partial, N, H, W, C, ew_rev(1));
   if (int e = b2h::check_launch("bn_relu_bwd_reduce")) return e;
   return launch_reduce_partials(partial, blocks, 2 * C, sums, st);
 }
@@ -620,11 +695,11 @@ int b200unet_bn_relu_bwd_apply(const void* g1, int g1_cs, const void* g_pool, co
   if (pool)
     bn_bwd_apply_kernel<true><<<blocks, EW_THREADS, 0, st>>>(s, gamma, scale, shift, mean, rstd, sums, count, sums_local,
                                                              static_cast<__nv_bfloat16*>(dy), dy_cs, dgamma, dbeta, N, H,
-                                                             W, C);
+                                                             W, C, ew_rev(2));
   else
     bn_bwd_apply_kernel<false><<<blocks, EW_THREADS, 0, st>>>(s, gamma, scale, shift, mean, rstd, sums, count, sums_local,
                                                               static_cast<__nv_bfloat16*>(dy), dy_cs, dgamma, dbeta, N,
-                                                              H, W, C);
+                                                              H, W, C, ew_rev(2));
   return b2h::check_launch("bn_relu_bwd_apply");
 }
 

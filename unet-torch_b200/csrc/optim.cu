@@ -51,14 +51,12 @@ __device__ __forceinline__ float sgd_update(float& w, float g, float& buf, const
 //   op1[a][tap][b]                                   (conv3: fprop operand [K][rs][C]; convT: dgrad operand [ci][ij][d])
 //   ROT ? op2[b][TAPS-1-tap][a] : op2[tap][b][a]     (conv3: dgrad operand [C][8-rs][K]; convT: fprop operand [ij][d][ci])
 template <int TAPS, bool ROT>
-__global__ void __launch_bounds__(256) sgd_weight_kernel(float* __restrict__ w, const float* __restrict__ g,
-                                                         float* __restrict__ buf, float* __restrict__ buf2,
-                                                         __nv_bfloat16* __restrict__ op1, __nv_bfloat16* __restrict__ op2,
-                                                         int A, int B, SgdHyper h) {
+__device__ __forceinline__ void weight_tile(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ buf,
+                                            float* __restrict__ buf2, __nv_bfloat16* __restrict__ op1,
+                                            __nv_bfloat16* __restrict__ op2, int A, int B, int a0, int b0, const SgdHyper& h) {
   constexpr int TA = 32, TB = 64;
   constexpr int ROW4 = TB * TAPS / 4;  // float4's per a-row of the tile (contiguous in the parameter tensor)
   __shared__ __align__(16) __nv_bfloat16 sm[TA][TAPS][TB];
-  const int b0 = blockIdx.x * TB, a0 = blockIdx.y * TA;
   const bool have_buf = (buf != nullptr) && !h.first_step;
   for (int v = threadIdx.x; v < TA * ROW4; v += 256) {
     const int aa = v / ROW4, r4 = v - aa * ROW4;
@@ -112,6 +110,39 @@ __global__ void __launch_bounds__(256) sgd_weight_kernel(float* __restrict__ w, 
       *reinterpret_cast<uint4*>(op2 + row * A + a0 + q * 8) = *reinterpret_cast<const uint4*>(v);
     }
   }
+}
+
+template <int TAPS, bool ROT>
+__global__ void __launch_bounds__(256) sgd_weight_kernel(float* __restrict__ w, const float* __restrict__ g,
+                                                         float* __restrict__ buf, float* __restrict__ buf2,
+                                                         __nv_bfloat16* __restrict__ op1, __nv_bfloat16* __restrict__ op2,
+                                                         int A, int B, SgdHyper h) {
+  weight_tile<TAPS, ROT>(w, g, buf, buf2, op1, op2, A, B, blockIdx.y * 32, blockIdx.x * 64, h);
+}
+
+// All conv (or all convT) weights of the network in ONE launch: most of the 21 weight tensors are small (64x64x9 = two
+// tiles), so one launch per tensor is latency-bound; a flat tile list keeps every SM busy with the few large ones.
+constexpr int MAX_MULTI = 24;
+struct WeightTable {
+  float* w[MAX_MULTI];
+  const float* g[MAX_MULTI];
+  float* buf[MAX_MULTI];
+  float* buf2[MAX_MULTI];
+  __nv_bfloat16* op1[MAX_MULTI];
+  __nv_bfloat16* op2[MAX_MULTI];
+  int A[MAX_MULTI], B[MAX_MULTI];
+  int tile_start[MAX_MULTI + 1];
+  int count;
+};
+
+template <int TAPS, bool ROT>
+__global__ void __launch_bounds__(256) sgd_weight_multi_kernel(const __grid_constant__ WeightTable t, SgdHyper h) {
+  int ti = 0;
+  while (ti + 1 < t.count && static_cast<int>(blockIdx.x) >= t.tile_start[ti + 1]) ++ti;
+  const int lt = blockIdx.x - t.tile_start[ti];
+  const int tiles_b = t.B[ti] / 64;
+  weight_tile<TAPS, ROT>(t.w[ti], t.g[ti], t.buf[ti], t.buf2[ti], t.op1[ti], t.op2[ti], t.A[ti], t.B[ti], (lt / tiles_b) * 32,
+                         (lt % tiles_b) * 64, h);
 }
 
 // small tensors (BatchNorm affine, biases, head, inc.conv1): up to 48 per launch, one block column per tensor
@@ -193,9 +224,69 @@ int launch_small(float* const* w, const float* const* grad, float* const* buf, f
   return 0;
 }
 
+// kind 0: conv3x3 weights [K][C][3][3] (op1 = fprop operand, op2 = dgrad operand); kind 1: ConvTranspose2d weights
+// [Cin][Cup][2][2] (op1 = dgrad operand, op2 = fprop operand)
+int launch_multi(int kind, float* const* w, const float* const* grad, float* const* buf, float* const* buf2,
+                 void* const* w_fprop, void* const* w_dgrad, const int* dim_a, const int* dim_b, int count, const SgdHyper& h,
+                 cudaStream_t st, const char* what) {
+  if (count < 0 || (kind != 0 && kind != 1)) {
+    b2h::set_error("%s: bad kind / count", what);
+    return 1;
+  }
+  for (int base = 0; base < count; base += MAX_MULTI) {
+    WeightTable t;
+    t.count = count - base < MAX_MULTI ? count - base : MAX_MULTI;
+    int tiles = 0;
+    for (int i = 0; i < t.count; ++i) {
+      const int j = base + i;
+      if (dim_a[j] % 32 != 0 || dim_b[j] % 64 != 0 || w[j] == nullptr || grad[j] == nullptr || w_fprop[j] == nullptr ||
+          w_dgrad[j] == nullptr || (h.momentum != 0.f && buf[j] == nullptr) || (h.adam && buf2[j] == nullptr)) {
+        b2h::set_error("%s: tensor %d: dims (%d, %d) must be multiples of (32, 64) and no pointer may be null", what, j, dim_a[j],
+                       dim_b[j]);
+        return 1;
+      }
+      t.w[i] = w[j];
+      t.g[i] = grad[j];
+      t.buf[i] = buf ? buf[j] : nullptr;
+      t.buf2[i] = buf2 ? buf2[j] : nullptr;
+      t.op1[i] = static_cast<__nv_bfloat16*>(kind == 0 ? w_fprop[j] : w_dgrad[j]);
+      t.op2[i] = static_cast<__nv_bfloat16*>(kind == 0 ? w_dgrad[j] : w_fprop[j]);
+      t.A[i] = dim_a[j];
+      t.B[i] = dim_b[j];
+      t.tile_start[i] = tiles;
+      tiles += (dim_a[j] / 32) * (dim_b[j] / 64);
+    }
+    t.tile_start[t.count] = tiles;
+    if (tiles == 0) continue;
+    if (kind == 0)
+      sgd_weight_multi_kernel<9, true><<<tiles, 256, 0, st>>>(t, h);
+    else
+      sgd_weight_multi_kernel<4, false><<<tiles, 256, 0, st>>>(t, h);
+    if (int e = b2h::check_launch(what)) return e;
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int b200unet_sgd_weights(int kind, float* const* w, const float* const* grad, float* const* momentum_buf, void* const* w_fprop,
+                         void* const* w_dgrad, const int* dim_a, const int* dim_b, int count, float lr, float momentum,
+                         float dampening, float weight_decay, int nesterov, int first_step, b200_stream_t stream) {
+  return launch_multi(kind, w, grad, momentum_buf, nullptr, w_fprop, w_dgrad, dim_a, dim_b, count,
+                      sgd_hyper(lr, momentum, dampening, weight_decay, nesterov, first_step), static_cast<cudaStream_t>(stream),
+                      "sgd_weights");
+}
+
+int b200unet_adam_weights(int kind, float* const* w, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq,
+                          void* const* w_fprop, void* const* w_dgrad, const int* dim_a, const int* dim_b, int count, double beta1,
+                          double beta2, float eps, float weight_decay, float step_size, float inv_sqrt_bc2, int first_step,
+                          b200_stream_t stream) {
+  return launch_multi(kind, w, grad, exp_avg, exp_avg_sq, w_fprop, w_dgrad, dim_a, dim_b, count,
+                      adam_hyper(beta1, beta2, eps, weight_decay, step_size, inv_sqrt_bc2, first_step),
+                      static_cast<cudaStream_t>(stream), "adam_weights");
+}
 
 int b200unet_sgd_conv3x3_weight(float* w_oihw, const float* grad, float* momentum_buf, void* w_fprop, void* w_dgrad,
                                 int K, int C, float lr, float momentum, float dampening, float weight_decay,

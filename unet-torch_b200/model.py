@@ -229,12 +229,17 @@ class UNetEngine:
                 rstd = torch.empty(c, dtype=torch.float32, device=dev)
                 ops.bn_eval_stats(bn.running_mean, bn.running_var, bn.eps, mean, rstd)
             return scale, shift, mean, rstd, count
-        sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
-        ops.bn_reduce_partials(stats_partial, rows, c, sums)
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         rstd = torch.empty(c, dtype=torch.float32, device=dev)
         mom = bn.momentum if bn.momentum is not None else 0.1
         track = bn.track_running_stats and bn.running_mean is not None
+        if dp is None or not dp.sync_bn:  # single GPU: partial rows -> statistics -> affine -> running buffers, one launch
+            ops.bn_reduce_finalize(stats_partial, rows, count, bn.weight, bn.bias, bn.eps, mom,
+                                   bn.running_mean if track else None, bn.running_var if track else None,
+                                   bn.num_batches_tracked if track else None, mean, rstd, scale, shift)
+            return scale, shift, mean, rstd, count
+        sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
+        ops.bn_reduce_partials(stats_partial, rows, c, sums)
         if dp is not None and dp.sync_bn:
             count = count * dp.world_size
             if dp.has_nvl and 2 * c <= dp.nvl_max_doubles:  # one kernel: NVLink one-shot all-reduce of [sum, sum^2] + finalisation
@@ -587,6 +592,18 @@ class _UNetFn(torch.autograd.Function):
         with torch.cuda.device(ctx.device):  # a CPU input was rejected in forward
             if ctx.step is not None:
                 grads = ctx.step.backward(ctx.epoch, dlogits[0].contiguous().float())
+                if ctx.engine.net._share_grads:
+                    # hand the graph's static gradient tensors to .grad directly: autograd would copy every one of them
+                    # (they stay referenced by the graph, so it cannot adopt them) - 124 MB of device copies per step
+                    for p in ctx.params:
+                        g = grads.get(p)
+                        if g is None or not p.requires_grad:
+                            continue
+                        if p.grad is None:
+                            p.grad = g
+                        elif p.grad.data_ptr() != g.data_ptr():
+                            p.grad.add_(g)   # a gradient from elsewhere is already there: accumulate like autograd
+                    return (None, None) + tuple(None for _ in ctx.params)
                 return (None, None) + tuple(grads.get(p) for p in ctx.params)
             if ctx.saved is None:
                 raise RuntimeError("UNet backward called twice: activations are consumed in place")
@@ -623,16 +640,22 @@ class UNet(nn.Module):
         self._generic = None
         self._check_fp32 = os.environ.get("B200UNET_CHECK_FP32", "0") not in ("", "0")
         self._cuda_graphs = os.environ.get("B200UNET_CUDA_GRAPHS", "0") not in ("", "0")
+        self._share_grads = False
 
     def _topology(self):
         """(inc, [down1..4], [([up1..4], outc)]) - what the engines execute."""
         return self.inc, [self.down1, self.down2, self.down3, self.down4], [
             ([self.up1, self.up2, self.up3, self.up4], self.outc)]
 
-    def enable_cuda_graphs(self, flag: bool = True):
+    def enable_cuda_graphs(self, flag: bool = True, share_grads: bool = False):
         """Replay forward/backward as captured CUDA graphs (per input shape; first call of a shape runs eagerly).
-        Off by default: outputs are copies of static buffers and one forward per shape may be in flight."""
+        Off by default: outputs are copies of static buffers and one forward per shape may be in flight.
+        share_grads=True additionally makes `p.grad` the graph's own static gradient tensors instead of copies of them
+        (saves 124 MB of device copies per step): they are valid until the next backward of the same input shape, so clear
+        them with `zero_grad(set_to_none=True)` (torch's default) every step and do not accumulate gradients over several
+        backward calls in this mode."""
         self._cuda_graphs = bool(flag)
+        self._share_grads = bool(flag) and bool(share_grads)
         if self._engine is not None:
             self._engine._graphs.clear()
         return self
@@ -762,6 +785,7 @@ class UNet_multitask(UNet):
         self._generic = None
         self._check_fp32 = False
         self._cuda_graphs = False
+        self._share_grads = False
 
     def _topology(self):
         return self.inc, [self.down1, self.down2, self.down3, self.down4], [
@@ -837,6 +861,7 @@ class UNet_attention(UNet):
         self._generic = None
         self._check_fp32 = True
         self._cuda_graphs = False
+        self._share_grads = False
 
     def _attention_gates(self):
         """Gate of decoder block j = 0..3 (up1..up4)."""

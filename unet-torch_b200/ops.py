@@ -267,6 +267,14 @@ def bn_finalize(sums_f64, count, gamma, beta, eps, momentum, running_mean, runni
               _ptr(running_mean), _ptr(running_var), _f32(mean), _f32(rstd), _f32(scale), _f32(shift), c, _stream())
 
 
+def bn_reduce_finalize(stats_partial, rows, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked,
+                       mean, rstd, scale, shift):
+    """bn_reduce_partials + bn_finalize + `num_batches_tracked += 1` in one launch (single-GPU forward)."""
+    _lib.call("b200unet_bn_reduce_finalize", _f32(stats_partial), rows, gamma.numel(), float(count), _f32(gamma), _f32(beta),
+              eps, momentum, _ptr(running_mean), _ptr(running_var), _ptr(num_batches_tracked), _f32(mean), _f32(rstd),
+              _f32(scale), _f32(shift), _stream())
+
+
 def bn_eval_affine(gamma, beta, running_mean, running_var, eps, scale, shift):
     _lib.call("b200unet_bn_eval_affine", _f32(gamma), _f32(beta), _f32(running_mean), _f32(running_var), eps,
               _f32(scale), _f32(shift), gamma.numel(), _stream())

@@ -18,6 +18,25 @@ import torch
 from . import _lib
 
 
+def _launch_weights(entry, kind, items, hyper, stream):
+    """One launch for all conv3x3 (kind "conv3") or ConvTranspose2d (kind "convt") weights: update + both bf16 operands.
+    items: (param, grad, buf1_ptr, buf2_ptr or None, w_fprop, w_dgrad, holder)."""
+    n = len(items)
+    PtrArr, IntArr = ctypes.c_void_p * n, ctypes.c_int * n
+    args = [0 if kind == "conv3" else 1,
+            PtrArr(*[it[0].data_ptr() for it in items]), PtrArr(*[it[1].data_ptr() for it in items]),
+            PtrArr(*[it[2] for it in items]) if items[0][2] is not None else None]
+    if entry == "b200unet_adam_weights":
+        args.append(PtrArr(*[it[3] for it in items]))
+    args += [PtrArr(*[it[4].data_ptr() for it in items]), PtrArr(*[it[5].data_ptr() for it in items]),
+             IntArr(*[it[0].shape[0] for it in items]), IntArr(*[it[0].shape[1] for it in items]), n, *hyper, stream]
+    _lib.call(entry, *args)
+    for it in items:
+        p, holder = it[0], it[6]
+        torch.autograd.graph.increment_version(p)
+        holder._ver = (p._version, p.data_ptr())  # operands are current: no lazy re-cast
+
+
 class FusedSGD(torch.optim.Optimizer):
     def __init__(self, net, lr=1e-3, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False):
         from .model import UNet
@@ -56,6 +75,7 @@ class FusedSGD(torch.optim.Optimizer):
             lr, mom, damp = float(group["lr"]), float(group["momentum"]), float(group["dampening"])
             wd, nest = float(group["weight_decay"]), int(bool(group["nesterov"]))
             small = {True: [], False: []}  # keyed by first_step
+            bigs = {}                      # (kind, first_step) -> conv / convT weights, ONE launch per key
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -75,18 +95,11 @@ class FusedSGD(torch.optim.Optimizer):
                 if p in big:
                     holder, kind = big[p]
                     wf, wd_op = holder.operands()  # allocates the operand tensors on first use
-                    if kind == "conv3":
-                        k, c = p.shape[0], p.shape[1]
-                        _lib.call("b200unet_sgd_conv3x3_weight", p.data_ptr(), g.data_ptr(), buf_ptr, wf.data_ptr(),
-                                  wd_op.data_ptr(), k, c, lr, mom, damp, wd, nest, first, stream)
-                    else:
-                        cin, cup = p.shape[0], p.shape[1]
-                        _lib.call("b200unet_sgd_convt2x2_weight", p.data_ptr(), g.data_ptr(), buf_ptr, wf.data_ptr(),
-                                  wd_op.data_ptr(), cin, cup, lr, mom, damp, wd, nest, first, stream)
-                    torch.autograd.graph.increment_version(p)
-                    holder._ver = (p._version, p.data_ptr())  # operands are current: no lazy re-cast
+                    bigs.setdefault((kind, first), []).append((p, g, buf_ptr, None, wf, wd_op, holder))
                 else:
                     small[bool(first)].append((p, g, buf_ptr))
+            for (kind, first), items in bigs.items():
+                _launch_weights("b200unet_sgd_weights", kind, items, (lr, mom, damp, wd, nest, int(first)), stream)
             for first, items in small.items():
                 if not items:
                     continue
@@ -130,6 +143,7 @@ class FusedAdam(FusedSGD):
         for group in self.param_groups:
             lr, (b1, b2), eps, wd = float(group["lr"]), group["betas"], float(group["eps"]), float(group["weight_decay"])
             small = {}  # (step_size, inv_sqrt_bc2, first) -> items: parameters of one group normally share their step count
+            bigs = {}   # (kind, step_size, inv_sqrt_bc2, first) -> conv / convT weights, ONE launch per key
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -153,13 +167,11 @@ class FusedAdam(FusedSGD):
                 if p in big:
                     holder, kind = big[p]
                     wf, wd_op = holder.operands()
-                    name = "b200unet_adam_conv3x3_weight" if kind == "conv3" else "b200unet_adam_convt2x2_weight"
-                    _lib.call(name, p.data_ptr(), g.data_ptr(), m_ptr, v_ptr, wf.data_ptr(), wd_op.data_ptr(), p.shape[0],
-                              p.shape[1], b1, b2, eps, wd, step_size, inv_sqrt_bc2, first, stream)
-                    torch.autograd.graph.increment_version(p)
-                    holder._ver = (p._version, p.data_ptr())
+                    bigs.setdefault((kind, step_size, inv_sqrt_bc2, first), []).append((p, g, m_ptr, v_ptr, wf, wd_op, holder))
                 else:
                     small.setdefault((step_size, inv_sqrt_bc2, first), []).append((p, g, m_ptr, v_ptr))
+            for (kind, step_size, inv_sqrt_bc2, first), items in bigs.items():
+                _launch_weights("b200unet_adam_weights", kind, items, (b1, b2, eps, wd, step_size, inv_sqrt_bc2, int(first)), stream)
             for (step_size, inv_sqrt_bc2, first), items in small.items():
                 n = len(items)
                 PtrArr, IntArr = ctypes.c_void_p * n, ctypes.c_int * n
