@@ -37,13 +37,16 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   }
 }
 
-// z[j] (j < ncls) of pixel p0 + lane (rows >= P are read as zero: callers do not store them). The whole warp must call.
-__device__ __forceinline__ void logits_warp32(const __nv_bfloat16* __restrict__ a, int a_cs, const float* wsm,
-                                              uint32_t* stage, const float* __restrict__ bias, long long p0, long long P,
-                                              int Cin, int ncls, float (&z)[MAXC]) {
+// z[j] (j < NCLS) of pixel p0 + lane (rows >= P are read as zero: callers do not store them). The whole warp must call.
+// Compiled per class count: with a run-time count the 64 x ncls FMAs per pixel carry predicates and the kernels were
+// issue-bound at 35-45 % of the HBM rate.
+template <int NCLS>
+__device__ __forceinline__ void logits_warp32_n(const __nv_bfloat16* __restrict__ a, int a_cs, const float* wsm,
+                                                uint32_t* stage, const float* __restrict__ bias, long long p0, long long P,
+                                                int Cin, float (&z)[MAXC]) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int j = 0; j < MAXC; ++j) z[j] = (j < ncls) ? __ldg(bias + j) : 0.f;
+  for (int j = 0; j < MAXC; ++j) z[j] = (j < NCLS) ? __ldg(bias + j) : 0.f;
   for (int c0 = 0; c0 < Cin; c0 += 64) {
     uint4 v[8];
 #pragma unroll
@@ -64,8 +67,8 @@ __device__ __forceinline__ void logits_warp32(const __nv_bfloat16* __restrict__ 
       float f[8];
       unpack8(*reinterpret_cast<const uint4*>(stage + lane * ROW_WORDS + c8 * 4), f);
 #pragma unroll
-      for (int j = 0; j < MAXC; ++j) {
-        if (j < ncls) {
+      for (int j = 0; j < NCLS; ++j) {
+        {
           // 128-bit broadcast reads (Cin % 64 == 0 keeps every row 16-byte aligned): the scalar form issues 64 x ncls
           // shared-memory loads per pixel and is bound by the load/store pipe, not by HBM
           const float4 w0 = *reinterpret_cast<const float4*>(wsm + j * Cin + c0 + c8 * 8);
@@ -85,6 +88,22 @@ __device__ __forceinline__ void logits_warp32(const __nv_bfloat16* __restrict__ 
     }
   }
   __syncwarp();
+}
+
+// run-time class count -> the compiled instance (warp-uniform switch, once per 32 pixels)
+__device__ __forceinline__ void logits_warp32(const __nv_bfloat16* __restrict__ a, int a_cs, const float* wsm,
+                                              uint32_t* stage, const float* __restrict__ bias, long long p0, long long P,
+                                              int Cin, int ncls, float (&z)[MAXC]) {
+  switch (ncls) {
+    case 1: logits_warp32_n<1>(a, a_cs, wsm, stage, bias, p0, P, Cin, z); break;
+    case 2: logits_warp32_n<2>(a, a_cs, wsm, stage, bias, p0, P, Cin, z); break;
+    case 3: logits_warp32_n<3>(a, a_cs, wsm, stage, bias, p0, P, Cin, z); break;
+    case 4: logits_warp32_n<4>(a, a_cs, wsm, stage, bias, p0, P, Cin, z); break;
+    case 5: logits_warp32_n<5>(a, a_cs, wsm, stage, bias, p0, P, Cin, z); break;
+    case 6: logits_warp32_n<6>(a, a_cs, wsm, stage, bias, p0, P, Cin, z); break;
+    case 7: logits_warp32_n<7>(a, a_cs, wsm, stage, bias, p0, P, Cin, z); break;
+    default: logits_warp32_n<8>(a, a_cs, wsm, stage, bias, p0, P, Cin, z); break;
+  }
 }
 
 }  // namespace b2head

@@ -58,40 +58,99 @@ __device__ __forceinline__ void softmax_px(const float* __restrict__ z, long lon
   for (int j = 0; j < MAXC; ++j)
     if (j < ncls) p[j] = p[j] / sum;
   lse = logf(sum);
-  // keep raw logits reachable through p/m/lse only; callers that need z[target] reload it
 }
 
+// The training-loss kernels are compiled per class count (all loops over classes unroll, no run-time predicates) and walk
+// V = 4 consecutive pixels of one image per thread with 128-bit loads / stores (V = 1 when H*W is not a multiple of 4):
+// the run-time-ncls scalar version spent 130 us on 50 MB (instruction-bound); same per-pixel arithmetic, so same bits.
+template <int NCLS>
+__device__ __forceinline__ void softmax_n(const float (&zz)[NCLS], float (&p)[NCLS], float& m, float& lse) {
+  m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NCLS; ++j) m = fmaxf(m, zz[j]);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NCLS; ++j) {
+    p[j] = expf(zz[j] - m);
+    sum += p[j];
+  }
+#pragma unroll
+  for (int j = 0; j < NCLS; ++j) p[j] = p[j] / sum;
+  lse = logf(sum);
+}
+
+template <int V>
+__device__ __forceinline__ void load_v(const float* __restrict__ src, float (&dst)[V]) {
+  if (V == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[V - 1] = t.w;
+  } else {
+    dst[0] = __ldg(src);
+  }
+}
+
+template <int NCLS, int V>
 __global__ void __launch_bounds__(LOSS_THREADS) ce_dice_fwd_kernel(const float* __restrict__ z,
                                                                    const float* __restrict__ target,
                                                                    double* __restrict__ sums, int* __restrict__ err,
-                                                                   long long P, long long HW, int ncls) {
-  float acc[1 + 3 * MAXC];
+                                                                   long long groups, long long HW) {
+  constexpr int NA = 1 + 3 * NCLS;
+  float acc[NA];
 #pragma unroll
-  for (int i = 0; i < 1 + 3 * MAXC; ++i) acc[i] = 0.f;
-  for (long long px = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; px < P;
-       px += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = px / HW, hw = px - n * HW;
-    const long long base = n * ncls * HW + hw;
-    float p[MAXC], m, lse;
-    softmax_px(z, base, HW, ncls, p, m, lse);
-    const float t = __ldg(target + px);
-    const long long ti = static_cast<long long>(t);  // .long(): truncation toward zero
-    if (ti < 0 || ti >= ncls) {
-      *err = 1;
-    } else {
-      const float zt = __ldg(z + base + ti * HW);
-      acc[0] += -(zt - m - lse);
-    }
+  for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+  const long long HWv = HW / V;
+  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups;
+       g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = g / HWv, hw = (g - n * HWv) * V;
+    const long long base = n * NCLS * HW + hw;
+    float zz[NCLS][V], tt[V];
 #pragma unroll
-    for (int j = 0; j < MAXC; ++j)
-      if (j < ncls) {
+    for (int j = 0; j < NCLS; ++j) load_v<V>(z + base + j * HW, zz[j]);
+    load_v<V>(target + n * HW + hw, tt);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float zp[NCLS], p[NCLS], m, lse;
+#pragma unroll
+      for (int j = 0; j < NCLS; ++j) zp[j] = zz[j][v];
+      softmax_n<NCLS>(zp, p, m, lse);
+      const float t = tt[v];
+      const long long ti = static_cast<long long>(t);  // .long(): truncation toward zero
+      if (ti < 0 || ti >= NCLS) {
+        *err = 1;
+      } else {
+        float zt = zp[0];
+#pragma unroll
+        for (int j = 1; j < NCLS; ++j) zt = (ti == j) ? zp[j] : zt;
+        acc[0] += -(zt - m - lse);
+      }
+#pragma unroll
+      for (int j = 0; j < NCLS; ++j) {
         const float oh = (t == static_cast<float>(j)) ? 1.f : 0.f;  // _one_hot_encoder: target == j
         acc[1 + j] = fmaf(p[j], oh, acc[1 + j]);
-        acc[1 + MAXC + j] = fmaf(p[j], p[j], acc[1 + MAXC + j]);
-        acc[1 + 2 * MAXC + j] += oh;
+        acc[1 + NCLS + j] = fmaf(p[j], p[j], acc[1 + NCLS + j]);
+        acc[1 + 2 * NCLS + j] += oh;
       }
+    }
   }
-  block_reduce_atomic<1 + 3 * MAXC>(acc, 1 + 3 * MAXC, sums);
+  // block reduction; slot of accumulator i in the MAXC-strided sums layout [CE, I[MAXC], Z[MAXC], Y[MAXC]]
+  __shared__ float sh[LOSS_THREADS / 32][NA];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    float x = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sh[warp][i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NA) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < LOSS_THREADS / 32; ++w) t += static_cast<double>(sh[w][threadIdx.x]);
+    const int i = threadIdx.x;
+    const int slot = i == 0 ? 0 : 1 + ((i - 1) / NCLS) * MAXC + (i - 1) % NCLS;
+    atomicAdd(sums + slot * SUM_STRIDE, t);
+  }
 }
 
 // sums layout inside the kernels: [CE, I[MAXC], Z[MAXC], Y[MAXC]] (fixed MAXC stride)
@@ -115,50 +174,62 @@ __global__ void ce_dice_finalize_kernel(const double* __restrict__ sums, float* 
   loss_out[0] = (mode == 0) ? 0.5f * static_cast<float>(ce) + 0.5f * static_cast<float>(dice) : static_cast<float>(ce);
 }
 
+template <int NCLS, int V>
 __global__ void __launch_bounds__(LOSS_THREADS) ce_dice_bwd_kernel(const float* __restrict__ z,
                                                                    const float* __restrict__ target,
                                                                    const double* __restrict__ sums,
                                                                    const float* __restrict__ grad_out,
-                                                                   float* __restrict__ dz, long long P, long long HW,
-                                                                   int ncls, int mode) {
+                                                                   float* __restrict__ dz, long long groups, long long HW,
+                                                                   long long P, int mode) {
   const float go = grad_out[0];
   const float w_ce = (mode == 0 ? 0.5f : 1.f) / static_cast<float>(P);
   const float w_dice = (mode == 0) ? 0.5f : 0.f;
-  float cN[MAXC], cD[MAXC];  // g_j = a_j * t_j + b_j * p_j,  a_j = -(2/C)/D_j,  b_j = (2/C) N_j / D_j^2
+  float cN[NCLS], cD[NCLS];  // g_j = a_j * t_j + b_j * p_j,  a_j = -(2/C)/D_j,  b_j = (2/C) N_j / D_j^2
 #pragma unroll
-  for (int j = 0; j < MAXC; ++j) {
-    cN[j] = 0.f;
-    cD[j] = 0.f;
-    if (j < ncls) {
-      const double N = 2.0 * sums[(1 + j) * SUM_STRIDE] + 1e-5;
-      const double D = sums[(1 + MAXC + j) * SUM_STRIDE] + sums[(1 + 2 * MAXC + j) * SUM_STRIDE] + 1e-5;
-      cN[j] = static_cast<float>(-(2.0 / ncls) / D);
-      cD[j] = static_cast<float>((2.0 / ncls) * N / (D * D));
-    }
+  for (int j = 0; j < NCLS; ++j) {
+    const double N = 2.0 * sums[(1 + j) * SUM_STRIDE] + 1e-5;
+    const double D = sums[(1 + MAXC + j) * SUM_STRIDE] + sums[(1 + 2 * MAXC + j) * SUM_STRIDE] + 1e-5;
+    cN[j] = static_cast<float>(-(2.0 / NCLS) / D);
+    cD[j] = static_cast<float>((2.0 / NCLS) * N / (D * D));
   }
-  for (long long px = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; px < P;
-       px += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = px / HW, hw = px - n * HW;
-    const long long base = n * ncls * HW + hw;
-    float p[MAXC], m, lse;
-    softmax_px(z, base, HW, ncls, p, m, lse);
-    const float t = __ldg(target + px);
-    const long long ti = static_cast<long long>(t);
-    float g[MAXC], dot = 0.f;
+  const long long HWv = HW / V;
+  for (long long gi = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; gi < groups;
+       gi += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = gi / HWv, hw = (gi - n * HWv) * V;
+    const long long base = n * NCLS * HW + hw;
+    float zz[NCLS][V], tt[V], out[NCLS][V];
 #pragma unroll
-    for (int j = 0; j < MAXC; ++j)
-      if (j < ncls) {
+    for (int j = 0; j < NCLS; ++j) load_v<V>(z + base + j * HW, zz[j]);
+    load_v<V>(target + n * HW + hw, tt);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float zp[NCLS], p[NCLS], m, lse;
+#pragma unroll
+      for (int j = 0; j < NCLS; ++j) zp[j] = zz[j][v];
+      softmax_n<NCLS>(zp, p, m, lse);
+      const float t = tt[v];
+      const long long ti = static_cast<long long>(t);
+      float g[NCLS], dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < NCLS; ++j) {
         const float oh = (t == static_cast<float>(j)) ? 1.f : 0.f;
         g[j] = cN[j] * oh + cD[j] * p[j];
         dot = fmaf(p[j], g[j], dot);
       }
 #pragma unroll
-    for (int j = 0; j < MAXC; ++j)
-      if (j < ncls) {
+      for (int j = 0; j < NCLS; ++j) {
         const float tce = (ti == j) ? 1.f : 0.f;
         const float d = w_ce * (p[j] - tce) + w_dice * p[j] * (g[j] - dot);
-        dz[base + j * HW] = go * d;
+        out[j][v] = go * d;
       }
+    }
+#pragma unroll
+    for (int j = 0; j < NCLS; ++j) {
+      if (V == 4)
+        *reinterpret_cast<float4*>(dz + base + j * HW) = make_float4(out[j][0], out[j][1], out[j][2], out[j][V - 1]);
+      else
+        dz[base + j * HW] = out[j][0];
+    }
   }
 }
 
@@ -236,7 +307,17 @@ int b200unet_loss_ce_dice_fwd(const float* logits, const float* target, double* 
   const long long P = static_cast<long long>(N) * HW;
   cudaMemsetAsync(sums, 0, sizeof(double) * SUM_SLOTS * SUM_STRIDE, st);
   cudaMemsetAsync(err_flag, 0, sizeof(int), st);
-  ce_dice_fwd_kernel<<<loss_blocks(P), LOSS_THREADS, 0, st>>>(logits, target, sums, err_flag, P, HW, ncls);
+  const bool vec = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(logits) % 16 == 0) && (reinterpret_cast<uintptr_t>(target) % 16 == 0);
+  const long long groups = vec ? P / 4 : P;
+#define B2_CE_FWD(NC)                                                                                                  \
+  case NC:                                                                                                            \
+    if (vec)                                                                                                          \
+      ce_dice_fwd_kernel<NC, 4><<<loss_blocks(groups), LOSS_THREADS, 0, st>>>(logits, target, sums, err_flag, groups, HW); \
+    else                                                                                                              \
+      ce_dice_fwd_kernel<NC, 1><<<loss_blocks(groups), LOSS_THREADS, 0, st>>>(logits, target, sums, err_flag, groups, HW); \
+    break;
+  switch (ncls) { B2_CE_FWD(1) B2_CE_FWD(2) B2_CE_FWD(3) B2_CE_FWD(4) B2_CE_FWD(5) B2_CE_FWD(6) B2_CE_FWD(7) B2_CE_FWD(8) }
+#undef B2_CE_FWD
   if (int e = b2h::check_launch("loss_ce_dice_fwd")) return e;
   ce_dice_finalize_kernel<<<1, 32, 0, st>>>(sums, loss_out, static_cast<double>(P), ncls, mode);
   return b2h::check_launch("loss_ce_dice_finalize");
@@ -246,8 +327,21 @@ int b200unet_loss_ce_dice_bwd(const float* logits, const float* target, const do
                               float* dlogits, int N, int ncls, int64_t HW, int mode, b200_stream_t stream) {
   B2_REQUIRE(ncls >= 1 && ncls <= MAXC, "loss_ce_dice_bwd: n_classes=%d must be in [1,%d]", ncls, MAXC);
   const long long P = static_cast<long long>(N) * HW;
-  ce_dice_bwd_kernel<<<loss_blocks(P), LOSS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, target, sums, grad_out, dlogits, P, HW, ncls, mode);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(logits) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(target) % 16 == 0) && (reinterpret_cast<uintptr_t>(dlogits) % 16 == 0);
+  const long long groups = vec ? P / 4 : P;
+#define B2_CE_BWD(NC)                                                                                                   \
+  case NC:                                                                                                             \
+    if (vec)                                                                                                           \
+      ce_dice_bwd_kernel<NC, 4><<<loss_blocks(groups), LOSS_THREADS, 0, st>>>(logits, target, sums, grad_out, dlogits,   \
+                                                                              groups, HW, P, mode);                    \
+    else                                                                                                               \
+      ce_dice_bwd_kernel<NC, 1><<<loss_blocks(groups), LOSS_THREADS, 0, st>>>(logits, target, sums, grad_out, dlogits,   \
+                                                                              groups, HW, P, mode);                    \
+    break;
+  switch (ncls) { B2_CE_BWD(1) B2_CE_BWD(2) B2_CE_BWD(3) B2_CE_BWD(4) B2_CE_BWD(5) B2_CE_BWD(6) B2_CE_BWD(7) B2_CE_BWD(8) }
+#undef B2_CE_BWD
   return b2h::check_launch("loss_ce_dice_bwd");
 }
 
