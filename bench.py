@@ -269,7 +269,7 @@ def run_ours(args):
         raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     dist_on = world > 1
-    dp = U.init_from_env(sync_bn=True) if dist_on else None
+    dp = U.init_from_env(sync_bn=True, graphs=not args.no_graphs) if dist_on else None
     if dist_on and not train:
         U.DataParallelContext.disable()  # inference: replicas only, no data-path collective (process group kept for timing)
         dp = None

@@ -156,6 +156,12 @@ int b200unet_bn_relu_fwd(const void* y, int y_cs, const float* scale, const floa
  * pooled-only); g_pool/pool_idx = gradient w.r.t. the pooled tensor (NULL if the layer is not pooled).
  * Pass 1 (reduce): per-block partial sums of da and da*xhat where da = (g1 + unpool(g_pool)) * [a > 0]. */
 int64_t b200unet_bn_bwd_workspace_floats(int N, int H, int W, int C);
+/* (b200unet_bn_relu_bwd_reduce_rows: pass 1 only - leaves the block partials [*rows_out][2][C] in `partial` for a fused
+ * cross-rank reduction, b200unet_nvl_rows_allreduce) */
+int b200unet_bn_relu_bwd_reduce_rows(const void* g1, int g1_cs, const void* g_pool, const uint8_t* pool_idx, const void* y,
+                                     int y_cs, const float* scale, const float* shift, const float* mean,
+                                     const float* rstd, float* partial, int* rows_out, int N, int H, int W, int C,
+                                     b200_stream_t stream);
 int b200unet_bn_relu_bwd_reduce(const void* g1, int g1_cs, const void* g_pool, const uint8_t* pool_idx,
                                 const void* y, int y_cs, const float* scale, const float* shift, const float* mean,
                                 const float* rstd, float* partial, double* sums, int N, int H, int W, int C,
@@ -245,7 +251,18 @@ int b200unet_nvl_bn_sync_finalize(const double* local_sums, double* global_sums,
                                   int rank, int64_t seq, double global_count, const float* gamma, const float* beta,
                                   float eps, float momentum, float* running_mean, float* running_var, float* mean,
                                   float* rstd, float* scale, float* shift, int C, b200_stream_t stream);
-/* Bound on the wait for a peer inside the two kernels above (default 600 000 ms, like NCCL's watchdog; 0 = wait forever).
+/* The fast path of both: take the UNREDUCED partial rows [rows][2][C] (conv epilogue statistics, or the block partials of
+ * b200unet_bn_relu_bwd_reduce_rows), reduce them, exchange them over NVLink and (forward) finalise BatchNorm in ONE
+ * multi-block kernel (one block per 32 channels, each with its own device-side sequence counter: graph-replayable).
+ * C <= 2048. sums_local / sums_global: fp64 [2C] each, either may be NULL. */
+int b200unet_nvl_rows_allreduce(const float* partial, int64_t rows, int C, void* const* peer_bufs, int world, int rank,
+                                double* sums_local, double* sums_global, b200_stream_t stream);
+int b200unet_nvl_bn_rows_sync_finalize(const float* stats_partial, int64_t rows, int C, void* const* peer_bufs, int world,
+                                       int rank, double global_count, const float* gamma, const float* beta, float eps,
+                                       float momentum, float* running_mean, float* running_var,
+                                       int64_t* num_batches_tracked, float* mean, float* rstd, float* scale, float* shift,
+                                       b200_stream_t stream);
+/* Bound on the wait for a peer inside the kernels above (default 600 000 ms, like NCCL's watchdog; 0 = wait forever).
  * On expiry the kernel records the failure in its own buffer, writes NaN to its outputs and returns - it does not trap. */
 int b200unet_nvl_set_timeout_ms(int64_t ms);
 /* Host read (synchronises `stream`) of this rank's buffer: out3 = {reductions issued through the device-side counter,

@@ -3,6 +3,7 @@ caches, real clocks - unlike ncu's serialised replays) and the IDLE time between
 named. Answers "where does measured step time - summed kernel time go".
 
     GRAPHS=1 python scripts/timeline.py > gpurun_out/timeline.txt
+    torchrun --nproc-per-node N scripts/timeline.py     # data parallel + SyncBN: rank 0's timeline (all streams)
 """
 import os
 import sys
@@ -16,6 +17,13 @@ B = int(os.environ.get("B", 16))
 S = int(os.environ.get("S", 512))
 GRAPHS = os.environ.get("GRAPHS", "1") != "0"
 NSTEP = 3
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+if WORLD > 1:
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    U.init_from_env(sync_bn=True)
+    if RANK != 0:
+        sys.stdout = open(os.devnull, "w")
 torch.manual_seed(0)
 net = U.UNet(3, 2).cuda().train()
 U.loss.CLASS_NUMBER = 2
@@ -85,5 +93,25 @@ for k, v in sorted(bucket.items(), key=lambda kv: -kv[1])[:20]:
     print(f"  {v / NSTEP:8.1f}  {k}")
 tot = sum(v[1] for v in rows.values())
 print(f"summed device time {tot / NSTEP / 1e3:.3f} ms/step")
+comm = {k: v for k, v in rows.items() if "nccl" in k.lower() or "nvl_" in k.lower()}
+if comm:
+    print("communication kernels (rank 0): " + "; ".join(f"{k[:50]} x{v[0] // NSTEP} {v[1] / NSTEP / 1e3:.3f} ms/step" for k, v in comm.items()))
 for name, (cnt, t) in sorted(rows.items(), key=lambda kv: -kv[1][1])[:45]:
     print(f"{t / NSTEP / 1e3:9.3f} ms/step {100 * t / tot:5.1f}%  x{cnt // NSTEP:4d}  {name[:120]}")
+
+if WORLD > 1:
+    import torch.distributed as dist
+
+    # per-rank split: who waits for whom? A rank that arrives late at a SyncBN exchange spends ~no time in nvl_*; the others
+    # spend their lead there. compute = everything except the exchange / NCCL kernels.
+    mine = {"rank": RANK, "span_ms": span / 1e3, "busy_ms": busy / 1e3,
+            "nvl_ms": sum(v[1] for k, v in rows.items() if "nvl_" in k) / NSTEP / 1e3,
+            "nccl_ms": sum(v[1] for k, v in rows.items() if "nccldevkernel" in k.lower()) / NSTEP / 1e3,
+            "compute_ms": sum(v[1] for k, v in rows.items() if "nvl_" not in k and "nccl" not in k.lower()) / NSTEP / 1e3}
+    allr = [None] * WORLD
+    dist.all_gather_object(allr, mine)
+    print("per-rank (ms/step): rank span busy compute nvl_exchange nccl")
+    for r in allr:
+        print(f"  {r['rank']}  {r['span_ms']:.3f}  {r['busy_ms']:.3f}  {r['compute_ms']:.3f}  {r['nvl_ms']:.3f}  {r['nccl_ms']:.3f}")
+    U.DataParallelContext.disable()
+    dist.destroy_process_group()

@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200unet_bn_eval_stats": (c_int, [_P, _P, _F, _P, _P, _I, _P]),
     "b200unet_bn_relu_fwd": (c_int, [_P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
     "b200unet_bn_bwd_workspace_floats": (c_int64, [_I, _I, _I, _I]),
+    "b200unet_bn_relu_bwd_reduce_rows": (c_int, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200unet_bn_relu_bwd_reduce": (c_int, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200unet_bn_relu_bwd_apply": (
         c_int,
@@ -104,6 +105,8 @@ SIGNATURES = {
     "b200unet_nvl_buffer_bytes": (c_int64, []),
     "b200unet_nvl_allreduce_f64": (c_int, [_P, _P, _I, _P, _I, _I, _L, _P]),
     "b200unet_nvl_bn_sync_finalize": (c_int, [_P, _P, _P, _I, _I, _L, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "b200unet_nvl_rows_allreduce": (c_int, [_P, _L, _I, _P, _I, _I, _P, _P, _P]),
+    "b200unet_nvl_bn_rows_sync_finalize": (c_int, [_P, _L, _I, _P, _I, _I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200unet_nvl_set_timeout_ms": (c_int, [_L]),
     "b200unet_nvl_status": (c_int, [_P, _P, _P]),
     "b200unet_sgd_conv3x3_weight": (c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _I, _P]),

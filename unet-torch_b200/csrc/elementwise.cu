@@ -662,9 +662,20 @@ int64_t b200unet_bn_bwd_workspace_floats(int N, int H, int W, int C) {
 int b200unet_bn_relu_bwd_reduce(const void* g1, int g1_cs, const void* g_pool, const uint8_t* pool_idx, const void* y,
                                 int y_cs, const float* scale, const float* shift, const float* mean, const float* rstd,
                                 float* partial, double* sums, int N, int H, int W, int C, b200_stream_t stream) {
+  B2_REQUIRE(sums != nullptr, "bn_relu_bwd_reduce: null sums");
+  int rows = 0;
+  if (int e = b200unet_bn_relu_bwd_reduce_rows(g1, g1_cs, g_pool, pool_idx, y, y_cs, scale, shift, mean, rstd, partial, &rows, N,
+                                               H, W, C, stream))
+    return e;
+  return launch_reduce_partials(partial, rows, 2 * C, sums, static_cast<cudaStream_t>(stream));
+}
+
+int b200unet_bn_relu_bwd_reduce_rows(const void* g1, int g1_cs, const void* g_pool, const uint8_t* pool_idx, const void* y,
+                                     int y_cs, const float* scale, const float* shift, const float* mean, const float* rstd,
+                                     float* partial, int* rows_out, int N, int H, int W, int C, b200_stream_t stream) {
   B2_REQUIRE(ok_channels(C), "bn_relu_bwd_reduce: C=%d must be a power of two in [64, 2048]", C);
   B2_REQUIRE(g1 != nullptr || g_pool != nullptr, "bn_relu_bwd_reduce: no gradient source");
-  B2_REQUIRE(y && scale && shift && mean && rstd && partial && sums,
+  B2_REQUIRE(y && scale && shift && mean && rstd && partial && rows_out,
              "bn_relu_bwd_reduce: null argument (eval-mode forwards must save mean/rstd: b200unet_bn_eval_stats)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BwdSrc s{static_cast<const __nv_bfloat16*>(g1), g1_cs, static_cast<const __nv_bfloat16*>(g_pool), pool_idx,
@@ -676,8 +687,8 @@ int b200unet_bn_relu_bwd_reduce(const void* g1, int g1_cs, const void* g_pool, c
     bn_bwd_reduce_kernel<true><<<blocks, EW_THREADS, 0, st>>>(s, scale, shift, mean, rstd, partial, N, H, W, C, ew_rev(1));
   else
     bn_bwd_reduce_kernel<false><<<blocks, EW_THREADS, 0, st>>>(s, scale, shift, mean, rstd, partial, N, H, W, C, ew_rev(1));
-  if (int e = b2h::check_launch("bn_relu_bwd_reduce")) return e;
-  return launch_reduce_partials(partial, blocks, 2 * C, sums, st);
+  *rows_out = blocks;
+  return b2h::check_launch("bn_relu_bwd_reduce");
 }
 
 int b200unet_bn_relu_bwd_apply(const void* g1, int g1_cs, const void* g_pool, const uint8_t* pool_idx, const void* y,

@@ -29,7 +29,15 @@ constexpr int SLOT_DOUBLES = 2048;                                   // 2 * Cmax
 constexpr size_t FLAG_OFFSET = size_t(2) * MAX_WORLD * SLOT_DOUBLES * 8;  // bytes: data region first, then flags
 constexpr size_t COUNTER_OFFSET = FLAG_OFFSET + 2 * MAX_WORLD * 8;  // this rank's own reduction counter (device-side seq)
 constexpr size_t ERROR_OFFSET = COUNTER_OFFSET + 8;  // {failed sequence number, bit mask of ranks that never arrived}
-constexpr size_t BUFFER_BYTES = COUNTER_OFFSET + 64;
+constexpr size_t LEGACY_BYTES = COUNTER_OFFSET + 64;
+// ---- second region: the multi-block "rows" reductions (one block per 32 channels, see nvl_rows_kernel)
+constexpr int ROWS_MAX_BLOCKS = 64;    // 2048 channels / 32
+constexpr int ROWS_BLOCK_DOUBLES = 64;  // {sum, sum of squares} x 32 channels
+constexpr size_t ROWS_DATA_OFFSET = (LEGACY_BYTES + 127) / 128 * 128;
+constexpr size_t ROWS_DATA_BYTES = size_t(2) * MAX_WORLD * ROWS_MAX_BLOCKS * ROWS_BLOCK_DOUBLES * 8;
+constexpr size_t ROWS_FLAG_OFFSET = ROWS_DATA_OFFSET + ROWS_DATA_BYTES;          // [2][MAX_WORLD][ROWS_MAX_BLOCKS] u64
+constexpr size_t ROWS_COUNTER_OFFSET = ROWS_FLAG_OFFSET + size_t(2) * MAX_WORLD * ROWS_MAX_BLOCKS * 8;  // [ROWS_MAX_BLOCKS] u64
+constexpr size_t BUFFER_BYTES = ROWS_COUNTER_OFFSET + ROWS_MAX_BLOCKS * 8;
 unsigned long long g_timeout_ns = 600ull * 1000000000ull;
 
 struct PeerTable {
@@ -157,6 +165,130 @@ __global__ void __launch_bounds__(256) nvl_allreduce_kernel(const double* __rest
   }
 }
 
+// One kernel for "reduce the partial rows of this rank -> exchange with all ranks -> (finalise BatchNorm)":
+//   partial [rows][2][C] fp32 (a conv epilogue's statistics rows, or the block partials of bn_bwd_reduce_kernel).
+// grid = C / 32 blocks of 1024 threads. Block b owns channels [32b, 32b + 32): it reduces its 64 columns over the rows
+// (32 row-lanes, fp64, fixed order), publishes the 64 doubles into slot[seq_b & 1][rank][b] of EVERY rank's buffer, raises
+// flag[slot][rank][b] = seq_b everywhere, waits for all ranks' flags of the same (slot, b), sums the `world` vectors in rank
+// order and writes local / global sums and - forward - the BatchNorm finalisation of its 32 channels. Every block keeps its
+// OWN sequence counter (all ranks issue the same launches with the same grids, so block b's counters agree across ranks), so
+// the launch is graph-replayable and no block waits for another block of its own grid. Compared with reduce_partials + the
+// single-block nvl_allreduce_kernel this removes a launch from the critical path and spreads the work over C/32 SMs
+// (measured at 2 ranks: 36 single-block reductions cost 0.86 ms per step, 24 us each).
+struct RowsArgs {
+  const float* partial;
+  long long rows;
+  int C;
+  double* sums_local;   // [2C] or null
+  double* sums_global;  // [2C] or null
+  long long* num_batches;
+  int finalize;
+};
+
+__global__ void __launch_bounds__(1024) nvl_rows_kernel(RowsArgs a, PeerTable peers, int world, int rank, FinalizeArgs fin,
+                                                        unsigned long long timeout_ns) {
+  __shared__ double sh[2][32][33];
+  __shared__ double tot[ROWS_BLOCK_DOUBLES];
+  __shared__ unsigned long long seq_sh;
+  __shared__ unsigned int missing_sh;
+  const int b = blockIdx.x, C = a.C;
+  const int lane_c = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = b * 32 + lane_c;
+  unsigned char* mine = peers.buf[rank];
+  if (threadIdx.x == 0) {
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(mine + ROWS_COUNTER_OFFSET) + b;
+    seq_sh = *counter + 1;
+    *counter = seq_sh;
+    missing_sh = reinterpret_cast<const unsigned long long*>(mine + ERROR_OFFSET)[0] != 0ull ? 0x80000000u : 0u;
+  }
+  // 1. reduce this rank's rows
+  double a1 = 0.0, a2 = 0.0;
+  if (c < C) {
+#pragma unroll 4
+    for (long long r = rl; r < a.rows; r += 32) {
+      a1 += static_cast<double>(__ldg(a.partial + r * 2 * C + c));
+      a2 += static_cast<double>(__ldg(a.partial + r * 2 * C + C + c));
+    }
+  }
+  sh[0][rl][lane_c] = a1;
+  sh[1][rl][lane_c] = a2;
+  __syncthreads();
+  const unsigned long long seq = seq_sh;
+  const bool already_failed = missing_sh != 0u;
+  const int slot = static_cast<int>(seq & 1ull);
+  const int t = threadIdx.x;  // t < 64: stat = t >> 5, channel lane = t & 31
+  if (t < ROWS_BLOCK_DOUBLES) {
+    double v = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v += sh[t >> 5][i][t & 31];
+    const int cc = b * 32 + (t & 31);
+    if (a.sums_local != nullptr && cc < C) a.sums_local[(t >> 5) * C + cc] = v;
+    // 2. publish to every rank (plain stores to mapped peer memory), then make them visible system-wide
+    const size_t off = ((static_cast<size_t>(slot) * MAX_WORLD + rank) * ROWS_MAX_BLOCKS + b) * ROWS_BLOCK_DOUBLES + t;
+    for (int p = 0; p < world; ++p) reinterpret_cast<double*>(peers.buf[p] + ROWS_DATA_OFFSET)[off] = v;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (t < world)
+    st_release_sys(reinterpret_cast<unsigned long long*>(peers.buf[t] + ROWS_FLAG_OFFSET) +
+                       (static_cast<size_t>(slot) * MAX_WORLD + rank) * ROWS_MAX_BLOCKS + b, seq);
+  // 3. wait for every rank's vector of this (block, sequence number)
+  if (t < world && !already_failed) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + ROWS_FLAG_OFFSET) +
+                                  (static_cast<size_t>(slot) * MAX_WORLD + t) * ROWS_MAX_BLOCKS + b;
+    unsigned long long t0 = 0;
+    unsigned int it = 0;
+    while (ld_acquire_sys(f) != seq) {
+      if ((++it & 0xfffu) == 0 && timeout_ns != 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > timeout_ns) {
+          atomicOr(&missing_sh, 1u << t);
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const bool failed = missing_sh != 0u;
+  if (failed && t == 0) {
+    unsigned long long* err = reinterpret_cast<unsigned long long*>(mine + ERROR_OFFSET);
+    if (atomicCAS(err, 0ull, seq) == 0ull) err[1] = missing_sh;
+  }
+  // 4. sum in rank order (bit-identical on all ranks); NaN after a failure so that it is loud
+  if (t < ROWS_BLOCK_DOUBLES) {
+    double v = 0.0;
+    const double* d = reinterpret_cast<const double*>(mine + ROWS_DATA_OFFSET) +
+                      (static_cast<size_t>(slot) * MAX_WORLD * ROWS_MAX_BLOCKS + b) * ROWS_BLOCK_DOUBLES + t;
+    for (int r = 0; r < world; ++r) v += ld_volatile_f64(d + static_cast<size_t>(r) * ROWS_MAX_BLOCKS * ROWS_BLOCK_DOUBLES);
+    if (failed) v = __longlong_as_double(0x7ff8000000000000ll);
+    tot[t] = v;
+    const int cc = b * 32 + (t & 31);
+    if (a.sums_global != nullptr && cc < C) a.sums_global[(t >> 5) * C + cc] = v;
+  }
+  if (!a.finalize) return;
+  __syncthreads();
+  if (b == 0 && t == 0 && a.num_batches != nullptr) *a.num_batches += 1;
+  if (t < 32 && c < C) {
+    const double m = tot[t] / fin.count;
+    double var = tot[32 + t] / fin.count - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mf = static_cast<float>(m);
+    const float rs = static_cast<float>(1.0 / sqrt(var + static_cast<double>(fin.eps)));
+    fin.mean[c] = mf;
+    fin.rstd[c] = rs;
+    const float sc = fin.gamma[c] * rs;
+    fin.scale[c] = sc;
+    fin.shift[c] = fin.beta[c] - mf * sc;
+    if (fin.running_mean != nullptr) {
+      const double unbiased = fin.count > 1.0 ? var * fin.count / (fin.count - 1.0) : var;
+      fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * mf;
+      fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * static_cast<float>(unbiased);
+    }
+  }
+}
+
 int fill_table(PeerTable* t, void* const* peer_bufs, int world, int rank, int n) {
   if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) {
     b2h::set_error("nvl: world %d / rank %d out of range (max %d ranks)", world, rank, MAX_WORLD);
@@ -204,6 +336,32 @@ int b200unet_nvl_bn_sync_finalize(const double* local_sums, double* global_sums,
   nvl_allreduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(local_sums, global_sums, 2 * C, t, world, rank,
                                                                         static_cast<unsigned long long>(seq), fin, g_timeout_ns);
   return b2h::check_launch("nvl_bn_sync_finalize");
+}
+
+int b200unet_nvl_rows_allreduce(const float* partial, int64_t rows, int C, void* const* peer_bufs, int world, int rank,
+                                double* sums_local, double* sums_global, b200_stream_t stream) {
+  PeerTable t;
+  if (int e = fill_table(&t, peer_bufs, world, rank, 2)) return e;
+  B2_REQUIRE(partial != nullptr && rows > 0 && C > 0 && C <= 32 * ROWS_MAX_BLOCKS, "nvl_rows_allreduce: C=%d out of range (max %d)",
+             C, 32 * ROWS_MAX_BLOCKS);
+  RowsArgs a{partial, rows, C, sums_local, sums_global, nullptr, 0};
+  FinalizeArgs fin{};
+  nvl_rows_kernel<<<(C + 31) / 32, 1024, 0, static_cast<cudaStream_t>(stream)>>>(a, t, world, rank, fin, g_timeout_ns);
+  return b2h::check_launch("nvl_rows_allreduce");
+}
+
+int b200unet_nvl_bn_rows_sync_finalize(const float* stats_partial, int64_t rows, int C, void* const* peer_bufs, int world,
+                                       int rank, double global_count, const float* gamma, const float* beta, float eps,
+                                       float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                       float* mean, float* rstd, float* scale, float* shift, b200_stream_t stream) {
+  PeerTable t;
+  if (int e = fill_table(&t, peer_bufs, world, rank, 2)) return e;
+  B2_REQUIRE(stats_partial && gamma && beta && mean && rstd && scale && shift && rows > 0 && C > 0 && C <= 32 * ROWS_MAX_BLOCKS &&
+                 global_count > 0, "nvl_bn_rows_sync_finalize: bad arguments (C=%d, max %d)", C, 32 * ROWS_MAX_BLOCKS);
+  RowsArgs a{stats_partial, rows, C, nullptr, nullptr, reinterpret_cast<long long*>(num_batches_tracked), 1};
+  FinalizeArgs fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, global_count, eps, momentum, C};
+  nvl_rows_kernel<<<(C + 31) / 32, 1024, 0, static_cast<cudaStream_t>(stream)>>>(a, t, world, rank, fin, g_timeout_ns);
+  return b2h::check_launch("nvl_bn_rows_sync_finalize");
 }
 
 int b200unet_nvl_set_timeout_ms(int64_t ms) {

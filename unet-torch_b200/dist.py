@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 
 class FlatGrads:
-    def __init__(self, ctx: "DataParallelContext", params):
+    def __init__(self, ctx: "DataParallelContext", params, flat=None):
         self.ctx = ctx
         self.params = list(params)
         self.offsets = {}
@@ -30,7 +30,9 @@ class FlatGrads:
             self.offsets[p] = total
             total += (p.numel() + 63) // 64 * 64  # keep every view 256-byte aligned
         dev = self.params[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        # `flat`: the buffer of an earlier backward over the same parameters (every element that is read is rewritten by
+        # each backward; the alignment padding was zeroed once) - no 124 MB allocation + memset per step
+        self.flat = flat if flat is not None else torch.zeros(total, dtype=torch.float32, device=dev)
         self.total = total
         # buckets: contiguous ranges in backward order, closed when >= bucket_bytes
         self.buckets = []
@@ -81,7 +83,7 @@ class DataParallelContext:
 
     _current = None
 
-    def __init__(self, sync_bn=True, bucket_mb=25.0, group=None):
+    def __init__(self, sync_bn=True, bucket_mb=25.0, group=None, graphs=None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = group
@@ -90,14 +92,20 @@ class DataParallelContext:
         self.sync_bn = sync_bn and self.world_size > 1
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
-        # B200UNET_DP_GRAPHS=1: CUDA-graph replay of the data-parallel step (the NVLink SyncBN kernels and the NCCL gradient
-        # all-reduces are captured with the compute kernels). Opt-in: validated on 2 B200 (replay == eager launches bit
-        # for bit, tests/dp_worker.py; 23.65 vs 23.75 ms/step), not yet at 8 ranks. Needs the NVLink SyncBN path (the
-        # NCCL fallback would put 36 tiny collectives per step into the graph) - decided after _setup_nvl below.
+        # graphs=True / B200UNET_DP_GRAPHS=1: net.enable_cuda_graphs() may replay the data-parallel step as CUDA graphs (the
+        # NVLink SyncBN kernels and the NCCL gradient all-reduces are captured with the compute kernels). Opt-in: replay ==
+        # eager launches bit for bit on 2 B200 (tests/dp_worker.py); measured on 8 B200: 5431 -> 5448 img/s device-resident,
+        # 5272 -> 5347 img/s end to end. Graphs holding NCCL kernels must be dropped before destroy_process_group()
+        # (DataParallelContext.disable()). Needs the NVLink SyncBN path (the NCCL fallback would put 36 tiny collectives
+        # per step into the graph) - decided after _setup_nvl below.
+        env = os.environ.get("B200UNET_DP_GRAPHS", "")
         self._want_graphs = (torch.cuda.is_available() and dist.get_backend() == "nccl"
-                             and os.environ.get("B200UNET_DP_GRAPHS", "0") not in ("", "0"))
+                             and (env not in ("", "0") if env != "" else bool(graphs)))
         self.graph_capturable = False
         self._graph_owners = weakref.WeakSet()  # engines holding graphs captured under this context
+        self._flat_cache = {}                   # parameter-id tuple -> flat gradient buffer of the last backward
+        # NCCL averages in the collective itself (ReduceOp.AVG); gloo (CPU tests) sums and scales afterwards
+        self._nccl = dist.get_backend(group) == "nccl"
         self.extra_wait_streams = []  # streams (besides the current one) whose work a gradient bucket depends on
         # SyncBN statistics over NVLink peer memory (csrc/nvl_sync.cu): symmetric buffer + peer pointer table
         self._nvl = None
@@ -184,6 +192,27 @@ class DataParallelContext:
                   bn.running_var.data_ptr() if track else None, mean.data_ptr(), rstd.data_ptr(), scale.data_ptr(),
                   shift.data_ptr(), c, torch.cuda.current_stream().cuda_stream)
 
+    def bn_rows_sync_finalize(self, stats_partial, rows, global_count, bn, eps, momentum, track, mean, rstd, scale, shift):
+        """Forward SyncBN in ONE kernel: reduce this rank's partial statistics rows, exchange them over NVLink, finalise
+        BatchNorm (running statistics and num_batches_tracked included)."""
+        from . import _lib
+
+        _lib.call("b200unet_nvl_bn_rows_sync_finalize", stats_partial.data_ptr(), int(rows), bn.num_features, self._nvl[2],
+                  self.world_size, self.rank, float(global_count), bn.weight.data_ptr(), bn.bias.data_ptr(), float(eps),
+                  float(momentum), bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
+                  bn.num_batches_tracked.data_ptr() if track else None, mean.data_ptr(), rstd.data_ptr(), scale.data_ptr(),
+                  shift.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+    def rows_allreduce(self, partial, rows, c, sums_local, sums_global):
+        """Backward SyncBN: block partials [rows][2][c] -> local and all-rank fp64 sums [2c], one kernel over NVLink."""
+        from . import _lib
+
+        _lib.call("b200unet_nvl_rows_allreduce", partial.data_ptr(), int(rows), int(c), self._nvl[2], self.world_size, self.rank,
+                  sums_local.data_ptr(), sums_global.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+    def supports_rows(self, c):
+        return self._nvl is not None and c <= 2048 and os.environ.get("B200UNET_NVL_ROWS", "1") not in ("", "0")
+
     # ---- global registration
     @classmethod
     def enable(cls, **kw):
@@ -222,7 +251,23 @@ class DataParallelContext:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def make_flat_grads(self, params):
-        return FlatGrads(self, params)
+        """Flat gradient buffer for one backward. Outside CUDA-graph capture the buffer of the previous backward over the
+        same parameters is reused once the optimizer has consumed it: the caller's .grad tensors are VIEWS of it, so it is
+        only recycled when they have been released (zero_grad(set_to_none=True), torch's default) - otherwise a new one is
+        allocated, exactly as before."""
+        params = list(params)
+        key = tuple(id(p) for p in params)
+        flat = None
+        capturing = params[0].is_cuda and torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            old = self._flat_cache.get(key)
+            if old is not None and all(p.grad is None or p.grad.untyped_storage().data_ptr() != old.untyped_storage().data_ptr()
+                                       for p in params):
+                flat = old
+        fg = FlatGrads(self, params, flat)
+        if not capturing:
+            self._flat_cache[key] = fg.flat
+        return fg
 
     def all_reduce_mean_async(self, t, works):
         if t.is_cuda:
@@ -233,8 +278,11 @@ class DataParallelContext:
                 self.comm_stream.wait_event(ev)
                 for st in self.extra_wait_streams:
                     self.comm_stream.wait_stream(st)
-                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-                t.mul_(1.0 / self.world_size)
+                if self._nccl:
+                    dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)  # one pass: no separate 1/world scaling
+                else:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                    t.mul_(1.0 / self.world_size)
             works.append(None)
         else:
             w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -250,7 +298,7 @@ class DataParallelContext:
         works.clear()
 
 
-def init_from_env(sync_bn=True, bucket_mb=25.0):
+def init_from_env(sync_bn=True, bucket_mb=25.0, graphs=None):
     """torchrun-style bring-up: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world == 1:
@@ -266,4 +314,4 @@ def init_from_env(sync_bn=True, bucket_mb=25.0):
     if not dist.is_initialized():
         kw = {"device_id": torch.device("cuda", local)} if backend == "nccl" else {}
         dist.init_process_group(backend=backend, **kw)
-    return DataParallelContext.enable(sync_bn=sync_bn, bucket_mb=bucket_mb)
+    return DataParallelContext.enable(sync_bn=sync_bn, bucket_mb=bucket_mb, graphs=graphs)

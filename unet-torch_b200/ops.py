@@ -4,6 +4,8 @@ shape [N, H, W, C]; a tensor may be a channel slice of a wider buffer (stride(2)
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -297,7 +299,8 @@ def bn_relu_bwd(g1, g_pool, pool_idx, y, gamma, scale, shift, mean, rstd, dy, dg
                 allreduce=None, frozen=False):
     """Backward of BN->ReLU(->skip+pool). g1: gradient w.r.t. the activation (may be a channel slice, or None);
     g_pool/pool_idx: gradient through the 2x2 max pool (or None). Writes dy (may alias y), dgamma, dbeta.
-    allreduce: optional callable(sums_f64) applied between the two passes (SyncBN).
+    allreduce: optional DataParallelContext (SyncBN): the sums are exchanged between the two passes - one fused NVLink kernel
+    on the unreduced block partials when available, otherwise reduce_partials + all_reduce_sum.
     frozen: the forward normalised with RUNNING statistics (module.eval() under autograd): mean/rstd are the running ones,
     statistics do not depend on y, so dy = gamma * rstd * da (the batch-statistics correction terms vanish: the apply pass
     gets an all-zero sums vector) while dgamma / dbeta keep the reduced sums."""
@@ -310,17 +313,24 @@ def bn_relu_bwd(g1, g_pool, pool_idx, y, gamma, scale, shift, mean, rstd, dy, dg
     dp, dcs, *_ = _nhwc(dy)
     ws = _workspace(_lib.query("b200unet_bn_bwd_workspace_floats", n, h, w, c), y.device)
     sums = torch.empty((2 * c,), dtype=torch.float64, device=y.device)
-    _lib.call("b200unet_bn_relu_bwd_reduce", g1p, g1cs, _ptr(g_pool), _ptr(pool_idx), yp, ycs, _f32(scale), _f32(shift),
-              _f32(mean), _f32(rstd), ws.data_ptr(), sums.data_ptr(), n, h, w, c, _stream())
     sums_local = None
     if count is None:
         count = n * h * w
-    if frozen:
-        sums_local = sums
-        sums = torch.zeros_like(sums)
-    elif allreduce is not None:
-        sums_local = sums.clone()
-        allreduce(sums)
+    if allreduce is not None and not frozen and allreduce.supports_rows(c):
+        rows = ctypes.c_int(0)
+        _lib.call("b200unet_bn_relu_bwd_reduce_rows", g1p, g1cs, _ptr(g_pool), _ptr(pool_idx), yp, ycs, _f32(scale),
+                  _f32(shift), _f32(mean), _f32(rstd), ws.data_ptr(), ctypes.byref(rows), n, h, w, c, _stream())
+        sums_local = torch.empty_like(sums)
+        allreduce.rows_allreduce(ws, rows.value, c, sums_local, sums)
+    else:
+        _lib.call("b200unet_bn_relu_bwd_reduce", g1p, g1cs, _ptr(g_pool), _ptr(pool_idx), yp, ycs, _f32(scale), _f32(shift),
+                  _f32(mean), _f32(rstd), ws.data_ptr(), sums.data_ptr(), n, h, w, c, _stream())
+        if frozen:
+            sums_local = sums
+            sums = torch.zeros_like(sums)
+        elif allreduce is not None:
+            sums_local = sums.clone()
+            allreduce.all_reduce_sum(sums)
     _lib.call("b200unet_bn_relu_bwd_apply", g1p, g1cs, _ptr(g_pool), _ptr(pool_idx), yp, ycs, _f32(gamma), _f32(scale),
               _f32(shift), _f32(mean), _f32(rstd), sums.data_ptr(), float(count), _ptr(sums_local), dp, dcs,
               _f32(dgamma), _f32(dbeta), n, h, w, c, _stream())
