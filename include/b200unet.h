@@ -92,6 +92,18 @@ int b200unet_first_im2col(const float* x_nchw, void* col, int col_cs, int N, int
                           b200_stream_t stream);
 /* nn.Conv2d weight OIHW fp32 [Cout][Cin][3][3] -> bf16 [Cout][64] operand matching the im2col columns. */
 int b200unet_prep_first_weight(const float* w_oihw, void* w1, int Cout, int Cin, b200_stream_t stream);
+/* inc.conv1 (Model.py:111 -> :15-16) FUSED: y = conv3x3(x) straight from the fp32 NCHW network input; the im2col rows are
+ * built in shared memory inside the tcgen05 GEMM kernel, no im2col tensor reaches HBM. w1 = b200unet_prep_first_weight's
+ * [Cout][64] bf16 operand; stats_partial as b200unet_conv1x1_c64_igemm (rows = b200unet_conv1x1_c64_stat_rows). Cin <= 7. */
+int b200unet_conv3x3_first_igemm(const float* x_nchw, const void* w1, void* y, int y_cs, float* stats_partial, int N, int H,
+                                 int W, int Cin, int Cout, b200_stream_t stream);
+/* its eval-mode form: a = bf16(relu(scale * conv + shift)) */
+int b200unet_conv3x3_first_bn_relu_igemm(const float* x_nchw, const void* w1, const float* scale, const float* shift,
+                                         void* a, int a_cs, int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
+/* and its weight gradient dw (fp32 OIHW [Cout][Cin][3][3]) from x and dy, im2col rows again built in shared memory */
+int64_t b200unet_conv3x3_first_tc_wgrad_workspace_floats(int N, int H, int W, int Cout);
+int b200unet_conv3x3_first_tc_wgrad(const float* x_nchw, const void* dy, int dy_cs, float* partial, float* dw_oihw, int N,
+                                    int H, int W, int Cin, int Cout, b200_stream_t stream);
 /* y[n,h,w,k] = sum_j x[n,h,w,j] w[k,j], j < 64 (1x1 convolution of a 64-channel tensor; tcgen05, persistent CTAs,
  * weights resident). stats_partial as for b200unet_conv3x3_igemm with rows = b200unet_conv1x1_c64_stat_rows(). */
 int b200unet_conv1x1_c64_stat_rows(int N, int H, int W, int Cout);

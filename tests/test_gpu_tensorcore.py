@@ -166,7 +166,8 @@ def test_conv3x3_reads_and_writes_channel_slices(ops):
     assert float(yout[..., :c].float().abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 24, 1, 64), (3, 64, 72, 3, 64), (1, 40, 24, 4, 128)])
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 24, 1, 64), (3, 64, 72, 3, 64), (1, 40, 24, 4, 128), (2, 48, 200, 7, 64),
+                                            (4, 256, 256, 3, 64)])
 def test_first_layer_im2col_gemm_and_wgrad(ops, n, h, w, cin, cout):
     """inc.conv1 (Model.py:111): fp32 NCHW input -> bf16 im2col -> 1x1 tcgen05 GEMM (+ BN statistics), and its wgrad."""
     g = torch.Generator().manual_seed(16)
@@ -198,6 +199,27 @@ def test_first_layer_im2col_gemm_and_wgrad(ops, n, h, w, cin, cout):
     dw = torch.empty(cout, cin, 3, 3, device="cuda")
     ops.conv1x1_c64_wgrad(col, to_nhwc_bf16(dy), dw)
     assert rel_l2(dw, wv.grad) < 1e-4
+    # ---- the FUSED forms the engine uses: im2col rows built in shared memory inside the GEMM kernels (no `col` in HBM).
+    # Same operands, same MMA order -> the very same bits as the materialised path.
+    y2 = torch.full((n, h, w, 2 * cout), 5.0, dtype=BF16, device="cuda")
+    st2 = torch.zeros(rows * 2 * cout, device="cuda")
+    ops.conv3x3_first_tc(x.cuda(), w1, y2[..., cout:], st2)          # into a channel slice, like a concat buffer
+    assert torch.equal(y2[..., cout:], y) and bool((y2[..., :cout] == 5.0).all())
+    assert torch.equal(st2, st)
+    dw2 = torch.empty(cout, cin, 3, 3, device="cuda")
+    ops.conv3x3_first_tc_wgrad(x.cuda(), to_nhwc_bf16(dy), dw2)
+    assert torch.equal(dw2, dw)
+    # eval form: BatchNorm (running statistics) + ReLU folded
+    gm, bt = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.2
+    rm, rv = torch.randn(cout, generator=g) * 0.2, torch.rand(cout, generator=g) + 0.5
+    scale, shift = torch.empty(cout, device="cuda"), torch.empty(cout, device="cuda")
+    ops.bn_eval_affine(gm.cuda(), bt.cuda(), rm.cuda(), rv.cuda(), 1e-5, scale, shift)
+    a1 = torch.empty(n, h, w, cout, dtype=BF16, device="cuda")
+    a2 = torch.empty(n, h, w, cout, dtype=BF16, device="cuda")
+    ops.conv1x1_c64_bn_relu(col, w1, scale, shift, a1)
+    ops.conv3x3_first_tc_bn_relu(x.cuda(), w1, scale, shift, a2)
+    assert torch.equal(a1, a2)
+    assert rel_l2(from_nhwc(a2), O.relu(O.batchnorm_eval(want, gm, bt, rm, rv))) < TOL
 
 
 UP_SHAPES = [(1, 8, 16, 128, 64), (2, 4, 8, 256, 128), (1, 12, 20, 128, 64),

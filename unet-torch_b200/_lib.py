@@ -40,6 +40,10 @@ SIGNATURES = {
     "b200unet_convt2x2_wgrad": (c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200unet_first_im2col": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "b200unet_prep_first_weight": (c_int, [_P, _P, _I, _I, _P]),
+    "b200unet_conv3x3_first_igemm": (c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "b200unet_conv3x3_first_bn_relu_igemm": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b200unet_conv3x3_first_tc_wgrad_workspace_floats": (c_int64, [_I, _I, _I, _I]),
+    "b200unet_conv3x3_first_tc_wgrad": (c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200unet_conv1x1_c64_stat_rows": (c_int, [_I, _I, _I, _I]),
     "b200unet_conv1x1_c64_igemm": (c_int, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _P]),
     "b200unet_conv1x1_c64_wgrad_workspace_floats": (c_int64, [_I, _I, _I, _I]),

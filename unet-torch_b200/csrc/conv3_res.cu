@@ -16,6 +16,7 @@
 //     (Model.py:17,21) of the STORED bf16 values in registers; one partial row per CTA at the end.
 #include "../../include/b200unet.h"
 #include "host_common.h"
+#include "first_tile.cuh"
 #include "tc_common.cuh"
 
 #include <stdlib.h>
@@ -51,13 +52,19 @@ struct ResArgs {
   const float* bias;  // UP: [cup] or null
   const float* scale;  // CONV: eval-mode BatchNorm + ReLU folded into the epilogue: [ncols] each, or null
   const float* shift;
+  const float* x_nchw;  // FIRST: the fp32 NCHW network input the im2col rows are built from
 };
 
 // What the GEMM is:            A operand per K block                      epilogue
 //   RES_CONV (TAPS 9 or 1)      tmA[0], channel block cb                   one output map, BN statistics
 //   RES_UP     (TAPS 1)         tmA[0], channel block cb                   + bias, one strided output map per (i,j)
 //   RES_GATHER (TAPS 1)         tmA[ij], K block kb = ij * (KB/4) + cb     one output map
-enum { RES_CONV = 0, RES_UP = 1, RES_GATHER = 2 };
+//   RES_FIRST  (TAPS 1, KB 1)   im2col rows of the fp32 NCHW input built   one output map, BN statistics
+//                               in shared memory by 8 builder warps (first_tile.cuh): inc.conv1 without an HBM im2col
+enum { RES_CONV = 0, RES_UP = 1, RES_GATHER = 2, RES_FIRST = 3 };
+
+// epilogue groups per CTA (see the comment at res_threads below)
+constexpr int res_epi_groups(int ob) { return ob == 2 ? 2 : 1; }
 
 template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV>
 struct ResPlan {
@@ -69,12 +76,21 @@ struct ResPlan {
   static constexpr int BAR_OFF = OUT_OFF + OUT_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024 /* alignment slack */;
   static_assert(TOTAL <= 227 * 1024, "shared memory plan exceeds 227 KiB");
-  static_assert(4 * 2 * BN * 4 <= OUT_BYTES, "final statistics reduction aliases the staging buffer");
+  static_assert(res_epi_groups(OB) * 4 * 2 * BN * 4 <= OUT_BYTES, "final statistics reduction aliases the staging buffer");
 };
 
-template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV>
-__global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant__ ResArgs args) {
+// Epilogue groups. With few output channels per tile (BN = 64) the main loop of a tile is short (1x1: 4 MMAs, 3x3 over 64
+// channels: 36) and ONE group of four epilogue warps (tcgen05.ld -> bf16 -> staging -> TMA store -> BatchNorm statistics,
+// ~1.15 us per tile) was the bottleneck: every BN = 64 kernel ran at exactly that rate whatever its K (64->64 3x3: 1.26 us
+// per tile = 54-57 % tensor pipe). Instantiations with two staging buffers (OB = 2) therefore run TWO epilogue groups that
+// alternate tiles: group g drains TMEM buffer g into staging buffer g.
+// warps: 0 TMA producer, 1 MMA issuer, then 4 epilogue warps per group; RES_FIRST appends two groups of four im2col builders
+constexpr int res_threads(int kind, int ob) { return 64 + 128 * res_epi_groups(ob) + (kind == RES_FIRST ? 256 : 0); }
+
+template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV, int CIN = 0>
+__global__ void __launch_bounds__(res_threads(KIND, OB), 1) conv3_res_kernel(const __grid_constant__ ResArgs args) {
   using P = ResPlan<BN, KB, NA, OB, TAPS, KIND>;
+  static_assert(KIND != RES_FIRST || (TAPS == 1 && KB == 1 && CIN >= 1 && CIN <= 7), "RES_FIRST: one K block of im2col rows");
   static_assert(KIND == RES_CONV || TAPS == 1, "the transposed-convolution GEMMs have no spatial taps");
   static_assert(KIND != RES_GATHER || KB % 4 == 0, "gather: K blocks split evenly over the four (i,j) maps");
   using G = TileGeom<TAPS>;
@@ -94,6 +110,7 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
   const uint32_t tmem_slot = bars + 8u * (5 + 2 * NA);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + P::BAR_OFF + 8 * (5 + 2 * NA));
 
+  constexpr int EG = res_epi_groups(OB);
   const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const int nt = blockIdx.x % args.ntiles_n;
@@ -107,7 +124,7 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
     prefetch_tmap(&args.tmO[0]);
     mbar_init(W_full, 1);
     for (int i = 0; i < NA; ++i) {
-      mbar_init(A_full(i), 1);
+      mbar_init(A_full(i), KIND == RES_FIRST ? 4 : 1);  // FIRST: one arrival per builder warp of the tile's group
       mbar_init(A_empty(i), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -117,6 +134,10 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (KIND == RES_FIRST) {  // columns >= 9*CIN of every im2col row stay zero for the whole launch
+    b2first::zero_smem(sA, NA * A_STAGE, threadIdx.x, res_threads(KIND, OB));
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -142,7 +163,7 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
           tma_load_2d(sW + (tap * KB + cb) * (BN * 128), &args.tmW, W_full, (tap * KB + cb) * 64, n0);
       int sa = 0, pa = 0;
 #pragma unroll 1
-      for (int j = 0; j < ntiles_mine; ++j) {
+      for (int j = 0; j < (KIND == RES_FIRST ? 0 : ntiles_mine); ++j) {
         int img, h0, w0;
         tile_coords(j, img, h0, w0);
 #pragma unroll 1
@@ -197,11 +218,38 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
       }
     }
     __syncwarp();
-  } else {
-    // ================================================================= epilogue (4 warps, 128 threads)
+  } else if (KIND == RES_FIRST && warp >= 2 + 4 * EG) {
+    // ================================================================= im2col builders (2 groups x 4 warps)
+    // Group g builds the tiles j = g, g + 2, ...: thread r of the group owns pixel row r of the 16 x 8 tile (row r >> 3,
+    // column r & 7 - the order a {64, 8, 16} TMA box would have). The 9*CIN loads of a row are issued before the wait for
+    // the stage, so two tiles' worth of loads are in flight per CTA.
+    const int bt = threadIdx.x - 32 * (2 + 4 * EG);
+    const int grp = bt >> 7, r = bt & 127;
+    constexpr int CI = CIN > 0 ? CIN : 1;
+#pragma unroll 1
+    for (int j = grp; j < ntiles_mine; j += 2) {
+      const int sa = j % NA, pa = (j / NA) & 1;
+      int img, h0, w0;
+      if (j + 8 < ntiles_mine) {  // pull the input lines of a tile four rounds ahead into L2
+        tile_coords(j + 8, img, h0, w0);
+        b2first::prefetch_tile_l2<CI, RTH, RTW>(args.x_nchw, img, h0, w0, args.H, args.W, r);
+      }
+      tile_coords(j, img, h0, w0);
+      b2first::Row<CI> row;  // the loads are issued before the wait for the stage: two tiles' worth in flight per CTA
+      b2first::load_row<CI>(args.x_nchw, img, h0 + (r >> 3), w0 + (r & 7), args.H, args.W, row);
+      mbar_wait(A_empty(sa), pa ^ 1);
+      b2first::store_row<CI>(sA + sa * A_STAGE, r, row);
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(A_full(sa));
+    }
+  } else if (warp >= 2 && warp < 2 + 4 * EG) {
+    // ================================================================= epilogue (EG groups of 4 warps = 128 threads)
+    const int eg = (warp - 2) >> 2;     // group: takes the tiles j = eg, eg + EG, ...
     const int quad = warp & 3;          // TMEM lanes [32*quad, 32*quad+32)
     const int row = quad * 32 + lane;   // pixel of the tile: (row >> 3, row & 7)
-    const int et = threadIdx.x - 64;    // 0..127
+    const int et = (threadIdx.x - 64) & 127;  // 0..127 inside the group
+    const int gbar = 1 + eg;            // named barrier of the group
     const int cp = et & 31, rq = et >> 5;  // statistics: channel pair within a 64-channel chunk, 32-row quarter
     const bool want_stats = args.stats != nullptr;
     float s1[BN / 64][2], s2[BN / 64][2];
@@ -209,7 +257,7 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
     for (int q = 0; q < BN / 64; ++q) s1[q][0] = s1[q][1] = s2[q][0] = s2[q][1] = 0.f;
 
 #pragma unroll 1
-    for (int j = 0; j < ntiles_mine; ++j) {
+    for (int j = eg; j < ntiles_mine; j += EG) {
       const int buf = j & 1;
       const uint32_t stage = sO + (OB == 1 ? 0 : (j & 1)) * ((BN / 64) * OUT_CHUNK);
       int img, h0, w0;
@@ -223,7 +271,7 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
           uint32_t v[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN + q * 64 + half * 32, v);
           tmem_ld_wait();
-          if (KIND == RES_CONV && args.scale != nullptr)
+          if ((KIND == RES_CONV || KIND == RES_FIRST) && args.scale != nullptr)
             affine_relu32(v, args.scale + n0 + q * 64 + half * 32, args.shift + n0 + q * 64 + half * 32);
           if (KIND == RES_UP && args.bias != nullptr) {
             const float* bp = args.bias + (n0 + q * 64 + half * 32) % args.cup;
@@ -248,8 +296,7 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(T_empty(buf));
       fence_proxy_async_smem();
-      if (OB == 2 && et == 0) tma_store_wait_read0();  // the store issued one tile ago (other buffer) has read its smem
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory");
       if (et == 0) {
 #pragma unroll
         for (int q = 0; q < BN / 64; ++q) {
@@ -283,29 +330,30 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
           }
         }
       }
-      if (OB == 1) {
-        if (et == 0) tma_store_wait_read0();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
+      // the group's staging buffer is free again once its store has read it (by then the statistics pass above is done too)
+      if (et == 0) tma_store_wait_read0();
+      asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory");
     }
-    if (et == 0) tma_store_wait_read0();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (EG == 2) asm volatile("bar.sync 3, 256;" ::: "memory");  // both groups' stores have read the staging buffers
     if (want_stats) {
       // cross-quarter reduction through the (now idle) staging buffer: red[rq][stat][BN]
       float* red = reinterpret_cast<float*>(smem_gen + P::OUT_OFF);
 #pragma unroll
       for (int q = 0; q < BN / 64; ++q) {
-        red[(rq * 2 + 0) * BN + q * 64 + cp * 2 + 0] = s1[q][0];
-        red[(rq * 2 + 0) * BN + q * 64 + cp * 2 + 1] = s1[q][1];
-        red[(rq * 2 + 1) * BN + q * 64 + cp * 2 + 0] = s2[q][0];
-        red[(rq * 2 + 1) * BN + q * 64 + cp * 2 + 1] = s2[q][1];
+        red[((eg * 4 + rq) * 2 + 0) * BN + q * 64 + cp * 2 + 0] = s1[q][0];
+        red[((eg * 4 + rq) * 2 + 0) * BN + q * 64 + cp * 2 + 1] = s1[q][1];
+        red[((eg * 4 + rq) * 2 + 1) * BN + q * 64 + cp * 2 + 0] = s2[q][0];
+        red[((eg * 4 + rq) * 2 + 1) * BN + q * 64 + cp * 2 + 1] = s2[q][1];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (EG == 2) asm volatile("bar.sync 3, 256;" ::: "memory");
+      else asm volatile("bar.sync 1, 128;" ::: "memory");
       float* dst = args.stats + static_cast<size_t>(pw) * 2 * args.ncols + n0;
-      for (int i = et; i < 2 * BN; i += 128) {
+      for (int i = et + eg * 128; i < 2 * BN; i += 128 * EG) {
         const int stat = i / BN, ch = i - stat * BN;
-        dst[stat * args.ncols + ch] = red[(0 * 2 + stat) * BN + ch] + red[(1 * 2 + stat) * BN + ch] +
-                                      red[(2 * 2 + stat) * BN + ch] + red[(3 * 2 + stat) * BN + ch];
+        float t = 0.f;
+#pragma unroll
+        for (int part = 0; part < 4 * EG; ++part) t += red[(part * 2 + stat) * BN + ch];  // fixed order: reproducible
+        dst[stat * args.ncols + ch] = t;
       }
     }
     tc_fence_before();
@@ -315,11 +363,11 @@ __global__ void __launch_bounds__(192, 1) conv3_res_kernel(const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV>
+template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV, int CIN = 0>
 int launch_res(const ResArgs& a, cudaStream_t st) {
   using P = ResPlan<BN, KB, NA, OB, TAPS, KIND>;
   static unsigned long long configured = 0;  // one bit per CUDA device
-  auto kern = conv3_res_kernel<BN, KB, NA, OB, TAPS, KIND>;
+  auto kern = conv3_res_kernel<BN, KB, NA, OB, TAPS, KIND, CIN>;
   if (b2h::first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) {
@@ -327,7 +375,7 @@ int launch_res(const ResArgs& a, cudaStream_t st) {
       return 2;
     }
   }
-  kern<<<a.workers * a.ntiles_n, 192, P::TOTAL, st>>>(a);
+  kern<<<a.workers * a.ntiles_n, res_threads(KIND, OB), P::TOTAL, st>>>(a);
   return b2h::check_launch("conv3_res");
 }
 
@@ -390,6 +438,7 @@ int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, 
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
   a.cup = Cout;
   a.bias = nullptr;
+  a.x_nchw = nullptr;
   if (int e = make_tmap_4d(&a.tmA[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TileGeom<9>::IN_W, TileGeom<9>::IN_H)) return e;
   if (int e = make_tmap_2d(&a.tmW, w, static_cast<uint64_t>(9) * Cin, Cout, bn)) return e;
   if (int e = make_tmap_4d(&a.tmO[0], y, Cout, W, H, N, ys, ys * W, ys * W * H, RTW, RTH)) return e;
@@ -422,11 +471,46 @@ int conv1x1_c64_launch(const void* x, int x_cs, const void* w, void* y, int y_cs
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
   a.cup = Cout;
   a.bias = nullptr;
+  a.x_nchw = nullptr;
   if (int e = make_tmap_4d(&a.tmA[0], x, 64, W, H, N, xs, xs * W, xs * W * H, RTW, RTH)) return e;
   if (int e = make_tmap_2d(&a.tmW, w, 64, Cout, 64)) return e;
   if (int e = make_tmap_4d(&a.tmO[0], y, Cout, W, H, N, ys, ys * W, ys * W * H, RTW, RTH)) return e;
   for (int i = 1; i < 4; ++i) { a.tmA[i] = a.tmA[0]; a.tmO[i] = a.tmO[0]; }
   return launch_res<64, 1, 4, 2, 1>(a, st);
+}
+
+// inc.conv1 straight from the fp32 NCHW network input: the im2col rows are built in shared memory (RES_FIRST).
+int conv3x3_first_launch(const float* x_nchw, const void* w1, void* y, int y_cs, float* stats_partial, int N, int H, int W,
+                         int Cin, int Cout, cudaStream_t st, const float* scale, const float* shift) {
+  ResArgs a;
+  res_geometry(N, H, W, 64, Cout, &a.ntiles_n, &a.workers, &a.tiles_total);
+  a.tiles_w = ceil_div(W, RTW);
+  a.tiles_h = ceil_div(H, RTH);
+  a.H = H;
+  a.W = W;
+  a.ncols = Cout;
+  a.stats = stats_partial;
+  a.scale = scale;
+  a.shift = shift;
+  a.cup = Cout;
+  a.bias = nullptr;
+  a.x_nchw = x_nchw;
+  const uint64_t ys = static_cast<uint64_t>(y_cs) * 2;
+  if (int e = make_tmap_2d(&a.tmW, w1, 64, Cout, 64)) return e;
+  if (int e = make_tmap_4d(&a.tmO[0], y, Cout, W, H, N, ys, ys * W, ys * W * H, RTW, RTH)) return e;
+  for (int i = 0; i < 4; ++i) a.tmA[i] = a.tmO[0];  // unused by RES_FIRST (prefetch target only)
+  for (int i = 1; i < 4; ++i) a.tmO[i] = a.tmO[0];
+  switch (Cin) {
+    case 1: return launch_res<64, 1, 4, 2, 1, RES_FIRST, 1>(a, st);
+    case 2: return launch_res<64, 1, 4, 2, 1, RES_FIRST, 2>(a, st);
+    case 3: return launch_res<64, 1, 4, 2, 1, RES_FIRST, 3>(a, st);
+    case 4: return launch_res<64, 1, 4, 2, 1, RES_FIRST, 4>(a, st);
+    case 5: return launch_res<64, 1, 4, 2, 1, RES_FIRST, 5>(a, st);
+    case 6: return launch_res<64, 1, 4, 2, 1, RES_FIRST, 6>(a, st);
+    case 7: return launch_res<64, 1, 4, 2, 1, RES_FIRST, 7>(a, st);
+  }
+  b2h::set_error("conv3x3_first: Cin=%d must be in [1,7]", Cin);
+  return 1;
 }
 
 // ---- ConvTranspose2d(k2,s2) forward as a resident-weight GEMM with the pixel-shuffle scatter epilogue.
@@ -448,6 +532,7 @@ int convt_res_fprop_launch(const void* x, int x_cs, const void* w_fprop, const f
   a.stats = nullptr;
   a.scale = nullptr;
   a.shift = nullptr;
+  a.x_nchw = nullptr;
   a.bias = bias;
   const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, os = static_cast<uint64_t>(out_cs) * 2;
   if (int e = make_tmap_4d(&a.tmA[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, RTW, RTH)) return e;
@@ -479,6 +564,7 @@ int convt_res_dgrad_launch(const void* du, int du_cs, const void* w_dgrad, void*
   a.stats = nullptr;
   a.scale = nullptr;
   a.shift = nullptr;
+  a.x_nchw = nullptr;
   a.bias = nullptr;
   const uint64_t us = static_cast<uint64_t>(du_cs) * 2, xs = static_cast<uint64_t>(dx_cs) * 2;
   for (int ij = 0; ij < 4; ++ij) {

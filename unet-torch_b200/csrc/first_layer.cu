@@ -5,6 +5,9 @@
 // which is one 128-byte swizzle row per pixel. The convolution is then a 1x1 GEMM over `col` (persistent
 // resident-weight kernel, conv3_res.cu, TAPS = 1, same BatchNorm-statistics epilogue), and its weight gradient a
 // plain pixel-reduction GEMM (wgrad.cu KIND_PLAIN). Both are bound by the 128 B/pixel they stream, not by math.
+// Since round 2 the engine uses the FUSED forms (b200unet_conv3x3_first_igemm / _first_tc_wgrad): the same GEMMs with the
+// im2col rows built in shared memory (first_tile.cuh), so `col` never exists in HBM; the materialising kernel below stays as
+// an entry point (and as the reference the fused path is tested against).
 #include "../../include/b200unet.h"
 #include "host_common.h"
 
@@ -93,6 +96,23 @@ int b200unet_prep_first_weight(const float* w_oihw, void* w1, int Cout, int Cin,
   prep_first_kernel<<<(Cout * 64 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w_oihw, static_cast<__nv_bfloat16*>(w1), Cout, Cin * 9);
   return b2h::check_launch("prep_first_weight");
+}
+
+int b200unet_conv3x3_first_igemm(const float* x_nchw, const void* w1, void* y, int y_cs, float* stats_partial, int N, int H,
+                                 int W, int Cin, int Cout, b200_stream_t stream) {
+  B2_REQUIRE(Cin >= 1 && Cin <= 7 && Cout % 64 == 0 && Cout > 0, "conv3x3_first_igemm: Cin=%d must be in [1,7], Cout=%d a multiple of 64", Cin, Cout);
+  B2_REQUIRE(x_nchw && w1 && y && y_cs >= Cout && y_cs % 8 == 0 && N > 0 && H > 0 && W > 0, "conv3x3_first_igemm: bad arguments");
+  return b2h::conv3x3_first_launch(x_nchw, w1, y, y_cs, stats_partial, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream));
+}
+
+int b200unet_conv3x3_first_bn_relu_igemm(const float* x_nchw, const void* w1, const float* scale, const float* shift, void* a,
+                                         int a_cs, int N, int H, int W, int Cin, int Cout, b200_stream_t stream) {
+  B2_REQUIRE(Cin >= 1 && Cin <= 7 && Cout % 64 == 0 && Cout > 0, "conv3x3_first_bn_relu_igemm: Cin=%d must be in [1,7], Cout=%d a multiple of 64", Cin, Cout);
+  B2_REQUIRE(x_nchw && w1 && a && a_cs >= Cout && a_cs % 8 == 0 && N > 0 && H > 0 && W > 0, "conv3x3_first_bn_relu_igemm: bad arguments");
+  B2_REQUIRE(scale != nullptr && shift != nullptr && reinterpret_cast<uintptr_t>(scale) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(shift) % 16 == 0,
+             "conv3x3_first_bn_relu_igemm: scale and shift are required, 16-byte aligned");
+  return b2h::conv3x3_first_launch(x_nchw, w1, a, a_cs, nullptr, N, H, W, Cin, Cout, static_cast<cudaStream_t>(stream), scale, shift);
 }
 
 int b200unet_conv1x1_c64_stat_rows(int N, int H, int W, int Cout) { return b2h::conv1x1_c64_stat_rows(N, H, W, Cout); }

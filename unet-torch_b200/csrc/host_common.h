@@ -71,4 +71,8 @@ int conv1x1_c64_launch(const void* x, int x_cs, const void* w, void* y, int y_cs
                        int W, int Cout, cudaStream_t st, const float* scale = nullptr,
                        const float* shift = nullptr);
 
+// inc.conv1 from the fp32 NCHW input, im2col rows built in shared memory (conv3_res.cu RES_FIRST); w1 = [Cout][64] bf16
+int conv3x3_first_launch(const float* x_nchw, const void* w1, void* y, int y_cs, float* stats_partial, int N, int H, int W,
+                         int Cin, int Cout, cudaStream_t st, const float* scale = nullptr, const float* shift = nullptr);
+
 }  // namespace b2h

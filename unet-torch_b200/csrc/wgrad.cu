@@ -3,6 +3,8 @@
 //   KIND_CONV3  dW[k][r][s][c] = sum_{n,h,w} dy[n,h,w,k] * x[n,h+r-1,w+s-1,c]     (nn.Conv2d backward-weight)
 //   KIND_UP     dW[ci][d][i][j] = sum_{n,h,w} x[n,h,w,ci] * du[n,2h+i,2w+j,d]      (nn.ConvTranspose2d k2 s2)
 //   KIND_PLAIN  dW[k][j]        = sum_{n,h,w} dy[n,h,w,k] * col[n,h,w,j]            (inc.conv1 on its im2col'ed input)
+//   KIND_FIRST  the same with the im2col rows col[.][c*9+r*3+s] = x[n,c,h+r-1,w+s-1] built in shared memory from the fp32
+//               NCHW network input by the four (otherwise idle) epilogue warps - no im2col tensor in HBM (first_tile.cuh)
 // A CTA owns a 128 (A-side channels) x BNC (B-side channels) x TAPS accumulator set in TMEM and streams a
 // contiguous range of 8x16 pixel tiles through a TMA ring (split-K over pixels across CTAs). For the 3x3 case
 // a CTA handles one horizontal tap s; its x tile carries two halo rows and the three vertical taps r are
@@ -10,6 +12,7 @@
 // in a fixed order (deterministic) into the parameter's own layout.
 #include "../../include/b200unet.h"
 #include "host_common.h"
+#include "first_tile.cuh"
 #include "tc_common.cuh"
 
 #include <stdlib.h>
@@ -19,7 +22,7 @@ namespace {
 using namespace b2;
 
 constexpr int TH = 8, TW = 16, BM = TH * TW;
-enum { KIND_CONV3 = 0, KIND_UP = 1, KIND_PLAIN = 2 };
+enum { KIND_CONV3 = 0, KIND_UP = 1, KIND_PLAIN = 2, KIND_FIRST = 3 };
 
 struct WgradArgs {
   CUtensorMap tmA;     // A-side activations (conv3: dy, up: x)
@@ -28,9 +31,11 @@ struct WgradArgs {
   int mtiles, ntiles, splits;
   int Ca, Cb;          // channel counts of the A and B side
   float* partial;      // [splits][Ca][TAPS_TOTAL][Cb]
+  const float* x_nchw;  // KIND_FIRST: fp32 NCHW network input
+  int H, W;
 };
 
-template <int KIND, int BNC>
+template <int KIND, int BNC, int CIN = 0>
 struct WPlan {
   static constexpr int TAPS = (KIND == KIND_CONV3) ? 3 : (KIND == KIND_UP ? 4 : 1);        // accumulators per CTA
   static constexpr int TAPS_TOTAL = (KIND == KIND_CONV3) ? 9 : (KIND == KIND_UP ? 4 : 1);  // taps in the partial layout
@@ -46,9 +51,14 @@ struct WPlan {
   static_assert(NS >= 2, "need at least a double buffer");
 };
 
-template <int KIND, int BNC>
-__global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradArgs args) {
+// warps: 0 TMA producer, 1 MMA issuer, 2-5 epilogue (KIND_FIRST: also im2col builders of the even tiles); KIND_FIRST adds
+// warps 6-9, the builders of the odd tiles
+constexpr int wgrad_threads(int kind) { return kind == 3 /* KIND_FIRST */ ? 320 : 192; }
+
+template <int KIND, int BNC, int CIN = 0>
+__global__ void __launch_bounds__(wgrad_threads(KIND), 1) wgrad_kernel(const __grid_constant__ WgradArgs args) {
   using P = WPlan<KIND, BNC>;
+  static_assert(KIND != KIND_FIRST || (BNC == 64 && CIN >= 1 && CIN <= 7), "KIND_FIRST: 64 im2col columns");
   constexpr int NS = P::NS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -77,13 +87,18 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     prefetch_tmap(&args.tmA);
     prefetch_tmap(&args.tmB[0]);
     for (int i = 0; i < NS; ++i) {
-      mbar_init(full(i), 1);
+      mbar_init(full(i), KIND == KIND_FIRST ? 5 : 1);  // FIRST: the TMA producer + one arrival per builder warp
       mbar_init(empty(i), 1);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, P::TMEM_COLS);
+  if (KIND == KIND_FIRST) {  // columns >= 9*CIN of the B tiles stay zero for the whole launch
+    for (int i = 0; i < NS; ++i)
+      b2first::zero_smem(smem_base + i * P::STAGE_BYTES + P::A_BYTES, P::B_BYTES, threadIdx.x, wgrad_threads(KIND));
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -98,12 +113,14 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         const int img = t / (args.tiles_w * args.tiles_h);
         const int h0 = thi * TH, w0 = twi * TW;
         mbar_wait(empty(st), ph ^ 1);
-        mbar_arrive_expect_tx(full(st), P::STAGE_BYTES);
+        mbar_arrive_expect_tx(full(st), KIND == KIND_FIRST ? P::A_BYTES : P::STAGE_BYTES);
         const uint32_t sA = smem_base + st * P::STAGE_BYTES;
         const uint32_t sB = sA + P::A_BYTES;
         tma_load_4d(sA, &args.tmA, full(st), m0, w0, h0, img);
         tma_load_4d(sA + BM * 128, &args.tmA, full(st), m0 + 64, w0, h0, img);
-        if (KIND == KIND_CONV3) {
+        if (KIND == KIND_FIRST) {
+          // B is built by warps 2-5
+        } else if (KIND == KIND_CONV3) {
 #pragma unroll
           for (int j = 0; j < BNC / 64; ++j)
             tma_load_4d(sB + j * P::B_BOX, &args.tmB[0], full(st), n0 + 64 * j, w0 + s - 1, h0 - 1, img);
@@ -151,6 +168,30 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int ka = m0 + row;
+    const bool second_builders = KIND == KIND_FIRST && warp >= 6;
+    if (KIND == KIND_FIRST) {
+      // im2col builders during the main loop: two groups of 128 threads alternate tiles; thread `row` of a group owns pixel
+      // row `row` of its 8 x 16 tiles (tile row row >> 4, column row & 15 - the order a {64, 16, 8} TMA box would have).
+      // The loads are issued before the wait for the stage.
+      constexpr int CI = CIN > 0 ? CIN : 1;
+      const int tiles_img = args.tiles_w * args.tiles_h;
+#pragma unroll 1
+      for (int i = second_builders ? 1 : 0; t_begin + i < t_end; i += 2) {
+        const int t = t_begin + i, st = i % NS, ph = (i / NS) & 1;
+        if (t + 8 < t_end)
+          b2first::prefetch_tile_l2<CI, TH, TW>(args.x_nchw, (t + 8) / tiles_img, (((t + 8) / args.tiles_w) % args.tiles_h) * TH,
+                                                ((t + 8) % args.tiles_w) * TW, args.H, args.W, row);
+        b2first::Row<CI> r;
+        b2first::load_row<CI>(args.x_nchw, t / tiles_img, ((t / args.tiles_w) % args.tiles_h) * TH + (row >> 4),
+                              (t % args.tiles_w) * TW + (row & 15), args.H, args.W, r);
+        mbar_wait(empty(st), ph ^ 1);
+        b2first::store_row<CI>(smem_base + st * P::STAGE_BYTES + P::A_BYTES, row, r);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full(st));
+      }
+    }
+    if (!second_builders) {
     mbar_wait(acc_full, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -173,6 +214,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       }
     }
     tc_fence_before();
+    }  // !second_builders
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, P::TMEM_COLS);
@@ -276,11 +318,11 @@ int pick_splits(int base_ctas, int tiles_total) {
   return best_z;
 }
 
-template <int KIND, int BNC>
+template <int KIND, int BNC, int CIN = 0>
 int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   using P = WPlan<KIND, BNC>;
   static unsigned long long configured = 0;  // one bit per CUDA device
-  auto kern = wgrad_kernel<KIND, BNC>;
+  auto kern = wgrad_kernel<KIND, BNC, CIN>;
   if (b2h::first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) {
@@ -289,7 +331,7 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
     }
   }
   const int grid = a.mtiles * a.ntiles * (KIND == KIND_CONV3 ? 3 : 1) * a.splits;
-  kern<<<grid, 192, P::TOTAL, st>>>(a);
+  kern<<<grid, wgrad_threads(KIND), P::TOTAL, st>>>(a);
   return b2h::check_launch("wgrad");
 }
 
@@ -624,6 +666,45 @@ int b200unet_conv1x1_c64_wgrad(const void* col, int col_cs, const void* dy, int 
   if (int e = launch_wgrad<KIND_PLAIN, 64>(a, st)) return e;
   reduce_plain_kernel<<<b2h::ceil_div(Cout * T, 256), 256, 0, st>>>(partial, dw, a.splits, Cout, T);
   return b2h::check_launch("conv1x1_c64_wgrad_reduce");
+}
+
+int64_t b200unet_conv3x3_first_tc_wgrad_workspace_floats(int N, int H, int W, int Cout) {
+  return b200unet_conv1x1_c64_wgrad_workspace_floats(N, H, W, Cout);
+}
+
+int b200unet_conv3x3_first_tc_wgrad(const float* x_nchw, const void* dy, int dy_cs, float* partial, float* dw_oihw, int N, int H,
+                                    int W, int Cin, int Cout, b200_stream_t stream) {
+  B2_REQUIRE(Cin >= 1 && Cin <= 7 && Cout % 64 == 0 && Cout > 0, "conv3x3_first_tc_wgrad: Cin=%d must be in [1,7], Cout=%d a multiple of 64", Cin, Cout);
+  B2_REQUIRE(x_nchw && dy && partial && dw_oihw && dy_cs % 8 == 0 && dy_cs >= Cout, "conv3x3_first_tc_wgrad: bad arguments");
+  WgradArgs a;
+  plain_wgrad_geometry(N, H, W, Cout, &a.mtiles, &a.tiles_total, &a.splits);
+  a.ntiles = 1;
+  a.tiles_w = b2h::ceil_div(W, TW);
+  a.tiles_h = b2h::ceil_div(H, TH);
+  a.Ca = Cout;
+  a.Cb = 64;
+  a.partial = partial;
+  a.x_nchw = x_nchw;
+  a.H = H;
+  a.W = W;
+  const uint64_t ys = static_cast<uint64_t>(dy_cs) * 2;
+  if (int e = b2h::make_tmap_4d(&a.tmA, dy, Cout, W, H, N, ys, ys * W, ys * W * H, TW, TH)) return e;
+  for (int i = 0; i < 4; ++i) a.tmB[i] = a.tmA;  // unused (prefetch target only)
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int e = 1;
+  switch (Cin) {
+    case 1: e = launch_wgrad<KIND_FIRST, 64, 1>(a, st); break;
+    case 2: e = launch_wgrad<KIND_FIRST, 64, 2>(a, st); break;
+    case 3: e = launch_wgrad<KIND_FIRST, 64, 3>(a, st); break;
+    case 4: e = launch_wgrad<KIND_FIRST, 64, 4>(a, st); break;
+    case 5: e = launch_wgrad<KIND_FIRST, 64, 5>(a, st); break;
+    case 6: e = launch_wgrad<KIND_FIRST, 64, 6>(a, st); break;
+    case 7: e = launch_wgrad<KIND_FIRST, 64, 7>(a, st); break;
+  }
+  if (e) return e;
+  const int T = Cin * 9;
+  reduce_plain_kernel<<<b2h::ceil_div(Cout * T, 256), 256, 0, st>>>(partial, dw_oihw, a.splits, Cout, T);
+  return b2h::check_launch("conv3x3_first_tc_wgrad_reduce");
 }
 
 }  // extern "C"

@@ -158,6 +158,8 @@ class UNetEngine:
         # eval forward without saving for backward: BN + ReLU are folded into the conv epilogues (the four pooled layers
         # are followed by a plain max-pool pass); B200UNET_FOLD_EVAL_BN=0 keeps the separate BN-apply pass
         self.fold_eval_bn = os.environ.get("B200UNET_FOLD_EVAL_BN", "1") not in ("", "0")
+        # inc.conv1 with the im2col rows built in shared memory (no 537 MB im2col tensor); B200UNET_FIRST_FUSED=0 = round-1 path
+        self.first_fused = os.environ.get("B200UNET_FIRST_FUSED", "1") not in ("", "0")
         # ... but under data parallel it pays: the weight-gradient kernels fill the bubbles in which the main stream waits for
         # the slowest rank inside a SyncBN exchange (8 x B200: 5364 -> 5431 img/s, +1.3 %). Unset = on under data parallel only.
         env = os.environ.get("B200UNET_WGRAD_STREAM", "")
@@ -291,7 +293,9 @@ class UNetEngine:
             if not training and not save and self.fold_eval_bn:
                 # inference: BatchNorm (running statistics) + ReLU folded into the conv epilogue; y never reaches HBM
                 scale, shift, _, _, _ = self._bn_affine(cb, None, 0, n * hh * ww, False, None)
-                if cb.first:
+                if cb.first and self.first_fused:
+                    ops.conv3x3_first_tc_bn_relu(inp, cb.operands()[0], scale, shift, a_out)
+                elif cb.first:
                     col = torch.empty((n, hh, ww, 64), dtype=BF16, device=dev)
                     ops.first_im2col(inp, col)
                     ops.conv1x1_c64_bn_relu(col, cb.operands()[0], scale, shift, a_out)
@@ -303,14 +307,17 @@ class UNetEngine:
             y = torch.empty((n, hh, ww, c_out), dtype=BF16, device=dev)
             stats = None
             if cb.first:
-                col = torch.empty((n, hh, ww, 64), dtype=BF16, device=dev)
-                ops.first_im2col(inp, col)
-                inp = col  # saved for the weight gradient
                 rows = ops.conv1x1_c64_stat_rows(n, hh, ww, c_out)
                 if training:
                     stats = torch.empty(rows * 2 * c_out, dtype=torch.float32, device=dev)
                 w1, _ = cb.operands()
-                ops.conv1x1_c64(col, w1, y, stats)
+                if self.first_fused:  # im2col rows built in shared memory; the fp32 input itself is saved for the wgrad
+                    ops.conv3x3_first_tc(inp, w1, y, stats)
+                else:
+                    col = torch.empty((n, hh, ww, 64), dtype=BF16, device=dev)
+                    ops.first_im2col(inp, col)
+                    inp = col  # saved for the weight gradient
+                    ops.conv1x1_c64(col, w1, y, stats)
             else:
                 rows = ops.conv3x3_stat_rows(n, hh, ww, inp.shape[3], c_out)
                 if training:
@@ -439,7 +446,9 @@ class UNetEngine:
             rec_t = dict(cb=cb, g1=g1, g_pool=g_pool, pool_idx=pool_idx, dy=dy, dgamma=dgamma, dbeta=dbeta, inp=inp) \
                 if self.trace is not None else None
             dw = gbuf(cb.conv.weight)
-            if cb.first:
+            if cb.first and inp.dtype == torch.float32:
+                on_wgrad_stream(lambda: ops.conv3x3_first_tc_wgrad(inp, dy, dw))
+            elif cb.first:
                 on_wgrad_stream(lambda: ops.conv1x1_c64_wgrad(inp, dy, dw))
             else:
                 on_wgrad_stream(lambda: ops.conv3x3_wgrad(inp, dy, dw))

@@ -174,6 +174,45 @@ def prep_first_weight(w: torch.Tensor, out=None):
     return w1
 
 
+def conv3x3_first_tc(x_nchw: torch.Tensor, w1: torch.Tensor, out: torch.Tensor, stats_partial=None):
+    """inc.conv1 fused: out = conv3x3(x) from the fp32 NCHW input with the im2col rows built in shared memory inside the
+    tcgen05 kernel (no im2col tensor in HBM). w1 = prep_first_weight(w); statistics rows as conv1x1_c64()."""
+    if x_nchw.dtype != torch.float32 or not x_nchw.is_cuda or not x_nchw.is_contiguous() or x_nchw.dim() != 4:
+        raise ValueError("conv3x3_first_tc: expected a contiguous CUDA fp32 NCHW tensor")
+    n, cin, h, w = x_nchw.shape
+    op, ocs, n2, h2, w2, cout = _nhwc(out)
+    if (n, h, w) != (n2, h2, w2) or tuple(w1.shape) != (cout, 64) or w1.dtype != BF16:
+        raise ValueError("conv3x3_first_tc: shape mismatch")
+    if stats_partial is not None and stats_partial.numel() < conv1x1_c64_stat_rows(n, h, w, cout) * 2 * cout:
+        raise ValueError("conv3x3_first_tc: stats_partial too small")
+    _lib.call("b200unet_conv3x3_first_igemm", x_nchw.data_ptr(), w1.data_ptr(), op, ocs, _f32(stats_partial), n, h, w, cin, cout,
+              _stream())
+    return out
+
+
+def conv3x3_first_tc_bn_relu(x_nchw, w1, scale, shift, out):
+    """Eval mode of conv3x3_first_tc: BatchNorm (running statistics) + ReLU folded into the epilogue."""
+    n, cin, h, w = x_nchw.shape
+    op, ocs, n2, h2, w2, cout = _nhwc(out)
+    if (n, h, w) != (n2, h2, w2) or tuple(w1.shape) != (cout, 64) or w1.dtype != BF16 or x_nchw.dtype != torch.float32:
+        raise ValueError("conv3x3_first_tc_bn_relu: shape mismatch")
+    _lib.call("b200unet_conv3x3_first_bn_relu_igemm", x_nchw.contiguous().data_ptr(), w1.data_ptr(), _f32(scale), _f32(shift), op,
+              ocs, n, h, w, cin, cout, _stream())
+    return out
+
+
+def conv3x3_first_tc_wgrad(x_nchw, dy, dw_out):
+    """dw_out (fp32 OIHW [Cout,Cin,3,3]) = weight gradient of inc.conv1 from the fp32 NCHW input and dy (fused im2col)."""
+    n, cin, h, w = x_nchw.shape
+    yp, ycs, n2, h2, w2, cout = _nhwc(dy)
+    if (n, h, w) != (n2, h2, w2) or tuple(dw_out.shape) != (cout, cin, 3, 3) or x_nchw.dtype != torch.float32:
+        raise ValueError("conv3x3_first_tc_wgrad: shape mismatch")
+    ws = _workspace(_lib.query("b200unet_conv3x3_first_tc_wgrad_workspace_floats", n, h, w, cout), dy.device)
+    _lib.call("b200unet_conv3x3_first_tc_wgrad", x_nchw.data_ptr(), yp, ycs, ws.data_ptr(), _f32(dw_out), n, h, w, cin, cout,
+              _stream())
+    return dw_out
+
+
 def conv1x1_c64_stat_rows(n, h, w, cout):
     return _lib.query("b200unet_conv1x1_c64_stat_rows", n, h, w, cout)
 
