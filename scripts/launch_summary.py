@@ -1,5 +1,6 @@
 """Aggregate an ncu launch list (gpu__time_duration.sum per launch, csv) into a per-kernel table for ONE training step:
-the launches between two consecutive first_im2col_kernel launches. Usage: python scripts/launch_summary.py x.csv"""
+the launches between two consecutive launches of the first-layer kernel (conv3_res_kernel<..., TAPS=1, KIND=3 (RES_FIRST), CIN>;
+first_im2col_kernel in round-1 captures). Usage: python scripts/launch_summary.py x.csv"""
 import csv
 import sys
 from collections import OrderedDict
@@ -18,7 +19,10 @@ def main(path):
         unit = r.get("Metric Unit", "ns")
         ns = v * {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1.0)
         rows.append((r["Kernel Name"], ns))
-    starts = [i for i, (n, _) in enumerate(rows) if "first_im2col" in n]
+    import re
+
+    first = re.compile(r"first_im2col|conv3_res_kernel<\d+, \d+, \d+, \d+, 1, 3, \d+>")
+    starts = [i for i, (n, _) in enumerate(rows) if first.search(n)]
     if len(starts) >= 2:
         step = rows[starts[0]:starts[1]]
         note = f"one step = launches {starts[0]}..{starts[1] - 1} of the capture"

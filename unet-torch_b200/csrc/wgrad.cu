@@ -488,6 +488,159 @@ __global__ void __launch_bounds__(192, 1) wgrad_swap_kernel(const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, P::TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Cin = Cout = 64 (inc.conv2, up4.conv2 at 512^2), round 2: the THREE HORIZONTAL TAPS STACKED ON N.
+// wgrad_swap_kernel<1> issues six 128x64x16 MMAs per 16-pixel K step; each reads 4 KB (A) + 2 KB (B) of shared memory per 32
+// tensor cycles = 192 B/clk against the 128 B/clk the SM delivers (ncu: 51 % of the bf16 peak, tensor pipe 58 %). Here the
+// dy operand carries a one-pixel horizontal halo and its MN-major descriptor takes N = 192 = three 64-channel blocks ONE PIXEL
+// (LBO = 128 B) apart: block b is "dy shifted by b pixels", i.e. tap s = 2 - b, because
+//     dW[k,c,r,s] = sum_q x[q + (r-1, 0), c] * dy[q + (0, 1-s), k]          (the sum re-indexed by the x pixel q).
+// With the two vertical taps stacked on M as before (LBO = one x row = 2048 B) a K step is TWO 128x192x16 MMAs (taps
+// (0..1, 0..2) and (2..3, 0..2), r = 3 discarded): 4 KB + 6 KB per 96 cycles = 107 B/clk - no longer bound by shared memory.
+// x tile: {64 ch, 16, 8 + 2 rows} (vertical halo only); dy tile: {64 ch, 16 + 2, 8}. Partials as wgrad_swap_kernel.
+struct WS3Plan {
+  static constexpr int X_BOX = (TH + 2) * TW * 128;                       // 20480
+  static constexpr int X_PAD = ((TH + 3) * TW * 128 + 1023) / 1024 * 1024;  // + the junk row tap r = 3 touches
+  static constexpr int Y_BOX = TH * (TW + 2) * 128;                       // 18432
+  static constexpr int Y_PAD = (Y_BOX + 2 * 128 + 1023) / 1024 * 1024;    // + the two pixels block b = 2 reads past the last row
+  static constexpr int STAGE = X_PAD + Y_PAD;
+  static constexpr int NS_MAX = (227 * 1024 - 2048) / STAGE;
+  static constexpr int NS = NS_MAX > 5 ? 5 : NS_MAX;
+  static constexpr int BAR_OFF = NS * STAGE;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1) wgrad_swap3_kernel(const __grid_constant__ WgradArgs args) {
+  using P = WS3Plan;
+  constexpr int NS = P::NS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + P::BAR_OFF;
+  auto full = [&](int i) { return bars + 8u * i; };
+  auto empty = [&](int i) { return bars + 8u * (NS + i); };
+  const uint32_t acc_full = bars + 8u * (2 * NS);
+  const uint32_t tmem_slot = acc_full + 8;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + P::BAR_OFF + 8 * (2 * NS) + 8);
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  const int z = static_cast<int>(blockIdx.x);
+  const int t_begin = static_cast<int>(static_cast<long long>(args.tiles_total) * z / args.splits);
+  const int t_end = static_cast<int>(static_cast<long long>(args.tiles_total) * (z + 1) / args.splits);
+
+  if (warp == 0 && elect_one_sync()) {
+    prefetch_tmap(&args.tmA);
+    prefetch_tmap(&args.tmB[0]);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(full(i), 1);
+      mbar_init(empty(i), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int st = 0, ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int twi = t % args.tiles_w;
+        const int thi = (t / args.tiles_w) % args.tiles_h;
+        const int img = t / (args.tiles_w * args.tiles_h);
+        const int h0 = thi * TH, w0 = twi * TW;
+        mbar_wait(empty(st), ph ^ 1);
+        mbar_arrive_expect_tx(full(st), P::X_BOX + P::Y_BOX);
+        const uint32_t sX = smem_base + st * P::STAGE;
+        tma_load_4d(sX, &args.tmB[0], full(st), 0, w0, h0 - 1, img);            // x, vertical halo
+        tma_load_4d(sX + P::X_PAD, &args.tmA, full(st), 0, w0 - 1, h0, img);    // dy, horizontal halo
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 192, 1, 1);
+      constexpr uint32_t d_hi = umma_desc_hi_sw128(1024);
+      int st = 0, ph = 0;
+      uint32_t acc = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(full(st), ph);
+        tc_fence_after();
+        const uint32_t sX = smem_base + st * P::STAGE;
+        const uint32_t sY = sX + P::X_PAD;
+#pragma unroll
+        for (int k = 0; k < TH; ++k) {  // one tile row = 16 x pixels per K step
+          // B: dy pixels (k, j + b), b = 0..2 <-> tap s = 2 - b; consecutive blocks one pixel (128 B) apart
+          const uint32_t b_lo = umma_desc_lo(sY + (k * (TW + 2)) * 128, 128);
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr)  // A: x rows (k + 2 pr) and (k + 2 pr + 1) of the vertical-halo tile, 64 channels each
+            umma_bf16_lh(tmem_base + pr * 192, umma_desc_lo(sX + ((k + 2 * pr) * TW) * 128, TW * 128), d_hi, b_lo, d_hi, idesc, acc);
+          acc = 1;
+        }
+        umma_commit(empty(st));
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int Cin = args.Cb;
+#pragma unroll 1
+    for (int a = 0; a < 6; ++a) {
+      const int pr = a / 3, b = a - pr * 3;
+      const int r = 2 * pr + (row >> 6), s = 2 - b, c = row & 63;
+      float* dst = args.partial + ((static_cast<size_t>(z) * 9 + (r * 3 + s)) * Cin + c) * 64;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + pr * 192 + b * 64 + h * 32, v);
+        tmem_ld_wait();
+        if (r < 3) {
+          float4* d4 = reinterpret_cast<float4*>(dst + h * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int launch_wgrad_swap3(const WgradArgs& a, cudaStream_t st) {
+  using P = WS3Plan;
+  static unsigned long long configured = 0;  // one bit per CUDA device
+  if (b2h::first_use_on_device(configured)) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_swap3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
+    if (e != cudaSuccess) {
+      b2h::set_error("wgrad_swap3: cudaFuncSetAttribute(smem=%d): %s", P::TOTAL, cudaGetErrorString(e));
+      return 2;
+    }
+  }
+  wgrad_swap3_kernel<<<a.splits, 192, P::TOTAL, st>>>(a);
+  return b2h::check_launch("wgrad_swap3");
+}
+
+// B200UNET_WGRAD_SWAP3=0 keeps wgrad_swap_kernel<1> for the 64 -> 64 layers
+bool use_swap3() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("B200UNET_WGRAD_SWAP3");
+    on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return on == 1;
+}
+
 // partial [Z][9][C][64] -> dw OIHW [64][C][3][3]
 __global__ void reduce_conv3_swapped_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Z, int C) {
   const int total = 9 * C * 64;
@@ -583,8 +736,14 @@ int b200unet_conv3x3_wgrad(const void* x, int x_cs, const void* dy, int dy_cs, f
   for (int i = 1; i < 4; ++i) a.tmB[i] = a.tmB[0];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_swap(Cin, Cout)) {
-    if (int e = b2h::make_tmap_4d(&a.tmB[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TW + 2, TH + 2)) return e;
-    if (int e = (Cin == 64) ? launch_wgrad_swap<1>(a, st) : launch_wgrad_swap<2>(a, st)) return e;
+    if (Cin == 64 && use_swap3()) {  // the three horizontal taps stacked on N: x with a vertical, dy with a horizontal halo
+      if (int e = b2h::make_tmap_4d(&a.tmB[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TW, TH + 2)) return e;
+      if (int e = b2h::make_tmap_4d(&a.tmA, dy, Cout, W, H, N, ys, ys * W, ys * W * H, TW + 2, TH)) return e;
+      if (int e = launch_wgrad_swap3(a, st)) return e;
+    } else {
+      if (int e = b2h::make_tmap_4d(&a.tmB[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TW + 2, TH + 2)) return e;
+      if (int e = (Cin == 64) ? launch_wgrad_swap<1>(a, st) : launch_wgrad_swap<2>(a, st)) return e;
+    }
     reduce_conv3_swapped_kernel<<<b2h::ceil_div(9 * Cin * 64, 256), 256, 0, st>>>(partial, dw_oihw, a.splits, Cin);
     return b2h::check_launch("conv3x3_wgrad_reduce");
   }
