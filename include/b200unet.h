@@ -60,6 +60,15 @@ int b200unet_conv3x3_stat_rows(int N, int H, int W, int Cin, int Cout);
 int b200unet_set_kernel_choice(int resident, int resident_pairs, int streaming_pairs);
 int b200unet_conv3x3_igemm(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial,
                            int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
+/* Backward-data launch whose OUTPUT y is the gradient g at the output of a BatchNorm+ReLU (Model.py:17-18 / 21-22 of the layer
+ * in front): the first pass of that BatchNorm's backward (b200unet_bn_relu_bwd_reduce) is fused into the epilogue. bn_y = that
+ * layer's saved pre-BN tensor (pitch bn_y_cs), scale/shift/mean/rstd its affine and statistics ([Cout] each); partial receives
+ * [rows][2][Cout] = (sum da, sum da*xhat) with da = g * [scale*bn_y + shift > 0], rows = b200unet_conv3x3_dgrad_bnred_rows(...)
+ * (0 = this shape has no fused form: use b200unet_conv3x3_igemm + b200unet_bn_relu_bwd_reduce). Saves one 4 B/element pass. */
+int b200unet_conv3x3_dgrad_bnred_rows(int N, int H, int W, int Cin, int Cout);
+int b200unet_conv3x3_igemm_bnred(const void* x, int x_cs, const void* w, void* y, int y_cs, const void* bn_y, int bn_y_cs,
+                                 const float* scale, const float* shift, const float* mean, const float* rstd,
+                                 float* partial, int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
 /* Eval-mode variant (running statistics, Model.py:17-18 with module.eval()): BatchNorm folded to a per-channel
  * scale/shift ([Cout] fp32 each, 16-byte aligned; b200unet_bn_eval_affine produces them) and applied with the ReLU in the
  * epilogue on the fp32 accumulators: a = bf16(relu(scale * conv(x) + shift)). The pre-BN tensor never reaches HBM. */

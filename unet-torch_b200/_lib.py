@@ -30,6 +30,8 @@ SIGNATURES = {
     "b200unet_set_kernel_choice": (c_int, [_I, _I, _I]),
     "b200unet_conv3x3_stat_rows": (c_int, [_I, _I, _I, _I, _I]),
     "b200unet_conv3x3_igemm": (c_int, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "b200unet_conv3x3_dgrad_bnred_rows": (c_int, [_I, _I, _I, _I, _I]),
+    "b200unet_conv3x3_igemm_bnred": (c_int, [_P, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200unet_conv3x3_bn_relu_igemm": (c_int, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200unet_conv1x1_c64_bn_relu_igemm": (c_int, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200unet_convt2x2_fprop": (c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

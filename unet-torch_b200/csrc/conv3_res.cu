@@ -53,6 +53,11 @@ struct ResArgs {
   const float* scale;  // CONV: eval-mode BatchNorm + ReLU folded into the epilogue: [ncols] each, or null
   const float* shift;
   const float* x_nchw;  // FIRST: the fp32 NCHW network input the im2col rows are built from
+  // BNRED (backward-data launches whose output is the gradient g at a BatchNorm+ReLU output): the pre-BN tensor y of THAT
+  // BatchNorm and its affine / statistics; `stats` then receives [workers][2][ncols] = (sum da, sum da*xhat), da = g*[bn(y) > 0]
+  CUtensorMap tmY;
+  const float* bn_mean;
+  const float* bn_rstd;
 };
 
 // What the GEMM is:            A operand per K block                      epilogue
@@ -66,14 +71,16 @@ enum { RES_CONV = 0, RES_UP = 1, RES_GATHER = 2, RES_FIRST = 3 };
 // epilogue groups per CTA (see the comment at res_threads below)
 constexpr int res_epi_groups(int ob) { return ob == 2 ? 2 : 1; }
 
-template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV>
+template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV, bool BNRED = false>
 struct ResPlan {
   static constexpr int A_STAGE = TileGeom<TAPS>::A_STAGE;
   static constexpr int W_BYTES = TAPS * KB * BN * 128;
   static constexpr int A_OFF = W_BYTES;
   static constexpr int OUT_OFF = A_OFF + NA * A_STAGE;
   static constexpr int OUT_BYTES = OB * (BN / 64) * OUT_CHUNK;
-  static constexpr int BAR_OFF = OUT_OFF + OUT_BYTES;
+  static constexpr int Y_OFF = OUT_OFF + OUT_BYTES;                      // BNRED: one y tile per epilogue group
+  static constexpr int Y_BYTES = BNRED ? 2 * (BN / 64) * OUT_CHUNK : 0;
+  static constexpr int BAR_OFF = Y_OFF + Y_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024 /* alignment slack */;
   static_assert(TOTAL <= 227 * 1024, "shared memory plan exceeds 227 KiB");
   static_assert(res_epi_groups(OB) * 4 * 2 * BN * 4 <= OUT_BYTES, "final statistics reduction aliases the staging buffer");
@@ -87,9 +94,10 @@ struct ResPlan {
 // warps: 0 TMA producer, 1 MMA issuer, then 4 epilogue warps per group; RES_FIRST appends two groups of four im2col builders
 constexpr int res_threads(int kind, int ob) { return 64 + 128 * res_epi_groups(ob) + (kind == RES_FIRST ? 256 : 0); }
 
-template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV, int CIN = 0>
+template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV, int CIN = 0, bool BNRED = false>
 __global__ void __launch_bounds__(res_threads(KIND, OB), 1) conv3_res_kernel(const __grid_constant__ ResArgs args) {
-  using P = ResPlan<BN, KB, NA, OB, TAPS, KIND>;
+  using P = ResPlan<BN, KB, NA, OB, TAPS, KIND, BNRED>;
+  static_assert(!BNRED || (KIND == RES_CONV && OB == 2), "BNRED: conv epilogue with one staging buffer per epilogue group");
   static_assert(KIND != RES_FIRST || (TAPS == 1 && KB == 1 && CIN >= 1 && CIN <= 7), "RES_FIRST: one K block of im2col rows");
   static_assert(KIND == RES_CONV || TAPS == 1, "the transposed-convolution GEMMs have no spatial taps");
   static_assert(KIND != RES_GATHER || KB % 4 == 0, "gather: K blocks split evenly over the four (i,j) maps");
@@ -109,6 +117,9 @@ __global__ void __launch_bounds__(res_threads(KIND, OB), 1) conv3_res_kernel(con
   auto T_empty = [&](int i) { return bars + 8u * (3 + 2 * NA + i); };
   const uint32_t tmem_slot = bars + 8u * (5 + 2 * NA);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + P::BAR_OFF + 8 * (5 + 2 * NA));
+  auto Y_full = [&](int i) { return bars + 8u * (6 + 2 * NA + i); };
+  auto Y_empty = [&](int i) { return bars + 8u * (8 + 2 * NA + i); };
+  const uint32_t sY = smem_base + P::Y_OFF;
 
   constexpr int EG = res_epi_groups(OB);
   const int warp = warp_idx_uniform();
@@ -130,7 +141,12 @@ __global__ void __launch_bounds__(res_threads(KIND, OB), 1) conv3_res_kernel(con
     for (int i = 0; i < 2; ++i) {
       mbar_init(T_full(i), 1);
       mbar_init(T_empty(i), 4);  // one arrival per epilogue warp
+      if (BNRED) {
+        mbar_init(Y_full(i), 1);
+        mbar_init(Y_empty(i), 4);
+      }
     }
+    if (BNRED) prefetch_tmap(&args.tmY);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
@@ -175,6 +191,14 @@ __global__ void __launch_bounds__(res_threads(KIND, OB), 1) conv3_res_kernel(con
           else
             tma_load_4d(sA + sa * A_STAGE, &args.tmA[0], A_full(sa), cb * 64, w0 - G::HALO, h0 - G::HALO, img);
           if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+        if (BNRED) {  // the consumer BatchNorm's pre-activation tile of the same pixels / channels, for the epilogue
+          const int buf = j & 1;
+          mbar_wait(Y_empty(buf), ((j >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(Y_full(buf), (BN / 64) * OUT_CHUNK);
+#pragma unroll
+          for (int q = 0; q < BN / 64; ++q)
+            tma_load_4d(sY + (buf * (BN / 64) + q) * OUT_CHUNK, &args.tmY, Y_full(buf), n0 + q * 64, w0, h0, img);
         }
       }
     }
@@ -255,6 +279,16 @@ __global__ void __launch_bounds__(res_threads(KIND, OB), 1) conv3_res_kernel(con
     float s1[BN / 64][2], s2[BN / 64][2];
 #pragma unroll
     for (int q = 0; q < BN / 64; ++q) s1[q][0] = s1[q][1] = s2[q][0] = s2[q][1] = 0.f;
+    float bsc[BN / 64][2], bsh[BN / 64][2];  // BNRED: scale / shift of this thread's channel pair
+    if (BNRED) {
+#pragma unroll
+      for (int q = 0; q < BN / 64; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          bsc[q][e] = __ldg(args.scale + n0 + q * 64 + cp * 2 + e);
+          bsh[q][e] = __ldg(args.shift + n0 + q * 64 + cp * 2 + e);
+        }
+    }
 
 #pragma unroll 1
     for (int j = eg; j < ntiles_mine; j += EG) {
@@ -271,7 +305,7 @@ __global__ void __launch_bounds__(res_threads(KIND, OB), 1) conv3_res_kernel(con
           uint32_t v[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN + q * 64 + half * 32, v);
           tmem_ld_wait();
-          if ((KIND == RES_CONV || KIND == RES_FIRST) && args.scale != nullptr)
+          if (!BNRED && (KIND == RES_CONV || KIND == RES_FIRST) && args.scale != nullptr)
             affine_relu32(v, args.scale + n0 + q * 64 + half * 32, args.shift + n0 + q * 64 + half * 32);
           if (KIND == RES_UP && args.bias != nullptr) {
             const float* bp = args.bias + (n0 + q * 64 + half * 32) % args.cup;
@@ -311,23 +345,44 @@ __global__ void __launch_bounds__(res_threads(KIND, OB), 1) conv3_res_kernel(con
       }
       if (want_stats) {
         const bool full = (h0 + RTH <= args.H) && (w0 + RTW <= args.W);
+        if (BNRED) {
+          mbar_wait(Y_full(buf), (j >> 1) & 1);
+        }
 #pragma unroll
         for (int q = 0; q < BN / 64; ++q) {
           const uint32_t base = stage + q * OUT_CHUNK + (cp & 3) * 4;
+          const uint32_t ybase = sY + (buf * (BN / 64) + q) * OUT_CHUNK + (cp & 3) * 4;
 #pragma unroll 8
           for (int i = 0; i < 32; ++i) {
             const int r = rq * 32 + i;
+            const uint32_t off = r * 128 + ((static_cast<uint32_t>(cp >> 2) ^ (r & 7)) << 4);
             uint32_t u;
-            asm volatile("ld.shared.b32 %0, [%1];"
-                         : "=r"(u)
-                         : "r"(base + r * 128 + ((static_cast<uint32_t>(cp >> 2) ^ (r & 7)) << 4)));
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(base + off));
             float x0 = __uint_as_float(u << 16), x1 = __uint_as_float(u & 0xffff0000u);
             if (!full && !((h0 + (r >> 3) < args.H) && (w0 + (r & 7) < args.W))) x0 = x1 = 0.f;
-            s1[q][0] += x0;
-            s1[q][1] += x1;
-            s2[q][0] = fmaf(x0, x0, s2[q][0]);
-            s2[q][1] = fmaf(x1, x1, s2[q][1]);
+            if (BNRED) {
+              // the stored gradient g, masked by the ReLU of the consumer BatchNorm: da = g * [scale*y + shift > 0];
+              // accumulates (sum da, sum da*y) - turned into (sum da, sum da*xhat) once per CTA below
+              uint32_t uy;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(uy) : "r"(ybase + off));
+              const float y0 = __uint_as_float(uy << 16), y1 = __uint_as_float(uy & 0xffff0000u);
+              if (!(fmaf(bsc[q][0], y0, bsh[q][0]) > 0.f)) x0 = 0.f;
+              if (!(fmaf(bsc[q][1], y1, bsh[q][1]) > 0.f)) x1 = 0.f;
+              s1[q][0] += x0;
+              s1[q][1] += x1;
+              s2[q][0] = fmaf(x0, y0, s2[q][0]);
+              s2[q][1] = fmaf(x1, y1, s2[q][1]);
+            } else {
+              s1[q][0] += x0;
+              s1[q][1] += x1;
+              s2[q][0] = fmaf(x0, x0, s2[q][0]);
+              s2[q][1] = fmaf(x1, x1, s2[q][1]);
+            }
           }
+        }
+        if (BNRED) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(Y_empty(buf));
         }
       }
       // the group's staging buffer is free again once its store has read it (by then the statistics pass above is done too)
@@ -353,6 +408,13 @@ __global__ void __launch_bounds__(res_threads(KIND, OB), 1) conv3_res_kernel(con
         float t = 0.f;
 #pragma unroll
         for (int part = 0; part < 4 * EG; ++part) t += red[(part * 2 + stat) * BN + ch];  // fixed order: reproducible
+        if (BNRED && stat == 1) {  // sum da*y -> sum da*xhat = rstd * (sum da*y - mean * sum da)
+          float t0 = 0.f;
+#pragma unroll
+          for (int part = 0; part < 4 * EG; ++part) t0 += red[(part * 2 + 0) * BN + ch];
+          t = static_cast<float>(static_cast<double>(__ldg(args.bn_rstd + n0 + ch)) *
+                                 (static_cast<double>(t) - static_cast<double>(__ldg(args.bn_mean + n0 + ch)) * static_cast<double>(t0)));
+        }
         dst[stat * args.ncols + ch] = t;
       }
     }
@@ -363,11 +425,11 @@ __global__ void __launch_bounds__(res_threads(KIND, OB), 1) conv3_res_kernel(con
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV, int CIN = 0>
+template <int BN, int KB, int NA, int OB, int TAPS, int KIND = RES_CONV, int CIN = 0, bool BNRED = false>
 int launch_res(const ResArgs& a, cudaStream_t st) {
-  using P = ResPlan<BN, KB, NA, OB, TAPS, KIND>;
+  using P = ResPlan<BN, KB, NA, OB, TAPS, KIND, BNRED>;
   static unsigned long long configured = 0;  // one bit per CUDA device
-  auto kern = conv3_res_kernel<BN, KB, NA, OB, TAPS, KIND, CIN>;
+  auto kern = conv3_res_kernel<BN, KB, NA, OB, TAPS, KIND, CIN, BNRED>;
   if (b2h::first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL);
     if (e != cudaSuccess) {
@@ -419,6 +481,37 @@ int conv3_res_stat_rows(int N, int H, int W, int Cin, int Cout) {
   int ntn, workers, tiles;
   res_geometry(N, H, W, res_bn(Cin, Cout), Cout, &ntn, &workers, &tiles);
   return workers;
+}
+
+// BatchNorm-backward reduction fused into a backward-data launch (Cin = Cout = 64: the level-0 layers, where the separate
+// reduce pass reads 1.07 GB): bn_y = pre-BN tensor of the BatchNorm whose OUTPUT gradient this launch produces.
+bool conv3_res_bnred_applicable(int Cin, int Cout) { return Cin == 64 && Cout == 64; }
+
+int conv3_res_bnred_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, const void* bn_y, int bn_y_cs,
+                           const float* scale, const float* shift, const float* mean, const float* rstd, float* partial, int N,
+                           int H, int W, int Cin, int Cout, cudaStream_t st) {
+  ResArgs a;
+  res_geometry(N, H, W, 64, Cout, &a.ntiles_n, &a.workers, &a.tiles_total);
+  a.tiles_w = ceil_div(W, RTW);
+  a.tiles_h = ceil_div(H, RTH);
+  a.H = H;
+  a.W = W;
+  a.ncols = Cout;
+  a.stats = partial;
+  a.scale = scale;
+  a.shift = shift;
+  a.bn_mean = mean;
+  a.bn_rstd = rstd;
+  a.cup = Cout;
+  a.bias = nullptr;
+  a.x_nchw = nullptr;
+  const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2, bs = static_cast<uint64_t>(bn_y_cs) * 2;
+  if (int e = make_tmap_4d(&a.tmA[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TileGeom<9>::IN_W, TileGeom<9>::IN_H)) return e;
+  if (int e = make_tmap_2d(&a.tmW, w, static_cast<uint64_t>(9) * Cin, Cout, 64)) return e;
+  if (int e = make_tmap_4d(&a.tmO[0], y, Cout, W, H, N, ys, ys * W, ys * W * H, RTW, RTH)) return e;
+  if (int e = make_tmap_4d(&a.tmY, bn_y, Cout, W, H, N, bs, bs * W, bs * W * H, RTW, RTH)) return e;
+  for (int i = 1; i < 4; ++i) { a.tmA[i] = a.tmA[0]; a.tmO[i] = a.tmO[0]; }
+  return launch_res<64, 1, 3, 2, 9, RES_CONV, 0, true>(a, st);
 }
 
 int conv3_res_launch(const void* x, int x_cs, const void* w, void* y, int y_cs, float* stats_partial, int N, int H,

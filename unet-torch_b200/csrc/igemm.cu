@@ -412,6 +412,28 @@ int b200unet_conv3x3_bn_relu_igemm(const void* x, int x_cs, const void* w, const
   return conv3x3_dispatch(x, x_cs, w, a, a_cs, nullptr, scale, shift, N, H, W, Cin, Cout, stream);
 }
 
+int b200unet_conv3x3_dgrad_bnred_rows(int N, int H, int W, int Cin, int Cout) {
+  if (!(use_resident(Cin, Cout) && !use_pairs(N, H, W, Cin, Cout) && b2h::conv3_res_bnred_applicable(Cin, Cout))) return 0;
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("B200UNET_NO_BNRED");
+    off = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
+  return off ? 0 : b2h::conv3_res_stat_rows(N, H, W, Cin, Cout);
+}
+
+int b200unet_conv3x3_igemm_bnred(const void* x, int x_cs, const void* w, void* y, int y_cs, const void* bn_y, int bn_y_cs,
+                                 const float* scale, const float* shift, const float* mean, const float* rstd,
+                                 float* partial, int N, int H, int W, int Cin, int Cout, b200_stream_t stream) {
+  B2_REQUIRE(b200unet_conv3x3_dgrad_bnred_rows(N, H, W, Cin, Cout) > 0,
+             "conv3x3_igemm_bnred: no fused form for Cin=%d Cout=%d at %dx%d (query b200unet_conv3x3_dgrad_bnred_rows first)", Cin,
+             Cout, H, W);
+  B2_REQUIRE(x && w && y && bn_y && scale && shift && mean && rstd && partial, "conv3x3_igemm_bnred: null argument");
+  B2_REQUIRE(x_cs % 8 == 0 && y_cs % 8 == 0 && bn_y_cs % 8 == 0 && bn_y_cs >= Cout, "conv3x3_igemm_bnred: bad pitches");
+  return b2h::conv3_res_bnred_launch(x, x_cs, w, y, y_cs, bn_y, bn_y_cs, scale, shift, mean, rstd, partial, N, H, W, Cin, Cout,
+                                     static_cast<cudaStream_t>(stream));
+}
+
 int b200unet_set_kernel_choice(int resident, int resident_pairs, int streaming_pairs) {
   B2_REQUIRE(resident >= -1 && resident <= 1 && resident_pairs >= -1 && resident_pairs <= 1 && streaming_pairs >= -1 &&
                  streaming_pairs <= 1,

@@ -436,12 +436,16 @@ class UNetEngine:
                 side.wait_event(ev)
                 launch()
 
-        def bn_conv_bwd(cb: _ConvBN, rec, g1, g_pool, pool_idx, hh, ww, need_dx, dx_colsum=None):
+        def bn_conv_bwd(cb: _ConvBN, rec, g1, g_pool, pool_idx, hh, ww, need_dx, dx_colsum=None, pre=None, fuse_next=None):
+            """Backward of one conv+BN+ReLU. pre: (partial, rows) if the kernel that produced g1 already reduced this
+            layer's BatchNorm sums; fuse_next: the record of the layer in FRONT (whose output is this conv's input): its
+            BatchNorm reduction is fused into this layer's backward-data launch when a fused form exists. Returns dx, or
+            (dx, pre_for_next) when fuse_next is given."""
             inp, y, scale, shift, mean, rstd, count, frozen = rec
             bn = cb.bn
             dgamma, dbeta = gbuf(bn.weight), gbuf(bn.bias)
             ops.bn_relu_bwd(g1, g_pool, pool_idx, y, bn.weight.detach(), scale, shift, mean, rstd, y, dgamma, dbeta,
-                            count=count, allreduce=None if frozen else sync, frozen=frozen)
+                            count=count, allreduce=None if frozen else sync, frozen=frozen, pre=pre)
             dy = y  # dy overwrote y in place
             rec_t = dict(cb=cb, g1=g1, g_pool=g_pool, pool_idx=pool_idx, dy=dy, dgamma=dgamma, dbeta=dbeta, inp=inp) \
                 if self.trace is not None else None
@@ -462,6 +466,14 @@ class UNetEngine:
             _, wd = cb.operands()
             cdx = wd.shape[0]
             dx = torch.empty((n, hh, ww, cdx), dtype=BF16, device=dev)
+            if fuse_next is not None:
+                _, y_n, scale_n, shift_n, mean_n, rstd_n, _, _ = fuse_next
+                pre_n = ops.conv3x3_dgrad_bnred(dy, wd, dx, y_n, scale_n, shift_n, mean_n, rstd_n)
+                if pre_n is None:
+                    ops.conv3x3(dy, wd, dx)
+                if rec_t is not None:
+                    rec_t["dx"] = dx.clone() if len(self.decoders) > 1 else dx
+                return dx, pre_n
             if dx_colsum is None:
                 ops.conv3x3(dy, wd, dx)
             else:
@@ -492,10 +504,10 @@ class UNetEngine:
                 l = 3 - j
                 d_in, r1, r2, _ = saved.dec[k][j]
                 c1, c2 = dec[j]
-                g = bn_conv_bwd(c2, r2, g, None, None, hs[l], wsz[l], True)
+                g, pre = bn_conv_bwd(c2, r2, g, None, None, hs[l], wsz[l], True, fuse_next=r1)
                 upo = ups[j]
                 db, dwu = gbuf(upo.up.bias), gbuf(upo.up.weight)
-                dcat = bn_conv_bwd(c1, r1, g, None, None, hs[l], wsz[l], True, dx_colsum=(ch[l], db))
+                dcat = bn_conv_bwd(c1, r1, g, None, None, hs[l], wsz[l], True, dx_colsum=(ch[l], db), pre=pre)
                 if skip_grads[l] is None:
                     skip_grads[l] = dcat[..., : ch[l]]
                 else:
@@ -519,10 +531,10 @@ class UNetEngine:
             r1, r2, _, idx = saved.enc[l]
             c1, c2 = self.enc[l]
             if l == 4:
-                g1 = bn_conv_bwd(c2, r2, g, None, None, hs[l], wsz[l], True)
+                g1, pre = bn_conv_bwd(c2, r2, g, None, None, hs[l], wsz[l], True, fuse_next=r1)
             else:
-                g1 = bn_conv_bwd(c2, r2, skip_grads[l], g_pool, idx, hs[l], wsz[l], True)
-            g_pool = bn_conv_bwd(c1, r1, g1, None, None, hs[l], wsz[l], need_dx=(l > 0))
+                g1, pre = bn_conv_bwd(c2, r2, skip_grads[l], g_pool, idx, hs[l], wsz[l], True, fuse_next=r1)
+            g_pool = bn_conv_bwd(c1, r1, g1, None, None, hs[l], wsz[l], need_dx=(l > 0), pre=pre)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)  # join
         if flat is not None:

@@ -92,6 +92,24 @@ def conv3x3(x: torch.Tensor, w_op: torch.Tensor, out: torch.Tensor, stats_partia
     return out
 
 
+def conv3x3_dgrad_bnred(dy, w_dgrad, dx, bn_y, scale, shift, mean, rstd):
+    """dx = conv3x3(dy, dgrad operand) with the first pass of the CONSUMER BatchNorm's backward fused into the epilogue
+    (dx is the gradient at that BatchNorm+ReLU's output, bn_y its saved pre-BN tensor). Returns (partial, rows) for
+    bn_relu_bwd(pre=...), or None when this shape has no fused form (the caller then runs the separate reduce pass)."""
+    xp, xcs, n, h, w, cin = _nhwc(dy)
+    op, ocs, n2, h2, w2, cout = _nhwc(dx)
+    rows = _lib.query("b200unet_conv3x3_dgrad_bnred_rows", n, h, w, cin, cout)
+    if rows <= 0 or mean is None or rstd is None:
+        return None
+    yp, ycs, n3, h3, w3, c3 = _nhwc(bn_y)
+    if (n, h, w) != (n2, h2, w2) or (n3, h3, w3, c3) != (n, h, w, cout) or tuple(w_dgrad.shape) != (cout, 3, 3, cin):
+        raise ValueError("conv3x3_dgrad_bnred: shape mismatch")
+    partial = torch.empty(rows * 2 * cout, dtype=torch.float32, device=dy.device)
+    _lib.call("b200unet_conv3x3_igemm_bnred", xp, xcs, w_dgrad.data_ptr(), op, ocs, yp, ycs, _f32(scale), _f32(shift), _f32(mean),
+              _f32(rstd), partial.data_ptr(), n, h, w, cin, cout, _stream())
+    return partial, rows
+
+
 def conv3x3_bn_relu(x, w_op, scale, shift, out):
     """Eval mode: out = bf16(relu(scale * conv3x3(x) + shift)), BatchNorm (running statistics) and ReLU folded into the
     conv epilogue on the fp32 accumulators; `out` may be a channel slice of a concat buffer."""
@@ -335,11 +353,13 @@ def bn_relu_fwd(y, scale, shift, a, pooled=None, pool_idx=None):
 
 
 def bn_relu_bwd(g1, g_pool, pool_idx, y, gamma, scale, shift, mean, rstd, dy, dgamma, dbeta, count=None,
-                allreduce=None, frozen=False):
+                allreduce=None, frozen=False, pre=None):
     """Backward of BN->ReLU(->skip+pool). g1: gradient w.r.t. the activation (may be a channel slice, or None);
     g_pool/pool_idx: gradient through the 2x2 max pool (or None). Writes dy (may alias y), dgamma, dbeta.
     allreduce: optional DataParallelContext (SyncBN): the sums are exchanged between the two passes - one fused NVLink kernel
     on the unreduced block partials when available, otherwise reduce_partials + all_reduce_sum.
+    pre: (partial, rows) already produced by the epilogue of the kernel that computed g1 (conv3x3_dgrad_bnred): the reduce
+    pass over g1 and y is skipped.
     frozen: the forward normalised with RUNNING statistics (module.eval() under autograd): mean/rstd are the running ones,
     statistics do not depend on y, so dy = gamma * rstd * da (the batch-statistics correction terms vanish: the apply pass
     gets an all-zero sums vector) while dgamma / dbeta keep the reduced sums."""
@@ -355,12 +375,28 @@ def bn_relu_bwd(g1, g_pool, pool_idx, y, gamma, scale, shift, mean, rstd, dy, dg
     sums_local = None
     if count is None:
         count = n * h * w
-    if allreduce is not None and not frozen and allreduce.supports_rows(c):
-        rows = ctypes.c_int(0)
-        _lib.call("b200unet_bn_relu_bwd_reduce_rows", g1p, g1cs, _ptr(g_pool), _ptr(pool_idx), yp, ycs, _f32(scale),
-                  _f32(shift), _f32(mean), _f32(rstd), ws.data_ptr(), ctypes.byref(rows), n, h, w, c, _stream())
-        sums_local = torch.empty_like(sums)
-        allreduce.rows_allreduce(ws, rows.value, c, sums_local, sums)
+    use_rows = allreduce is not None and not frozen and allreduce.supports_rows(c)
+    if pre is not None or use_rows:
+        if pre is not None:
+            if g_pool is not None:
+                raise ValueError("bn_relu_bwd: a fused reduction cannot include a pooled gradient")
+            ws, nrows = pre
+        else:
+            rows = ctypes.c_int(0)
+            _lib.call("b200unet_bn_relu_bwd_reduce_rows", g1p, g1cs, _ptr(g_pool), _ptr(pool_idx), yp, ycs, _f32(scale),
+                      _f32(shift), _f32(mean), _f32(rstd), ws.data_ptr(), ctypes.byref(rows), n, h, w, c, _stream())
+            nrows = rows.value
+        if use_rows:
+            sums_local = torch.empty_like(sums)
+            allreduce.rows_allreduce(ws, nrows, c, sums_local, sums)
+        else:
+            bn_reduce_partials(ws, nrows, c, sums)
+            if frozen:
+                sums_local = sums
+                sums = torch.zeros_like(sums)
+            elif allreduce is not None:
+                sums_local = sums.clone()
+                allreduce.all_reduce_sum(sums)
     else:
         _lib.call("b200unet_bn_relu_bwd_reduce", g1p, g1cs, _ptr(g_pool), _ptr(pool_idx), yp, ycs, _f32(scale), _f32(shift),
                   _f32(mean), _f32(rstd), ws.data_ptr(), sums.data_ptr(), n, h, w, c, _stream())
