@@ -251,3 +251,52 @@ def test_conv_transpose_fprop_dgrad_wgrad(ops, n, h, w, cin, cup):
     dw = torch.empty(cin, cup, 2, 2, device="cuda")
     ops.convt2x2_wgrad(to_nhwc_bf16(xv.detach()), dcat[..., cup:], dw)
     assert rel_l2(dw, wv.grad) < 1e-4
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 16, 8), (2, 40, 72), (4, 64, 96), (3, 20, 12)])
+def test_dgrad_with_fused_batchnorm_backward_reduction(ops, n, h, w):
+    """conv3x3_dgrad_bnred (64 -> 64): the backward-data output dx must be the plain kernel's bits, and the partial rows the
+    epilogue produces - (sum da, sum da*xhat) with da = dx * [scale*y + shift > 0] of the BatchNorm in front (Model.py:17-18)
+    - must reduce to what the host computes from the very same dx and y; ragged tiles (20 x 12) included."""
+    g = torch.Generator().manual_seed(31)
+    c = 64
+    dy = to_nhwc_bf16(torch.randn(n, c, h, w, generator=g))
+    wt = torch.randn(c, c, 3, 3, generator=g) * (2.0 / (9 * c)) ** 0.5
+    _, wd = ops.prep_conv3x3_weight(wt.cuda())
+    y_bn = to_nhwc_bf16(torch.randn(n, c, h, w, generator=g) * 1.5 + 0.3)
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
+    yf = y_bn.float().cpu()
+    mean, var = yf.mean((0, 1, 2)), yf.var((0, 1, 2), unbiased=False)
+    rstd = 1.0 / torch.sqrt(var + 1e-5)
+    scale, shift = gamma * rstd, beta - mean * gamma * rstd
+    dev = lambda t: t.float().cuda().contiguous()  # noqa: E731
+    dx_plain = torch.empty(n, h, w, c, dtype=BF16, device="cuda")
+    ops.conv3x3(dy, wd, dx_plain)
+    dx = torch.empty(n, h, w, c, dtype=BF16, device="cuda")
+    sc_d, sh_d, mean_d, rstd_d = dev(scale), dev(shift), dev(mean), dev(rstd)
+    pre = ops.conv3x3_dgrad_bnred(dy, wd, dx, y_bn, sc_d, sh_d, mean_d, rstd_d)
+    assert pre is not None, "the 64 -> 64 backward-data launch has a fused form"
+    partial, rows = pre
+    assert torch.equal(dx, dx_plain)
+    sums = torch.empty(2 * c, dtype=torch.float64, device="cuda")
+    ops.bn_reduce_partials(partial, rows, c, sums)
+    dxf = dx.float().cpu().double()
+    da = dxf * ((scale.double() * yf.double() + shift.double()) > 0)
+    xhat = (yf.double() - mean.double()) * rstd.double()
+    want = torch.cat([da.sum((0, 1, 2)), (da * xhat).sum((0, 1, 2))])
+    err = float((sums.cpu() - want).abs().max() / want.abs().max())
+    assert err < 1e-4, err
+    # and the two-pass path gives the same sums
+    ws = torch.empty(int(__import__("unet_torch_b200")._lib.query("b200unet_bn_bwd_workspace_floats", n, h, w, c)), device="cuda")
+    sums2 = torch.empty(2 * c, dtype=torch.float64, device="cuda")
+    import unet_torch_b200
+
+    unet_torch_b200._lib.call("b200unet_bn_relu_bwd_reduce", dx.data_ptr(), c, None, None, y_bn.data_ptr(), c, sc_d.data_ptr(),
+                              sh_d.data_ptr(), mean_d.data_ptr(), rstd_d.data_ptr(), ws.data_ptr(), sums2.data_ptr(), n,
+                              h, w, c, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert float((sums - sums2).abs().max() / want.abs().max()) < 1e-5
+    # shapes without a fused form report it instead of guessing
+    assert ops.conv3x3_dgrad_bnred(to_nhwc_bf16(torch.zeros(1, 256, 16, 16)), ops.prep_conv3x3_weight(torch.zeros(256, 256, 3, 3).cuda())[1],
+                                   torch.empty(1, 16, 16, 256, dtype=BF16, device="cuda"), to_nhwc_bf16(torch.zeros(1, 256, 16, 16)),
+                                   *(torch.zeros(256, device="cuda") for _ in range(4))) is None
