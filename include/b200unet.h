@@ -126,6 +126,68 @@ int64_t b200unet_conv1x1_c64_wgrad_workspace_floats(int N, int H, int W, int Cou
 int b200unet_conv1x1_c64_wgrad(const void* col, int col_cs, const void* dy, int dy_cs, float* partial, float* dw,
                                int N, int H, int W, int T, int Cout, b200_stream_t stream);
 
+/* ---- 1x1 convolutions of the attention gates (Attention_block W_q / W_x, Model.py:260-275) ------------------ */
+/* nn.Conv2d(Cin, Cout, 1) + bias as a tcgen05 GEMM over NHWC bf16: y[n,h,w,k] = b[k] + sum_c x[n,h,w,c] w[k][c], w bf16
+ * [Cout][Cin]. Also its backward-data (x = dy, w = the transposed operand [Cin][Cout], bias NULL). stats_partial: NULL or
+ * fp32 [b200unet_conv1x1_stat_rows][2][stat_channels] sums / sums of squares of the first stat_channels <= Cout channels of
+ * the bf16 outputs (feeds the BatchNorm2d that follows, Model.py:263,272). Requires Cin % 64 == 0 and Cout % 64 == 0 (the host pads a 32-channel gate with zero weights). */
+int b200unet_conv1x1_stat_rows(int N, int H, int W);
+int b200unet_conv1x1_fprop(const void* x, int x_cs, const void* w, const float* bias, void* y, int y_cs, float* stats_partial,
+                           int stat_channels, int N, int H, int W, int Cin, int Cout, b200_stream_t stream);
+/* dw[k][c] = sum_{n,h,w} dy[n,h,w,k] x[n,h,w,c] for k < Cout_real, fp32 [Cout_real][Cin] (= the OIHW gradient). */
+int64_t b200unet_conv1x1_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout);
+int b200unet_conv1x1_wgrad(const void* x, int x_cs, const void* dy, int dy_cs, float* partial, float* dw, int N, int H, int W,
+                           int Cin, int Cout, int Cout_real, b200_stream_t stream);
+/* b200unet_convt2x2_fprop with the BatchNorm statistics of its output: stats_partial fp32
+ * [b200unet_convt2x2_stat_rows][2][stat_channels] (the first stat_channels <= Cup channels). The gate's `up` followed by W_q (Model.py:287-288) is ONE ConvTranspose2d with the
+ * composed weight, so the C_q-channel upsampled map never exists. */
+int b200unet_convt2x2_stat_rows(int N, int H, int W);
+int b200unet_convt2x2_fprop_stats(const void* x, int x_cs, const void* w_fprop, const float* bias, void* out, int out_cs,
+                                  float* stats_partial, int stat_channels, int N, int H, int W, int Cin, int Cup, int H2,
+                                  int W2, int pad_top, int pad_left, b200_stream_t stream);
+
+/* ---- attention gate, bandwidth-bound part (Attention_block.forward, Model.py:286-296) ----------------------------
+ * q1 / x1: the pre-BatchNorm maps W_q(up(q)) and W_x(x), NHWC bf16 with C real channels (32, 64, 128 or 256) and pitches
+ * q1_cs / x1_cs; scale_* / shift_*: the BatchNorm affine of each ([C] fp32); w_psi [C], b_psi [1]: the psi convolution.
+ * E = relu(Q1 + X1) and A are never stored; s (fp32, one value per pixel) is psi's output before its BatchNorm2d(1). */
+int64_t b200unet_gate_workspace_floats(int C);
+int b200unet_gate_stat_rows(int64_t pixels, int C);
+/* s = b_psi + sum_c w_psi[c] * relu(scale_q*q1 + shift_q + scale_x*x1 + shift_x)[c]; stats_partial: NULL or fp32
+ * [b200unet_gate_stat_rows][2] (sum s, sum s^2) for BatchNorm2d(1) (Model.py:280). */
+int b200unet_gate_psi_fwd(const void* q1, int q1_cs, const void* x1, int x1_cs, const float* scale_q, const float* shift_q,
+                          const float* scale_x, const float* shift_x, const float* w_psi, const float* b_psi, float* s,
+                          float* stats_partial, int64_t pixels, int C, b200_stream_t stream);
+/* out = x * sigmoid(scale_p * s + shift_p) over Cx channels (Model.py:295-296); out may be a channel slice (concat buffer). */
+int b200unet_gate_apply_fwd(const void* x, int x_cs, const float* s, const float* scale_p, const float* shift_p, void* out,
+                            int out_cs, int64_t pixels, int Cx, b200_stream_t stream);
+/* Backward of the product: A = sigmoid(scale_p*s + shift_p); dx = g * A (bf16); dz = (sum_c g*x) * A * (1 - A) (fp32, one per
+ * pixel); sums2 = fp64 [sum dz, sum dz * shat] with shat = (s - mean_p) * rstd_p (BatchNorm2d(1) backward). */
+int b200unet_gate_apply_bwd(const void* g, int g_cs, const void* x, int x_cs, const float* s, const float* scale_p,
+                            const float* shift_p, const float* mean_p, const float* rstd_p, void* dx, int dx_cs, float* dz,
+                            float* workspace, double* sums2, int64_t pixels, int Cx, b200_stream_t stream);
+/* ds = BatchNorm2d(1) backward of dz (sums2 = the, under SyncBN all-reduced, sums above; count = pixels per channel);
+ * dE = ds * w_psi * [E > 0]. sums fp64 [4C + 8]: [0,C) sum dE, [C,2C) sum dE*Qhat, [2C,3C) sum dE*Xhat, [3C,4C) sum ds*E,
+ * [4C] sum ds. */
+int b200unet_gate_bwd_reduce(const void* q1, int q1_cs, const void* x1, int x1_cs, const float* scale_q, const float* shift_q,
+                             const float* scale_x, const float* shift_x, const float* mean_q, const float* rstd_q,
+                             const float* mean_x, const float* rstd_x, const float* w_psi, const float* s, const float* dz,
+                             const float* gamma_p, const float* mean_p, const float* rstd_p, const double* sums2, double count,
+                             float* ds, float* workspace, double* sums, int64_t pixels, int C, b200_stream_t stream);
+/* q1 <- BN_q backward of dE, x1 <- BN_x backward of dE (bf16, in place); parameter gradients from sums_local (NULL = sums)
+ * and sums2_local; dbias fp32 [2C] = per-channel sums of the two stored gradients (the bias gradients of the two convs). */
+int b200unet_gate_bwd_apply(void* q1, int q1_cs, void* x1, int x1_cs, const float* scale_q, const float* shift_q,
+                            const float* scale_x, const float* shift_x, const float* gamma_q, const float* mean_q,
+                            const float* rstd_q, const float* gamma_x, const float* mean_x, const float* rstd_x,
+                            const float* w_psi, const float* ds, const double* sums, const double* sums_local,
+                            const double* sums2_local, double count, float* dgamma_q, float* dbeta_q, float* dgamma_x,
+                            float* dbeta_x, float* dw_psi, float* db_psi, float* dgamma_p, float* dbeta_p, float* workspace,
+                            float* dbias, int64_t pixels, int C, b200_stream_t stream);
+/* C[z][m][n] (+)= sum_k A[z][m][k] B[z][k][n] (+ bias_m[m]), fp32, arbitrary ELEMENT strides (am, ak, ...; az/bz/cz between
+ * batch entries). Weight-side algebra of the gates: W'[c,h,i,j] = sum_d W_up[c,d,i,j] W_q[h,d] and its backward. */
+int b200unet_sgemm_strided(const float* A, const float* B, float* C, const float* bias_m, int M, int N, int K, int64_t am,
+                           int64_t ak, int64_t bk, int64_t bn, int64_t cm, int64_t cn, int batch, int64_t az, int64_t bz,
+                           int64_t cz, int accumulate, b200_stream_t stream);
+
 /* ---- first layer and head (tiny channel counts: bandwidth-bound CUDA-core kernels) ------------------------ */
 /* inc.conv1: x fp32 NCHW [N][Cin<=4][H][W] (Trainer.py:700-702 hands fp32 NCHW) -> y bf16 NHWC [..][Cout] + stats. */
 int b200unet_conv3x3_first_fprop(const float* x_nchw, const float* w_oihw, void* y, int y_cs, float* stats_partial,

@@ -117,6 +117,20 @@ SIGNATURES = {
     "b200unet_nvl_status": (c_int, [_P, _P, _P]),
     "b200unet_sgd_conv3x3_weight": (c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_sgd_convt2x2_weight": (c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _I, _I, _P]),
+    "b200unet_conv1x1_stat_rows": (c_int, [_I, _I, _I]),
+    "b200unet_conv1x1_fprop": (c_int, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b200unet_conv1x1_wgrad_workspace_floats": (c_int64, [_I, _I, _I, _I, _I]),
+    "b200unet_conv1x1_wgrad": (c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b200unet_convt2x2_stat_rows": (c_int, [_I, _I, _I]),
+    "b200unet_convt2x2_fprop_stats": (c_int, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "b200unet_gate_workspace_floats": (c_int64, [_I]),
+    "b200unet_gate_stat_rows": (c_int, [_L, _I]),
+    "b200unet_gate_psi_fwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
+    "b200unet_gate_apply_fwd": (c_int, [_P, _I, _P, _P, _P, _P, _I, _L, _I, _P]),
+    "b200unet_gate_apply_bwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _L, _I, _P]),
+    "b200unet_gate_bwd_reduce": (c_int, [_P, _I, _P, _I] + [_P] * 15 + [_D, _P, _P, _P, _L, _I, _P]),
+    "b200unet_gate_bwd_apply": (c_int, [_P, _I, _P, _I] + [_P] * 15 + [_D] + [_P] * 10 + [_L, _I, _P]),
+    "b200unet_sgemm_strided": (c_int, [_P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _L, _L, _L, _I, _P]),
     "b200unet_sgd_small": (c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_sgd_weights": (c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_adam_weights": (c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _D, _D, _F, _F, _F, _F, _I, _P]),

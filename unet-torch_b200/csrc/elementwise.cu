@@ -583,6 +583,16 @@ int bwd_blocks(int N, int H, int W, int C, bool pool) {
 
 }  // namespace
 
+namespace b2h {
+int reduce_partials_launch(const float* partial, long long rows, int ncols, double* sums, cudaStream_t st) {
+  return launch_reduce_partials(partial, rows, ncols, sums, st);
+}
+int partial_colsum_launch(const float* partial, long long rows, int row_pitch, int col_lo, int n, float* out, cudaStream_t st) {
+  partial_colsum_kernel<<<(n + 31) / 32, 256, 0, st>>>(partial, rows, row_pitch, col_lo, n, out);
+  return check_launch("partial_colsum");
+}
+}  // namespace b2h
+
 extern "C" {
 
 int b200unet_bn_reduce_partials(const float* stats_partial, int64_t mtiles, int C, double* sums, b200_stream_t stream) {

@@ -80,4 +80,8 @@ int conv1x1_c64_launch(const void* x, int x_cs, const void* w, void* y, int y_cs
 int conv3x3_first_launch(const float* x_nchw, const void* w1, void* y, int y_cs, float* stats_partial, int N, int H, int W,
                          int Cin, int Cout, cudaStream_t st, const float* scale = nullptr, const float* shift = nullptr);
 
+// elementwise.cu: partial [rows][ncols] fp32 -> sums[ncols] fp64 (fixed order); out[c] = sum over rows of column col_lo + c
+int reduce_partials_launch(const float* partial, long long rows, int ncols, double* sums, cudaStream_t st);
+int partial_colsum_launch(const float* partial, long long rows, int row_pitch, int col_lo, int n, float* out, cudaStream_t st);
+
 }  // namespace b2h

@@ -36,6 +36,7 @@ struct IgemmArgs {
   int ncols;             // GEMM N (all output channels)
   int ntiles_n;          // ncols / BN
   int cup;               // MODE_UP: channels per (i,j) group of the N dimension
+  int stat_c;            // channels of a statistics row (<= cup: a gate whose channels were padded to 64 keeps its real count)
   float* stats;          // [mtiles][2][ncols] or null
   const float* bias;     // MODE_UP: [cup] or null
   const float* scale;    // MODE_CONV3: eval-mode BatchNorm + ReLU folded into the epilogue: [ncols] each, or null
@@ -235,8 +236,9 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ Igem
       }
       tma_store_commit();
     }
-    if (MODE == MODE_CONV3 && args.stats != nullptr) {
-      // per-channel sum and sum of squares over the valid pixels of this tile, from the bf16 values stored
+    if (MODE != MODE_GATHER4 && args.stats != nullptr) {
+      // per-channel sum and sum of squares over the valid pixels of this tile, from the bf16 values stored. Row layout
+      // [m tile][column group][2][cup]: one group for a convolution, the four (i,j) sub-positions for ConvTranspose2d
       const int c = et & 63, hf = et >> 6;
 #pragma unroll 1
       for (int q = 0; q < BN / 64; ++q) {
@@ -257,10 +259,13 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ Igem
         red[(hf * 2 + 1) * BN + q * 64 + c] = s2;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      float* dst = args.stats + static_cast<size_t>(mt) * 2 * args.ncols + n0;
+      const int groups = args.ncols / args.cup;
       for (int ch = et; ch < BN; ch += 128) {
-        dst[ch] = red[0 * BN + ch] + red[2 * BN + ch];
-        dst[args.ncols + ch] = red[1 * BN + ch] + red[3 * BN + ch];
+        const int col = n0 + ch, g = col / args.cup, cc = col - g * args.cup;
+        if (cc >= args.stat_c) continue;
+        float* dst = args.stats + (static_cast<size_t>(mt) * groups + g) * 2 * args.stat_c;
+        dst[cc] = red[0 * BN + ch] + red[2 * BN + ch];
+        dst[args.stat_c + cc] = red[1 * BN + ch] + red[3 * BN + ch];
       }
     }
     if (et == 0) tma_store_wait_read0();
@@ -381,6 +386,7 @@ int conv3x3_dispatch(const void* x, int x_cs, const void* w, void* y, int y_cs, 
   a.ktap = Cin;
   a.ncols = Cout;
   a.cup = Cout;
+  a.stat_c = Cout;
   a.stats = stats_partial;
   a.scale = scale;
   a.shift = shift;
@@ -394,6 +400,44 @@ int conv3x3_dispatch(const void* x, int x_cs, const void* w, void* y, int y_cs, 
   for (int i = 1; i < 4; ++i) a.tmO[i] = a.tmO[0];
   return launch_mode<MODE_CONV3>(a, bn, N * a.tiles_w * a.tiles_h, static_cast<cudaStream_t>(stream));
 }
+
+int convt2x2_fprop_impl(const void* x, int x_cs, const void* w_fprop, const float* bias, void* out, int out_cs, float* stats,
+                        int stat_c, int N, int H, int W, int Cin, int Cup, int H2, int W2, int pad_top, int pad_left,
+                        b200_stream_t stream) {
+  B2_REQUIRE(Cin % 64 == 0 && Cup % 64 == 0, "convt2x2_fprop: Cin (%d) and Cup (%d) must be multiples of 64", Cin, Cup);
+  B2_REQUIRE(pad_top >= 0 && pad_left >= 0 && 2 * H + pad_top <= H2 && 2 * W + pad_left <= W2,
+             "convt2x2_fprop: upsampled map (%dx%d)+pad(%d,%d) does not fit canvas %dx%d", 2 * H, 2 * W, pad_top, pad_left, H2, W2);
+  B2_REQUIRE(x_cs % 8 == 0 && out_cs % 8 == 0, "convt2x2_fprop: pitches must be multiples of 8");
+  if (stats == nullptr && use_resident(64, 64) && b2h::convt_res_applicable(Cin, Cup))
+    return b2h::convt_res_fprop_launch(x, x_cs, w_fprop, bias, out, out_cs, N, H, W, Cin, Cup, H2, W2, pad_top, pad_left,
+                                       static_cast<cudaStream_t>(stream));
+  IgemmArgs a;
+  a.tiles_w = b2h::ceil_div(W, TW);
+  a.tiles_h = b2h::ceil_div(H, TH);
+  a.H = H;
+  a.W = W;
+  a.kblocks = Cin / 64;
+  a.ktap = Cin;
+  a.ncols = 4 * Cup;
+  a.cup = Cup;
+  a.stat_c = stat_c;
+  a.stats = stats;
+  a.scale = nullptr;
+  a.shift = nullptr;
+  a.bias = bias;
+  const int bn = (env_bn() == 0) ? 256 : pick_bn(4 * Cup, 256);  // all four (i,j) sub-positions of 64 channels per CTA
+  const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, os = static_cast<uint64_t>(out_cs) * 2;
+  if (int e = b2h::make_tmap_4d(&a.tmA[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TW, TH)) return e;
+  for (int i = 1; i < 4; ++i) a.tmA[i] = a.tmA[0];
+  if (int e = b2h::make_tmap_2d(&a.tmB, w_fprop, Cin, static_cast<uint64_t>(4) * Cup, bn)) return e;
+  for (int ij = 0; ij < 4; ++ij) {
+    const int i = ij >> 1, j = ij & 1;
+    const uint8_t* base = static_cast<const uint8_t*>(out) + (static_cast<uint64_t>(pad_top + i) * W2 + pad_left + j) * os;
+    if (int e = b2h::make_tmap_4d(&a.tmO[ij], base, Cup, W, H, N, 2 * os, 2 * os * W2, os * W2 * H2, TW, TH)) return e;
+  }
+  return launch_mode<MODE_UP>(a, bn, N * a.tiles_w * a.tiles_h, static_cast<cudaStream_t>(stream));
+}
+
 
 }  // namespace
 
@@ -454,13 +498,29 @@ int b200unet_conv3x3_stat_rows(int N, int H, int W, int Cin, int Cout) {
 int b200unet_convt2x2_fprop(const void* x, int x_cs, const void* w_fprop, const float* bias, void* out, int out_cs,
                             int N, int H, int W, int Cin, int Cup, int H2, int W2, int pad_top, int pad_left,
                             b200_stream_t stream) {
-  B2_REQUIRE(Cin % 64 == 0 && Cup % 64 == 0, "convt2x2_fprop: Cin (%d) and Cup (%d) must be multiples of 64", Cin, Cup);
-  B2_REQUIRE(pad_top >= 0 && pad_left >= 0 && 2 * H + pad_top <= H2 && 2 * W + pad_left <= W2,
-             "convt2x2_fprop: upsampled map (%dx%d)+pad(%d,%d) does not fit canvas %dx%d", 2 * H, 2 * W, pad_top, pad_left, H2, W2);
-  B2_REQUIRE(x_cs % 8 == 0 && out_cs % 8 == 0, "convt2x2_fprop: pitches must be multiples of 8");
-  if (use_resident(64, 64) && b2h::convt_res_applicable(Cin, Cup))
-    return b2h::convt_res_fprop_launch(x, x_cs, w_fprop, bias, out, out_cs, N, H, W, Cin, Cup, H2, W2, pad_top, pad_left,
-                                       static_cast<cudaStream_t>(stream));
+  return convt2x2_fprop_impl(x, x_cs, w_fprop, bias, out, out_cs, nullptr, Cup, N, H, W, Cin, Cup, H2, W2, pad_top, pad_left, stream);
+}
+
+int b200unet_convt2x2_stat_rows(int N, int H, int W) { return 4 * N * b2h::ceil_div(H, TH) * b2h::ceil_div(W, TW); }
+
+int b200unet_convt2x2_fprop_stats(const void* x, int x_cs, const void* w_fprop, const float* bias, void* out, int out_cs,
+                                  float* stats_partial, int stat_channels, int N, int H, int W, int Cin, int Cup, int H2,
+                                  int W2, int pad_top, int pad_left, b200_stream_t stream) {
+  B2_REQUIRE(stats_partial != nullptr, "convt2x2_fprop_stats: stats_partial is required (b200unet_convt2x2_stat_rows x 2 x stat_channels floats)");
+  B2_REQUIRE(stat_channels >= 1 && stat_channels <= Cup, "convt2x2_fprop_stats: stat_channels=%d must be in [1, Cup]", stat_channels);
+  return convt2x2_fprop_impl(x, x_cs, w_fprop, bias, out, out_cs, stats_partial, stat_channels, N, H, W, Cin, Cup, H2, W2, pad_top,
+                             pad_left, stream);
+}
+
+int b200unet_conv1x1_stat_rows(int N, int H, int W) { return N * b2h::ceil_div(H, TH) * b2h::ceil_div(W, TW); }
+
+int b200unet_conv1x1_fprop(const void* x, int x_cs, const void* w, const float* bias, void* y, int y_cs, float* stats_partial,
+                           int stat_channels, int N, int H, int W, int Cin, int Cout, b200_stream_t stream) {
+  B2_REQUIRE(x && w && y, "conv1x1_fprop: null argument");
+  B2_REQUIRE(stats_partial == nullptr || (stat_channels >= 1 && stat_channels <= Cout), "conv1x1_fprop: stat_channels=%d must be in [1, Cout]", stat_channels);
+  B2_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv1x1_fprop: Cin (%d) and Cout (%d) must be multiples of 64", Cin, Cout);
+  B2_REQUIRE(N > 0 && H > 0 && W > 0, "conv1x1_fprop: empty tensor");
+  B2_REQUIRE(x_cs >= Cin && y_cs >= Cout && x_cs % 8 == 0 && y_cs % 8 == 0, "conv1x1_fprop: bad pitches %d %d", x_cs, y_cs);
   IgemmArgs a;
   a.tiles_w = b2h::ceil_div(W, TW);
   a.tiles_h = b2h::ceil_div(H, TH);
@@ -468,24 +528,23 @@ int b200unet_convt2x2_fprop(const void* x, int x_cs, const void* w_fprop, const 
   a.W = W;
   a.kblocks = Cin / 64;
   a.ktap = Cin;
-  a.ncols = 4 * Cup;
-  a.cup = Cup;
-  a.stats = nullptr;
+  a.ncols = Cout;
+  a.cup = Cout;  // one column group: the scatter epilogue of the ConvTranspose2d mode degenerates to a plain NHWC store
+  a.stat_c = stat_channels;
+  a.stats = stats_partial;
   a.scale = nullptr;
   a.shift = nullptr;
   a.bias = bias;
-  const int bn = (env_bn() == 0) ? 256 : pick_bn(4 * Cup, 256);  // all four (i,j) sub-positions of 64 channels per CTA
-  const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, os = static_cast<uint64_t>(out_cs) * 2;
+  const int bn = pick_bn(Cout, 256);
+  const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(y_cs) * 2;
   if (int e = b2h::make_tmap_4d(&a.tmA[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TW, TH)) return e;
   for (int i = 1; i < 4; ++i) a.tmA[i] = a.tmA[0];
-  if (int e = b2h::make_tmap_2d(&a.tmB, w_fprop, Cin, static_cast<uint64_t>(4) * Cup, bn)) return e;
-  for (int ij = 0; ij < 4; ++ij) {
-    const int i = ij >> 1, j = ij & 1;
-    const uint8_t* base = static_cast<const uint8_t*>(out) + (static_cast<uint64_t>(pad_top + i) * W2 + pad_left + j) * os;
-    if (int e = b2h::make_tmap_4d(&a.tmO[ij], base, Cup, W, H, N, 2 * os, 2 * os * W2, os * W2 * H2, TW, TH)) return e;
-  }
+  if (int e = b2h::make_tmap_2d(&a.tmB, w, Cin, Cout, bn)) return e;
+  if (int e = b2h::make_tmap_4d(&a.tmO[0], y, Cout, W, H, N, ys, ys * W, ys * W * H, TW, TH)) return e;
+  for (int i = 1; i < 4; ++i) a.tmO[i] = a.tmO[0];
   return launch_mode<MODE_UP>(a, bn, N * a.tiles_w * a.tiles_h, static_cast<cudaStream_t>(stream));
 }
+
 
 int b200unet_convt2x2_dgrad(const void* du, int du_cs, const void* w_dgrad, void* dx, int dx_cs, int N, int H, int W,
                             int Cin, int Cup, int H2, int W2, int pad_top, int pad_left, b200_stream_t stream) {
@@ -504,6 +563,7 @@ int b200unet_convt2x2_dgrad(const void* du, int du_cs, const void* w_dgrad, void
   a.ktap = Cup;
   a.ncols = Cin;
   a.cup = Cin;
+  a.stat_c = Cin;
   a.stats = nullptr;
   a.scale = nullptr;
   a.shift = nullptr;

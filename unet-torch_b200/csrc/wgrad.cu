@@ -255,13 +255,15 @@ __global__ void reduce_up_kernel(const float* __restrict__ partial, float* __res
   }
 }
 
-// partial [Z][K][64] -> dw [K][T] (T <= 64 real columns: inc.conv1's OIHW gradient flattened as [k][c*9 + r*3 + s])
-__global__ void reduce_plain_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Z, int K, int T) {
+// partial [Z][Ka][pitch] -> dw [K][T] (the first K <= Ka rows and T <= pitch columns are real: inc.conv1's OIHW gradient
+// flattened as [k][c*9 + r*3 + s]; a 1x1 convolution whose output channels were padded to a multiple of 64)
+__global__ void reduce_plain_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Z, int Ka, int K, int T,
+                                    int pitch) {
   const int total = K * T;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i / T, j = i - k * T;
     float acc = 0.f;
-    for (int z = 0; z < Z; ++z) acc += partial[(static_cast<size_t>(z) * K + k) * 64 + j];
+    for (int z = 0; z < Z; ++z) acc += partial[(static_cast<size_t>(z) * Ka + k) * pitch + j];
     dw[i] = acc;
   }
 }
@@ -823,8 +825,46 @@ int b200unet_conv1x1_c64_wgrad(const void* col, int col_cs, const void* dy, int 
   for (int i = 1; i < 4; ++i) a.tmB[i] = a.tmB[0];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int e = launch_wgrad<KIND_PLAIN, 64>(a, st)) return e;
-  reduce_plain_kernel<<<b2h::ceil_div(Cout * T, 256), 256, 0, st>>>(partial, dw, a.splits, Cout, T);
+  reduce_plain_kernel<<<b2h::ceil_div(Cout * T, 256), 256, 0, st>>>(partial, dw, a.splits, Cout, Cout, T, 64);
   return b2h::check_launch("conv1x1_c64_wgrad_reduce");
+}
+
+static void conv1x1_wgrad_geometry(int N, int H, int W, int Cin, int Cout, int* mtiles, int* ntiles, int* tiles, int* splits) {
+  *mtiles = b2h::ceil_div(Cout, 128);
+  *ntiles = Cin / 64;
+  *tiles = N * b2h::ceil_div(H, TH) * b2h::ceil_div(W, TW);
+  *splits = pick_splits(*mtiles * *ntiles, *tiles);
+}
+
+int64_t b200unet_conv1x1_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout) {
+  int mt, nt, tiles, z;
+  conv1x1_wgrad_geometry(N, H, W, Cin, Cout, &mt, &nt, &tiles, &z);
+  return static_cast<int64_t>(z) * Cout * Cin;
+}
+
+int b200unet_conv1x1_wgrad(const void* x, int x_cs, const void* dy, int dy_cs, float* partial, float* dw, int N, int H, int W,
+                           int Cin, int Cout, int Cout_real, b200_stream_t stream) {
+  B2_REQUIRE(x && dy && partial && dw, "conv1x1_wgrad: null argument");
+  B2_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0 && Cout_real >= 1 && Cout_real <= Cout,
+             "conv1x1_wgrad: Cin=%d and Cout=%d must be multiples of 64, Cout_real=%d in [1, Cout]", Cin, Cout, Cout_real);
+  B2_REQUIRE(x_cs % 8 == 0 && dy_cs % 8 == 0 && x_cs >= Cin && dy_cs >= Cout, "conv1x1_wgrad: bad pitches");
+  WgradArgs a;
+  conv1x1_wgrad_geometry(N, H, W, Cin, Cout, &a.mtiles, &a.ntiles, &a.tiles_total, &a.splits);
+  a.tiles_w = b2h::ceil_div(W, TW);
+  a.tiles_h = b2h::ceil_div(H, TH);
+  a.Ca = Cout;
+  a.Cb = Cin;
+  a.partial = partial;
+  const uint64_t xs = static_cast<uint64_t>(x_cs) * 2, ys = static_cast<uint64_t>(dy_cs) * 2;
+  if (int e = b2h::make_tmap_4d(&a.tmA, dy, Cout, W, H, N, ys, ys * W, ys * W * H, TW, TH)) return e;
+  if (int e = b2h::make_tmap_4d(&a.tmB[0], x, Cin, W, H, N, xs, xs * W, xs * W * H, TW, TH)) return e;
+  for (int i = 1; i < 4; ++i) a.tmB[i] = a.tmB[0];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = launch_wgrad<KIND_PLAIN, 64>(a, st)) return e;
+  const int total = Cout_real * Cin;
+  reduce_plain_kernel<<<b2h::ceil_div(total, 256) < 148 * 8 ? b2h::ceil_div(total, 256) : 148 * 8, 256, 0, st>>>(
+      partial, dw, a.splits, Cout, Cout_real, Cin, Cin);
+  return b2h::check_launch("conv1x1_wgrad_reduce");
 }
 
 int64_t b200unet_conv3x3_first_tc_wgrad_workspace_floats(int N, int H, int W, int Cout) {
@@ -862,7 +902,7 @@ int b200unet_conv3x3_first_tc_wgrad(const float* x_nchw, const void* dy, int dy_
   }
   if (e) return e;
   const int T = Cin * 9;
-  reduce_plain_kernel<<<b2h::ceil_div(Cout * T, 256), 256, 0, st>>>(partial, dw_oihw, a.splits, Cout, T);
+  reduce_plain_kernel<<<b2h::ceil_div(Cout * T, 256), 256, 0, st>>>(partial, dw_oihw, a.splits, Cout, Cout, T, 64);
   return b2h::check_launch("conv3x3_first_tc_wgrad_reduce");
 }
 

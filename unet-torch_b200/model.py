@@ -122,6 +122,63 @@ class _UpOp:
         return self.wf, self.wd
 
 
+class _BNRef:
+    """A BatchNorm2d that does not follow a conv3x3 (the gates' three): what UNetEngine._bn_affine needs of a _ConvBN."""
+
+    def __init__(self, bn: nn.BatchNorm2d):
+        self.bn = bn
+
+
+class _GateOp:
+    """One Attention_block (Model.py:257-296) on the tensor-core engine. `up` (ConvTranspose2d C_q -> C_q) is only consumed by
+    W_q (1x1, C_q -> C_h), so the two are ONE ConvTranspose2d C_q -> C_h with the composed weight
+        W'[c,h,i,j] = sum_d W_up[c,d,i,j] W_q[h,d],   b'[h] = b_q[h] + sum_d W_q[h,d] b_up[d]
+    (the C_q-channel upsampled map - 1 GB at level 0 of config 2 - never exists; 4x fewer GEMM FLOPs). The composition and
+    its backward are fp32 GEMMs on the weights. Channel counts are padded to a multiple of 64 for the GEMMs (level 0 of a
+    width-64 network has C_h = 32): zero weight rows, so the padded channels of the two maps are exact zeros."""
+
+    def __init__(self, att):
+        self.att = att
+        self.cq = att.up.weight.shape[0]
+        self.ch, self.cx = att.W_x[0].weight.shape[0], att.W_x[0].weight.shape[1]
+        self.chp = (self.ch + 63) // 64 * 64
+        self.bn_q, self.bn_x, self.bn_p = _BNRef(att.W_q[1]), _BNRef(att.W_x[1]), _BNRef(att.psi[1])
+        self._ver = None
+        self.wc = self.bc = self.wcf = self.wcd = self.wxf = self.wxd = self.bx = None
+
+    def params(self):
+        a = self.att
+        return [a.up.weight, a.up.bias, a.W_q[0].weight, a.W_q[0].bias, a.W_x[0].weight, a.W_x[0].bias]
+
+    def operands(self):
+        """(composed convT fprop operand, its dgrad operand, composed bias, W_x operand, its transpose, W_x bias)."""
+        ps = self.params()
+        key = tuple((p._version, p.data_ptr()) for p in ps)
+        if key != self._ver:
+            w_up, b_up, w_q, b_q, w_x, b_x = [p.detach() for p in ps]
+            cq, ch, chp, cx = self.cq, self.ch, self.chp, self.cx
+            dev = w_up.device
+            with torch.no_grad():
+                if self.wc is None or self.wc.device != dev:  # allocated once: captured CUDA graphs hold the addresses
+                    self.wc = torch.zeros((cq, chp, 2, 2), dtype=torch.float32, device=dev)
+                    self.bc = torch.zeros((chp,), dtype=torch.float32, device=dev)
+                    self.bx = torch.zeros((chp,), dtype=torch.float32, device=dev)
+                    self.wxf = torch.zeros((chp, cx), dtype=BF16, device=dev)
+                    self.wxd = torch.zeros((cx, chp), dtype=BF16, device=dev)
+                    self.wcf = self.wcd = None
+                # per (i,j): W'[:, :, ij] = W_up[:, :, ij] @ W_q^T
+                ops.sgemm_strided(w_up, w_q, self.wc, cq, ch, cq, (4 * cq, 4), (1, cq), (4 * chp, 4), batch=4,
+                                  batch_strides=(1, 0, 1))
+                ops.sgemm_strided(w_q, b_up, self.bc, ch, 1, cq, (cq, 1), (1, 1), (1, 1), bias_m=b_q)
+                self.wcf, self.wcd = ops.prep_convt2x2_weight(self.wc, out=(self.wcf, self.wcd))
+                w2 = w_x.view(ch, cx)
+                self.wxf[:ch].copy_(w2)
+                self.wxd[:, :ch].copy_(w2.t())
+                self.bx[:ch].copy_(b_x)
+            self._ver = key
+        return self.wcf, self.wcd, self.bc, self.wxf, self.wxd, self.bx
+
+
 class _Saved:
     __slots__ = ("x", "enc", "dec", "head_in", "shapes", "dp")
 
@@ -150,6 +207,9 @@ class UNetEngine:
         self.ups = [u for d in self.decoders for u in d[0]]
         self.dec = [c for d in self.decoders for c in d[1]]
         self.head = self.decoders[0][2]
+        # UNet_attention: one gate per decoder block (j = 0..3 <-> attenion4..attenion1), else None
+        gates = net._attention_gates() if hasattr(net, "_attention_gates") else None
+        self.gates = [_GateOp(a) for a in gates] if gates else None
         self._graphs = {}     # (shape, device, training, save) -> _GraphedStep
         self._seen = set()    # keys that already ran once eagerly (kernel attributes configured, allocator warm)
         # B200UNET_WGRAD_STREAM=1: weight-gradient kernels on a second stream (nothing downstream in backward depends on
@@ -202,6 +262,8 @@ class UNetEngine:
             c2.operands()
         for u in self.ups:
             u.operands()
+        for g in self.gates or ():
+            g.operands()
 
     # parameters in the order their gradients are produced by backward (used for DP bucketing)
     def params_in_backward_order(self):
@@ -212,6 +274,11 @@ class UNetEngine:
                 c1, c2 = dec[j]
                 out += [c2.bn.weight, c2.bn.bias, c2.conv.weight, c1.bn.weight, c1.bn.bias, c1.conv.weight,
                         ups[j].up.bias, ups[j].up.weight]
+                if self.gates is not None:
+                    a = self.gates[j].att
+                    out += [a.psi[1].weight, a.psi[1].bias, a.psi[0].weight, a.psi[0].bias, a.W_q[1].weight, a.W_q[1].bias,
+                            a.W_x[1].weight, a.W_x[1].bias, a.W_x[0].weight, a.W_x[0].bias, a.W_q[0].weight, a.W_q[0].bias,
+                            a.up.weight, a.up.bias]
         for l in (4, 3, 2, 1, 0):
             c1, c2 = self.enc[l]
             out += [c2.bn.weight, c2.bn.bias, c2.conv.weight, c1.bn.weight, c1.bn.bias, c1.conv.weight]
@@ -262,6 +329,124 @@ class UNetEngine:
         if track:
             bn.num_batches_tracked += 1
         return scale, shift, mean, rstd, count
+
+    # ------------------------------------------------------------------ attention gates
+    def _gate_forward(self, gate: _GateOp, q, xs, out, training, dp, save):
+        """Attention_block.forward(q, x) (Model.py:286-296): out = xs * sigmoid(BN(psi(relu(BN(W_q(up(q))) + BN(W_x(xs)))))).
+        q: [n, h/2, w/2, C_q], xs: [n, h, w, C_x], out: the skip half of the concat buffer."""
+        n, h, w, cx = xs.shape
+        dev = xs.device
+        ch, chp = gate.ch, gate.chp
+        wcf, _, bc, wxf, _, bx = gate.operands()
+        q1 = torch.empty((n, h, w, chp), dtype=BF16, device=dev)   # W_q(up(q)) before its BatchNorm
+        x1 = torch.empty((n, h, w, chp), dtype=BF16, device=dev)   # W_x(xs) before its BatchNorm
+        rows_q, rows_x = ops.convt2x2_stat_rows(n, h // 2, w // 2), ops.conv1x1_stat_rows(n, h, w)
+        st_q = st_x = None
+        if training:
+            st_q = torch.empty(rows_q * 2 * ch, dtype=torch.float32, device=dev)
+            st_x = torch.empty(rows_x * 2 * ch, dtype=torch.float32, device=dev)
+            ops.convt2x2_stats(q, wcf, bc, q1, st_q, ch)
+        else:
+            ops.convt2x2(q, wcf, bc, q1)
+        ops.conv1x1(xs, wxf, bx, x1, st_x, ch)
+        count = n * h * w
+        aq = self._bn_affine(gate.bn_q, st_q, rows_q, count, training, dp, need_stats=save)
+        ax = self._bn_affine(gate.bn_x, st_x, rows_x, count, training, dp, need_stats=save)
+        psi = gate.att.psi[0]
+        w_psi, b_psi = psi.weight.detach().view(-1), psi.bias.detach()
+        s = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+        rows_p = ops.gate_stat_rows(count, ch)
+        st_p = torch.empty(rows_p * 2, dtype=torch.float32, device=dev) if training else None
+        q1v, x1v = q1[..., :ch], x1[..., :ch]
+        ops.gate_psi_fwd(q1v, x1v, aq[0], aq[1], ax[0], ax[1], w_psi, b_psi, s, st_p)
+        ap = self._bn_affine(gate.bn_p, st_p, rows_p, count, training, dp, need_stats=save)
+        ops.gate_apply_fwd(xs, s, ap[0], ap[1], out)
+        if self.trace is not None:
+            self._tr("gate", gate=gate, q=q, x=xs, q1=q1v.clone(), x1=x1v.clone(), s=s, aq=aq, ax=ax, ap=ap, out=out,
+                     training=training)
+        if not save:
+            return None
+        return (q1, x1, s, aq, ax, ap, xs, not training)
+
+    def _gate_backward(self, gate: _GateOp, grec, g, q, gbuf, done, grads, sync, on_wgrad_stream):
+        """Backward of _gate_forward. g: gradient w.r.t. the gated skip (a slice of dcat). Returns (gradient w.r.t. xs,
+        gradient w.r.t. q). The two maps q1 / x1 are overwritten with their gradients."""
+        q1, x1, s, aq, ax, ap, xs, frozen = grec
+        att = gate.att
+        n, h, w, cx = xs.shape
+        dev = xs.device
+        ch, chp, cq = gate.ch, gate.chp, gate.cq
+        _, wcd, _, _, wxd, _ = gate.operands()
+        q1v, x1v = q1[..., :ch], x1[..., :ch]
+        scale_p, shift_p, mean_p, rstd_p, count = ap
+        psi, bn_p, bn_q, bn_x = att.psi[0], att.psi[1], att.W_q[1], att.W_x[1]
+        w_psi = psi.weight.detach().view(-1)
+        # ---- the product x * A and the sigmoid
+        dxs = torch.empty((n, h, w, cx), dtype=BF16, device=dev)
+        dz = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+        sums2 = torch.empty(2, dtype=torch.float64, device=dev)
+        ops.gate_apply_bwd(g, xs, s, scale_p, shift_p, mean_p, rstd_p, dxs, dz, sums2)
+        sums2_local = sums2
+        if frozen:
+            sums2 = torch.zeros_like(sums2)       # running statistics: no batch-statistics correction terms
+        elif sync is not None:
+            sums2_local = sums2.clone()
+            sync.all_reduce_sum(sums2)
+        # ---- BatchNorm2d(1) + psi + ReLU + the two BatchNorms
+        ds = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+        sums = torch.empty(4 * ch + 8, dtype=torch.float64, device=dev)
+        ops.gate_bwd_reduce(q1v, x1v, aq[:4], ax[:4], w_psi, s, dz, bn_p.weight.detach(), mean_p, rstd_p, sums2, count, ds, sums)
+        sums_local = None
+        if frozen:
+            sums_local, sums = sums, torch.zeros_like(sums)
+        elif sync is not None:
+            sums_local = sums.clone()
+            sync.all_reduce_sum(sums)
+        names = (bn_q.weight, bn_q.bias, bn_x.weight, bn_x.bias, psi.weight, psi.bias, bn_p.weight, bn_p.bias)
+        outs = [gbuf(p) for p in names]
+        dbias = torch.empty(2 * ch, dtype=torch.float32, device=dev)
+        ops.gate_bwd_apply(q1v, x1v, aq[:4], ax[:4], bn_q.weight.detach(), bn_x.weight.detach(), w_psi, ds, sums, sums_local,
+                           sums2_local, aq[4], outs, dbias)
+        for p, o in zip(names, outs):
+            grads[p] = o
+        done(*names)
+        dq1, dx1 = q1, x1   # gradients at the two pre-BatchNorm maps (padded channels are still exact zeros)
+        # ---- W_x: backward-data into the skip gradient, weight and bias gradients
+        dx_gate = torch.empty((n, h, w, cx), dtype=BF16, device=dev)
+        ops.conv1x1(dx1, wxd, None, dx_gate)
+        ops.nhwc_add(dxs, dx_gate)
+        wx, bxp = att.W_x[0].weight, att.W_x[0].bias
+        dwx, dbx = gbuf(wx), gbuf(bxp)
+        on_wgrad_stream(lambda: ops.conv1x1_wgrad(xs, dx1, dwx))
+        dbx.copy_(dbias[ch:])
+        grads[wx], grads[bxp] = dwx, dbx
+        done(wx, bxp)
+        # ---- the composed ConvTranspose2d: backward-data into q's gradient, then the weight gradient split into up / W_q
+        dq = torch.empty((n, h // 2, w // 2, cq), dtype=BF16, device=dev)
+        ops.convt2x2_dgrad(dq1, wcd, dq)
+        w_up, b_up, w_q, b_q = att.up.weight, att.up.bias, att.W_q[0].weight, att.W_q[0].bias
+        dwup, dbup, dwq, dbq = gbuf(w_up), gbuf(b_up), gbuf(w_q), gbuf(b_q)
+
+        def weight_side():
+            dwc = torch.empty((cq, chp, 2, 2), dtype=torch.float32, device=dev)
+            ops.convt2x2_wgrad(q, dq1, dwc)
+            # dW_up[c,d,ij] = sum_h dW'[c,h,ij] W_q[h,d];  dW_q[h,d] = sum_{c,ij} dW'[c,h,ij] W_up[c,d,ij]
+            ops.sgemm_strided(dwc, w_q.detach(), dwup, cq, cq, ch, (4 * chp, 4), (cq, 1), (4 * cq, 4), batch=4,
+                              batch_strides=(1, 0, 1))
+            for ij in range(4):
+                ops.sgemm_strided(dwc, w_up.detach(), dwq, ch, cq, cq, (4, 4 * chp), (4 * cq, 4), (cq, 1), accumulate=ij > 0,
+                                  offsets=(ij, ij, 0))
+            # b' = b_q + W_q b_up:  db_q = db',  db_up[d] = sum_h W_q[h,d] db'[h]
+            ops.sgemm_strided(w_q.detach(), dbias, dbup, cq, 1, ch, (1, cq), (1, 1), (1, 1))
+
+        on_wgrad_stream(weight_side)
+        dbq.copy_(dbias[:ch])
+        grads[w_up], grads[b_up], grads[w_q], grads[b_q] = dwup, dbup, dwq, dbq
+        done(w_up, b_up, w_q, b_q)
+        if self.trace is not None:
+            self._tr("gate_bwd", gate=gate, g=g, dxs=dxs, dq=dq, dq1=dq1[..., :ch], dx1=dx1[..., :ch], ds=ds, dz=dz,
+                     grads={p: grads[p] for p in (*names, wx, bxp, w_up, b_up, w_q, b_q)})
+        return dxs, dq
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, training: bool, save: bool, head: str = "logits", head_arg: float = 0.0):
@@ -338,7 +523,8 @@ class UNetEngine:
             a1 = torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
             r1 = conv_bn_relu(c1, inp, ch[l], hs[l], wsz[l], a1)
             if l < 4:
-                a2 = cat[l][..., : ch[l]]
+                # the skip activation goes straight into the concat buffer - unless an attention gate sits in between
+                a2 = cat[l][..., : ch[l]] if self.gates is None else torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
                 pooled = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l]), dtype=BF16, device=dev)
                 idx = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l]), dtype=torch.uint8, device=dev) if save else None
                 r2 = conv_bn_relu(c2, a1, ch[l], hs[l], wsz[l], a2, pooled, idx)
@@ -362,6 +548,9 @@ class UNetEngine:
             for j in range(4):
                 l = 3 - j
                 upo = ups[j]
+                grec = None
+                if self.gates is not None:  # x_l_attention = attenion_l(q = d_in, x = skip) -> skip half of the concat buffer
+                    grec = self._gate_forward(self.gates[j], d_in, enc_rec[l][2], catk[l][..., : ch[l]], training, dp, save)
                 wf, _ = upo.operands()
                 ops.convt2x2(d_in, wf, upo.up.bias.detach(), catk[l][..., ch[l]:])
                 self._tr("convt", up=upo, x=d_in, out=catk[l][..., ch[l]:], cat=catk[l], skip=enc_rec[l][2])
@@ -370,7 +559,7 @@ class UNetEngine:
                 r1 = conv_bn_relu(c1, catk[l], ch[l], hs[l], wsz[l], a1)
                 a2 = torch.empty((n, hs[l], wsz[l], ch[l]), dtype=BF16, device=dev)
                 r2 = conv_bn_relu(c2, a1, ch[l], hs[l], wsz[l], a2)
-                rec.append((d_in, r1, r2, a2))
+                rec.append((d_in, r1, r2, a2, grec))
                 d_in = a2
             dec_rec.append(rec)
             heads_in.append(d_in)
@@ -502,13 +691,17 @@ class UNetEngine:
             done(hw_, hb_)
             for j in (3, 2, 1, 0):
                 l = 3 - j
-                d_in, r1, r2, _ = saved.dec[k][j]
+                d_in, r1, r2, _, grec = saved.dec[k][j]
                 c1, c2 = dec[j]
                 g, pre = bn_conv_bwd(c2, r2, g, None, None, hs[l], wsz[l], True, fuse_next=r1)
                 upo = ups[j]
                 db, dwu = gbuf(upo.up.bias), gbuf(upo.up.weight)
                 dcat = bn_conv_bwd(c1, r1, g, None, None, hs[l], wsz[l], True, dx_colsum=(ch[l], db), pre=pre)
-                if skip_grads[l] is None:
+                dq_gate = None
+                if grec is not None:  # through the attention gate: gradient w.r.t. the skip activation and w.r.t. q = d_in
+                    skip_grads[l], dq_gate = self._gate_backward(self.gates[j], grec, dcat[..., : ch[l]], d_in, gbuf, done, grads,
+                                                                 sync, on_wgrad_stream)
+                elif skip_grads[l] is None:
                     skip_grads[l] = dcat[..., : ch[l]]
                 else:
                     ops.nhwc_add(skip_grads[l], dcat[..., : ch[l]])
@@ -519,6 +712,8 @@ class UNetEngine:
                 _, wd = upo.operands()
                 g = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l + 1]), dtype=BF16, device=dev)
                 ops.convt2x2_dgrad(du, wd, g)
+                if dq_gate is not None:
+                    ops.nhwc_add(g, dq_gate)
                 if self.trace is not None:
                     multi = len(self.decoders) > 1
                     self._tr("convt_bwd", up=upo, x=d_in, dcat=dcat, du=du.clone() if multi else du, dw=dwu, db=db,
@@ -858,9 +1053,10 @@ class UNet_attention(UNet):
     `x_l_attention = attenion_l(q = decoder input, x = skip)` (the misspelt attribute names are the reference's and fix the
     state_dict keys). Same constructor, RNG consumption (the gates keep torch's default init: no `.apply(weights_init)`,
     Model.py:325-341), 200 state_dict keys and forward(x) -> logits.
-    Runs on the library's generic fp32 CUDA engine (csrc/generic_f32.cu): reference precision, not tensor-core tuned - the
-    gates' 1x1 convolutions and the C_q -> C_q transposed convolution have no tcgen05 kernels yet. H and W must be divisible
-    by 16 (the reference's gate adds maps whose sizes only match then)."""
+    Default width (initial_feature_map = 64, no dropout): the tensor-core engine - the U-Net body as in UNet, the gates as
+    tcgen05 GEMMs (`up` and W_q composed into one ConvTranspose2d C_q -> C_h, W_x as a 1x1 GEMM) plus the bandwidth-bound
+    kernels of csrc/gate.cu. Other variants, and `set_check_mode(True)`: the generic fp32 CUDA engine (csrc/generic_f32.cu,
+    reference precision). H and W must be divisible by 16 (the reference's gate adds maps whose sizes only match then)."""
 
     def __init__(self, n_channels, n_classes, initial_feature_map=64, usa_cuda=True, dropout=False, dropout_p=0.5):
         nn.Module.__init__(self)
@@ -887,7 +1083,7 @@ class UNet_attention(UNet):
         add("outc", OutConv(f, n_classes), True)
         self._engine = None
         self._generic = None
-        self._check_fp32 = True
+        self._check_fp32 = os.environ.get("B200UNET_CHECK_FP32", "0") not in ("", "0")
         self._cuda_graphs = False
         self._share_grads = False
 
@@ -896,22 +1092,19 @@ class UNet_attention(UNet):
         return [self.attenion4, self.attenion3, self.attenion2, self.attenion1]
 
     def _fast_supported(self) -> bool:
-        return False
+        # the gate kernels take hidden widths 32..256 (csrc/gate.cu): base width 64
+        return self.initial_feature_map == 64 and self.n_channels <= 7 and self.n_classes <= 8 and not self.dropout
 
     def _engine_for(self, x):
         if x.dim() == 4 and (x.shape[2] % 16 or x.shape[3] % 16):
             raise ValueError("UNet_attention needs H and W divisible by 16 (its gates add a 2x-upsampled map to the skip)")
         return super()._engine_for(x)
 
-    def set_check_mode(self, flag: bool = True):
-        if not flag:
-            raise NotImplementedError("UNet_attention runs on the generic fp32 engine only")
-        return self
-
-    def enable_cuda_graphs(self, flag: bool = True):
-        if flag:
-            raise NotImplementedError("CUDA-graph replay covers UNet only")
-        return self
+    def refresh_operands(self, force: bool = True):
+        if self._engine is not None and force:
+            for g in self._engine.gates or ():
+                g._ver = None
+        return super().refresh_operands(force)
 
     def _fused_head(self, x, head, head_arg=0.0):
         raise NotImplementedError("fused inference heads cover UNet only; apply predict_mask / F.relu / sigmoid to net(x)")

@@ -456,6 +456,125 @@ def channel_sum(x, out):
     return out
 
 
+# --------------------------------------------------------------------------------------------- attention gates
+def convt2x2_stats(x, w_fprop, bias, out, stats_partial, stat_channels):
+    """convt2x2() into a plain [N,2H,2W,Cup] tensor, also filling the BatchNorm partial-statistics rows of the first
+    stat_channels channels of its output ([convt2x2_stat_rows][2][stat_channels] fp32)."""
+    xp, xcs, n, h, w, cin = _nhwc(x)
+    op, ocs, n2, h2, w2, cup = _nhwc(out)
+    if tuple(w_fprop.shape) != (4 * cup, cin) or (n2, h2, w2) != (n, 2 * h, 2 * w):
+        raise ValueError("convt2x2_stats: shape mismatch")
+    _lib.call("b200unet_convt2x2_fprop_stats", xp, xcs, w_fprop.data_ptr(), _f32(bias), op, ocs, _f32(stats_partial), stat_channels,
+              n, h, w, cin, cup, h2, w2, 0, 0, _stream())
+    return out
+
+
+def convt2x2_stat_rows(n, h, w):
+    return _lib.query("b200unet_convt2x2_stat_rows", n, h, w)
+
+
+def conv1x1_stat_rows(n, h, w):
+    return _lib.query("b200unet_conv1x1_stat_rows", n, h, w)
+
+
+def conv1x1(x, w_op, bias, out, stats_partial=None, stat_channels=None):
+    """out = 1x1 convolution of x with a bf16 [Cout, Cin] operand (+ fp32 bias [Cout] or None); optional BatchNorm
+    partial-statistics rows [conv1x1_stat_rows][2][stat_channels] (default Cout). With the transposed operand it is the
+    backward-data."""
+    xp, xcs, n, h, w, cin = _nhwc(x)
+    op, ocs, n2, h2, w2, cout = _nhwc(out)
+    if (n, h, w) != (n2, h2, w2) or tuple(w_op.shape) != (cout, cin) or w_op.dtype != BF16 or not w_op.is_contiguous():
+        raise ValueError(f"conv1x1: shape mismatch x{tuple(x.shape)} w{tuple(w_op.shape)} out{tuple(out.shape)}")
+    _lib.call("b200unet_conv1x1_fprop", xp, xcs, w_op.data_ptr(), _f32(bias), op, ocs, _f32(stats_partial),
+              cout if stat_channels is None else stat_channels, n, h, w, cin, cout, _stream())
+    return out
+
+
+def conv1x1_wgrad(x, dy, dw_out):
+    """dw_out fp32 [Cout_real, Cin(,1,1)] = sum over pixels of dy[.., k] * x[.., c]; dy may carry zero-padded channels beyond
+    Cout_real."""
+    xp, xcs, n, h, w, cin = _nhwc(x)
+    yp, ycs, n2, h2, w2, cout = _nhwc(dy)
+    creal = dw_out.shape[0]
+    if (n, h, w) != (n2, h2, w2) or dw_out.numel() != creal * cin or creal > cout:
+        raise ValueError("conv1x1_wgrad: shape mismatch")
+    ws = _workspace(_lib.query("b200unet_conv1x1_wgrad_workspace_floats", n, h, w, cin, cout), x.device)
+    _lib.call("b200unet_conv1x1_wgrad", xp, xcs, yp, ycs, ws.data_ptr(), _f32(dw_out), n, h, w, cin, cout, creal, _stream())
+    return dw_out
+
+
+def sgemm_strided(a, b, c, m, n, k, a_strides, b_strides, c_strides, bias_m=None, batch=1, batch_strides=(0, 0, 0),
+                  accumulate=False, offsets=(0, 0, 0)):
+    """c[z][i][j] (+)= sum_l a[z][i][l] * b[z][l][j] (+ bias_m[i]) over fp32 tensors addressed by ELEMENT strides
+    (a_strides = (row, k), b_strides = (k, col), c_strides = (row, col)); offsets are element offsets into a, b, c."""
+    for t in (a, b, c):
+        if t.dtype != torch.float32 or not t.is_cuda:
+            raise ValueError("sgemm_strided: fp32 CUDA tensors expected")
+    _lib.call("b200unet_sgemm_strided", a.data_ptr() + 4 * offsets[0], b.data_ptr() + 4 * offsets[1], c.data_ptr() + 4 * offsets[2],
+              _ptr(bias_m), m, n, k, a_strides[0], a_strides[1], b_strides[0], b_strides[1], c_strides[0], c_strides[1], batch,
+              batch_strides[0], batch_strides[1], batch_strides[2], 1 if accumulate else 0, _stream())
+    return c
+
+
+def gate_stat_rows(pixels, c):
+    return _lib.query("b200unet_gate_stat_rows", pixels, c)
+
+
+def gate_psi_fwd(q1, x1, scale_q, shift_q, scale_x, shift_x, w_psi, b_psi, s, stats_partial=None):
+    """s[n,h,w] = b_psi + sum_c w_psi[c] * relu(scale_q*q1 + shift_q + scale_x*x1 + shift_x)[c] over the C real channels of
+    the two pre-BatchNorm maps (channel slices of possibly wider tensors)."""
+    qp, qcs, n, h, w, c = _nhwc(q1)
+    xp, xcs, *sx = _nhwc(x1)
+    if sx != [n, h, w, c] or s.numel() != n * h * w:
+        raise ValueError("gate_psi_fwd: shape mismatch")
+    _lib.call("b200unet_gate_psi_fwd", qp, qcs, xp, xcs, _f32(scale_q), _f32(shift_q), _f32(scale_x), _f32(shift_x), _f32(w_psi),
+              _f32(b_psi), _f32(s), _f32(stats_partial), n * h * w, c, _stream())
+    return s
+
+
+def gate_apply_fwd(x, s, scale_p, shift_p, out):
+    xp, xcs, n, h, w, c = _nhwc(x)
+    op, ocs, *so = _nhwc(out)
+    if so != [n, h, w, c] or s.numel() != n * h * w:
+        raise ValueError("gate_apply_fwd: shape mismatch")
+    _lib.call("b200unet_gate_apply_fwd", xp, xcs, _f32(s), _f32(scale_p), _f32(shift_p), op, ocs, n * h * w, c, _stream())
+    return out
+
+
+def gate_apply_bwd(g, x, s, scale_p, shift_p, mean_p, rstd_p, dx, dz, sums2):
+    gp, gcs, n, h, w, c = _nhwc(g)
+    xp, xcs, *sx = _nhwc(x)
+    dp, dcs, *sd = _nhwc(dx)
+    if sx != [n, h, w, c] or sd != [n, h, w, c] or s.numel() != n * h * w or dz.numel() != n * h * w:
+        raise ValueError("gate_apply_bwd: shape mismatch")
+    ws = _workspace(_lib.query("b200unet_gate_workspace_floats", 32), g.device)
+    _lib.call("b200unet_gate_apply_bwd", gp, gcs, xp, xcs, _f32(s), _f32(scale_p), _f32(shift_p), _f32(mean_p), _f32(rstd_p), dp, dcs,
+              _f32(dz), ws.data_ptr(), sums2.data_ptr(), n * h * w, c, _stream())
+
+
+def gate_bwd_reduce(q1, x1, aff_q, aff_x, w_psi, s, dz, gamma_p, mean_p, rstd_p, sums2, count, ds, sums):
+    """aff_q / aff_x = (scale, shift, mean, rstd) of the two BatchNorms. Fills ds and sums (fp64 [4C + 8])."""
+    qp, qcs, n, h, w, c = _nhwc(q1)
+    xp, xcs, *_ = _nhwc(x1)
+    ws = _workspace(_lib.query("b200unet_gate_workspace_floats", c), q1.device)
+    _lib.call("b200unet_gate_bwd_reduce", qp, qcs, xp, xcs, _f32(aff_q[0]), _f32(aff_q[1]), _f32(aff_x[0]), _f32(aff_x[1]),
+              _f32(aff_q[2]), _f32(aff_q[3]), _f32(aff_x[2]), _f32(aff_x[3]), _f32(w_psi), _f32(s), _f32(dz), _f32(gamma_p),
+              _f32(mean_p), _f32(rstd_p), sums2.data_ptr(), float(count), _f32(ds), ws.data_ptr(), sums.data_ptr(), n * h * w, c,
+              _stream())
+
+
+def gate_bwd_apply(q1, x1, aff_q, aff_x, gamma_q, gamma_x, w_psi, ds, sums, sums_local, sums2_local, count, grads, dbias):
+    """Overwrites q1 / x1 with the gradients at the two pre-BatchNorm maps. grads = (dgamma_q, dbeta_q, dgamma_x, dbeta_x,
+    dw_psi, db_psi, dgamma_p, dbeta_p) fp32 outputs; dbias fp32 [2C] = channel sums of the two stored gradients."""
+    qp, qcs, n, h, w, c = _nhwc(q1)
+    xp, xcs, *_ = _nhwc(x1)
+    ws = _workspace(_lib.query("b200unet_gate_workspace_floats", c), q1.device)
+    _lib.call("b200unet_gate_bwd_apply", qp, qcs, xp, xcs, _f32(aff_q[0]), _f32(aff_q[1]), _f32(aff_x[0]), _f32(aff_x[1]),
+              _f32(gamma_q), _f32(aff_q[2]), _f32(aff_q[3]), _f32(gamma_x), _f32(aff_x[2]), _f32(aff_x[3]), _f32(w_psi), _f32(ds),
+              sums.data_ptr(), _ptr(sums_local), sums2_local.data_ptr(), float(count), *[g.data_ptr() for g in grads],
+              ws.data_ptr(), _f32(dbias), n * h * w, c, _stream())
+
+
 # --------------------------------------------------------------------------------------------- losses / inference
 def loss_ce_dice_fwd(logits, target, mode):
     n, ncls, h, w = logits.shape
