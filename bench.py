@@ -49,6 +49,12 @@ WORKLOADS = {
     "reg768": dict(kind="train", ch=3, cls=2, H=768, W=768, batch=8, loss="mseMC", relu=True,
                    metric="unet_train_img_per_s_768_regression", gflop_per_img=2599.23, scaling="weak", cpu_sample=2,
                    what="BASELINE configs[4]: UNet(3,2) regression training step (fwd + F.relu + mseMC loss + bwd + SGD), 3x768x768"),
+    # the attention-gated network (Model.py:257-391) at config 2's shape. gflop_per_img counts the gates as the
+    # reference executes them (ConvTranspose2d C_q->C_q, two 1x1 convolutions, psi: 47.3 GFLOP forward per image); the B200
+    # path composes up and W_q on the weight side and executes about a third of the gates' FLOPs.
+    "attn512": dict(kind="train", model="UNet_attention", ch=3, cls=2, H=512, W=512, batch=16, loss="dice_bce_mc", relu=False,
+                    metric="unet_attention_train_img_per_s_512", gflop_per_img=1297.0, scaling="weak", cpu_sample=2,
+                    what="UNet_attention(3,2) training step (fwd + dice_bce_mc loss + bwd + SGD), 3x512x512"),
 }
 
 
@@ -176,7 +182,7 @@ def reference_cpu_step(wl, batch, seed=0):
     if ref_loader.available():
         RefModel, ref_loss = ref_loader.load()
         torch.manual_seed(seed)
-        net = RefModel.UNet(wl["ch"], wl["cls"])
+        net = getattr(RefModel, wl.get("model", "UNet"))(wl["ch"], wl["cls"])
         ref_loss.CLASS_NUMBER = wl["cls"]
         if wl["kind"] == "infer":
             net.eval()
@@ -201,6 +207,9 @@ def reference_cpu_step(wl, batch, seed=0):
         return step, "reference"
     from oracle import cpu_baseline
 
+    if wl.get("model", "UNet") != "UNet":
+        raise RuntimeError(f"the oracle port covers UNet only; workload {wl['metric']} needs the staged reference (oracle/_ref, "
+                           "python oracle/build_ref.py in the build container)")
     return cpu_baseline.make_step(wl["ch"], wl["cls"], batch, wl["H"], wl["W"], seed, loss_type=wl["loss"],
                                   relu=wl["relu"], train=wl["kind"] == "train", sgd=SGD), "port"
 
@@ -276,7 +285,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
 
     torch.manual_seed(0)
-    net = U.UNet(wl["ch"], wl["cls"]).to(dev)
+    net = getattr(U, wl.get("model", "UNet"))(wl["ch"], wl["cls"]).to(dev)
     net = net.train() if train else net.eval()
     U.loss.CLASS_NUMBER = wl["cls"]
     if dist_on:

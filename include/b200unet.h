@@ -209,6 +209,10 @@ int b200unet_head_bwd(const float* dz_nchw, const void* a, int a_cs, const float
  *   sums[0..C)   = sum y, sums[C..2C) = sum y^2 (fp64, so SyncBN can all-reduce them between the two calls). */
 int b200unet_bn_reduce_partials(const float* stats_partial, int64_t mtiles, int C, double* sums,
                                 b200_stream_t stream);
+/* Pre-reduction of statistics rows: out[b][col] = sum of partial[r][col] over r = b (mod out_rows), fixed order. For epilogues
+ * that emit one row per pixel tile (the attention gates' GEMMs: up to 131 072 rows) ahead of the one-block-per-32-channels
+ * finalisation kernels. ncols = 2 * C: a power of two <= 256 or a multiple of 256. */
+int b200unet_fold_rows(const float* partial, int64_t rows, int ncols, float* out, int out_rows, b200_stream_t stream);
 /* count = number of elements per channel behind `sums` (global count under SyncBN). Writes mean/rstd (saved for
  * backward), scale = gamma*rstd, shift = beta - mean*scale; if running_mean != NULL also
  * running_mean = (1-mom)*rm + mom*mean, running_var = (1-mom)*rv + mom*var*count/(count-1). */

@@ -3,6 +3,7 @@ caches, real clocks - unlike ncu's serialised replays) and the IDLE time between
 named. Answers "where does measured step time - summed kernel time go".
 
     GRAPHS=1 python scripts/timeline.py > gpurun_out/timeline.txt
+    MODEL=UNet_attention python scripts/timeline.py  # the attention-gated network
     torchrun --nproc-per-node N scripts/timeline.py     # data parallel + SyncBN: rank 0's timeline (all streams)
 """
 import os
@@ -25,7 +26,7 @@ if WORLD > 1:
     if RANK != 0:
         sys.stdout = open(os.devnull, "w")
 torch.manual_seed(0)
-net = U.UNet(3, 2).cuda().train()
+net = getattr(U, os.environ.get("MODEL", "UNet"))(3, 2).cuda().train()
 U.loss.CLASS_NUMBER = 2
 opt = U.FusedSGD(net, lr=0.01, momentum=0.9, weight_decay=1e-4)
 x = torch.randn(B, 3, S, S, device="cuda")

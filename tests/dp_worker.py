@@ -10,6 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import unet_torch_b200 as U  # noqa: E402
 
+MODEL = os.environ.get("DP_MODEL", "UNet")  # UNet | UNet_attention (attention gates: three more SyncBN layers per gate)
+Net = getattr(U, MODEL)
+
 
 def rel(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
@@ -33,7 +36,7 @@ def main():
         assert torch.equal(v, ref) or float((v - ref).abs().max() / ref.abs().max()) < 1e-15, (it, nel)
     per, hw = 2, 48
     torch.manual_seed(0)
-    net = U.UNet(3, 2).to(dev).train()
+    net = Net(3, 2).to(dev).train()
     U.loss.CLASS_NUMBER = 2
     g = torch.Generator().manual_seed(5)
     x = torch.randn(per * world, 3, hw, hw, generator=g)
@@ -57,7 +60,7 @@ def main():
     # kernels) against the eager launches: three optimizer steps each (eager warm-up, capture, replay)
     def run_steps(graphs):
         torch.manual_seed(0)
-        m = U.UNet(3, 2).to(dev).train().enable_cuda_graphs(graphs)
+        m = Net(3, 2).to(dev).train().enable_cuda_graphs(graphs)
         opt = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9)
         res = []
         for it in range(4):
@@ -87,7 +90,7 @@ def main():
     # ---- the same global batch on one GPU, no data parallelism
     U.DataParallelContext.disable()
     torch.manual_seed(0)
-    net1 = U.UNet(3, 2).to(dev).train()
+    net1 = Net(3, 2).to(dev).train()
     out1 = net1(x.to(dev))
     losses = [U.calc_loss(out1[r * per:(r + 1) * per], y[r * per:(r + 1) * per].to(dev), loss_type="dice_bce_mc")
               for r in range(world)]
@@ -95,14 +98,20 @@ def main():
     torch.cuda.synchronize()
     e_out = rel(dp_out, out1.detach()[sl])
     worst, worst_n = 0.0, ""
+    # gradients that are analytically zero (a bias in front of a BatchNorm: the gates' conv biases) are rounding noise on both
+    # sides: measured against 1e-6 x the largest gradient norm of the net
+    floor = 1e-6 * max(float(p.grad.double().norm()) for p in net1.parameters())
     for n, p in net1.named_parameters():
-        e = rel(dp_grads[n], p.grad)
+        e = float((dp_grads[n].double() - p.grad.double()).norm()) / max(float(p.grad.double().norm()), floor)
         if e > worst:
             worst, worst_n = e, n
     e_rm = rel(dp_rm, net1.inc.double_conv[1].running_mean)
     print(f"rank {rank}: logits rel {e_out:.3e}, worst grad rel {worst:.3e} ({worst_n}), running_mean rel {e_rm:.3e}", flush=True)
-    assert e_out < 2e-3, e_out
-    assert worst < 2e-2, (worst, worst_n)
+    # the two runs differ in summation order only, but bf16 storage amplifies that; the gated network (sigmoid gates behind
+    # one-channel BatchNorms) more than the plain one
+    tol_out, tol_grad = (2e-3, 2e-2) if MODEL == "UNet" else (1e-2, 1e-1)
+    assert e_out < tol_out, e_out
+    assert worst < tol_grad, (worst, worst_n)
     assert e_rm < 1e-5, e_rm
     dist.barrier()
     if rank == 0:

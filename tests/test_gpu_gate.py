@@ -309,3 +309,34 @@ def test_attention_eval_mode_backward_and_graph_replay():
     for k in sa:
         if sa[k].is_floating_point():
             assert torch.allclose(sa[k], sb[k], rtol=1e-4, atol=1e-6), k
+
+
+def test_fold_rows_and_folded_statistics_path(monkeypatch):
+    """fold_rows (pre-reduction of one-row-per-tile statistics) against a torch sum, and a network step with the folding
+    threshold lowered so that small maps take the folded path: identical BatchNorm buffers up to fp32 summation order."""
+    import unet_torch_b200 as U
+    from unet_torch_b200 import _lib, ops
+
+    torch.manual_seed(1)
+    for rows, ncols in ((5000, 64), (777, 2), (9001, 512), (300, 256)):
+        part = torch.randn(rows, ncols, device="cuda")
+        out_rows = min(296, rows)
+        out = torch.full((out_rows, ncols), float("nan"), device="cuda")
+        _lib.call("b200unet_fold_rows", part.data_ptr(), rows, ncols, out.data_ptr(), out_rows, torch.cuda.current_stream().cuda_stream)
+        want = torch.stack([part[b::out_rows].double().sum(0) for b in range(out_rows)])
+        assert torch.allclose(out.double(), want, rtol=1e-5, atol=1e-4)
+    U.loss.CLASS_NUMBER = 2
+    x = torch.randn(2, 3, 64, 64, device="cuda")
+    y = (torch.rand(2, 64, 64, device="cuda") > 0.5).float()
+    res = []
+    for above in (ops.FOLD_ROWS_ABOVE, 8):
+        monkeypatch.setattr(ops, "FOLD_ROWS_ABOVE", above)
+        monkeypatch.setattr(ops, "FOLD_ROWS_TO", 296 if above > 8 else 7)
+        torch.manual_seed(2)
+        net = U.UNet_attention(3, 2).cuda().train()
+        out = net(x)
+        U.calc_loss(out, y, loss_type="dice_bce_mc").backward()
+        res.append((out.detach(), {k: v.clone() for k, v in net.state_dict().items() if "running" in k}))
+    assert rel_l2(res[1][0], res[0][0]) < 2e-2
+    for k in res[0][1]:
+        assert rel_l2(res[1][1][k], res[0][1][k]) < 1e-3, k

@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200unet_head_bwd_workspace_floats": (c_int64, [_I, _I, _I, _I, _I]),
     "b200unet_head_bwd": (c_int, [_P, _P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200unet_bn_reduce_partials": (c_int, [_P, _L, _I, _P, _P]),
+    "b200unet_fold_rows": (c_int, [_P, _L, _I, _P, _I, _P]),
     "b200unet_bn_finalize": (c_int, [_P, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P]),
     "b200unet_bn_reduce_finalize": (c_int, [_P, _L, _I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200unet_bn_eval_affine": (c_int, [_P, _P, _P, _P, _F, _P, _P, _I, _P]),

@@ -80,6 +80,32 @@ int launch_reduce_partials(const float* partial, long long rows, int ncols, doub
   return b2h::check_launch("reduce_partials");
 }
 
+// partial [rows][ncols] -> out [out_rows][ncols], out[b] = sum of the rows r = b (mod out_rows) in increasing order (fixed order,
+// no atomics). The one-tile-per-CTA GEMM epilogues of the attention gates emit one statistics row per 128-pixel tile (131 072
+// rows for a 32-channel map at 512^2): the finalisation kernels above run one block per 32 channels, so they get this
+// machine-wide pre-reduction first.
+__global__ void __launch_bounds__(256) fold_rows_kernel(const float* __restrict__ partial, long long rows, int ncols,
+                                                        float* __restrict__ out, int out_rows) {
+  __shared__ float sh[256];
+  const int width = ncols < 256 ? ncols : 256;  // ncols is a power of two >= 2 or a multiple of 256
+  const int lanes = 256 / width;
+  const int cl = threadIdx.x % width, rl = threadIdx.x / width;
+  for (int c0 = 0; c0 < ncols; c0 += width) {
+    float acc = 0.f;
+    if (rl < lanes)
+      for (long long r = blockIdx.x + static_cast<long long>(out_rows) * rl; r < rows; r += static_cast<long long>(out_rows) * lanes)
+        acc += __ldg(partial + r * ncols + c0 + cl);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0) {
+      float t = 0.f;
+      for (int i = 0; i < lanes; ++i) t += sh[i * width + cl];
+      out[static_cast<size_t>(blockIdx.x) * ncols + c0 + cl] = t;
+    }
+    __syncthreads();
+  }
+}
+
 // The forward statistics path in ONE launch (single GPU): reduce the conv epilogue's partial rows [rows][2][C] (fp64, fixed
 // order) and finalise BatchNorm2d for the block's 32 channels - mean, rstd, scale = gamma*rstd, shift = beta - mean*scale,
 // running statistics (unbiased variance) and num_batches_tracked += 1 (Model.py:17,21). Replaces memset + reduce_partials +
@@ -597,6 +623,15 @@ extern "C" {
 
 int b200unet_bn_reduce_partials(const float* stats_partial, int64_t mtiles, int C, double* sums, b200_stream_t stream) {
   return launch_reduce_partials(stats_partial, mtiles, 2 * C, sums, static_cast<cudaStream_t>(stream));
+}
+
+int b200unet_fold_rows(const float* partial, int64_t rows, int ncols, float* out, int out_rows, b200_stream_t stream) {
+  B2_REQUIRE(partial && out && rows > 0 && out_rows > 0 && out_rows <= rows, "fold_rows: bad arguments (rows=%lld out_rows=%d)",
+             static_cast<long long>(rows), out_rows);
+  B2_REQUIRE(ncols >= 2 && ((ncols <= 256 && (ncols & (ncols - 1)) == 0) || ncols % 256 == 0),
+             "fold_rows: ncols=%d must be a power of two in [2, 256] or a multiple of 256", ncols);
+  fold_rows_kernel<<<out_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, rows, ncols, out, out_rows);
+  return b2h::check_launch("fold_rows");
 }
 
 int b200unet_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps,

@@ -217,7 +217,7 @@ int launch_small(float* const* w, const float* const* grad, float* const* buf, f
       if (t.n[i] > maxn) maxn = t.n[i];
     }
     int bx = (maxn + 255) / 256;
-    if (bx > 64) bx = 64;
+    if (bx > 296) bx = 296;  // a few multi-million-element tensors (the gates' ConvTranspose2d weights) ride along here
     sgd_small_kernel<<<dim3(bx, t.count), 256, 0, st>>>(t, h);
     if (int e = b2h::check_launch(what)) return e;
   }

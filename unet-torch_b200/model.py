@@ -303,6 +303,7 @@ class UNetEngine:
             return scale, shift, mean, rstd, count
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         rstd = torch.empty(c, dtype=torch.float32, device=dev)
+        stats_partial, rows = ops.fold_rows(stats_partial, rows, 2 * c)
         mom = bn.momentum if bn.momentum is not None else 0.1
         track = bn.track_running_stats and bn.running_mean is not None
         if dp is None or not dp.sync_bn:  # single GPU: partial rows -> statistics -> affine -> running buffers, one launch
@@ -436,10 +437,12 @@ class UNetEngine:
             for ij in range(4):
                 ops.sgemm_strided(dwc, w_up.detach(), dwq, ch, cq, cq, (4, 4 * chp), (4 * cq, 4), (cq, 1), accumulate=ij > 0,
                                   offsets=(ij, ij, 0))
-            # b' = b_q + W_q b_up:  db_q = db',  db_up[d] = sum_h W_q[h,d] db'[h]
-            ops.sgemm_strided(w_q.detach(), dbias, dbup, cq, 1, ch, (1, cq), (1, 1), (1, 1))
 
+        # (the closure only touches tensors that live until backward returns - q, the saved maps, parameters, gradient buffers -
+        # and what it allocates itself: the side stream is invisible to the caching allocator)
         on_wgrad_stream(weight_side)
+        # b' = b_q + W_q b_up:  db_q = db',  db_up[d] = sum_h W_q[h,d] db'[h]
+        ops.sgemm_strided(w_q.detach(), dbias, dbup, cq, 1, ch, (1, cq), (1, 1), (1, 1))
         dbq.copy_(dbias[:ch])
         grads[w_up], grads[b_up], grads[w_q], grads[b_q] = dwup, dbup, dwq, dbq
         done(w_up, b_up, w_q, b_q)
@@ -678,6 +681,7 @@ class UNetEngine:
 
         # ---- decoder(s): head, then up4 -> up1; the skip and bottleneck gradients of several decoders are summed
         skip_grads = [None] * 4
+        keep_alive = []   # tensors read on the weight-gradient stream that nothing else references until backward returns
         g5 = None
         for k in reversed(range(len(self.decoders))):
             ups, dec, head_conv = self.decoders[k]
@@ -698,6 +702,10 @@ class UNetEngine:
                 db, dwu = gbuf(upo.up.bias), gbuf(upo.up.weight)
                 dcat = bn_conv_bwd(c1, r1, g, None, None, hs[l], wsz[l], True, dx_colsum=(ch[l], db), pre=pre)
                 dq_gate = None
+                # the side stream reads dcat's upsampled half (ConvTranspose2d weight gradient below). A plain single-decoder
+                # network keeps the storage referenced through skip_grads; behind a gate, or for a second decoder, nothing else
+                # would - and the caching allocator does not see the side stream
+                keep_alive.append(dcat)
                 if grec is not None:  # through the attention gate: gradient w.r.t. the skip activation and w.r.t. q = d_in
                     skip_grads[l], dq_gate = self._gate_backward(self.gates[j], grec, dcat[..., : ch[l]], d_in, gbuf, done, grads,
                                                                  sync, on_wgrad_stream)

@@ -334,6 +334,19 @@ def bn_reduce_finalize(stats_partial, rows, count, gamma, beta, eps, momentum, r
               _f32(scale), _f32(shift), _stream())
 
 
+FOLD_ROWS_ABOVE, FOLD_ROWS_TO = 4096, 296
+
+
+def fold_rows(stats_partial, rows, ncols):
+    """Statistics rows [rows][ncols] -> ([FOLD_ROWS_TO][ncols], FOLD_ROWS_TO) when there are more than FOLD_ROWS_ABOVE of them
+    (one per pixel tile from the attention gates' GEMM epilogues), else unchanged."""
+    if stats_partial is None or rows <= FOLD_ROWS_ABOVE:
+        return stats_partial, rows
+    out = torch.empty(FOLD_ROWS_TO * ncols, dtype=torch.float32, device=stats_partial.device)
+    _lib.call("b200unet_fold_rows", _f32(stats_partial), rows, ncols, out.data_ptr(), FOLD_ROWS_TO, _stream())
+    return out, FOLD_ROWS_TO
+
+
 def bn_eval_affine(gamma, beta, running_mean, running_var, eps, scale, shift):
     _lib.call("b200unet_bn_eval_affine", _f32(gamma), _f32(beta), _f32(running_mean), _f32(running_var), eps,
               _f32(scale), _f32(shift), gamma.numel(), _stream())
