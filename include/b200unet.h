@@ -188,6 +188,9 @@ int b200unet_sgemm_strided(const float* A, const float* B, float* C, const float
                            int64_t ak, int64_t bk, int64_t bn, int64_t cm, int64_t cn, int batch, int64_t az, int64_t bz,
                            int64_t cz, int accumulate, b200_stream_t stream);
 
+/* out[i] = sum_b part[b][i], b < batches, i < n (fixed order): joins batch-parallel partial products of the call above. */
+int b200unet_sum_batches(const float* part, float* out, int64_t n, int batches, b200_stream_t stream);
+
 /* ---- first layer and head (tiny channel counts: bandwidth-bound CUDA-core kernels) ------------------------ */
 /* inc.conv1: x fp32 NCHW [N][Cin<=4][H][W] (Trainer.py:700-702 hands fp32 NCHW) -> y bf16 NHWC [..][Cout] + stats. */
 int b200unet_conv3x3_first_fprop(const float* x_nchw, const float* w_oihw, void* y, int y_cs, float* stats_partial,

@@ -105,7 +105,13 @@ def test_strided_sgemm_composition_shapes():
         dwq = torch.full((ch, cq, 1, 1), float("nan"), device="cuda")
         for ij in range(4):
             ops.sgemm_strided(dwc, w_up, dwq, ch, cq, cq, (4, 4 * chp), (4 * cq, 4), (cq, 1), accumulate=ij > 0, offsets=(ij, ij, 0))
-        assert rel_l2(dwq.view(ch, cq), torch.einsum("chij,cdij->hd", dwc[:, :ch].double(), w_up.double())) < 1e-5
+        want_dwq = torch.einsum("chij,cdij->hd", dwc[:, :ch].double(), w_up.double())
+        assert rel_l2(dwq.view(ch, cq), want_dwq) < 1e-5
+        part = torch.full((4, ch, cq), float("nan"), device="cuda")  # the engine's form: four partial products in one launch
+        ops.sgemm_strided(dwc, w_up, part, ch, cq, cq, (4, 4 * chp), (4 * cq, 4), (cq, 1), batch=4, batch_strides=(1, 1, ch * cq))
+        dwq2 = torch.full((ch, cq, 1, 1), float("nan"), device="cuda")
+        ops.sum_batches(part, dwq2)
+        assert rel_l2(dwq2.view(ch, cq), want_dwq) < 1e-5
         dbias = torch.randn(2 * ch, device="cuda")
         dbup = torch.full((cq,), float("nan"), device="cuda")
         ops.sgemm_strided(w_q, dbias, dbup, cq, 1, ch, (1, cq), (1, 1), (1, 1))
@@ -267,6 +273,13 @@ def test_attention_tensor_core_engine_against_reference_yardstick(golden, case):
     with torch.no_grad():
         e_f, e_c = fast(x), chk(x)
     assert rel_l2(e_c, e_f) <= 1.5 * yard["logits_eval"] + 2e-3, rel_l2(e_c, e_f)
+    # fused inference heads (OutConv + softmax/argmax, + sigmoid threshold, + relu / divisor) run through the gated engine too
+    with torch.no_grad():
+        mask = fast.predict(x)
+        assert mask.dtype == torch.uint8 and (mask.long() != e_f.argmax(1)).float().mean() < 2e-3
+        assert (fast.predict_binary(x, 0.5).bool() != (torch.sigmoid(e_f[:, 0]) >= 0.5)).float().mean() < 2e-3
+        dens, sums = fast.predict_density(x, 200.0)
+        assert rel_l2(dens, torch.relu(e_f) / 200.0) < 5e-3 and rel_l2(sums, (torch.relu(e_f) / 200.0).double().sum((2, 3))) < 5e-3
 
 
 def test_attention_eval_mode_backward_and_graph_replay():

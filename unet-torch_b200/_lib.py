@@ -132,6 +132,7 @@ SIGNATURES = {
     "b200unet_gate_bwd_reduce": (c_int, [_P, _I, _P, _I] + [_P] * 15 + [_D, _P, _P, _P, _L, _I, _P]),
     "b200unet_gate_bwd_apply": (c_int, [_P, _I, _P, _I] + [_P] * 15 + [_D] + [_P] * 10 + [_L, _I, _P]),
     "b200unet_sgemm_strided": (c_int, [_P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _L, _L, _L, _I, _P]),
+    "b200unet_sum_batches": (c_int, [_P, _P, _L, _I, _P]),
     "b200unet_sgd_small": (c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_sgd_weights": (c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _I, _I, _P]),
     "b200unet_adam_weights": (c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _D, _D, _F, _F, _F, _F, _I, _P]),

@@ -110,25 +110,39 @@ __global__ void __launch_bounds__(GT) gate_psi_fwd_kernel(GateMaps m, const floa
   float a1 = 0.f, a2 = 0.f;
   const long long total = pixels * TPP;
   const long long stride = static_cast<long long>(gridDim.x) * GT;
-  for (long long i = static_cast<long long>(blockIdx.x) * GT + threadIdx.x;; i += stride) {
-    const bool valid = i < total;
-    if (!__any_sync(0xffffffffu, valid)) break;
-    const long long pix = i / TPP;
-    float p = 0.f;
-    if (valid) {
-      float qf[8], xf[8];
-      unpack8(ldg128(m.q + pix * m.q_cs + g * 8), qf);
-      unpack8(ldg128(m.x + pix * m.x_cs + g * 8), xf);
+  constexpr int U = 2;  // pixels per thread and iteration: all loads are issued before the arithmetic (bytes in flight)
+  for (long long i0 = static_cast<long long>(blockIdx.x) * GT + threadIdx.x;; i0 += stride * U) {
+    if (!__any_sync(0xffffffffu, i0 < total)) break;
+    uint4 qv[U], xv[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) p = fmaf(k.wp[j], k.e(j, qf[j], xf[j]), p);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total) {
+        qv[u] = ldg128(m.q + (i / TPP) * m.q_cs + g * 8);
+        xv[u] = ldg128(m.x + (i / TPP) * m.x_cs + g * 8);
+      }
     }
 #pragma unroll
-    for (int o = TPP / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-    if (valid && g == 0) {
-      const float s = p + b;
-      s_out[pix] = s;
-      a1 += s;
-      a2 = fmaf(s, s, a2);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      const bool valid = i < total;
+      const long long pix = i / TPP;
+      float p = 0.f;
+      if (valid) {
+        float qf[8], xf[8];
+        unpack8(qv[u], qf);
+        unpack8(xv[u], xf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p = fmaf(k.wp[j], k.e(j, qf[j], xf[j]), p);
+      }
+#pragma unroll
+      for (int o = TPP / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if (valid && g == 0) {
+        const float s = p + b;
+        s_out[pix] = s;
+        a1 += s;
+        a2 = fmaf(s, s, a2);
+      }
     }
   }
   if (partial != nullptr) block_sum2(a1, a2, partial + 2 * static_cast<size_t>(blockIdx.x));
@@ -248,24 +262,43 @@ __global__ void __launch_bounds__(GT) gate_bwd_reduce_kernel(GateMaps m, const f
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = s3[j] = s4[j] = 0.f;
   const long long total = pixels * TPP;
   const long long stride = static_cast<long long>(gridDim.x) * GT;
-  for (long long i = static_cast<long long>(blockIdx.x) * GT + threadIdx.x; i < total; i += stride) {
-    const long long pix = i / TPP;
-    float qf[8], xf[8];
-    unpack8(ldg128(m.q + pix * m.q_cs + g * 8), qf);
-    unpack8(ldg128(m.x + pix * m.x_cs + g * 8), xf);
-    const float ds = pb.ds(__ldg(dz + pix), __ldg(s + pix));
-    if (g == 0) {
-      ds_out[pix] = ds;
-      sds += ds;
+  constexpr int U = 2;
+  for (long long i0 = static_cast<long long>(blockIdx.x) * GT + threadIdx.x; i0 < total; i0 += stride * U) {
+    uint4 qv[U], xv[U];
+    float dzv[U], sv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total) {
+        const long long pix = i / TPP;
+        qv[u] = ldg128(m.q + pix * m.q_cs + g * 8);
+        xv[u] = ldg128(m.x + pix * m.x_cs + g * 8);
+        dzv[u] = __ldg(dz + pix);
+        sv[u] = __ldg(s + pix);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float e = k.e(j, qf[j], xf[j]);
-      const float de = e > 0.f ? ds * k.wp[j] : 0.f;
-      s1[j] += de;
-      s2[j] = fmaf(de, qf[j], s2[j]);
-      s3[j] = fmaf(de, xf[j], s3[j]);
-      s4[j] = fmaf(ds, e, s4[j]);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= total) break;
+      const long long pix = i / TPP;
+      float qf[8], xf[8];
+      unpack8(qv[u], qf);
+      unpack8(xv[u], xf);
+      const float ds = pb.ds(dzv[u], sv[u]);
+      if (g == 0) {
+        ds_out[pix] = ds;
+        sds += ds;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float e = k.e(j, qf[j], xf[j]);
+        const float de = e > 0.f ? ds * k.wp[j] : 0.f;
+        s1[j] += de;
+        s2[j] = fmaf(de, qf[j], s2[j]);
+        s3[j] = fmaf(de, xf[j], s3[j]);
+        s4[j] = fmaf(ds, e, s4[j]);
+      }
     }
   }
   __shared__ float red[GT][33];
@@ -306,7 +339,7 @@ struct GateBwdOut {
 
 // partial2 row layout (pitch 2C): [0,C) sum dQ; [C,2C) sum dX (of the bf16 values stored: the bias gradients of the two convs)
 template <int TPP>
-__global__ void __launch_bounds__(GT) gate_bwd_apply_kernel(GateMaps m, const float* __restrict__ gamma_q,
+__global__ void __launch_bounds__(GT, 2) gate_bwd_apply_kernel(GateMaps m, const float* __restrict__ gamma_q,
                                                             const float* __restrict__ mean_q, const float* __restrict__ rstd_q,
                                                             const float* __restrict__ gamma_x, const float* __restrict__ mean_x,
                                                             const float* __restrict__ rstd_x, const float* __restrict__ ds,
@@ -354,27 +387,44 @@ __global__ void __launch_bounds__(GT) gate_bwd_apply_kernel(GateMaps m, const fl
   }
   const long long total = pixels * TPP;
   const long long stride = static_cast<long long>(gridDim.x) * GT;
-  for (long long i = static_cast<long long>(blockIdx.x) * GT + threadIdx.x; i < total; i += stride) {
-    const long long pix = i / TPP;
-    float qf[8], xf[8], oq[8], ox[8];
-    unpack8(ldg128(m.q + pix * m.q_cs + g * 8), qf);
-    unpack8(ldg128(m.x + pix * m.x_cs + g * 8), xf);
-    const float dsv = __ldg(ds + pix);
+  constexpr int U = 2;
+  for (long long i0 = static_cast<long long>(blockIdx.x) * GT + threadIdx.x; i0 < total; i0 += stride * U) {
+    uint4 qv[U], xv[U];
+    float dsu[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float de = k.e(j, qf[j], xf[j]) > 0.f ? dsv * k.wp[j] : 0.f;
-      oq[j] = fmaf(q1[j], de, fmaf(q2[j], qf[j], q3[j]));
-      ox[j] = fmaf(x1[j], de, fmaf(x2[j], xf[j], x3[j]));
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total) {
+        const long long pix = i / TPP;
+        qv[u] = ldg128(m.q + pix * m.q_cs + g * 8);
+        xv[u] = ldg128(m.x + pix * m.x_cs + g * 8);
+        dsu[u] = __ldg(ds + pix);
+      }
     }
-    const uint4 pq = pack8(oq), px = pack8(ox);
-    *reinterpret_cast<uint4*>(dq + pix * m.q_cs + g * 8) = pq;
-    *reinterpret_cast<uint4*>(dxm + pix * m.x_cs + g * 8) = px;
-    unpack8(pq, oq);
-    unpack8(px, ox);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      aq[j] += oq[j];
-      ax[j] += ox[j];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= total) break;
+      const long long pix = i / TPP;
+      float qf[8], xf[8], oq[8], ox[8];
+      unpack8(qv[u], qf);
+      unpack8(xv[u], xf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float de = k.e(j, qf[j], xf[j]) > 0.f ? dsu[u] * k.wp[j] : 0.f;
+        oq[j] = fmaf(q1[j], de, fmaf(q2[j], qf[j], q3[j]));
+        ox[j] = fmaf(x1[j], de, fmaf(x2[j], xf[j], x3[j]));
+      }
+      const uint4 pq = pack8(oq), px = pack8(ox);
+      *reinterpret_cast<uint4*>(dq + pix * m.q_cs + g * 8) = pq;
+      *reinterpret_cast<uint4*>(dxm + pix * m.x_cs + g * 8) = px;
+      unpack8(pq, oq);
+      unpack8(px, ox);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        aq[j] += oq[j];
+        ax[j] += ox[j];
+      }
     }
   }
   __shared__ float red[GT][17];
@@ -398,7 +448,9 @@ __global__ void __launch_bounds__(GT) gate_bwd_apply_kernel(GateMaps m, const fl
 }
 
 // ------------------------------------------------------------------------------------------------ weight-side GEMM
-// C[z][m][n] (+)= sum_k A[z][m][k] * B[z][k][n] (+ bias[m]) over arbitrary element strides, fp32, 64 x 64 tiles.
+// C[z][m][n] (+)= sum_k A[z][m][k] * B[z][k][n] (+ bias[m]) over arbitrary element strides, fp32. 128 x 64 tile per CTA,
+// 8 x 4 outputs per thread, K in steps of 16 through a double-buffered shared-memory tile (the next step's global loads are
+// in flight while the current one is multiplied).
 struct SgemmArgs {
   const float *A, *B;
   float* C;
@@ -408,49 +460,80 @@ struct SgemmArgs {
   int accumulate;
 };
 
+constexpr int SG_TM = 128, SG_TN = 64, SG_BK = 16;
+
 __global__ void __launch_bounds__(256) sgemm_strided_kernel(SgemmArgs a) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
+  __shared__ __align__(16) float As[2][SG_BK][SG_TM + 4];
+  __shared__ __align__(16) float Bs[2][SG_BK][SG_TN + 4];
   const float* A = a.A + blockIdx.z * a.az;
   const float* B = a.B + blockIdx.z * a.bz;
   float* Cc = a.C + blockIdx.z * a.cz;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int m0 = blockIdx.y * SG_TM, n0 = blockIdx.x * SG_TN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const bool a_kfast = a.ak <= a.am, b_nfast = a.bn <= a.bk;
-  float acc[4][4];
+  float acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < a.K; k0 += 16) {
+  float ra[8], rb[4];
+  auto load_global = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = threadIdx.x + r * 256;
+      const int kk = a_kfast ? (e & 15) : (e >> 7), mm = a_kfast ? (e >> 4) : (e & 127);
+      const int gm = m0 + mm, gk = k0 + kk;
+      ra[r] = (gm < a.M && gk < a.K) ? __ldg(A + gm * a.am + gk * a.ak) : 0.f;
+    }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int e = threadIdx.x + r * 256;
-      int mm, kk;
-      if (a_kfast) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
-      const int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < a.M && gk < a.K) ? __ldg(A + gm * a.am + gk * a.ak) : 0.f;
-      int nn, kb;
-      if (b_nfast) { nn = e & 63; kb = e >> 6; } else { kb = e & 15; nn = e >> 4; }
-      const int gn = n0 + nn, gkb = k0 + kb;
-      Bs[kb][nn] = (gn < a.N && gkb < a.K) ? __ldg(B + gkb * a.bk + gn * a.bn) : 0.f;
+      const int kk = b_nfast ? (e >> 6) : (e & 15), nn = b_nfast ? (e & 63) : (e >> 4);
+      const int gn = n0 + nn, gk = k0 + kk;
+      rb[r] = (gn < a.N && gk < a.K) ? __ldg(B + gk * a.bk + gn * a.bn) : 0.f;
     }
-    __syncthreads();
+  };
+  auto store_shared = [&](int buf) {
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+    for (int r = 0; r < 8; ++r) {
+      const int e = threadIdx.x + r * 256;
+      const int kk = a_kfast ? (e & 15) : (e >> 7), mm = a_kfast ? (e >> 4) : (e & 127);
+      As[buf][kk][mm] = ra[r];
+    }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+    for (int r = 0; r < 4; ++r) {
+      const int e = threadIdx.x + r * 256;
+      const int kk = b_nfast ? (e >> 6) : (e & 15), nn = b_nfast ? (e & 63) : (e >> 4);
+      Bs[buf][kk][nn] = rb[r];
+    }
+  };
+  load_global(0);
+  store_shared(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < a.K; k0 += SG_BK) {
+    const bool more = k0 + SG_BK < a.K;
+    if (more) load_global(k0 + SG_BK);
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
     }
-    __syncthreads();
+    if (more) {
+      store_shared(buf ^ 1);  // the other buffer was last read before the barrier that ended the previous step
+      __syncthreads();
+      buf ^= 1;
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + ty * 8 + i;
     if (gm >= a.M) continue;
     const float bias = a.bias_m != nullptr ? a.bias_m[gm] : 0.f;
 #pragma unroll
@@ -462,6 +545,31 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(SgemmArgs a) {
       if (a.accumulate) v += *dst;
       *dst = v;
     }
+  }
+}
+
+// N = 1 (the two bias products of a gate): one warp per output row, lanes stride over k
+__global__ void __launch_bounds__(256) sgemv_strided_kernel(SgemmArgs a) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= a.M) return;
+  float acc = 0.f;
+  for (int k = lane; k < a.K; k += 32) acc = fmaf(__ldg(a.A + m * a.am + k * a.ak), __ldg(a.B + k * a.bk), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    float* dst = a.C + m * a.cm;
+    float v = acc + (a.bias_m != nullptr ? a.bias_m[m] : 0.f);
+    if (a.accumulate) v += *dst;
+    *dst = v;
+  }
+}
+
+// out[i] = sum_b part[b][i] (fixed order): the four (i,j) partial products of a gate's dW_q
+__global__ void sum_batches_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int batches) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < batches; ++b) acc += part[b * n + i];
+    out[i] = acc;
   }
 }
 
@@ -603,10 +711,21 @@ int b200unet_sgemm_strided(const float* A, const float* B, float* C, const float
   B2_REQUIRE(A && B && C, "sgemm_strided: null argument");
   B2_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && batch <= 65535, "sgemm_strided: empty problem (M=%d N=%d K=%d batch=%d)", M, N, K, batch);
   SgemmArgs a{A, B, C, bias_m, M, N, K, am, ak, bk, bn, cm, cn, az, bz, cz, accumulate};
-  dim3 grid((N + 63) / 64, (M + 63) / 64, batch);
+  if (N == 1 && batch == 1) {
+    sgemv_strided_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return b2h::check_launch("sgemv_strided");
+  }
+  dim3 grid((N + SG_TN - 1) / SG_TN, (M + SG_TM - 1) / SG_TM, batch);
   B2_REQUIRE(grid.y <= 65535, "sgemm_strided: M=%d too large", M);
   sgemm_strided_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return b2h::check_launch("sgemm_strided");
+}
+
+int b200unet_sum_batches(const float* part, float* out, int64_t n, int batches, b200_stream_t stream) {
+  B2_REQUIRE(part && out && n > 0 && batches > 0, "sum_batches: bad arguments");
+  const long long blocks = (n + 255) / 256;
+  sum_batches_kernel<<<static_cast<int>(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(part, out, n, batches);
+  return b2h::check_launch("sum_batches");
 }
 
 }  // extern "C"

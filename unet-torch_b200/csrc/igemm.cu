@@ -521,6 +521,10 @@ int b200unet_conv1x1_fprop(const void* x, int x_cs, const void* w, const float* 
   B2_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv1x1_fprop: Cin (%d) and Cout (%d) must be multiples of 64", Cin, Cout);
   B2_REQUIRE(N > 0 && H > 0 && W > 0, "conv1x1_fprop: empty tensor");
   B2_REQUIRE(x_cs >= Cin && y_cs >= Cout && x_cs % 8 == 0 && y_cs % 8 == 0, "conv1x1_fprop: bad pitches %d %d", x_cs, y_cs);
+  // K = 64 without bias / statistics (the backward-data of a 64-wide gate): one K block per 128-pixel tile is all prologue for
+  // a one-tile-per-CTA launch - the persistent resident-weight kernel streams the tiles instead
+  if (Cin == 64 && bias == nullptr && stats_partial == nullptr && use_resident(64, 64))
+    return b2h::conv1x1_c64_launch(x, x_cs, w, y, y_cs, nullptr, N, H, W, Cout, static_cast<cudaStream_t>(stream));
   IgemmArgs a;
   a.tiles_w = b2h::ceil_div(W, TW);
   a.tiles_h = b2h::ceil_div(H, TH);

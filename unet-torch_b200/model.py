@@ -434,9 +434,10 @@ class UNetEngine:
             # dW_up[c,d,ij] = sum_h dW'[c,h,ij] W_q[h,d];  dW_q[h,d] = sum_{c,ij} dW'[c,h,ij] W_up[c,d,ij]
             ops.sgemm_strided(dwc, w_q.detach(), dwup, cq, cq, ch, (4 * chp, 4), (cq, 1), (4 * cq, 4), batch=4,
                               batch_strides=(1, 0, 1))
-            for ij in range(4):
-                ops.sgemm_strided(dwc, w_up.detach(), dwq, ch, cq, cq, (4, 4 * chp), (4 * cq, 4), (cq, 1), accumulate=ij > 0,
-                                  offsets=(ij, ij, 0))
+            part = torch.empty((4, ch, cq), dtype=torch.float32, device=dev)  # one partial product per (i,j), in parallel
+            ops.sgemm_strided(dwc, w_up.detach(), part, ch, cq, cq, (4, 4 * chp), (4 * cq, 4), (cq, 1), batch=4,
+                              batch_strides=(1, 1, ch * cq))
+            ops.sum_batches(part, dwq)
 
         # (the closure only touches tensors that live until backward returns - q, the saved maps, parameters, gradient buffers -
         # and what it allocates itself: the side stream is invisible to the caching allocator)
@@ -1060,7 +1061,7 @@ class UNet_attention(UNet):
     """Attention U-Net of the reference (Model.py:299-391): UNet whose skip connections pass through attention gates,
     `x_l_attention = attenion_l(q = decoder input, x = skip)` (the misspelt attribute names are the reference's and fix the
     state_dict keys). Same constructor, RNG consumption (the gates keep torch's default init: no `.apply(weights_init)`,
-    Model.py:325-341), 200 state_dict keys and forward(x) -> logits.
+    Model.py:325-341), 210 state_dict keys and forward(x) -> logits.
     Default width (initial_feature_map = 64, no dropout): the tensor-core engine - the U-Net body as in UNet, the gates as
     tcgen05 GEMMs (`up` and W_q composed into one ConvTranspose2d C_q -> C_h, W_x as a 1x1 GEMM) plus the bandwidth-bound
     kernels of csrc/gate.cu. Other variants, and `set_check_mode(True)`: the generic fp32 CUDA engine (csrc/generic_f32.cu,
@@ -1113,10 +1114,6 @@ class UNet_attention(UNet):
             for g in self._engine.gates or ():
                 g._ver = None
         return super().refresh_operands(force)
-
-    def _fused_head(self, x, head, head_arg=0.0):
-        raise NotImplementedError("fused inference heads cover UNet only; apply predict_mask / F.relu / sigmoid to net(x)")
-
 
 def preprocess(img_org, input_size=None, device=None) -> torch.Tensor:
     """`preprocess(img_org, input_size)` of test_mc3serousv5.py:100-127 / the z-normalisation of DataLoader.py:661-671 on

@@ -529,6 +529,12 @@ def sgemm_strided(a, b, c, m, n, k, a_strides, b_strides, c_strides, bias_m=None
     return c
 
 
+def sum_batches(part, out):
+    """out = part.sum(0) for a contiguous fp32 [batches, ...] tensor (fixed summation order)."""
+    _lib.call("b200unet_sum_batches", _f32(part), _f32(out), out.numel(), part.shape[0], _stream())
+    return out
+
+
 def gate_stat_rows(pixels, c):
     return _lib.query("b200unet_gate_stat_rows", pixels, c)
 
