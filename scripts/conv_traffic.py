@@ -25,7 +25,7 @@ def main(path, out):
     # also runs the 1x1 first-layer GEMM and the ConvTranspose2d GEMMs, which are not part of this figure)
     def is_conv3(name):
         return ("conv3_pair_kernel" in name or "conv3_res2_kernel" in name
-                or re.search(r"conv3_res_kernel<\d+, \d+, \d+, \d+, 9, 0(, \d+)?>", name) is not None)
+                or re.search(r"conv3_res_kernel<\d+, \d+, \d+, \d+, 9, 0(, \d+)*>", name) is not None)
 
     rows = [d for d in per.values() if "dram__bytes_read.sum" in d and is_conv3(d["name"])]
     starts = [i for i, d in enumerate(rows)]

@@ -21,7 +21,7 @@ def main(path):
         rows.append((r["Kernel Name"], ns))
     import re
 
-    first = re.compile(r"first_im2col|conv3_res_kernel<\d+, \d+, \d+, \d+, 1, 3, \d+>")
+    first = re.compile(r"first_im2col|conv3_res_kernel<\d+, \d+, \d+, \d+, 1, 3, \d+(, \w+)?>")
     starts = [i for i, (n, _) in enumerate(rows) if first.search(n)]
     if len(starts) >= 2:
         step = rows[starts[0]:starts[1]]
