@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(GT) gate_bwd_reduce_kernel(GateMaps m, const f
     double t = 0.0;
     for (int th = 0; th < GT; th += TPP) t += static_cast<double>(red[th][32]);
     row[4 * C] = static_cast<float>(t);
+    for (int i = 1; i < 8; ++i) row[4 * C + i] = 0.f;  // alignment padding of the row: defined values for the row reduction
   }
 }
 
