@@ -129,3 +129,36 @@ def test_multitask_one_output_unused_and_optimizer_step():
     assert losses[-1] < losses[0]
     with pytest.raises(ValueError):
         net(torch.randn(1, 3, 30, 30, device="cuda"))
+
+
+def test_multitask_cuda_graph_replay_matches_eager():
+    """enable_cuda_graphs on the two-decoder network: four FusedSGD steps replayed as graphs (one output unused in step 2:
+    autograd hands None for it) equal the eager launches."""
+    import unet_torch_b200 as U
+
+    x = torch.randn(2, 3, 32, 48, device="cuda")
+    t = torch.rand(2, 2, 32, 48, device="cuda")
+    states = []
+    for graphs in (False, True):
+        torch.manual_seed(4)
+        net = U.UNet_multitask(3, 2).cuda().train()
+        net.enable_cuda_graphs(graphs, share_grads=graphs)
+        opt = U.FusedSGD(net, lr=0.01, momentum=0.9, weight_decay=1e-4)
+        losses = []
+        for it in range(5):
+            o1, o2 = net(x)
+            l = U.calc_loss(torch.relu(o1), t, loss_type="mseMC")
+            if it != 2:
+                l = l + U.calc_loss(torch.relu(o2), t, loss_type="mseMC")
+            opt.zero_grad(set_to_none=True)
+            l.backward()
+            opt.step()
+            losses.append(float(l))
+        if graphs:
+            assert len(net._get_engine()._graphs) == 1
+        states.append((losses, {k: v.clone() for k, v in net.state_dict().items()}))
+    (la, sa), (lb, sb) = states
+    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(la, lb)), (la, lb)
+    for k in sa:
+        if sa[k].is_floating_point():
+            assert torch.allclose(sa[k], sb[k], rtol=1e-4, atol=1e-6), k

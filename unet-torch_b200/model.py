@@ -244,7 +244,7 @@ class UNetEngine:
         dp = DataParallelContext.current() if training else None
         if dp is not None and not dp.graph_capturable:
             return None
-        if torch.cuda.is_current_stream_capturing() or len(self.decoders) > 1:
+        if torch.cuda.is_current_stream_capturing():
             return None
         key = (tuple(x.shape), x.device.index, bool(training), bool(save), dp is not None)
         st = self._graphs.get(key)
@@ -780,7 +780,8 @@ class _GraphedStep:
             self.fwd = g
         self.fwd.replay()
         self.epoch += 1
-        return self.logits.clone()  # the caller may keep its logits across the next replay
+        # the caller may keep its logits across the next replay (one tensor, or one per decoder)
+        return tuple(l.clone() for l in self.logits) if isinstance(self.logits, tuple) else self.logits.clone()
 
     def backward(self, epoch, dlogits):
         if epoch != self.epoch:
@@ -789,9 +790,14 @@ class _GraphedStep:
                                "net.enable_cuda_graphs(False) for this pattern)")
         if self.bwd_done_epoch == epoch:
             raise RuntimeError("UNet backward called twice: activations are consumed in place")
+        multi = isinstance(self.logits, tuple)
         if self.dlogits is None:
-            self.dlogits = torch.empty_like(self.logits)
-        self.dlogits.copy_(dlogits)
+            self.dlogits = tuple(torch.empty_like(l) for l in self.logits) if multi else torch.empty_like(self.logits)
+        if multi:
+            for dst, src in zip(self.dlogits, dlogits):
+                dst.zero_() if src is None else dst.copy_(src)
+        else:
+            self.dlogits.copy_(dlogits)
         if self.bwd is None:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self.pool, capture_error_mode=self.capture_mode):
@@ -823,7 +829,7 @@ class _UNetFn(torch.autograd.Function):
     def backward(ctx, *dlogits):
         with torch.cuda.device(ctx.device):  # a CPU input was rejected in forward
             if ctx.step is not None:
-                grads = ctx.step.backward(ctx.epoch, dlogits[0].contiguous().float())
+                grads = ctx.step.backward(ctx.epoch, dlogits if len(dlogits) > 1 else dlogits[0].contiguous().float())
                 if ctx.engine.net._share_grads:
                     # hand the graph's static gradient tensors to .grad directly: autograd would copy every one of them
                     # (they stay referenced by the graph, so it cannot adopt them) - 124 MB of device copies per step
@@ -1033,13 +1039,10 @@ class UNet_multitask(UNet):
         return self._get_engine()
 
     def set_check_mode(self, flag: bool = True):
-        raise NotImplementedError("the fp32 check engine covers UNet only")
-
-    def enable_cuda_graphs(self, flag: bool = True):
-        raise NotImplementedError("CUDA-graph replay covers UNet only")
+        raise NotImplementedError("the fp32 check engine covers UNet and UNet_attention")
 
     def _fused_head(self, x, head, head_arg=0.0):
-        raise NotImplementedError("fused inference heads cover UNet only; apply predict_mask / F.relu to the two outputs")
+        raise NotImplementedError("fused inference heads cover UNet / UNet_attention; apply predict_mask / F.relu to the two outputs")
 
 
 class Attention_block(_Holder):
