@@ -301,6 +301,11 @@ def test_attention_eval_mode_backward_and_graph_replay():
     assert rel_l2(o_f, o_c) < 0.05
     errs = {k: rel_l2(g_f[k], g_c[k]) for k in g_f if float(g_c[k].norm()) > 1e-6 * max(float(v.norm()) for v in g_c.values())}
     assert statistics.median(errs.values()) < 0.25, statistics.median(errs.values())
+    # behind a FROZEN BatchNorm the bias gradients of the gate convolutions are not zero: the composed-weight backward must then
+    # carry the rank-one term db' (x) b_up into dW_q (tests/test_host_logic.py::test_gate_weight_composition_algebra)
+    gate_w = {k: v for k, v in errs.items() if ".W_q.0." in k or ".up." in k and "attenion" in k}
+    print("frozen-BN gate weight-side gradients vs the fp32 engine:", {k: round(v, 4) for k, v in gate_w.items()})
+    assert len(gate_w) == 16 and max(gate_w.values()) < 0.3, gate_w
     # graphs: three FusedSGD steps eager vs replayed
     states = []
     for graphs in (False, True):

@@ -145,3 +145,36 @@ def test_product_path_never_touches_the_oracle_or_a_cpu_fallback():
         uses = any(isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n) for n in ast.walk(fn))
         if uses:
             assert fn.name in ("cpu_baseline_leg", "reference_arm", "run_reference", "cpu_port_step") or "cpu" in fn.name or "reference" in fn.name, fn.name
+
+
+def test_gate_weight_composition_algebra():
+    """The rewrite the tensor-core engine applies to an attention gate (model.py `_GateOp`): ConvTranspose2d(C_q, C_q, 2, 2)
+    followed by a 1x1 convolution (Model.py:287-288) equals ONE ConvTranspose2d with W'[c,h,i,j] = sum_d W_up[c,d,i,j] W_q[h,d],
+    b' = b_q + W_q b_up, and the gradients of the four original tensors follow from (dW', db') by the formulas the engine's
+    strided GEMMs evaluate. fp64 on the host against autograd through the reference's two-module form."""
+    import torch
+    import torch.nn.functional as F
+
+    torch.manual_seed(0)
+    cq, ch, n, h, w = 6, 3, 2, 4, 5
+    q = torch.randn(n, cq, h, w, dtype=torch.float64)
+    w_up = torch.randn(cq, cq, 2, 2, dtype=torch.float64, requires_grad=True)
+    b_up = torch.randn(cq, dtype=torch.float64, requires_grad=True)
+    w_q = torch.randn(ch, cq, 1, 1, dtype=torch.float64, requires_grad=True)
+    b_q = torch.randn(ch, dtype=torch.float64, requires_grad=True)
+    ref = F.conv2d(F.conv_transpose2d(q, w_up, b_up, stride=2), w_q, b_q)
+    g = torch.randn_like(ref)
+    (ref * g).sum().backward()
+    wq2 = w_q.detach().view(ch, cq)
+    wc = torch.einsum("cdij,hd->chij", w_up.detach(), wq2).requires_grad_(True)
+    bc = (b_q.detach() + wq2 @ b_up.detach()).requires_grad_(True)
+    out = F.conv_transpose2d(q, wc, bc, stride=2)
+    assert torch.allclose(out, ref.detach(), rtol=1e-12, atol=1e-12)
+    (out * g).sum().backward()
+    assert torch.allclose(torch.einsum("chij,hd->cdij", wc.grad, wq2), w_up.grad, rtol=1e-12, atol=1e-12)
+    # W_q enters W' AND b': the second path is the rank-one term db' (x) b_up (zero in expectation behind a train-mode BatchNorm,
+    # not behind a frozen one)
+    dwq = torch.einsum("chij,cdij->hd", wc.grad, w_up.detach()) + torch.outer(bc.grad, b_up.detach())
+    assert torch.allclose(dwq, w_q.grad.view(ch, cq), rtol=1e-12, atol=1e-12)
+    assert torch.allclose(wq2.t() @ bc.grad, b_up.grad, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(bc.grad, b_q.grad, rtol=1e-12, atol=1e-12)

@@ -133,8 +133,9 @@ class _GateOp:
     """One Attention_block (Model.py:257-296) on the tensor-core engine. `up` (ConvTranspose2d C_q -> C_q) is only consumed by
     W_q (1x1, C_q -> C_h), so the two are ONE ConvTranspose2d C_q -> C_h with the composed weight
         W'[c,h,i,j] = sum_d W_up[c,d,i,j] W_q[h,d],   b'[h] = b_q[h] + sum_d W_q[h,d] b_up[d]
-    (the C_q-channel upsampled map - 1 GB at level 0 of config 2 - never exists; 4x fewer GEMM FLOPs). The composition and
-    its backward are fp32 GEMMs on the weights. Channel counts are padded to a multiple of 64 for the GEMMs (level 0 of a
+    (the C_q-channel upsampled map - 1 GB at level 0 of config 2 - never exists; 3x fewer GEMM FLOPs). The composition and
+    its backward (dW_up = dW' W_q, dW_q = sum dW'^T W_up + db' (x) b_up, db_up = W_q^T db', db_q = db') are fp32 GEMMs on
+    the weights (tests/test_host_logic.py::test_gate_weight_composition_algebra). Channel counts are padded to a multiple of 64 for the GEMMs (level 0 of a
     width-64 network has C_h = 32): zero weight rows, so the padded channels of the two maps are exact zeros."""
 
     def __init__(self, att):
@@ -369,7 +370,7 @@ class UNetEngine:
             return None
         return (q1, x1, s, aq, ax, ap, xs, not training)
 
-    def _gate_backward(self, gate: _GateOp, grec, g, q, gbuf, done, grads, sync, on_wgrad_stream):
+    def _gate_backward(self, gate: _GateOp, grec, g, q, gbuf, done, grads, sync, on_wgrad_stream, keep_alive):
         """Backward of _gate_forward. g: gradient w.r.t. the gated skip (a slice of dcat). Returns (gradient w.r.t. xs,
         gradient w.r.t. q). The two maps q1 / x1 are overwritten with their gradients."""
         q1, x1, s, aq, ax, ap, xs, frozen = grec
@@ -431,16 +432,19 @@ class UNetEngine:
         def weight_side():
             dwc = torch.empty((cq, chp, 2, 2), dtype=torch.float32, device=dev)
             ops.convt2x2_wgrad(q, dq1, dwc)
-            # dW_up[c,d,ij] = sum_h dW'[c,h,ij] W_q[h,d];  dW_q[h,d] = sum_{c,ij} dW'[c,h,ij] W_up[c,d,ij]
+            # dW_up[c,d,ij] = sum_h dW'[c,h,ij] W_q[h,d];  dW_q[h,d] = sum_{c,ij} dW'[c,h,ij] W_up[c,d,ij] + db'[h] b_up[d]
             ops.sgemm_strided(dwc, w_q.detach(), dwup, cq, cq, ch, (4 * chp, 4), (cq, 1), (4 * cq, 4), batch=4,
                               batch_strides=(1, 0, 1))
             part = torch.empty((4, ch, cq), dtype=torch.float32, device=dev)  # one partial product per (i,j), in parallel
             ops.sgemm_strided(dwc, w_up.detach(), part, ch, cq, cq, (4, 4 * chp), (4 * cq, 4), (cq, 1), batch=4,
                               batch_strides=(1, 1, ch * cq))
             ops.sum_batches(part, dwq)
+            # ... + db' (x) b_up: W_q also enters the composed bias b' = b_q + W_q b_up
+            ops.sgemm_strided(dbias, b_up.detach(), dwq, ch, cq, 1, (1, 1), (1, 1), (cq, 1), accumulate=True)
 
-        # (the closure only touches tensors that live until backward returns - q, the saved maps, parameters, gradient buffers -
-        # and what it allocates itself: the side stream is invisible to the caching allocator)
+        # (the closure only touches tensors that live until backward returns - q, the saved maps, parameters, gradient buffers,
+        # dbias through keep_alive - and what it allocates itself: the side stream is invisible to the caching allocator)
+        keep_alive.append(dbias)
         on_wgrad_stream(weight_side)
         # b' = b_q + W_q b_up:  db_q = db',  db_up[d] = sum_h W_q[h,d] db'[h]
         ops.sgemm_strided(w_q.detach(), dbias, dbup, cq, 1, ch, (1, cq), (1, 1), (1, 1))
@@ -709,7 +713,7 @@ class UNetEngine:
                 keep_alive.append(dcat)
                 if grec is not None:  # through the attention gate: gradient w.r.t. the skip activation and w.r.t. q = d_in
                     skip_grads[l], dq_gate = self._gate_backward(self.gates[j], grec, dcat[..., : ch[l]], d_in, gbuf, done, grads,
-                                                                 sync, on_wgrad_stream)
+                                                                 sync, on_wgrad_stream, keep_alive)
                 elif skip_grads[l] is None:
                     skip_grads[l] = dcat[..., : ch[l]]
                 else:
