@@ -8,6 +8,7 @@
   train512_g128  the same with configs[2]'s FIXED global batch 128 (128/N images per GPU; strong scaling)
   infer1024      configs[3]: UNet(3,5).eval(), 32 x 3x1024x1024 tiles -> uint8 class mask (replicas only at N > 1)
   reg768         configs[4]: regression head, F.relu + 'mseMC' + SGD, 8 x 3x768x768 per GPU
+  attn512        UNet_attention(3,2) (Model.py:257-391) training step at train512's shape
 
 ours      : `value`   images/s with the batch already resident in HBM, CUDA-event timed, max over ranks.
             `e2e`     the same through the public API with HOST buffers: pinned-host -> device copy of inputs (and labels)

@@ -178,3 +178,36 @@ def test_gate_weight_composition_algebra():
     assert torch.allclose(dwq, w_q.grad.view(ch, cq), rtol=1e-12, atol=1e-12)
     assert torch.allclose(wq2.t() @ bc.grad, b_up.grad, rtol=1e-12, atol=1e-12)
     assert torch.allclose(bc.grad, b_q.grad, rtol=1e-12, atol=1e-12)
+
+
+def test_attention_engine_selection_and_parameter_coverage():
+    """Which engine a UNet_attention gets (no CUDA needed to decide): the tensor-core engine at the reference's default width
+    without dropout, the generic fp32 engine otherwise and in check mode; every parameter has a slot in the backward order
+    (data-parallel flat gradient buffer); the gate holders see the reference's channel plan (Model.py:325-341)."""
+    import torch
+
+    import unet_torch_b200 as U
+    from unet_torch_b200.generic import GenericEngine
+    from unet_torch_b200.model import UNetEngine
+
+    x = torch.zeros(1, 3, 32, 32)
+    net = U.UNet_attention(3, 2)
+    eng = net._engine_for(x)
+    assert isinstance(eng, UNetEngine) and len(eng.gates) == 4
+    assert [(g.cq, g.cx, g.ch, g.chp) for g in eng.gates] == [(1024, 512, 256, 256), (512, 256, 128, 128), (256, 128, 64, 64),
+                                                              (128, 64, 32, 64)]
+    order = eng.params_in_backward_order()
+    assert len(order) == len(set(order)) == len(list(net.parameters())) and set(order) == set(net.parameters())
+    assert isinstance(net.set_check_mode(True)._engine_for(x), GenericEngine)
+    for kw in (dict(initial_feature_map=128), dict(initial_feature_map=8), dict(dropout=True)):
+        small = U.UNet_attention(3, 2, **{"initial_feature_map": 8, **kw}) if "dropout" in kw else U.UNet_attention(3, 2, **kw)
+        assert isinstance(small._engine_for(x), GenericEngine), kw
+    try:
+        net._engine_for(torch.zeros(1, 3, 40, 40))
+    except ValueError:
+        pass
+    else:
+        raise AssertionError("UNet_attention must reject H, W not divisible by 16")
+    # the plain UNet's engine has no gates; the two-decoder network can be captured as CUDA graphs now
+    assert U.UNet(3, 2)._get_engine().gates is None
+    assert U.UNet_multitask(3, 2).enable_cuda_graphs(True)._cuda_graphs is True
