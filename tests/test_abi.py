@@ -55,6 +55,13 @@ def test_host_only_queries(lib):
     assert lib.query("b200unet_conv3x3_stat_rows", 16, 512, 512, 64, 64) == 148
     assert lib.query("b200unet_conv3x3_stat_rows", 16, 64, 64, 512, 512) > 0
     assert lib.query("b200unet_launch_count") == 0
+    # attention gates: one statistics row per 8x16 tile for the 1x1 GEMM, four (one per (i,j)) for the ConvTranspose2d; gate
+    # kernels: one row per block, at most 148 x 8; reduction workspace = 148 x 8 rows of 4C + 8 floats
+    assert lib.query("b200unet_conv1x1_stat_rows", 16, 512, 512) == 16 * 64 * 32
+    assert lib.query("b200unet_convt2x2_stat_rows", 16, 256, 256) == 4 * 16 * 32 * 16
+    assert lib.query("b200unet_gate_stat_rows", 16 * 512 * 512, 32) == 148 * 8 and lib.query("b200unet_gate_stat_rows", 64, 32) == 1
+    assert lib.query("b200unet_gate_workspace_floats", 256) == 148 * 8 * (4 * 256 + 8)
+    assert lib.query("b200unet_conv1x1_wgrad_workspace_floats", 16, 512, 512, 64, 64) % (64 * 64) == 0
 
 
 def test_bad_shapes_are_errors_not_fallbacks(lib):
@@ -64,6 +71,12 @@ def test_bad_shapes_are_errors_not_fallbacks(lib):
     with pytest.raises(RuntimeError, match="n_classes"):
         lib.call("b200unet_head_fprop", None, 64, None, None, None, 1, 8, 8, 64, 9, None)
     assert "n_classes" in lib.last_error()
+    with pytest.raises(RuntimeError, match="32, 64, 128 or 256"):   # gate kernels: hidden widths of a width-64 network only
+        lib.call("b200unet_gate_psi_fwd", None, 512, None, 512, None, None, None, None, None, None, None, None, 64, 512, None)
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        lib.call("b200unet_conv1x1_fprop", 1, 32, 1, None, 1, 64, None, 64, 1, 8, 16, 32, 64, None)
+    with pytest.raises(RuntimeError, match="empty problem"):
+        lib.call("b200unet_sgemm_strided", 1, 1, 1, None, 0, 4, 4, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, None)
 
 
 def test_header_is_plain_c_and_a_c_host_links_the_library(lib, tmp_path):
