@@ -13,6 +13,7 @@
 // A pixel is handled by C/8 consecutive lanes (one 128-bit load per map and lane); per-pixel channel reductions are
 // xor-shuffles inside that lane group.
 #include "../../include/b200unet.h"
+#include "ew_common.cuh"
 #include "host_common.h"
 
 #include <cuda_bf16.h>
@@ -23,22 +24,7 @@ namespace {
 constexpr int GT = 256;
 constexpr int G_MAX_BLOCKS = 148 * 8;
 
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-  }
-}
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-}
-__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+using namespace b2ew;
 __device__ __forceinline__ float sigmoidf(float v) { return 1.f / (1.f + __expf(-v)); }
 
 int gate_blocks(long long items, int per_sm) {
