@@ -211,3 +211,19 @@ def test_attention_engine_selection_and_parameter_coverage():
     # the plain UNet's engine has no gates; the two-decoder network can be captured as CUDA graphs now
     assert U.UNet(3, 2)._get_engine().gates is None
     assert U.UNet_multitask(3, 2).enable_cuda_graphs(True)._cuda_graphs is True
+
+
+def test_profile_summaries_parse_the_committed_launch_lists():
+    """scripts/launch_summary.py finds the step boundary (two launches of the fused first-layer kernel) in the committed ncu
+    launch lists - the kernel names carry template arguments that have changed between rounds."""
+    import os
+    import subprocess
+    import sys
+
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name, launches in (("r2_launches.csv", 192), ("r2_attn_launches.csv", 298)):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "launch_summary.py"), os.path.join(ROOT, "profiles", name)],
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        first = r.stdout.splitlines()[0]
+        assert first.startswith("one step = launches") and f"{launches} launches" in first, first
