@@ -160,11 +160,16 @@ int b200unet_gate_psi_fwd(const void* q1, int q1_cs, const void* x1, int x1_cs, 
 /* out = x * sigmoid(scale_p * s + shift_p) over Cx channels (Model.py:295-296); out may be a channel slice (concat buffer). */
 int b200unet_gate_apply_fwd(const void* x, int x_cs, const float* s, const float* scale_p, const float* shift_p, void* out,
                             int out_cs, int64_t pixels, int Cx, b200_stream_t stream);
-/* Backward of the product: A = sigmoid(scale_p*s + shift_p); dx = g * A (bf16); dz = (sum_c g*x) * A * (1 - A) (fp32, one per
- * pixel); sums2 = fp64 [sum dz, sum dz * shat] with shat = (s - mean_p) * rstd_p (BatchNorm2d(1) backward). */
+/* Backward of the product: A = sigmoid(scale_p*s + shift_p); dx = g * A (bf16; NULL = not written, see b200unet_gate_dx);
+ * dz = (sum_c g*x) * A * (1 - A) (fp32, one per pixel); sums2 = fp64 [sum dz, sum dz * shat] with shat = (s - mean_p) * rstd_p
+ * (BatchNorm2d(1) backward). */
 int b200unet_gate_apply_bwd(const void* g, int g_cs, const void* x, int x_cs, const float* s, const float* scale_p,
                             const float* shift_p, const float* mean_p, const float* rstd_p, void* dx, int dx_cs, float* dz,
                             float* workspace, double* sums2, int64_t pixels, int Cx, b200_stream_t stream);
+/* dx <- g * A + dx in place: the product's gradient added to the W_x backward-data already in dx (one pass instead of a store in
+ * b200unet_gate_apply_bwd plus a separate add). */
+int b200unet_gate_dx(const void* g, int g_cs, const float* s, const float* scale_p, const float* shift_p, void* dx, int dx_cs,
+                     int64_t pixels, int Cx, b200_stream_t stream);
 /* ds = BatchNorm2d(1) backward of dz (sums2 = the, under SyncBN all-reduced, sums above; count = pixels per channel);
  * dE = ds * w_psi * [E > 0]. sums fp64 [4C + 8]: [0,C) sum dE, [C,2C) sum dE*Qhat, [2C,3C) sum dE*Xhat, [3C,4C) sum ds*E,
  * [4C] sum ds. */

@@ -177,6 +177,14 @@ def test_gate_kernels_against_autograd(c, cx, n, h, w):
     gcat[..., :cx] = g
     ops.gate_apply_bwd(gcat[..., :cx], xs, s, *aff_p, dxs, dz, sums2)
     assert rel_l2(dxs.float().reshape(P, cx), xsd.grad) < 4e-3
+    # the engine's form: no dx store here, g * A added to the W_x backward-data by gate_dx in one pass
+    dz2, sums2b = torch.full_like(dz, float("nan")), torch.empty_like(sums2)
+    ops.gate_apply_bwd(gcat[..., :cx], xs, s, *aff_p, None, dz2, sums2b)
+    assert torch.equal(dz2, dz) and torch.equal(sums2b, sums2)
+    acc = _rand_bf16(n, h, w, cx)
+    want_dx = xsd.grad + acc.double().reshape(P, cx)
+    ops.gate_dx(gcat[..., :cx], s, aff_p[0], aff_p[1], acc)
+    assert rel_l2(acc.float().reshape(P, cx), want_dx) < 4e-3
     ds = torch.empty((n, h, w), device="cuda")
     sums = torch.empty(4 * c + 8, dtype=torch.float64, device="cuda")
     ops.gate_bwd_reduce(q1[..., :c], x1[..., :c], aff_q, aff_x, wp, s, dz, gp, aff_p[2], aff_p[3], sums2, P, ds, sums)

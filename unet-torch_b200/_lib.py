@@ -129,6 +129,7 @@ SIGNATURES = {
     "b200unet_gate_psi_fwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "b200unet_gate_apply_fwd": (c_int, [_P, _I, _P, _P, _P, _P, _I, _L, _I, _P]),
     "b200unet_gate_apply_bwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _L, _I, _P]),
+    "b200unet_gate_dx": (c_int, [_P, _I, _P, _P, _P, _P, _I, _L, _I, _P]),
     "b200unet_gate_bwd_reduce": (c_int, [_P, _I, _P, _I] + [_P] * 15 + [_D, _P, _P, _P, _L, _I, _P]),
     "b200unet_gate_bwd_apply": (c_int, [_P, _I, _P, _I] + [_P] * 15 + [_D] + [_P] * 10 + [_L, _I, _P]),
     "b200unet_sgemm_strided": (c_int, [_P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _L, _L, _L, _I, _P]),

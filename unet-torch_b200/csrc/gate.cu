@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(GT) gate_apply_fwd_kernel(const __nv_bfloat16*
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// TPP lanes per pixel, each covering GPT channel groups (Cx = 8 * TPP * GPT)
+// TPP lanes per pixel, each covering GPT channel groups (Cx = 8 * TPP * GPT); two pixels in flight per thread. dx == nullptr:
+// only dz and the sums (the engine adds g*A to the W_x backward-data later, gate_dx_kernel).
 template <int TPP, int GPT>
 __global__ void __launch_bounds__(GT) gate_apply_bwd_kernel(const __nv_bfloat16* __restrict__ gr, int g_cs,
                                                             const __nv_bfloat16* __restrict__ x, int x_cs,
@@ -163,53 +164,91 @@ __global__ void __launch_bounds__(GT) gate_apply_bwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ rstd_p, __nv_bfloat16* __restrict__ dx,
                                                             int dx_cs, float* __restrict__ dz, float* __restrict__ partial,
                                                             long long pixels) {
+  constexpr int U = 2;
   const int lg = threadIdx.x % TPP;
   const float sp = scale_p[0], tp = shift_p[0], mp = mean_p[0], rp = rstd_p[0];
   float a1 = 0.f, a2 = 0.f;
   const long long total = pixels * TPP;
   const long long stride = static_cast<long long>(gridDim.x) * GT;
-  for (long long i = static_cast<long long>(blockIdx.x) * GT + threadIdx.x;; i += stride) {
-    const bool valid = i < total;
-    if (!__any_sync(0xffffffffu, valid)) break;
-    const long long pix = i / TPP;
-    float gf[GPT][8];
-    float d = 0.f;
-    if (valid) {
-      uint4 gv[GPT], xv[GPT];
+  for (long long i0 = static_cast<long long>(blockIdx.x) * GT + threadIdx.x;; i0 += stride * U) {
+    if (!__any_sync(0xffffffffu, i0 < total)) break;
+    uint4 gv[U][GPT], xv[U][GPT];
+    float sv[U];
 #pragma unroll
-      for (int u = 0; u < GPT; ++u) {
-        gv[u] = ldg128(gr + pix * g_cs + (lg + u * TPP) * 8);
-        xv[u] = ldg128(x + pix * x_cs + (lg + u * TPP) * 8);
-      }
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total) {
+        const long long pix = i / TPP;
 #pragma unroll
-      for (int u = 0; u < GPT; ++u) {
-        float xf[8];
-        unpack8(gv[u], gf[u]);
-        unpack8(xv[u], xf);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d = fmaf(gf[u][j], xf[j], d);
+        for (int v = 0; v < GPT; ++v) {
+          gv[u][v] = ldg128(gr + pix * g_cs + (lg + v * TPP) * 8);
+          xv[u][v] = ldg128(x + pix * x_cs + (lg + v * TPP) * 8);
+        }
+        sv[u] = __ldg(s + pix);
       }
     }
 #pragma unroll
-    for (int o = TPP / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (valid) {
-      const float sv = __ldg(s + pix);
-      const float a = sigmoidf(fmaf(sp, sv, tp));
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      const bool valid = i < total;
+      const long long pix = i / TPP;
+      float d = 0.f;
+      if (valid) {
 #pragma unroll
-      for (int u = 0; u < GPT; ++u) {
+        for (int v = 0; v < GPT; ++v) {
+          float gf[8], xf[8];
+          unpack8(gv[u][v], gf);
+          unpack8(xv[u][v], xf);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gf[u][j] *= a;
-        *reinterpret_cast<uint4*>(dx + pix * dx_cs + (lg + u * TPP) * 8) = pack8(gf[u]);
+          for (int j = 0; j < 8; ++j) d = fmaf(gf[j], xf[j], d);
+        }
       }
-      if (lg == 0) {
-        const float v = d * a * (1.f - a);
-        dz[pix] = v;
-        a1 += v;
-        a2 = fmaf(v, (sv - mp) * rp, a2);
+#pragma unroll
+      for (int o = TPP / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (valid) {
+        const float a = sigmoidf(fmaf(sp, sv[u], tp));
+        if (dx != nullptr) {
+#pragma unroll
+          for (int v = 0; v < GPT; ++v) {
+            float gf[8];
+            unpack8(gv[u][v], gf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gf[j] *= a;
+            *reinterpret_cast<uint4*>(dx + pix * dx_cs + (lg + v * TPP) * 8) = pack8(gf);
+          }
+        }
+        if (lg == 0) {
+          const float v = d * a * (1.f - a);
+          dz[pix] = v;
+          a1 += v;
+          a2 = fmaf(v, (sv[u] - mp) * rp, a2);
+        }
       }
     }
   }
   block_sum2(a1, a2, partial + 2 * static_cast<size_t>(blockIdx.x));
+}
+
+// dx <- g * sigmoid(sp*s + tp) + dx: the gradient through the product x * A added to the W_x backward-data already in dx
+__global__ void __launch_bounds__(GT) gate_dx_kernel(const __nv_bfloat16* __restrict__ gr, int g_cs, const float* __restrict__ s,
+                                                     const float* __restrict__ scale_p, const float* __restrict__ shift_p,
+                                                     __nv_bfloat16* dx, int dx_cs, long long pixels, int cgx) {
+  const float sp = scale_p[0], tp = shift_p[0];
+  const long long total = pixels * cgx;
+  const long long stride = static_cast<long long>(gridDim.x) * GT;
+  for (long long i = static_cast<long long>(blockIdx.x) * GT + threadIdx.x; i < total; i += stride) {
+    const long long pix = i / cgx;
+    const int g = static_cast<int>(i - pix * cgx);
+    const uint4 gv = ldg128(gr + pix * g_cs + g * 8);
+    const uint4 dv = *reinterpret_cast<const uint4*>(dx + pix * dx_cs + g * 8);
+    const float a = sigmoidf(fmaf(sp, __ldg(s + pix), tp));
+    float gf[8], df[8];
+    unpack8(gv, gf);
+    unpack8(dv, df);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) df[j] = fmaf(gf[j], a, df[j]);
+    *reinterpret_cast<uint4*>(dx + pix * dx_cs + g * 8) = pack8(df);
+  }
 }
 
 // BatchNorm2d(1) backward of the psi branch for one pixel: ds = gamma*rstd*(dz - sum(dz)/m - shat*sum(dz*shat)/m)
@@ -617,9 +656,9 @@ int b200unet_gate_apply_fwd(const void* x, int x_cs, const float* s, const float
 int b200unet_gate_apply_bwd(const void* g, int g_cs, const void* x, int x_cs, const float* s, const float* scale_p,
                             const float* shift_p, const float* mean_p, const float* rstd_p, void* dx, int dx_cs, float* dz,
                             float* workspace, double* sums2, int64_t pixels, int Cx, b200_stream_t stream) {
-  B2_REQUIRE(g && x && s && scale_p && shift_p && mean_p && rstd_p && dx && dz && workspace && sums2, "gate_apply_bwd: null argument");
+  B2_REQUIRE(g && x && s && scale_p && shift_p && mean_p && rstd_p && dz && workspace && sums2, "gate_apply_bwd: null argument");
   B2_REQUIRE(Cx == 64 || Cx == 128 || Cx == 256 || Cx == 512 || Cx == 1024, "gate_apply_bwd: Cx=%d must be a power of two in [64, 1024]", Cx);
-  B2_REQUIRE(pixels > 0 && g_cs % 8 == 0 && x_cs % 8 == 0 && dx_cs % 8 == 0 && g_cs >= Cx && x_cs >= Cx && dx_cs >= Cx,
+  B2_REQUIRE(pixels > 0 && g_cs % 8 == 0 && x_cs % 8 == 0 && g_cs >= Cx && x_cs >= Cx && (dx == nullptr || (dx_cs % 8 == 0 && dx_cs >= Cx)),
              "gate_apply_bwd: bad pitches / empty tensor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(g);
@@ -638,6 +677,16 @@ int b200unet_gate_apply_bwd(const void* g, int g_cs, const void* x, int x_cs, co
 #undef GAB
   if (int e = b2h::check_launch("gate_apply_bwd")) return e;
   return b2h::reduce_partials_launch(workspace, blocks, 2, sums2, st);
+}
+
+int b200unet_gate_dx(const void* g, int g_cs, const float* s, const float* scale_p, const float* shift_p, void* dx, int dx_cs,
+                     int64_t pixels, int Cx, b200_stream_t stream) {
+  B2_REQUIRE(g && s && scale_p && shift_p && dx, "gate_dx: null argument");
+  B2_REQUIRE(pixels > 0 && Cx > 0 && Cx % 8 == 0 && g_cs % 8 == 0 && dx_cs % 8 == 0 && g_cs >= Cx && dx_cs >= Cx,
+             "gate_dx: Cx=%d and the pitches (%d, %d) must be multiples of 8 with pitch >= Cx", Cx, g_cs, dx_cs);
+  gate_dx_kernel<<<gate_blocks(pixels * (Cx / 8), 8), GT, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(g), g_cs, s, scale_p, shift_p, static_cast<__nv_bfloat16*>(dx), dx_cs, pixels, Cx / 8);
+  return b2h::check_launch("gate_dx");
 }
 
 int b200unet_gate_bwd_reduce(const void* q1, int q1_cs, const void* x1, int x1_cs, const float* scale_q, const float* shift_q,

@@ -383,11 +383,10 @@ class UNetEngine:
         scale_p, shift_p, mean_p, rstd_p, count = ap
         psi, bn_p, bn_q, bn_x = att.psi[0], att.psi[1], att.W_q[1], att.W_x[1]
         w_psi = psi.weight.detach().view(-1)
-        # ---- the product x * A and the sigmoid
-        dxs = torch.empty((n, h, w, cx), dtype=BF16, device=dev)
+        # ---- the product x * A and the sigmoid (the g * A term of the skip gradient joins the W_x backward-data below)
         dz = torch.empty((n, h, w), dtype=torch.float32, device=dev)
         sums2 = torch.empty(2, dtype=torch.float64, device=dev)
-        ops.gate_apply_bwd(g, xs, s, scale_p, shift_p, mean_p, rstd_p, dxs, dz, sums2)
+        ops.gate_apply_bwd(g, xs, s, scale_p, shift_p, mean_p, rstd_p, None, dz, sums2)
         sums2_local = sums2
         if frozen:
             sums2 = torch.zeros_like(sums2)       # running statistics: no batch-statistics correction terms
@@ -414,9 +413,9 @@ class UNetEngine:
         done(*names)
         dq1, dx1 = q1, x1   # gradients at the two pre-BatchNorm maps (padded channels are still exact zeros)
         # ---- W_x: backward-data into the skip gradient, weight and bias gradients
-        dx_gate = torch.empty((n, h, w, cx), dtype=BF16, device=dev)
-        ops.conv1x1(dx1, wxd, None, dx_gate)
-        ops.nhwc_add(dxs, dx_gate)
+        dxs = torch.empty((n, h, w, cx), dtype=BF16, device=dev)
+        ops.conv1x1(dx1, wxd, None, dxs)
+        ops.gate_dx(g, s, scale_p, shift_p, dxs)   # + g * A in the same pass
         wx, bxp = att.W_x[0].weight, att.W_x[0].bias
         dwx, dbx = gbuf(wx), gbuf(bxp)
         on_wgrad_stream(lambda: ops.conv1x1_wgrad(xs, dx1, dwx))

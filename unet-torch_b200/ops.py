@@ -561,14 +561,27 @@ def gate_apply_fwd(x, s, scale_p, shift_p, out):
 
 
 def gate_apply_bwd(g, x, s, scale_p, shift_p, mean_p, rstd_p, dx, dz, sums2):
+    """dz, sums2 (and dx = g * A unless dx is None: the engine adds that term with gate_dx afterwards)."""
     gp, gcs, n, h, w, c = _nhwc(g)
     xp, xcs, *sx = _nhwc(x)
-    dp, dcs, *sd = _nhwc(dx)
+    dp, dcs, sd = None, 0, [n, h, w, c]
+    if dx is not None:
+        dp, dcs, *sd = _nhwc(dx)
     if sx != [n, h, w, c] or sd != [n, h, w, c] or s.numel() != n * h * w or dz.numel() != n * h * w:
         raise ValueError("gate_apply_bwd: shape mismatch")
     ws = _workspace(_lib.query("b200unet_gate_workspace_floats", 32), g.device)
     _lib.call("b200unet_gate_apply_bwd", gp, gcs, xp, xcs, _f32(s), _f32(scale_p), _f32(shift_p), _f32(mean_p), _f32(rstd_p), dp, dcs,
               _f32(dz), ws.data_ptr(), sums2.data_ptr(), n * h * w, c, _stream())
+
+
+def gate_dx(g, s, scale_p, shift_p, dx):
+    """dx <- g * sigmoid(scale_p * s + shift_p) + dx, in place."""
+    gp, gcs, n, h, w, c = _nhwc(g)
+    dp, dcs, *sd = _nhwc(dx)
+    if sd != [n, h, w, c] or s.numel() != n * h * w:
+        raise ValueError("gate_dx: shape mismatch")
+    _lib.call("b200unet_gate_dx", gp, gcs, _f32(s), _f32(scale_p), _f32(shift_p), dp, dcs, n * h * w, c, _stream())
+    return dx
 
 
 def gate_bwd_reduce(q1, x1, aff_q, aff_x, w_psi, s, dz, gamma_p, mean_p, rstd_p, sums2, count, ds, sums):
