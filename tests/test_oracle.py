@@ -310,3 +310,34 @@ def test_attention_module_matches_reference_interface():
     assert Model.UNet_attention is U.UNet_attention
     with pytest.raises(RuntimeError):
         net.attenion4(torch.zeros(1), torch.zeros(1))   # containers are not the product path
+
+
+def test_attention_restatement_at_full_width_matches_reference_fp64():
+    """The oracle's UNet_attention at the reference's default width (64), pinned to the unmodified reference's fp64 run
+    (tests/golden/ref_attention_bf16_yardstick.pt, oracle/make_golden_attention_yardstick.py): same seed -> same weights
+    (checksums stored with the golden) -> logits, loss, the gradients of every small parameter, eval logits."""
+    import unet_torch_b200 as U
+
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "ref_attention_bf16_yardstick.pt"), weights_only=False)[
+        "att_w64_c3_k2_dicebce_64"]
+    ch, ncls, width, n, h, w, seed, loss_type = g["cfg"]
+    torch.manual_seed(seed)
+    sd0 = U.UNet_attention(ch, ncls, width).state_dict()
+    for k, v in sd0.items():
+        if v.is_floating_point():
+            assert abs(float(v.double().sum()) - g["sd0_checksum"][k]) <= 1e-9 * max(1.0, abs(g["sd0_checksum"][k])), k
+    sd = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else
+              (v.double() if v.is_floating_point() else v)) for k, v in sd0.items()}
+    out, nb = O.unet_attention_forward(sd, g["x"].double(), training=True)
+    loss = O.calc_loss(out, g["y"].double(), loss_type, ncls)
+    loss.backward()
+    assert rel(out.detach(), g["logits64"]) < 1e-5          # the golden keeps the fp64 logits as fp32
+    assert abs(float(loss) - g["loss64"]) < 1e-9 * max(1.0, abs(g["loss64"]))
+    for k, gr in g["small_grads64"].items():
+        assert float((sd[k].grad - gr.double()).norm()) / max(float(gr.double().norm()), g["grad_floor"]) < 1e-4, k
+    for k, v in g["buffers1"].items():
+        assert rel(nb[k], v) < 1e-5, k
+    sd_eval = {k: (v.double() if v.is_floating_point() else v) for k, v in sd0.items()}
+    sd_eval.update({k: v.double() for k, v in nb.items() if v.is_floating_point()})
+    oe, _ = O.unet_attention_forward(sd_eval, g["x"].double(), training=False)
+    assert rel(oe, g["logits_eval64"]) < 1e-5
