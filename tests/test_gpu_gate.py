@@ -366,3 +366,53 @@ def test_fold_rows_and_folded_statistics_path(monkeypatch):
     assert rel_l2(res[1][0], res[0][0]) < 2e-2
     for k in res[0][1]:
         assert rel_l2(res[1][1][k], res[0][1][k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("frozen", [False, True])
+def test_replay_every_gate_operator_from_the_engine_trace(frozen):
+    """Operator-by-operator replay of the four attention gates of one step (tests/gate_check.py): the engine records what each
+    gate read and wrote (`UNetEngine.trace`), the host recomputes every operator from the recorded inputs in the reference's
+    two-module form (ConvTranspose2d -> 1x1 conv, fp64) at one-operator tolerance - forward maps, BatchNorm statistics, s, the
+    gated skip; backward dz, ds, both BatchNorm backwards, every parameter gradient including the split of the composed
+    ConvTranspose2d's gradient into up / W_q, and the two data gradients. frozen: module.eval() under autograd (running
+    statistics), where the bias gradients of the gate convolutions do not vanish."""
+    import unet_torch_b200 as U
+    from gate_check import check_gate
+
+    def nchw(t):
+        return t.float().permute(0, 3, 1, 2).contiguous().cpu().double()
+
+    torch.manual_seed(21)
+    net = U.UNet_attention(3, 2).cuda().train()
+    U.loss.CLASS_NUMBER = 2
+    x = torch.randn(2, 3, 64, 64, device="cuda")
+    y = (torch.rand(2, 64, 64, device="cuda") > 0.5).float()
+    if frozen:
+        with torch.no_grad():
+            net(x)      # one training forward: non-trivial running statistics
+        net.eval()
+    eng = net._get_engine()
+    eng.trace = []
+    U.calc_loss(net(x), y, loss_type="dice_bce_mc").backward()
+    torch.cuda.synchronize()
+    trace, eng.trace = eng.trace, None
+    fwd = {id(r["gate"]): r for k, r in trace if k == "gate"}
+    bwd = {id(r["gate"]): r for k, r in trace if k == "gate_bwd"}
+    assert len(fwd) == 4 and set(fwd) == set(bwd)
+    c = lambda t: t.detach().double().cpu()  # noqa: E731
+    for key, f in fwd.items():
+        b, att = bwd[key], f["gate"].att
+        names = dict(W_up=att.up.weight, b_up=att.up.bias, W_q=att.W_q[0].weight, b_q=att.W_q[0].bias, W_x=att.W_x[0].weight,
+                     b_x=att.W_x[0].bias, gq=att.W_q[1].weight, bq=att.W_q[1].bias, gx=att.W_x[1].weight, bx=att.W_x[1].bias,
+                     wpsi=att.psi[0].weight, bpsi=att.psi[0].bias, gp=att.psi[1].weight, bp=att.psi[1].bias)
+        rec = dict(q=nchw(f["q"]), x=nchw(f["x"]), q1=nchw(f["q1"]), x1=nchw(f["x1"]), s=c(f["s"]), out=nchw(f["out"]),
+                   aq=tuple(c(t) for t in f["aq"][:4]), ax=tuple(c(t) for t in f["ax"][:4]), ap=tuple(c(t) for t in f["ap"][:4]),
+                   count=float(f["aq"][4]), frozen=frozen, params={k: c(p) for k, p in names.items()}, g=nchw(b["g"]),
+                   dxs=nchw(b["dxs"]), dq=nchw(b["dq"]), dq1=nchw(b["dq1"]), dx1=nchw(b["dx1"]), dz=c(b["dz"]), ds=c(b["ds"]),
+                   grads={k: c(b["grads"][p]) for k, p in names.items()})
+        assert rec["count"] == rec["s"].numel() and f["training"] == (not frozen)
+        bad = check_gate(rec, tol_map=6e-3, tol_sum=2e-4, tol_grad=4e-3, weights_rounded=lambda t: t.to(torch.bfloat16).double())
+        assert bad == [], (f["gate"].ch, bad)
+        # every recorded gradient IS the parameter's .grad
+        for k, p in names.items():
+            assert torch.equal(p.grad, b["grads"][p]), k

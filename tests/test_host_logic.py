@@ -227,3 +227,25 @@ def test_profile_summaries_parse_the_committed_launch_lists():
         assert r.returncode == 0, r.stderr
         first = r.stdout.splitlines()[0]
         assert first.startswith("one step = launches") and f"{launches} launches" in first, first
+
+
+def test_gate_checker_accepts_the_reference_and_flags_a_missing_term():
+    """tests/gate_check.py (the one-operator-deep host check the GPU gate-replay test applies to the engine's trace) on records
+    produced by an fp64 autograd run of the reference's gate: everything within 1e-9, in training and in frozen-BatchNorm mode;
+    and it notices when dW_q lacks the rank-one term db' (x) b_up (only visible behind a frozen BatchNorm)."""
+    import torch
+
+    from gate_check import check_gate, gate_reference_run
+
+    torch.manual_seed(0)
+    cq, cx, ch, n, h, w = 6, 5, 4, 2, 6, 8
+    r = lambda *s: torch.randn(*s, dtype=torch.float64)  # noqa: E731
+    p = dict(W_up=r(cq, cq, 2, 2), b_up=r(cq), W_q=r(ch, cq, 1, 1), b_q=r(ch), W_x=r(ch, cx, 1, 1), b_x=r(ch), gq=r(ch).abs() + 0.5,
+             bq=r(ch), gx=r(ch).abs() + 0.5, bx=r(ch), wpsi=r(ch), bpsi=r(1), gp=r(1).abs() + 0.5, bp=r(1))
+    q, x, g = r(n, cq, h // 2, w // 2), r(n, cx, h, w), r(n, cx, h, w)
+    stats = {"q": (r(ch), r(ch).abs() + 0.5), "x": (r(ch), r(ch).abs() + 0.5), "p": (r(1), r(1).abs() + 0.5)}
+    for frozen in (False, True):
+        rec = gate_reference_run(p, q, x, g, frozen=frozen, stats=stats)
+        assert check_gate(rec, tol_map=1e-9, tol_sum=1e-9, tol_grad=1e-9) == [], frozen
+    rec["grads"]["W_q"] = rec["grads"]["W_q"] - torch.outer(rec["grads"]["b_q"], p["b_up"]).view(ch, cq, 1, 1)
+    assert [b[0] for b in check_gate(rec, tol_map=1e-9, tol_sum=1e-9, tol_grad=1e-9)] == ["dW_q"]
