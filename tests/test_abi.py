@@ -98,6 +98,9 @@ def test_header_is_plain_c_and_a_c_host_links_the_library(lib, tmp_path):
         "int main(void) {\n"
         '  printf("%d %d %d %lld\\n", b200unet_version(), b200unet_tile_h(), b200unet_tile_w(),\n'
         "         (long long)b200unet_conv3x3_wgrad_workspace_floats(16, 32, 32, 1024, 1024));\n"
+        "  /* attention-gate entry points: host-only size queries, and argument validation before any launch */\n"
+        '  printf("%d %lld\\n", b200unet_gate_stat_rows(64, 32), (long long)b200unet_gate_workspace_floats(256));\n'
+        "  if (b200unet_gate_dx(0, 64, 0, 0, 0, 0, 64, 1, 64, 0) == 0) return 2;\n"
         "  /* a bad shape is an error code + message, never a fallback */\n"
         "  int rc = b200unet_head_fprop(0, 64, 0, 0, 0, 1, 8, 8, 64, 9, 0);\n"
         '  printf("%d %s\\n", rc, b200unet_last_error());\n'
@@ -109,7 +112,8 @@ def test_header_is_plain_c_and_a_c_host_links_the_library(lib, tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)
-    first, second = r.stdout.strip().splitlines()
+    first, gate, second = r.stdout.strip().splitlines()
     v, th, tw, ws = first.split()
     assert int(v) >= 100 and (int(th), int(tw)) == (8, 16) and int(ws) == 3 * 1024 * 9 * 1024
+    assert gate.split() == ["1", str(148 * 8 * (4 * 256 + 8))]
     assert second.split()[0] != "0" and "n_classes" in second
