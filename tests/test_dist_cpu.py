@@ -40,6 +40,18 @@ def _worker(rank, world, port, q):
     flat.mark_ready(params[3:])
     flat.finish()
     ok = all(torch.allclose(v, torch.full_like(v, (1 + 2) / 2 * (i + 1))) for i, v in enumerate(views))
+    # out of declared order (an attention gate's gradients are finished before the ConvTranspose2d of its Up block, which comes
+    # first in the declared order): buckets only leave once the contiguous prefix is ready, every value is still averaged once
+    flat2 = ctx.make_flat_grads(params)
+    views2 = [flat2.view_for(p) for p in params]
+    for i, v in enumerate(views2):
+        v.fill_(float(rank + 1) * (i + 2))
+    flat2.mark_ready(params[2:4])
+    ok = ok and flat2.next_bucket == 0          # nothing may be reduced before params[0] is there
+    flat2.mark_ready(params[4:])
+    flat2.mark_ready(params[:2])
+    flat2.finish()
+    ok = ok and all(torch.allclose(v, torch.full_like(v, (1 + 2) / 2 * (i + 2))) for i, v in enumerate(views2))
     # SyncBN: all-reduced [sum, sum^2] with the global count reproduce whole-batch statistics
     g = torch.Generator().manual_seed(7)
     full = torch.randn(4, 8, 6, 6, generator=g, dtype=torch.float64)
